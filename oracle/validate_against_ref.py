@@ -1,0 +1,101 @@
+"""Pin the CPU restatement (oracle/wb_oracle.c) against the compiled, unmodified reference
+(oracle/_ref/ref_driver, 1 thread, canonical order — SURVEY.md §8c).
+
+Runs only where oracle/_ref exists (it is built from /root/reference by `make -C oracle ref`).
+  python oracle/validate_against_ref.py [--golden]   # --golden also (re)writes tests/golden/*
+"""
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import wb_oracle  # noqa: E402
+from wolkenbase_b200 import synth  # noqa: E402
+
+REF = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+REF_TILE = np.dtype([("n", "<i4"), ("ex", "<i4"), ("ey", "<i4"), ("nPoints", "<i4"), ("treeFlags", "<i4"),
+                     ("nGround", "<i4"), ("density", "<f8"), ("hyperboloidSize", "<f8"), ("height", "<f8")])
+
+CASES = [  # name, scene, n, seed, params
+    ("street_20k", 1, 20000, 1, {}),
+    ("aerial_60k", 2, 60000, 2, {}),
+    ("urban_30k", 5, 30000, 5, {}),
+    ("terrestrial_40k", 4, 40000, 4, {}),
+    ("aerial_30k_thick", 2, 30000, 7, {"thickness": 0.05, "max_slope": 0.7, "tile_size": 2.0,
+                                       "min_hyperboloid_size": 0.2}),
+]
+
+
+def run_ref(las_paths, out_prefix, p):
+    cmd = [REF, "-t", "1", "-c", "-o", out_prefix,
+           "-T", repr(p.get("tile_size", 1.0)), "-S", repr(p.get("max_slope", 1.0)),
+           "-K", repr(p.get("thickness", 0.0)), "-M", repr(p.get("min_hyperboloid_size", 0.1))] + las_paths
+    out = subprocess.run(cmd, capture_output=True, text=True, cwd=os.path.dirname(out_prefix))
+    line = [l for l in out.stdout.splitlines() if l.lstrip().startswith("{") or "{\"points\"" in l][-1]
+    info = json.loads(line[line.index("{"):])
+    dump = open(out_prefix + ".dump", encoding="utf-8").read()
+    labels = np.fromfile(out_prefix + ".labels", dtype=np.uint8)
+    raw = open(out_prefix + ".tiles", "rb").read()
+    tiles = np.frombuffer(raw[32:], dtype=REF_TILE)
+    return info, dump, labels, tiles
+
+
+def compare(name, scene, n, seed, p, golden_dir=None):
+    cloud = synth.generate(scene, n, seed=seed)
+    with tempfile.TemporaryDirectory() as td:
+        las = os.path.join(td, name + ".las")
+        cloud.write(las)
+        info, rdump, rlabels, rtiles = run_ref([las], os.path.join(td, "ref"), p)
+    res = wb_oracle.run([wb_oracle.file_from_cloud(cloud)], **p)
+    ok = True
+    rep = {"case": name, "points": int(cloud.n)}
+    rep["root"] = (list(res.root_center) == info["root_center"] and res.root_side == info["root_side"])
+    rep["snake"] = (res.snake_index == info["snake_index"] and res.spacing == info["spacing"])
+    rep["dump_equal"] = (res.dump == rdump)
+    rep["leaves"] = len(res.leaves)
+    ot = res.tiles
+    rep["tiles"] = [len(ot), len(rtiles)]
+    if len(ot) == len(rtiles):
+        same_addr = bool((ot["n"] == rtiles["n"]).all() and (ot["ex"] == rtiles["ex"]).all() and (ot["ey"] == rtiles["ey"]).all())
+        rep["tile_addr_equal"] = same_addr
+        rep["tile_npoints_equal"] = bool((ot["nPoints"] == rtiles["nPoints"]).all())
+        rep["tile_treeflags_equal"] = bool((ot["treeFlags"] == rtiles["treeFlags"]).all())
+        for fld in ("density", "hyperboloidSize", "height"):
+            a, b = ot[fld], rtiles[fld]
+            rep["tile_%s_bitexact" % fld] = int((a.view(np.uint64) != b.view(np.uint64)).sum())
+    else:
+        ok = False
+    mism = int((res.labels != rlabels).sum())
+    rep["label_mismatch"] = mism
+    rep["labels_hist"] = np.bincount(rlabels, minlength=3)[:3].tolist()
+    rep["margin_points"] = int(res.margin_count)
+    for k in ("root", "snake", "dump_equal", "tile_addr_equal", "tile_npoints_equal", "tile_treeflags_equal"):
+        ok = ok and bool(rep.get(k))
+    for fld in ("density", "hyperboloidSize", "height"):
+        ok = ok and rep.get("tile_%s_bitexact" % fld) == 0
+    ok = ok and mism == 0
+    rep["ok"] = ok
+    if golden_dir and ok:
+        os.makedirs(golden_dir, exist_ok=True)
+        np.savez_compressed(os.path.join(golden_dir, name + ".npz"),
+                            scene=scene, n=n, seed=seed, params=json.dumps(p),
+                            ref_dump=np.frombuffer(rdump.encode("utf-8"), dtype=np.uint8),
+                            ref_labels=rlabels, ref_tiles=rtiles,
+                            ref_root=np.array(info["root_center"] + [info["root_side"]]),
+                            ref_spacing=info["spacing"], ref_snake_index=info["snake_index"])
+    return rep
+
+
+if __name__ == "__main__":
+    golden = os.path.join(ROOT, "tests", "golden") if "--golden" in sys.argv else None
+    allok = True
+    for c in CASES:
+        r = compare(*c, golden_dir=golden)
+        print(json.dumps(r))
+        allok = allok and r["ok"]
+    sys.exit(0 if allok else 1)
