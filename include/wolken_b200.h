@@ -1,0 +1,157 @@
+/* wolken_b200.h — C ABI of libwolken_b200.so, the B200 replacement for wolkenbase's worker pool.
+ *
+ * The reference runs its ground-extraction pipeline by flipping a thread-pool command
+ * (threads.h:51-58: TH_READ, TH_SCAN, TH_POSTSCAN, TH_SPLIT, TH_PAUSE) and letting every
+ * worker execute WolkenThread::operator() (threads.cpp:446-695).  This library replaces that
+ * pool: each phase is one call that launches sm_100a kernels.  A reference maintainer binds
+ * these entry points where the pool is driven today (INTEGRATION.md shows the shim):
+ *
+ *   phase (reference)                                   entry point here
+ *   ------------------------------------------------    ---------------------------------
+ *   startThreads(n)            threads.cpp:91-113        wb_create
+ *   octRoot.sizeFit, snake.setSize, initTiles            wb_add_extent (+ implicit in wb_build)
+ *        wolkencanvas.cpp:502-519, octree.cpp:268-310
+ *   ACT_READ: readPoint + embufferPoint + OctStore::put  wb_add_las / wb_add_las_device + wb_build
+ *        threads.cpp:477-590, las.cpp:735-820, octree.cpp:849-876
+ *   octStore.dump              octree.cpp:888-891        wb_num_leaves / wb_get_leaves
+ *   TH_SCAN: scanCylinder      scan.cpp:31-140           wb_scan
+ *   TH_POSTSCAN: postscanCylinder  scan.cpp:142-179      wb_postscan
+ *   TH_SPLIT: classifyCylinder classify.cpp:96-173       wb_classify
+ *   ACT_COUNT: countClasses    threads.cpp:425-444       wb_count_classes
+ *   ACT_WRITE: class byte of writePoint las.cpp:822-851  wb_get_labels / wb_patch_records
+ *
+ * Conventions: every function returns 0 on success and a negative code on failure (the
+ * reference has no error codes: it asserts or prints); wb_last_error gives the
+ * message.  Nothing throws.  All pointers are plain host pointers unless named d_*.  A context
+ * is used from one host thread at a time.  There is no CPU fallback: without a CUDA device
+ * wb_create fails.
+ */
+#ifndef WOLKEN_B200_H
+#define WOLKEN_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct wb_ctx wb_ctx;
+
+#define WB_RECORDS 537            /* leaf bucket capacity, octree.h:41 */
+#define WB_LEVELS 21              /* depth of the canonical Morton key */
+
+enum
+{
+  WB_OK=0,
+  WB_ERR_CUDA=-1,
+  WB_ERR_ARG=-2,
+  WB_ERR_STATE=-3,
+  WB_ERR_NOMEM=-4,
+  WB_ERR_FORMAT=-5
+};
+
+typedef struct wb_leaf              /* one octree leaf = one OctBuffer, octree.h:95-144 */
+{
+  uint64_t first;                   /* index of its first point in canonical (Morton) order */
+  uint32_t count;                   /* points in the bucket (<= 537 unless depth == WB_LEVELS) */
+  int32_t depth;                    /* cube side = root side / 2^depth */
+  double cx,cy,cz,half;             /* cube centre and half side (Octree::cube, octree.cpp:348-358) */
+  double low,high;                  /* z range of the bucket (OctBuffer::low/high, octree.cpp:650-653) */
+} wb_leaf;
+
+typedef struct wb_tile              /* tile.h:27-35 */
+{
+  int32_t n;                        /* flowsnake sequence number (flowsnake.cpp:240-254) */
+  int32_t ex,ey;                    /* Eisenstein address */
+  int32_t nPoints,treeFlags;
+  int32_t pad_;
+  double density,hyperboloidSize,height;
+} wb_tile;
+
+typedef struct wb_geometry
+{
+  double root_center[3],root_side;  /* Octree::sizeFit result */
+  double cube[4];                   /* bounding cube given to Flowsnake::setSize: cx,cy,cz,side */
+  double spacing,radius;            /* tile spacing and cylinder radius (spacing*41/71) */
+  int32_t snake_index,snake_lo,snake_hi,pad_;
+} wb_geometry;
+
+typedef struct wb_stats
+{
+  uint64_t n_points;                /* points in the store (after return-number-0 dropping) */
+  uint64_t n_dropped;               /* records dropped by the return-number rule, threads.cpp:527-530 */
+  uint64_t n_leaves;
+  uint64_t n_tiles_nonempty;
+  uint64_t n_memberships;           /* (point,tile) pairs = sum of tile nPoints */
+  uint64_t n_margin;                /* points with an in/out test within rel. 1e-12 of the surface */
+  uint64_t n_untiled;               /* points in no tile cylinder (left unclassified) */
+  uint64_t kernel_launches;         /* kernels launched by this context so far */
+  double ms_h2d,ms_decode,ms_build,ms_scan,ms_postscan,ms_classify,ms_d2h;  /* last run, CUDA events */
+  double ms_sort,ms_leaves,ms_hier,ms_pairs,ms_classify_kernel;
+} wb_stats;
+
+/* ---- life cycle ---------------------------------------------------------- */
+int wb_create(int device,wb_ctx **out);
+void wb_destroy(wb_ctx *ctx);
+const char *wb_last_error(wb_ctx *ctx);
+int wb_reserve(wb_ctx *ctx,uint64_t n_points);     /* pre-size device arrays (optional) */
+int wb_clear(wb_ctx *ctx);                          /* forget the cloud, keep the allocations */
+
+/* tileSize, maxSlope, thickness, minimumHyperboloidSize: mainwindow.cpp:398-411 defaults 1,1,0,0.1 */
+int wb_set_params(wb_ctx *ctx,double tile_size,double max_slope,double thickness,double min_hyperboloid_size);
+
+/* ---- read + build (TH_READ / ACT_READ) ----------------------------------- */
+/* Header corners of an input file (LasHeader::minCorner/maxCorner * unit). */
+int wb_add_extent(wb_ctx *ctx,const double min_corner[3],const double max_corner[3]);
+/* Point records of one file, host memory (pinned or pageable); copied in chunks and decoded
+ * on the device as they arrive.  fmt 0-3 and 6-8 (las.cpp:38). */
+int wb_add_las(wb_ctx *ctx,const uint8_t *recs,uint64_t n,int fmt,int rec_len,
+               const double scale[3],const double offset[3],double unit);
+/* Same, records already in device memory. */
+int wb_add_las_device(wb_ctx *ctx,const uint8_t *d_recs,uint64_t n,int fmt,int rec_len,
+                      const double scale[3],const double offset[3],double unit);
+/* Override the geometry derived from the extents (multi-GPU: every rank uses the global one). */
+int wb_set_geometry(wb_ctx *ctx,const double root_center[3],double root_side,const double cube[4]);
+int wb_get_geometry(wb_ctx *ctx,wb_geometry *out);
+/* Morton keys, radix sort, leaf split, bucket hierarchy. */
+int wb_build(wb_ctx *ctx);
+int wb_num_leaves(wb_ctx *ctx,uint64_t *n);
+int wb_get_leaves(wb_ctx *ctx,wb_leaf *out,uint64_t cap);
+/* canonical order: order[k] = input index of the k-th point; keys[k] = its 63-bit Morton key */
+int wb_get_order(wb_ctx *ctx,uint32_t *order,uint64_t *keys);
+/* decoded SoA columns in input order (any pointer may be NULL) */
+int wb_get_decoded(wb_ctx *ctx,int32_t *x,int32_t *y,int32_t *z,uint8_t *cls);
+
+/* ---- scan / postscan (TH_SCAN, TH_POSTSCAN) ------------------------------ */
+int wb_scan(wb_ctx *ctx);
+int wb_postscan(wb_ctx *ctx);
+int wb_num_tiles(wb_ctx *ctx,uint64_t *n);                 /* non-empty tiles */
+int wb_get_tiles(wb_ctx *ctx,wb_tile *out,uint64_t cap);   /* ascending n */
+/* Replace hyperboloidSize of the listed tiles (classify parity independent of scan parity). */
+int wb_set_tiles(wb_ctx *ctx,const wb_tile *tiles,uint64_t n);
+
+/* ---- classify (TH_SPLIT) -------------------------------------------------- */
+int wb_classify(wb_ctx *ctx);
+int wb_get_labels(wb_ctx *ctx,uint8_t *labels);            /* input order, one byte per record */
+int wb_count_classes(wb_ctx *ctx,uint64_t counts[256]);
+/* Write each point's class into its record (byte 15 low 5 bits for formats 0-5, byte 16 for
+ * 6-10: las.cpp:754-756, 771, 848, 857) — host records, in place. */
+int wb_patch_records(wb_ctx *ctx,uint8_t *recs,uint64_t first_point,uint64_t n,int fmt,int rec_len);
+
+/* ---- whole pipeline -------------------------------------------------------- */
+int wb_run(wb_ctx *ctx);                                    /* build, scan, postscan, classify */
+int wb_get_stats(wb_ctx *ctx,wb_stats *out);
+int wb_sync(wb_ctx *ctx);
+
+/* ---- host helpers --------------------------------------------------------- */
+int wb_host_alloc(void **p,uint64_t bytes);                 /* pinned host memory */
+int wb_host_free(void *p);
+/* host-side restatements used by the shims (no device work) */
+int wb_size_fit(const double *corners,int n_corners,double center[3],double *side);
+int wb_bbox_cube(const double *corners,int n_corners,double cube[4]);
+int wb_snake_set_size(double cube_side,double tile_size,double *spacing,int *lo,int *hi);
+int wb_ldecimal(double x,char *buf,int buflen);
+int wb_format_dump(const wb_leaf *leaves,uint64_t n_leaves,char *buf,uint64_t buflen);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,37 @@
+"""The CPU oracle reproduces the COMPILED, UNMODIFIED reference (1 thread, canonical order) on
+the committed golden fixtures: byte-identical octree dump, bit-identical tile table, identical
+class bytes.  Fixtures are written by oracle/validate_against_ref.py --golden."""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import wb_oracle as O
+from wolkenbase_b200 import synth
+
+CASES = sorted(os.path.basename(p)[:-4] for p in
+               glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+def test_fixtures_present():
+    assert len(CASES) >= 4
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_oracle_matches_reference_fixture(case, golden_dir):
+    g = np.load(os.path.join(golden_dir, case + ".npz"))
+    p = json.loads(str(g["params"]))
+    cloud = synth.generate(int(g["scene"]), int(g["n"]), seed=int(g["seed"]))
+    res = O.run([O.file_from_cloud(cloud)], **p)
+    assert list(res.root_center) + [res.root_side] == g["ref_root"].tolist()
+    assert res.spacing == float(g["ref_spacing"]) and res.snake_index == int(g["ref_snake_index"])
+    assert res.dump == bytes(g["ref_dump"]).decode("utf-8")
+    rt = g["ref_tiles"]
+    assert len(res.tiles) == len(rt)
+    for f in ("n", "ex", "ey", "nPoints", "treeFlags"):
+        assert (res.tiles[f] == rt[f]).all(), f
+    for f in ("density", "hyperboloidSize", "height"):
+        assert (res.tiles[f].view(np.uint64) == rt[f].view(np.uint64)).all(), f
+    assert (res.labels == g["ref_labels"]).all()

@@ -1,0 +1,278 @@
+"""ctypes binding of libwolken_b200.so (include/wolken_b200.h).
+
+Thin by design: every method is one C-ABI call, with the reference phase it replaces named in
+the docstring.  The library has no CPU fallback; constructing a Context without the .so or
+without a CUDA device raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libwolken_b200.so")
+_LIB = None
+
+WB_RECORDS = 537
+WB_LEVELS = 21
+
+LEAF_DTYPE = np.dtype([("first", "<u8"), ("count", "<u4"), ("depth", "<i4"), ("cx", "<f8"), ("cy", "<f8"),
+                       ("cz", "<f8"), ("half", "<f8"), ("low", "<f8"), ("high", "<f8")])
+TILE_DTYPE = np.dtype([("n", "<i4"), ("ex", "<i4"), ("ey", "<i4"), ("nPoints", "<i4"), ("treeFlags", "<i4"),
+                       ("pad_", "<i4"), ("density", "<f8"), ("hyperboloidSize", "<f8"), ("height", "<f8")])
+
+
+class Geometry(C.Structure):
+    _fields_ = [("root_center", C.c_double * 3), ("root_side", C.c_double), ("cube", C.c_double * 4),
+                ("spacing", C.c_double), ("radius", C.c_double), ("snake_index", C.c_int32),
+                ("snake_lo", C.c_int32), ("snake_hi", C.c_int32), ("pad_", C.c_int32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [(k, C.c_uint64) for k in ("n_points", "n_dropped", "n_leaves", "n_tiles_nonempty",
+                                          "n_memberships", "n_margin", "n_untiled", "kernel_launches")] + \
+               [(k, C.c_double) for k in ("ms_h2d", "ms_decode", "ms_build", "ms_scan", "ms_postscan",
+                                          "ms_classify", "ms_d2h", "ms_sort", "ms_leaves", "ms_hier",
+                                          "ms_pairs", "ms_classify_kernel")]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class WolkenError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load the CUDA library; fails loudly if it has not been built (no fallback)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise WolkenError("libwolken_b200.so is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        L = C.CDLL(LIB_PATH)
+        vp, u64, dp = C.c_void_p, C.c_uint64, C.POINTER(C.c_double)
+        sig = {
+            "wb_create": [C.c_int, C.POINTER(vp)],
+            "wb_destroy": [vp],
+            "wb_reserve": [vp, u64],
+            "wb_clear": [vp],
+            "wb_set_params": [vp, C.c_double, C.c_double, C.c_double, C.c_double],
+            "wb_add_extent": [vp, dp, dp],
+            "wb_add_las": [vp, vp, u64, C.c_int, C.c_int, dp, dp, C.c_double],
+            "wb_add_las_device": [vp, vp, u64, C.c_int, C.c_int, dp, dp, C.c_double],
+            "wb_set_geometry": [vp, dp, C.c_double, dp],
+            "wb_get_geometry": [vp, C.POINTER(Geometry)],
+            "wb_build": [vp],
+            "wb_num_leaves": [vp, C.POINTER(u64)],
+            "wb_get_leaves": [vp, vp, u64],
+            "wb_get_order": [vp, vp, vp],
+            "wb_get_decoded": [vp, vp, vp, vp, vp],
+            "wb_scan": [vp],
+            "wb_postscan": [vp],
+            "wb_num_tiles": [vp, C.POINTER(u64)],
+            "wb_get_tiles": [vp, vp, u64],
+            "wb_set_tiles": [vp, vp, u64],
+            "wb_classify": [vp],
+            "wb_get_labels": [vp, vp],
+            "wb_count_classes": [vp, vp],
+            "wb_patch_records": [vp, vp, u64, u64, C.c_int, C.c_int],
+            "wb_run": [vp],
+            "wb_get_stats": [vp, C.POINTER(Stats)],
+            "wb_sync": [vp],
+            "wb_host_alloc": [C.POINTER(vp), u64],
+            "wb_host_free": [vp],
+            "wb_size_fit": [vp, C.c_int, dp, dp],
+            "wb_bbox_cube": [vp, C.c_int, dp],
+            "wb_snake_set_size": [C.c_double, C.c_double, dp, C.POINTER(C.c_int), C.POINTER(C.c_int)],
+            "wb_ldecimal": [C.c_double, C.c_char_p, C.c_int],
+            "wb_format_dump": [vp, u64, C.c_char_p, u64],
+        }
+        for name, args in sig.items():
+            f = getattr(L, name)
+            f.argtypes = args
+            f.restype = C.c_int
+        L.wb_destroy.restype = None
+        L.wb_last_error.argtypes = [vp]
+        L.wb_last_error.restype = C.c_char_p
+        _LIB = L
+    return _LIB
+
+
+EXPORTS = ["wb_create", "wb_destroy", "wb_last_error", "wb_reserve", "wb_clear", "wb_set_params", "wb_add_extent",
+           "wb_add_las", "wb_add_las_device", "wb_set_geometry", "wb_get_geometry", "wb_build", "wb_num_leaves",
+           "wb_get_leaves", "wb_get_order", "wb_get_decoded", "wb_scan", "wb_postscan", "wb_num_tiles",
+           "wb_get_tiles", "wb_set_tiles", "wb_classify", "wb_get_labels", "wb_count_classes", "wb_patch_records",
+           "wb_run", "wb_get_stats", "wb_sync", "wb_host_alloc", "wb_host_free", "wb_size_fit", "wb_bbox_cube",
+           "wb_snake_set_size", "wb_ldecimal", "wb_format_dump"]
+
+
+def _d(v):
+    return (C.c_double * len(v))(*[float(x) for x in v])
+
+
+def ldecimal(x):
+    buf = C.create_string_buffer(64)
+    lib().wb_ldecimal(x, buf, 64)
+    return buf.value.decode()
+
+
+class PinnedBuffer:
+    """Pinned host memory (cudaHostAlloc) viewed as a numpy uint8 array."""
+
+    def __init__(self, nbytes):
+        self._p = C.c_void_p()
+        if lib().wb_host_alloc(C.byref(self._p), nbytes) != 0:
+            raise WolkenError("cudaHostAlloc(%d) failed" % nbytes)
+        self.nbytes = nbytes
+        self.array = np.ctypeslib.as_array(C.cast(self._p, C.POINTER(C.c_uint8)), (nbytes,))
+
+    def free(self):
+        if self._p:
+            self.array = None
+            lib().wb_host_free(self._p)
+            self._p = C.c_void_p()
+
+
+class Context:
+    """One GPU's worker-pool replacement (threads.h:92-113 -> wb_*)."""
+
+    def __init__(self, device=0):
+        self._L = lib()
+        self._h = C.c_void_p()
+        rc = self._L.wb_create(device, C.byref(self._h))
+        if rc != 0:
+            raise WolkenError("wb_create(device=%d) failed with %d: no usable CUDA device "
+                              "(this library has no CPU path)" % (device, rc))
+        self.device = device
+
+    def close(self):
+        if self._h:
+            self._L.wb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise WolkenError("%s (code %d)" % (self._L.wb_last_error(self._h).decode(), rc))
+
+    # ---- configuration
+    def set_params(self, tile_size=1.0, max_slope=1.0, thickness=0.0, min_hyperboloid_size=0.1):
+        self._ck(self._L.wb_set_params(self._h, tile_size, max_slope, thickness, min_hyperboloid_size))
+
+    def reserve(self, n):
+        self._ck(self._L.wb_reserve(self._h, n))
+
+    def clear(self):
+        self._ck(self._L.wb_clear(self._h))
+
+    # ---- read
+    def add_extent(self, mn, mx):
+        self._ck(self._L.wb_add_extent(self._h, _d(mn), _d(mx)))
+
+    def add_las(self, records, fmt, scale, offset, unit=1.0):
+        """ACT_READ (threads.cpp:477-566): records is an (n, rec_len) uint8 host array."""
+        assert records.dtype == np.uint8 and records.ndim == 2 and records.flags.c_contiguous
+        self._ck(self._L.wb_add_las(self._h, records.ctypes.data, records.shape[0], fmt, records.shape[1],
+                                    _d(scale), _d(offset), unit))
+
+    def add_las_device(self, dptr, n, fmt, rec_len, scale, offset, unit=1.0):
+        self._ck(self._L.wb_add_las_device(self._h, dptr, n, fmt, rec_len, _d(scale), _d(offset), unit))
+
+    def add_cloud(self, cloud, unit=1.0):
+        """Convenience for synth.Cloud: header corners + records."""
+        self.add_extent([c * unit for c in cloud.min_corner], [c * unit for c in cloud.max_corner])
+        self.add_las(cloud.records, cloud.fmt, cloud.scale, cloud.offset, unit)
+
+    def set_geometry(self, root_center, root_side, cube):
+        self._ck(self._L.wb_set_geometry(self._h, _d(root_center), root_side, _d(cube)))
+
+    def geometry(self):
+        g = Geometry()
+        self._ck(self._L.wb_get_geometry(self._h, C.byref(g)))
+        return g
+
+    # ---- phases
+    def build(self):
+        self._ck(self._L.wb_build(self._h))
+
+    def scan(self):
+        self._ck(self._L.wb_scan(self._h))
+
+    def postscan(self):
+        self._ck(self._L.wb_postscan(self._h))
+
+    def classify(self):
+        self._ck(self._L.wb_classify(self._h))
+
+    def run(self):
+        self._ck(self._L.wb_run(self._h))
+
+    def sync(self):
+        self._ck(self._L.wb_sync(self._h))
+
+    # ---- results
+    def leaves(self):
+        n = C.c_uint64()
+        self._ck(self._L.wb_num_leaves(self._h, C.byref(n)))
+        out = np.zeros(n.value, dtype=LEAF_DTYPE)
+        if n.value:
+            self._ck(self._L.wb_get_leaves(self._h, out.ctypes.data, n.value))
+        return out
+
+    def dump(self):
+        """octStore.dump text (octree.cpp:888-891)."""
+        lv = self.leaves()
+        buf = C.create_string_buffer(len(lv) * 128 + 64)
+        ln = self._L.wb_format_dump(lv.ctypes.data, len(lv), buf, len(buf))
+        if ln < 0:
+            raise WolkenError("wb_format_dump failed")
+        return buf.raw[:ln].decode("utf-8")
+
+    def order(self, n):
+        order = np.empty(n, dtype=np.uint32)
+        keys = np.empty(n, dtype=np.uint64)
+        self._ck(self._L.wb_get_order(self._h, order.ctypes.data, keys.ctypes.data))
+        return order, keys
+
+    def decoded(self, n):
+        x = np.empty(n, dtype=np.int32)
+        y = np.empty(n, dtype=np.int32)
+        z = np.empty(n, dtype=np.int32)
+        c = np.empty(n, dtype=np.uint8)
+        self._ck(self._L.wb_get_decoded(self._h, x.ctypes.data, y.ctypes.data, z.ctypes.data, c.ctypes.data))
+        return x, y, z, c
+
+    def tiles(self):
+        n = C.c_uint64()
+        self._ck(self._L.wb_num_tiles(self._h, C.byref(n)))
+        out = np.zeros(n.value, dtype=TILE_DTYPE)
+        if n.value:
+            self._ck(self._L.wb_get_tiles(self._h, out.ctypes.data, n.value))
+        return out
+
+    def set_tiles(self, tiles):
+        t = np.ascontiguousarray(tiles, dtype=TILE_DTYPE)
+        self._ck(self._L.wb_set_tiles(self._h, t.ctypes.data, len(t)))
+
+    def labels(self, n, out=None):
+        lab = out if out is not None else np.empty(n, dtype=np.uint8)
+        self._ck(self._L.wb_get_labels(self._h, lab.ctypes.data))
+        return lab
+
+    def count_classes(self):
+        c = np.zeros(256, dtype=np.uint64)
+        self._ck(self._L.wb_count_classes(self._h, c.ctypes.data))
+        return c
+
+    def patch_records(self, records, fmt, first=0):
+        self._ck(self._L.wb_patch_records(self._h, records.ctypes.data, first, records.shape[0], fmt, records.shape[1]))
+
+    def stats(self):
+        s = Stats()
+        self._ck(self._L.wb_get_stats(self._h, C.byref(s)))
+        return s.as_dict()

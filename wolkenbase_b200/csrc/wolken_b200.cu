@@ -1,0 +1,1027 @@
+// wolken_b200.cu — C ABI of libwolken_b200.so (see include/wolken_b200.h): context, device
+// memory, phase drivers and timing around the kernels in wb_kernels.cuh.
+#include <cstdio>
+#include <cstdarg>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include <cuda_runtime.h>
+#include "../../include/wolken_b200.h"
+#include "wb_host.h"
+#include "wb_kernels.cuh"
+#include "wb_sort.cuh"
+
+namespace
+{
+
+template <typename T> struct DevBuf
+{
+  T *p=nullptr;
+  uint64_t cap=0;
+  cudaError_t ensure(uint64_t n)
+  {
+    if (n<=cap)
+      return cudaSuccess;
+    if (p)
+      cudaFree(p);
+    p=nullptr;
+    cap=0;
+    cudaError_t e=cudaMalloc((void **)&p,(size_t)(n*sizeof(T)));
+    if (e==cudaSuccess)
+      cap=n;
+    return e;
+  }
+  void release()
+  {
+    if (p)
+      cudaFree(p);
+    p=nullptr;
+    cap=0;
+  }
+};
+
+enum Phase { PH_EMPTY=0,PH_LOADED,PH_BUILT,PH_SCANNED,PH_POSTSCANNED,PH_CLASSIFIED };
+
+} // namespace
+
+struct wb_ctx
+{
+  int device=0;
+  std::string err;
+  cudaStream_t st=nullptr,stCopy=nullptr;
+  cudaEvent_t evA=nullptr,evB=nullptr,evC=nullptr,evD=nullptr,evCopy[2]={nullptr,nullptr},evDec[2]={nullptr,nullptr};
+  WbParams prm{1,1,0,0.1};
+  Phase phase=PH_EMPTY;
+  // cloud
+  uint64_t n=0,nValid=0,reserved=0;
+  std::vector<WbSegment> segs;
+  std::vector<double> corners;
+  bool geomOverride=false;
+  wb_geometry geom{};
+  WbSnake snake{};
+  // device arrays (input order)
+  DevBuf<int> xi,yi,zi;
+  DevBuf<uint8_t> cls,ret,labelIn,labelSorted,leafDepth;
+  DevBuf<unsigned long long> keyA,keyB,pairKeyA,pairKeyB,counters;
+  DevBuf<uint32_t> idxA,idxB,scr0,scr1,winner,pairValA,pairValB,table,blockSums;
+  DevBuf<uint4> tilesOf;
+  DevBuf<double> sx,sy,sz;
+  DevBuf<uint8_t> staging[2];
+  DevBuf<WbSegments> dsegs;
+  DevBuf<WbNode> nodesA,nodesB;
+  DevBuf<WbLeafDev> leaves;
+  DevBuf<WbBound> bounds;
+  DevBuf<uint32_t> levelOff,levelCnt;
+  // tiles
+  uint32_t nTiles=0;
+  DevBuf<uint32_t> tStart,tCount;
+  DevBuf<int> tNPoints;
+  DevBuf<uint8_t> tTree;
+  DevBuf<double> tDensity,tHyp,tHeight;
+  // results of build
+  unsigned long long *keys=nullptr;   // sorted keys (keyA or keyB)
+  uint32_t *perm=nullptr;             // sorted -> input
+  uint64_t *pairKeys=nullptr;
+  uint32_t *pairVals=nullptr;
+  uint64_t nPairs=0;
+  uint32_t nLeaves=0,nChunks=0;
+  int nLevels=0;
+  std::vector<uint32_t> hLevelOff,hLevelCnt;
+  wb_stats stats{};
+  bool tablesUploaded=false;
+};
+
+namespace
+{
+
+int fail(wb_ctx *c,int code,const char *fmt,...)
+{
+  char buf[512];
+  va_list ap;
+  va_start(ap,fmt);
+  vsnprintf(buf,sizeof(buf),fmt,ap);
+  va_end(ap);
+  if (c)
+    c->err=buf;
+  return code;
+}
+
+#define CK(call) do { cudaError_t e_=(call); if (e_!=cudaSuccess) return fail(ctx,WB_ERR_CUDA,"%s: %s (%s:%d)",#call,cudaGetErrorString(e_),__FILE__,__LINE__); } while (0)
+#define KCHECK() CK(cudaGetLastError())
+
+inline unsigned gridFor(uint64_t n,unsigned block) { return (unsigned)((n+block-1)/block); }
+
+float elapsed(cudaEvent_t a,cudaEvent_t b)
+{
+  float ms=0;
+  cudaEventElapsedTime(&ms,a,b);
+  return ms;
+}
+
+int uploadTables(wb_ctx *ctx)
+{
+  if (ctx->tablesUploaded)
+    return WB_OK;
+  double t[512],co[512],si[512];
+  unsigned char fw[48];
+  wbhost::fillTanTables(t,co,si);
+  memset(fw,0,sizeof(fw));
+  for (int i=0;i<6;i++)
+    for (int j=0;j<7;j++)
+      fw[i*8+j]=wbhost::kFwdTable[i][j];
+  CK(cudaMemcpyToSymbol(g_tanTable,t,sizeof(t)));
+  CK(cudaMemcpyToSymbol(g_cosTable,co,sizeof(co)));
+  CK(cudaMemcpyToSymbol(g_sinTable,si,sizeof(si)));
+  CK(cudaMemcpyToSymbol(g_fwdTable,fw,sizeof(fw)));
+  ctx->tablesUploaded=true;
+  return WB_OK;
+}
+
+int ensurePointArrays(wb_ctx *ctx,uint64_t n)
+{
+  if (n<=ctx->xi.cap)
+    return WB_OK;
+  if (ctx->n)
+    return fail(ctx,WB_ERR_STATE,"point arrays too small (%llu > %llu): call wb_reserve before adding files",
+                (unsigned long long)n,(unsigned long long)ctx->xi.cap);
+  CK(ctx->xi.ensure(n)); CK(ctx->yi.ensure(n)); CK(ctx->zi.ensure(n));
+  CK(ctx->cls.ensure(n)); CK(ctx->ret.ensure(n));
+  ctx->reserved=n;
+  return WB_OK;
+}
+
+int computeGeometry(wb_ctx *ctx)
+{
+  wb_geometry &g=ctx->geom;
+  if (!ctx->geomOverride)
+  {
+    if (ctx->corners.empty())
+      return fail(ctx,WB_ERR_STATE,"no extents: call wb_add_extent (or wb_set_geometry) first");
+    wbhost::sizeFit(ctx->corners.data(),(int)(ctx->corners.size()/3),g.root_center,&g.root_side);
+    wbhost::bboxCube(ctx->corners.data(),(int)(ctx->corners.size()/3),g.cube);
+  }
+  if (!(g.root_side>0) || !(g.cube[3]>0))
+    return fail(ctx,WB_ERR_ARG,"degenerate extents (side %g, cube %g)",g.root_side,g.cube[3]);
+  int lo,hi;
+  g.snake_index=wbhost::snakeSetSize(g.cube[3],ctx->prm.tileSize,&g.spacing,&lo,&hi);
+  g.snake_lo=lo;
+  g.snake_hi=hi;
+  g.radius=g.spacing*41/71;                        // Flowsnake::cyl, flowsnake.cpp:265
+  ctx->snake.spacing=g.spacing;
+  ctx->snake.ccx=g.cube[0];
+  ctx->snake.ccy=g.cube[1];
+  ctx->snake.radius=g.radius;
+  ctx->snake.lo=lo;
+  ctx->snake.hi=hi;
+  ctx->nTiles=(uint32_t)((long long)hi-lo+1);
+  return WB_OK;
+}
+
+int decodeDevice(wb_ctx *ctx,const uint8_t *d,uint64_t first,uint64_t cnt,int fmt,int recLen,int dropZeros,cudaStream_t st)
+{
+  if (!cnt)
+    return WB_OK;
+  wb_decode_kernel<<<gridFor(cnt,WB_DEC_THREADS),WB_DEC_THREADS,0,st>>>(
+      d,cnt,fmt,recLen,dropZeros,ctx->xi.p+first,ctx->yi.p+first,ctx->zi.p+first,
+      ctx->cls.p+first,ctx->ret.p+first,ctx->counters.p+2);
+  ctx->stats.kernel_launches++;
+  KCHECK();
+  return WB_OK;
+}
+
+int addSegment(wb_ctx *ctx,uint64_t n,const double scale[3],const double offset[3],double unit)
+{
+  if (ctx->segs.size()>=WB_MAX_SEGMENTS)
+    return fail(ctx,WB_ERR_ARG,"too many input files (max %d)",WB_MAX_SEGMENTS);
+  WbSegment s;
+  s.first=ctx->n;
+  s.count=n;
+  for (int k=0;k<3;k++)
+  {
+    s.scale[k]=scale[k];
+    s.offset[k]=offset[k];
+  }
+  s.unit=unit;
+  ctx->segs.push_back(s);
+  ctx->n+=n;
+  ctx->phase=PH_LOADED;
+  return WB_OK;
+}
+
+int checkFormat(wb_ctx *ctx,int fmt,int recLen)
+{
+  static const int len[11]={20,28,26,34,57,63,30,36,38,59,67};   // las.cpp:38
+  if (fmt<0 || fmt>10)
+    return fail(ctx,WB_ERR_FORMAT,"point format %d unknown",fmt);
+  if (recLen<len[fmt])
+    return fail(ctx,WB_ERR_FORMAT,"record length %d shorter than format %d needs (%d)",recLen,fmt,len[fmt]);
+  if (recLen>WB_DEC_MAXLEN)
+    return fail(ctx,WB_ERR_FORMAT,"record length %d not supported (waveform formats 4,5,9,10 are out of scope)",recLen);
+  return WB_OK;
+}
+
+} // namespace
+
+// ============================================================================ life cycle
+
+extern "C" int wb_create(int device,wb_ctx **out)
+{
+  if (!out)
+    return WB_ERR_ARG;
+  *out=nullptr;
+  int ndev=0;
+  if (cudaGetDeviceCount(&ndev)!=cudaSuccess || ndev==0 || device<0 || device>=ndev)
+    return WB_ERR_CUDA;               // no CPU fallback
+  wb_ctx *ctx=new wb_ctx;
+  ctx->device=device;
+  if (cudaSetDevice(device)!=cudaSuccess)
+  {
+    delete ctx;
+    return WB_ERR_CUDA;
+  }
+  cudaStreamCreateWithFlags(&ctx->st,cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&ctx->stCopy,cudaStreamNonBlocking);
+  cudaEventCreate(&ctx->evA); cudaEventCreate(&ctx->evB); cudaEventCreate(&ctx->evC); cudaEventCreate(&ctx->evD);
+  for (int i=0;i<2;i++)
+  {
+    cudaEventCreateWithFlags(&ctx->evCopy[i],cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->evDec[i],cudaEventDisableTiming);
+  }
+  if (ctx->counters.ensure(8)!=cudaSuccess || ctx->dsegs.ensure(1)!=cudaSuccess)
+  {
+    delete ctx;
+    return WB_ERR_CUDA;
+  }
+  cudaMemset(ctx->counters.p,0,8*sizeof(unsigned long long));
+  cudaFuncSetAttribute(wb_classify_kernel,cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)(sizeof(WbClassifyWarp)*WB_CL_WARPS));
+  if (uploadTables(ctx)!=WB_OK)
+  {
+    delete ctx;
+    return WB_ERR_CUDA;
+  }
+  *out=ctx;
+  return WB_OK;
+}
+
+extern "C" void wb_destroy(wb_ctx *ctx)
+{
+  if (!ctx)
+    return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  ctx->xi.release(); ctx->yi.release(); ctx->zi.release(); ctx->cls.release(); ctx->ret.release();
+  ctx->labelIn.release(); ctx->labelSorted.release(); ctx->leafDepth.release();
+  ctx->keyA.release(); ctx->keyB.release(); ctx->pairKeyA.release(); ctx->pairKeyB.release(); ctx->counters.release();
+  ctx->idxA.release(); ctx->idxB.release(); ctx->scr0.release(); ctx->scr1.release(); ctx->winner.release();
+  ctx->pairValA.release(); ctx->pairValB.release(); ctx->table.release(); ctx->blockSums.release();
+  ctx->tilesOf.release(); ctx->sx.release(); ctx->sy.release(); ctx->sz.release();
+  ctx->staging[0].release(); ctx->staging[1].release(); ctx->dsegs.release();
+  ctx->nodesA.release(); ctx->nodesB.release(); ctx->leaves.release(); ctx->bounds.release();
+  ctx->levelOff.release(); ctx->levelCnt.release();
+  ctx->tStart.release(); ctx->tCount.release(); ctx->tNPoints.release(); ctx->tTree.release();
+  ctx->tDensity.release(); ctx->tHyp.release(); ctx->tHeight.release();
+  cudaStreamDestroy(ctx->st); cudaStreamDestroy(ctx->stCopy);
+  cudaEventDestroy(ctx->evA); cudaEventDestroy(ctx->evB); cudaEventDestroy(ctx->evC); cudaEventDestroy(ctx->evD);
+  for (int i=0;i<2;i++)
+  {
+    cudaEventDestroy(ctx->evCopy[i]);
+    cudaEventDestroy(ctx->evDec[i]);
+  }
+  delete ctx;
+}
+
+extern "C" const char *wb_last_error(wb_ctx *ctx)
+{
+  return ctx?ctx->err.c_str():"null context";
+}
+
+extern "C" int wb_reserve(wb_ctx *ctx,uint64_t n)
+{
+  if (!ctx)
+    return WB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  if (ctx->n)
+    return fail(ctx,WB_ERR_STATE,"wb_reserve must precede wb_add_las");
+  return ensurePointArrays(ctx,n);
+}
+
+extern "C" int wb_clear(wb_ctx *ctx)
+{
+  if (!ctx)
+    return WB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  CK(cudaStreamSynchronize(ctx->st));
+  ctx->n=ctx->nValid=0;
+  ctx->segs.clear();
+  ctx->corners.clear();
+  ctx->geomOverride=false;
+  ctx->phase=PH_EMPTY;
+  ctx->nPairs=0;
+  ctx->nLeaves=0;
+  uint64_t launches=ctx->stats.kernel_launches;
+  memset(&ctx->stats,0,sizeof(ctx->stats));
+  ctx->stats.kernel_launches=launches;
+  CK(cudaMemsetAsync(ctx->counters.p,0,8*sizeof(unsigned long long),ctx->st));
+  return WB_OK;
+}
+
+extern "C" int wb_set_params(wb_ctx *ctx,double tileSize,double maxSlope,double thickness,double minHyp)
+{
+  if (!ctx)
+    return WB_ERR_ARG;
+  if (!(tileSize>0) || !(maxSlope>0) || !(minHyp>=0) || !std::isfinite(thickness))
+    return fail(ctx,WB_ERR_ARG,"parameters out of range (tileSize>0, maxSlope>0, minHyperboloidSize>=0)");
+  ctx->prm.tileSize=tileSize;
+  ctx->prm.maxSlope=maxSlope;
+  ctx->prm.thickness=thickness;
+  ctx->prm.minHyp=minHyp;
+  return WB_OK;
+}
+
+// ============================================================================ read
+
+extern "C" int wb_add_extent(wb_ctx *ctx,const double mn[3],const double mx[3])
+{
+  if (!ctx || !mn || !mx)
+    return WB_ERR_ARG;
+  for (int k=0;k<3;k++)
+    ctx->corners.push_back(mn[k]);
+  for (int k=0;k<3;k++)
+    ctx->corners.push_back(mx[k]);
+  return WB_OK;
+}
+
+extern "C" int wb_set_geometry(wb_ctx *ctx,const double rc[3],double rs,const double cube[4])
+{
+  if (!ctx || !rc || !cube)
+    return WB_ERR_ARG;
+  for (int k=0;k<3;k++)
+    ctx->geom.root_center[k]=rc[k];
+  ctx->geom.root_side=rs;
+  for (int k=0;k<4;k++)
+    ctx->geom.cube[k]=cube[k];
+  ctx->geomOverride=true;
+  return WB_OK;
+}
+
+extern "C" int wb_get_geometry(wb_ctx *ctx,wb_geometry *out)
+{
+  if (!ctx || !out)
+    return WB_ERR_ARG;
+  int rc=computeGeometry(ctx);
+  if (rc)
+    return rc;
+  *out=ctx->geom;
+  return WB_OK;
+}
+
+extern "C" int wb_add_las_device(wb_ctx *ctx,const uint8_t *d,uint64_t n,int fmt,int recLen,
+                                 const double scale[3],const double offset[3],double unit)
+{
+  if (!ctx || (!d && n) || !scale || !offset)
+    return WB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  int rc=checkFormat(ctx,fmt,recLen);
+  if (rc)
+    return rc;
+  if (ctx->phase>PH_LOADED)
+    return fail(ctx,WB_ERR_STATE,"cloud already built: wb_clear first");
+  if ((rc=ensurePointArrays(ctx,ctx->n+n)))
+    return rc;
+  int dropZeros=0;
+  if (n)
+  {
+    uint8_t b14;
+    CK(cudaMemcpyAsync(&b14,d+14,1,cudaMemcpyDeviceToHost,ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    dropZeros=(fmt<6?(b14&7):(b14&15))!=0;          // threads.cpp:485-500: decided by record 0
+  }
+  CK(cudaEventRecord(ctx->evA,ctx->st));
+  if ((rc=decodeDevice(ctx,d,ctx->n,n,fmt,recLen,dropZeros,ctx->st)))
+    return rc;
+  CK(cudaEventRecord(ctx->evB,ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  ctx->stats.ms_decode+=elapsed(ctx->evA,ctx->evB);
+  return addSegment(ctx,n,scale,offset,unit);
+}
+
+extern "C" int wb_add_las(wb_ctx *ctx,const uint8_t *recs,uint64_t n,int fmt,int recLen,
+                          const double scale[3],const double offset[3],double unit)
+{
+  if (!ctx || (!recs && n) || !scale || !offset)
+    return WB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  int rc=checkFormat(ctx,fmt,recLen);
+  if (rc)
+    return rc;
+  if (ctx->phase>PH_LOADED)
+    return fail(ctx,WB_ERR_STATE,"cloud already built: wb_clear first");
+  if ((rc=ensurePointArrays(ctx,ctx->n+n)))
+    return rc;
+  int dropZeros=n?((fmt<6?(recs[14]&7):(recs[14]&15))!=0):0;
+  // double-buffered pipeline: copy chunk i+1 on the copy stream while chunk i is decoded
+  const uint64_t chunkRecs=(uint64_t)1<<21;          // 2 Mi records (multiple of 16: chunks stay 16-byte aligned)
+  const uint64_t chunkBytes=chunkRecs*recLen;
+  for (int b=0;b<2;b++)
+    CK(ctx->staging[b].ensure(std::min<uint64_t>(chunkBytes,n*recLen)+64));
+  CK(cudaEventRecord(ctx->evA,ctx->st));
+  uint64_t done=0;
+  int b=0,used[2]={0,0};
+  while (done<n)
+  {
+    uint64_t cnt=std::min(chunkRecs,n-done);
+    if (used[b])
+      CK(cudaStreamWaitEvent(ctx->stCopy,ctx->evDec[b],0));   // staging[b] free again?
+    CK(cudaMemcpyAsync(ctx->staging[b].p,recs+done*recLen,cnt*recLen,cudaMemcpyHostToDevice,ctx->stCopy));
+    CK(cudaEventRecord(ctx->evCopy[b],ctx->stCopy));
+    CK(cudaStreamWaitEvent(ctx->st,ctx->evCopy[b],0));
+    if ((rc=decodeDevice(ctx,ctx->staging[b].p,ctx->n+done,cnt,fmt,recLen,dropZeros,ctx->st)))
+      return rc;
+    CK(cudaEventRecord(ctx->evDec[b],ctx->st));
+    used[b]=1;
+    done+=cnt;
+    b^=1;
+  }
+  CK(cudaEventRecord(ctx->evB,ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  ctx->stats.ms_h2d+=elapsed(ctx->evA,ctx->evB);       // copy and decode overlap: one figure for both
+  return addSegment(ctx,n,scale,offset,unit);
+}
+
+// ============================================================================ build
+
+extern "C" int wb_build(wb_ctx *ctx)
+{
+  if (!ctx)
+    return WB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  if (ctx->phase<PH_LOADED || ctx->n==0)
+    return fail(ctx,WB_ERR_STATE,"no points loaded");
+  if (ctx->n>=(1ull<<32)-64)
+    return fail(ctx,WB_ERR_ARG,"more than 2^32 points per GPU are not supported");
+  int rc=computeGeometry(ctx);
+  if (rc)
+    return rc;
+  const uint64_t n=ctx->n;
+  cudaStream_t st=ctx->st;
+  CK(ctx->keyA.ensure(n)); CK(ctx->keyB.ensure(n)); CK(ctx->idxA.ensure(n)); CK(ctx->idxB.ensure(n));
+  CK(ctx->sx.ensure(n)); CK(ctx->sy.ensure(n)); CK(ctx->sz.ensure(n));
+  CK(ctx->scr0.ensure(n+1)); CK(ctx->scr1.ensure(n+1));
+  CK(ctx->leafDepth.ensure(n));
+  CK(ctx->labelIn.ensure(n)); CK(ctx->labelSorted.ensure(n));
+  CK(ctx->table.ensure(wb_div_up(n*3+16,WB_SORT_TILE)*256+256));
+  CK(ctx->blockSums.ensure(wb_div_up(std::max<uint64_t>(n*3+16,ctx->table.cap),WB_SCAN_TILE)+1024));
+  CK(cudaEventRecord(ctx->evA,st));
+  // ---- keys
+  for (size_t s=0;s<ctx->segs.size();s++)
+  {
+    const WbSegment &sg=ctx->segs[s];
+    if (!sg.count)
+      continue;
+    wb_keygen_kernel<<<gridFor(sg.count,256),256,0,st>>>(ctx->xi.p,ctx->yi.p,ctx->zi.p,ctx->ret.p,sg.first,sg.count,sg,
+        ctx->geom.root_center[0],ctx->geom.root_center[1],ctx->geom.root_center[2],ctx->geom.root_side,
+        ctx->keyA.p,ctx->idxA.p);
+    ctx->stats.kernel_launches++;
+  }
+  KCHECK();
+  // ---- sort (63 key bits -> 8 passes)
+  CK(cudaEventRecord(ctx->evC,st));
+  bool inA=true;
+  CK(wb_radix_sort((uint64_t *)ctx->keyA.p,ctx->idxA.p,(uint64_t *)ctx->keyB.p,ctx->idxB.p,n,0,64,
+                   ctx->table.p,ctx->table.cap,ctx->blockSums.p,ctx->blockSums.cap,st,&inA,&ctx->stats.kernel_launches));
+  ctx->keys=inA?ctx->keyA.p:ctx->keyB.p;
+  ctx->perm=inA?ctx->idxA.p:ctx->idxB.p;
+  CK(cudaEventRecord(ctx->evD,st));
+  // dropped records carry key ~0 and sit at the end
+  unsigned long long dropped=0;
+  CK(cudaMemcpyAsync(&dropped,ctx->counters.p+2,sizeof(dropped),cudaMemcpyDeviceToHost,st));
+  CK(cudaStreamSynchronize(st));
+  ctx->stats.ms_sort=elapsed(ctx->evC,ctx->evD);
+  ctx->nValid=n-dropped;
+  ctx->stats.n_dropped=dropped;
+  ctx->stats.n_points=ctx->nValid;
+  const uint64_t nv=ctx->nValid;
+  if (!nv)
+    return fail(ctx,WB_ERR_STATE,"every record was dropped");
+  // ---- canonical-order coordinates
+  {
+    WbSegments hs;
+    hs.n=(int)ctx->segs.size();
+    for (int i=0;i<hs.n;i++)
+      hs.s[i]=ctx->segs[i];
+    CK(cudaMemcpyAsync(ctx->dsegs.p,&hs,sizeof(hs),cudaMemcpyHostToDevice,st));
+    CK(cudaStreamSynchronize(st));
+  }
+  wb_gather_kernel<<<gridFor(nv,256),256,0,st>>>(ctx->perm,nv,ctx->xi.p,ctx->yi.p,ctx->zi.p,ctx->dsegs.p,
+                                                ctx->sx.p,ctx->sy.p,ctx->sz.p);
+  ctx->stats.kernel_launches++;
+  KCHECK();
+  // ---- leaves: level-synchronous top-down split
+  CK(cudaEventRecord(ctx->evC,st));
+  {
+    uint64_t nodeCap=nv/256+64;
+    CK(ctx->nodesA.ensure(nodeCap)); CK(ctx->nodesB.ensure(nodeCap));
+    CK(cudaMemsetAsync(ctx->leafDepth.p,0,nv,st));
+    CK(cudaMemsetAsync(ctx->counters.p+4,0,2*sizeof(unsigned long long),st));
+    WbNode root;
+    root.first=0;
+    root.count=(uint32_t)nv;
+    uint32_t nNodes=1;
+    WbNode *cur=ctx->nodesA.p,*nxt=ctx->nodesB.p;
+    CK(cudaMemcpyAsync(cur,&root,sizeof(root),cudaMemcpyHostToDevice,st));
+    uint32_t *nNext=(uint32_t *)(ctx->counters.p+4),*nLeavesDev=(uint32_t *)(ctx->counters.p+5);
+    for (int depth=0;depth<WB_LEVELS && nNodes;depth++)
+    {
+      CK(cudaMemsetAsync(nNext,0,sizeof(uint32_t),st));
+      wb_split_kernel<<<gridFor((uint64_t)nNodes*8,128),128,0,st>>>(ctx->keys,cur,nNodes,depth,nxt,nNext,
+                                                                    ctx->leafDepth.p,nLeavesDev);
+      ctx->stats.kernel_launches++;
+      CK(cudaMemcpyAsync(&nNodes,nNext,sizeof(uint32_t),cudaMemcpyDeviceToHost,st));
+      CK(cudaStreamSynchronize(st));
+      if (nNodes>nodeCap)
+        return fail(ctx,WB_ERR_NOMEM,"internal: node list overflow");
+      std::swap(cur,nxt);
+    }
+    KCHECK();
+    CK(cudaMemcpyAsync(&ctx->nLeaves,nLeavesDev,sizeof(uint32_t),cudaMemcpyDeviceToHost,st));
+    wb_leaf_flag_kernel<<<gridFor(nv,256),256,0,st>>>(ctx->leafDepth.p,nv,ctx->scr0.p);
+    CK(wb_exclusive_scan(ctx->scr0.p,ctx->scr1.p,nv,ctx->blockSums.p,ctx->blockSums.cap,st,&ctx->stats.kernel_launches));
+    CK(cudaStreamSynchronize(st));
+    CK(ctx->leaves.ensure(ctx->nLeaves+1));
+    wb_leaf_emit_kernel<<<gridFor(nv,256),256,0,st>>>(ctx->leafDepth.p,ctx->scr1.p,nv,ctx->leaves.p);
+    wb_leaf_finish_kernel<<<gridFor((uint64_t)ctx->nLeaves*32,256),256,0,st>>>(ctx->leaves.p,ctx->nLeaves,nv,ctx->sz.p);
+    ctx->stats.kernel_launches+=3;
+    KCHECK();
+  }
+  CK(cudaEventRecord(ctx->evD,st));
+  // ---- bucket chunks and the 32-ary hierarchy over them
+  {
+    ctx->nChunks=(uint32_t)wb_div_up(nv,32);
+    ctx->hLevelOff.clear();
+    ctx->hLevelCnt.clear();
+    uint64_t total=0;
+    uint32_t c=ctx->nChunks;
+    while (true)
+    {
+      ctx->hLevelOff.push_back((uint32_t)total);
+      ctx->hLevelCnt.push_back(c);
+      total+=c;
+      if (c<=32)
+        break;
+      c=(uint32_t)wb_div_up(c,32);
+    }
+    ctx->nLevels=(int)ctx->hLevelCnt.size();
+    CK(ctx->bounds.ensure(total));
+    CK(ctx->levelOff.ensure(16)); CK(ctx->levelCnt.ensure(16));
+    CK(cudaMemcpyAsync(ctx->levelOff.p,ctx->hLevelOff.data(),ctx->nLevels*sizeof(uint32_t),cudaMemcpyHostToDevice,st));
+    CK(cudaMemcpyAsync(ctx->levelCnt.p,ctx->hLevelCnt.data(),ctx->nLevels*sizeof(uint32_t),cudaMemcpyHostToDevice,st));
+    wb_chunk_bounds_kernel<<<gridFor((uint64_t)ctx->nChunks*32,256),256,0,st>>>(ctx->sx.p,ctx->sy.p,ctx->sz.p,nv,
+                                                                              ctx->bounds.p,ctx->nChunks);
+    ctx->stats.kernel_launches++;
+    for (int l=1;l<ctx->nLevels;l++)
+    {
+      wb_node_bounds_kernel<<<gridFor((uint64_t)ctx->hLevelCnt[l]*32,256),256,0,st>>>(
+          ctx->bounds.p+ctx->hLevelOff[l-1],ctx->hLevelCnt[l-1],ctx->bounds.p+ctx->hLevelOff[l],ctx->hLevelCnt[l]);
+      ctx->stats.kernel_launches++;
+    }
+    KCHECK();
+  }
+  CK(cudaEventRecord(ctx->evB,st));
+  CK(cudaStreamSynchronize(st));
+  ctx->stats.ms_leaves=elapsed(ctx->evC,ctx->evD);
+  ctx->stats.ms_hier=elapsed(ctx->evD,ctx->evB);
+  ctx->stats.ms_build=elapsed(ctx->evA,ctx->evB);
+  ctx->stats.n_leaves=ctx->nLeaves;
+  ctx->phase=PH_BUILT;
+  return WB_OK;
+}
+
+extern "C" int wb_num_leaves(wb_ctx *ctx,uint64_t *n)
+{
+  if (!ctx || !n)
+    return WB_ERR_ARG;
+  if (ctx->phase<PH_BUILT)
+    return fail(ctx,WB_ERR_STATE,"not built");
+  *n=ctx->nLeaves;
+  return WB_OK;
+}
+
+extern "C" int wb_get_leaves(wb_ctx *ctx,wb_leaf *out,uint64_t cap)
+{
+  if (!ctx || !out)
+    return WB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  if (ctx->phase<PH_BUILT)
+    return fail(ctx,WB_ERR_STATE,"not built");
+  if (cap<ctx->nLeaves)
+    return fail(ctx,WB_ERR_ARG,"leaf buffer too small");
+  std::vector<WbLeafDev> h(ctx->nLeaves);
+  std::vector<unsigned long long> firstKey(ctx->nLeaves);
+  CK(cudaMemcpy(h.data(),ctx->leaves.p,sizeof(WbLeafDev)*ctx->nLeaves,cudaMemcpyDeviceToHost));
+  // key of each leaf's first point -> cube
+  {
+    DevBuf<unsigned long long> tmp;
+    CK(tmp.ensure(ctx->nLeaves+1));
+    wb_leaf_keys_kernel<<<gridFor(ctx->nLeaves,256),256,0,ctx->st>>>(ctx->leaves.p,ctx->nLeaves,ctx->keys,tmp.p);
+    ctx->stats.kernel_launches++;
+    KCHECK();
+    CK(cudaMemcpyAsync(firstKey.data(),tmp.p,sizeof(unsigned long long)*ctx->nLeaves,cudaMemcpyDeviceToHost,ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    tmp.release();
+  }
+  for (uint32_t i=0;i<ctx->nLeaves;i++)
+  {
+    double c[3],half;
+    wbhost::leafCube(firstKey[i],h[i].depth,ctx->geom.root_center,ctx->geom.root_side,c,&half);
+    out[i].first=h[i].first;
+    out[i].count=h[i].count;
+    out[i].depth=h[i].depth;
+    out[i].cx=c[0]; out[i].cy=c[1]; out[i].cz=c[2];
+    out[i].half=half;
+    out[i].low=h[i].low;
+    out[i].high=h[i].high;
+  }
+  return WB_OK;
+}
+
+extern "C" int wb_get_order(wb_ctx *ctx,uint32_t *order,uint64_t *keys)
+{
+  if (!ctx)
+    return WB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  if (ctx->phase<PH_BUILT)
+    return fail(ctx,WB_ERR_STATE,"not built");
+  if (order)
+    CK(cudaMemcpy(order,ctx->perm,sizeof(uint32_t)*ctx->nValid,cudaMemcpyDeviceToHost));
+  if (keys)
+    CK(cudaMemcpy(keys,ctx->keys,sizeof(uint64_t)*ctx->nValid,cudaMemcpyDeviceToHost));
+  return WB_OK;
+}
+
+extern "C" int wb_get_decoded(wb_ctx *ctx,int32_t *x,int32_t *y,int32_t *z,uint8_t *cls)
+{
+  if (!ctx)
+    return WB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  if (ctx->phase<PH_LOADED)
+    return fail(ctx,WB_ERR_STATE,"nothing loaded");
+  if (x) CK(cudaMemcpy(x,ctx->xi.p,sizeof(int)*ctx->n,cudaMemcpyDeviceToHost));
+  if (y) CK(cudaMemcpy(y,ctx->yi.p,sizeof(int)*ctx->n,cudaMemcpyDeviceToHost));
+  if (z) CK(cudaMemcpy(z,ctx->zi.p,sizeof(int)*ctx->n,cudaMemcpyDeviceToHost));
+  if (cls) CK(cudaMemcpy(cls,ctx->cls.p,ctx->n,cudaMemcpyDeviceToHost));
+  return WB_OK;
+}
+
+// ============================================================================ scan / postscan
+
+extern "C" int wb_scan(wb_ctx *ctx)
+{
+  if (!ctx)
+    return WB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  if (ctx->phase<PH_BUILT)
+    return fail(ctx,WB_ERR_STATE,"not built");
+  const uint64_t nv=ctx->nValid;
+  const uint32_t T=ctx->nTiles;
+  cudaStream_t st=ctx->st;
+  CK(ctx->tilesOf.ensure(nv)); CK(ctx->winner.ensure(nv));
+  CK(ctx->tStart.ensure(T)); CK(ctx->tCount.ensure(T)); CK(ctx->tNPoints.ensure(T)); CK(ctx->tTree.ensure(T));
+  CK(ctx->tDensity.ensure(T)); CK(ctx->tHyp.ensure(T)); CK(ctx->tHeight.ensure(T));
+  CK(cudaEventRecord(ctx->evA,st));
+  wb_member_count_kernel<<<gridFor(nv,128),128,0,st>>>(ctx->sx.p,ctx->sy.p,nv,ctx->snake,ctx->scr0.p,ctx->tilesOf.p,ctx->winner.p);
+  ctx->stats.kernel_launches++;
+  KCHECK();
+  CK(cudaMemsetAsync(ctx->scr0.p+nv,0,sizeof(uint32_t),st));
+  CK(wb_exclusive_scan(ctx->scr0.p,ctx->scr1.p,nv+1,ctx->blockSums.p,ctx->blockSums.cap,st,&ctx->stats.kernel_launches));
+  uint32_t m=0;
+  CK(cudaMemcpyAsync(&m,ctx->scr1.p+nv,sizeof(uint32_t),cudaMemcpyDeviceToHost,st));
+  CK(cudaStreamSynchronize(st));
+  ctx->nPairs=m;
+  CK(ctx->pairKeyA.ensure(m+1)); CK(ctx->pairKeyB.ensure(m+1)); CK(ctx->pairValA.ensure(m+1)); CK(ctx->pairValB.ensure(m+1));
+  CK(ctx->table.ensure(wb_div_up((uint64_t)m+16,WB_SORT_TILE)*256+256));
+  CK(ctx->blockSums.ensure(wb_div_up(ctx->table.cap,WB_SCAN_TILE)+1024));
+  wb_member_fill_kernel<<<gridFor(nv,256),256,0,st>>>(ctx->scr0.p,ctx->scr1.p,ctx->tilesOf.p,nv,ctx->pairKeyA.p,ctx->pairValA.p);
+  ctx->stats.kernel_launches++;
+  KCHECK();
+  int bits=1;
+  while (bits<32 && (1ull<<bits)<T)
+    bits++;
+  bits=(bits+7)/8*8;
+  bool inA=true;
+  CK(wb_radix_sort((uint64_t *)ctx->pairKeyA.p,ctx->pairValA.p,(uint64_t *)ctx->pairKeyB.p,ctx->pairValB.p,m,0,bits,
+                   ctx->table.p,ctx->table.cap,ctx->blockSums.p,ctx->blockSums.cap,st,&inA,&ctx->stats.kernel_launches));
+  ctx->pairKeys=(uint64_t *)(inA?ctx->pairKeyA.p:ctx->pairKeyB.p);
+  ctx->pairVals=inA?ctx->pairValA.p:ctx->pairValB.p;
+  CK(cudaMemsetAsync(ctx->tStart.p,0,sizeof(uint32_t)*T,st));
+  CK(cudaMemsetAsync(ctx->tCount.p,0,sizeof(uint32_t)*T,st));
+  CK(cudaMemsetAsync(ctx->counters.p+3,0,sizeof(unsigned long long),st));
+  if (m)
+    wb_segment_kernel<<<gridFor(m,256),256,0,st>>>((const unsigned long long *)ctx->pairKeys,m,ctx->tStart.p,ctx->tCount.p);
+  CK(cudaEventRecord(ctx->evC,st));
+  wb_scan_kernel<<<gridFor(T,64),64,0,st>>>(ctx->tStart.p,ctx->tCount.p,T,ctx->pairVals,ctx->sx.p,ctx->sy.p,ctx->sz.p,
+                                            ctx->snake,ctx->prm.minHyp,ctx->tNPoints.p,ctx->tTree.p,ctx->tDensity.p,
+                                            ctx->tHyp.p,ctx->tHeight.p,ctx->counters.p+3);
+  ctx->stats.kernel_launches+=2;
+  KCHECK();
+  CK(cudaEventRecord(ctx->evB,st));
+  unsigned long long ne=0;
+  CK(cudaMemcpyAsync(&ne,ctx->counters.p+3,sizeof(ne),cudaMemcpyDeviceToHost,st));
+  CK(cudaStreamSynchronize(st));
+  ctx->stats.ms_pairs=elapsed(ctx->evA,ctx->evC);
+  ctx->stats.ms_scan=elapsed(ctx->evA,ctx->evB);
+  ctx->stats.n_tiles_nonempty=ne;
+  ctx->stats.n_memberships=m;
+  ctx->phase=PH_SCANNED;
+  return WB_OK;
+}
+
+extern "C" int wb_postscan(wb_ctx *ctx)
+{
+  if (!ctx)
+    return WB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  if (ctx->phase!=PH_SCANNED)
+    return fail(ctx,WB_ERR_STATE,"postscan follows scan (and runs once)");
+  cudaStream_t st=ctx->st;
+  CK(cudaEventRecord(ctx->evA,st));
+  wb_postscan_kernel<<<gridFor(ctx->nTiles,128),128,0,st>>>(ctx->tNPoints.p,ctx->tTree.p,ctx->nTiles,ctx->snake,ctx->tHyp.p);
+  ctx->stats.kernel_launches++;
+  KCHECK();
+  CK(cudaEventRecord(ctx->evB,st));
+  CK(cudaStreamSynchronize(st));
+  ctx->stats.ms_postscan=elapsed(ctx->evA,ctx->evB);
+  ctx->phase=PH_POSTSCANNED;
+  return WB_OK;
+}
+
+extern "C" int wb_num_tiles(wb_ctx *ctx,uint64_t *n)
+{
+  if (!ctx || !n)
+    return WB_ERR_ARG;
+  if (ctx->phase<PH_SCANNED)
+    return fail(ctx,WB_ERR_STATE,"not scanned");
+  *n=ctx->stats.n_tiles_nonempty;
+  return WB_OK;
+}
+
+extern "C" int wb_get_tiles(wb_ctx *ctx,wb_tile *out,uint64_t cap)
+{
+  if (!ctx || !out)
+    return WB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  if (ctx->phase<PH_SCANNED)
+    return fail(ctx,WB_ERR_STATE,"not scanned");
+  if (cap<ctx->stats.n_tiles_nonempty)
+    return fail(ctx,WB_ERR_ARG,"tile buffer too small");
+  const uint32_t T=ctx->nTiles;
+  std::vector<int> np(T);
+  std::vector<uint8_t> tr(T);
+  std::vector<double> de(T),hy(T),he(T);
+  CK(cudaMemcpy(np.data(),ctx->tNPoints.p,sizeof(int)*T,cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(tr.data(),ctx->tTree.p,T,cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(de.data(),ctx->tDensity.p,sizeof(double)*T,cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(hy.data(),ctx->tHyp.p,sizeof(double)*T,cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(he.data(),ctx->tHeight.p,sizeof(double)*T,cudaMemcpyDeviceToHost));
+  uint64_t k=0;
+  for (uint32_t t=0;t<T;t++)
+    if (np[t])
+    {
+      if (k>=cap)
+        break;
+      wb_tile &o=out[k++];
+      o.n=(int32_t)((long long)t+ctx->snake.lo);
+      // Eisenstein address: same integer recipe as the device (toFlowsnake)
+      {
+        int dig[11],ori=0;
+        long long v=(long long)o.n+1235829214LL;
+        for (int i=0;i<11;i++) { dig[i]=(int)(v%7); v/=7; }
+        for (int i=10;i>=0;i--) { int tt=wbhost::kFwdTable[ori][dig[i]]; ori=tt>>4; dig[i]=tt&7; }
+        int x=0,y=0,px=1,py=0;
+        for (int i=0;i<11;i++)
+        {
+          int d=dig[i]-3,dy=(d+4)/3-1,dx=d-2*dy;
+          x+=dx*px-dy*py;
+          y+=dx*py+dy*px-dy*py;
+          int nx=2*px+py,ny=3*py-px;
+          px=nx; py=ny;
+        }
+        o.ex=x; o.ey=y;
+      }
+      o.nPoints=np[t];
+      o.treeFlags=tr[t];
+      o.pad_=0;
+      o.density=de[t];
+      o.hyperboloidSize=hy[t];
+      o.height=he[t];
+    }
+  return WB_OK;
+}
+
+extern "C" int wb_set_tiles(wb_ctx *ctx,const wb_tile *tiles,uint64_t n)
+{
+  if (!ctx || (!tiles && n))
+    return WB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  if (ctx->phase<PH_SCANNED)
+    return fail(ctx,WB_ERR_STATE,"scan first (the tile table must exist)");
+  const uint32_t T=ctx->nTiles;
+  std::vector<double> hy(T);
+  CK(cudaMemcpy(hy.data(),ctx->tHyp.p,sizeof(double)*T,cudaMemcpyDeviceToHost));
+  for (uint64_t i=0;i<n;i++)
+  {
+    long long t=(long long)tiles[i].n-ctx->snake.lo;
+    if (t<0 || t>=(long long)T)
+      return fail(ctx,WB_ERR_ARG,"tile %d outside the flowsnake range",tiles[i].n);
+    hy[t]=tiles[i].hyperboloidSize;
+  }
+  CK(cudaMemcpy(ctx->tHyp.p,hy.data(),sizeof(double)*T,cudaMemcpyHostToDevice));
+  if (ctx->phase<PH_POSTSCANNED)
+    ctx->phase=PH_POSTSCANNED;
+  return WB_OK;
+}
+
+// ============================================================================ classify
+
+extern "C" int wb_classify(wb_ctx *ctx)
+{
+  if (!ctx)
+    return WB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  if (ctx->phase<PH_POSTSCANNED)
+    return fail(ctx,WB_ERR_STATE,"classify follows postscan");
+  const uint64_t nv=ctx->nValid;
+  cudaStream_t st=ctx->st;
+  CK(cudaEventRecord(ctx->evA,st));
+  CK(cudaMemsetAsync(ctx->counters.p,0,2*sizeof(unsigned long long),st));
+  wb_init_labels_kernel<<<gridFor(ctx->n,256),256,0,st>>>(ctx->cls.p,ctx->n,ctx->labelIn.p);
+  CK(cudaEventRecord(ctx->evC,st));
+  wb_classify_kernel<<<gridFor(ctx->nChunks,WB_CL_WARPS),WB_CL_WARPS*32,sizeof(WbClassifyWarp)*WB_CL_WARPS,st>>>(
+      ctx->sx.p,ctx->sy.p,ctx->sz.p,nv,ctx->nChunks,ctx->bounds.p,ctx->levelOff.p,ctx->levelCnt.p,ctx->nLevels,
+      ctx->winner.p,ctx->tHyp.p,ctx->prm.maxSlope,ctx->prm.thickness,ctx->cls.p,ctx->perm,ctx->labelSorted.p,ctx->counters.p);
+  CK(cudaEventRecord(ctx->evD,st));
+  wb_scatter_labels_kernel<<<gridFor(nv,256),256,0,st>>>(ctx->labelSorted.p,ctx->perm,nv,ctx->labelIn.p);
+  ctx->stats.kernel_launches+=3;
+  KCHECK();
+  CK(cudaEventRecord(ctx->evB,st));
+  unsigned long long c[2]={0,0};
+  CK(cudaMemcpyAsync(c,ctx->counters.p,sizeof(c),cudaMemcpyDeviceToHost,st));
+  CK(cudaStreamSynchronize(st));
+  ctx->stats.ms_classify=elapsed(ctx->evA,ctx->evB);
+  ctx->stats.ms_classify_kernel=elapsed(ctx->evC,ctx->evD);
+  ctx->stats.n_margin=c[0];
+  ctx->stats.n_untiled=c[1];
+  ctx->phase=PH_CLASSIFIED;
+  return WB_OK;
+}
+
+extern "C" int wb_get_labels(wb_ctx *ctx,uint8_t *labels)
+{
+  if (!ctx || !labels)
+    return WB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  if (ctx->phase<PH_CLASSIFIED)
+    return fail(ctx,WB_ERR_STATE,"not classified");
+  CK(cudaEventRecord(ctx->evA,ctx->st));
+  CK(cudaMemcpyAsync(labels,ctx->labelIn.p,ctx->n,cudaMemcpyDeviceToHost,ctx->st));
+  CK(cudaEventRecord(ctx->evB,ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  ctx->stats.ms_d2h=elapsed(ctx->evA,ctx->evB);
+  return WB_OK;
+}
+
+extern "C" int wb_count_classes(wb_ctx *ctx,uint64_t counts[256])
+{
+  if (!ctx || !counts)
+    return WB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  if (ctx->phase<PH_CLASSIFIED)
+    return fail(ctx,WB_ERR_STATE,"not classified");
+  DevBuf<unsigned long long> d;
+  CK(d.ensure(256));
+  CK(cudaMemsetAsync(d.p,0,256*sizeof(unsigned long long),ctx->st));
+  wb_count_classes_kernel<<<148*4,256,0,ctx->st>>>(ctx->labelIn.p,ctx->ret.p,ctx->n,d.p);
+  ctx->stats.kernel_launches++;
+  KCHECK();
+  CK(cudaMemcpyAsync(counts,d.p,256*sizeof(unsigned long long),cudaMemcpyDeviceToHost,ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  d.release();
+  return WB_OK;
+}
+
+extern "C" int wb_patch_records(wb_ctx *ctx,uint8_t *recs,uint64_t first,uint64_t n,int fmt,int recLen)
+{
+  if (!ctx || !recs)
+    return WB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  if (ctx->phase<PH_CLASSIFIED)
+    return fail(ctx,WB_ERR_STATE,"not classified");
+  if (first+n>ctx->n)
+    return fail(ctx,WB_ERR_ARG,"range outside the cloud");
+  std::vector<uint8_t> lab(n);
+  CK(cudaMemcpy(lab.data(),ctx->labelIn.p+first,n,cudaMemcpyDeviceToHost));
+  for (uint64_t i=0;i<n;i++)
+  {
+    uint8_t *r=recs+i*(uint64_t)recLen;
+    if (fmt<6)
+      r[15]=(uint8_t)((r[15]&0xe0)|(lab[i]&31));       // writePoint, las.cpp:848
+    else
+      r[16]=lab[i];                                      // las.cpp:857
+  }
+  return WB_OK;
+}
+
+extern "C" int wb_run(wb_ctx *ctx)
+{
+  int rc;
+  if ((rc=wb_build(ctx))) return rc;
+  if ((rc=wb_scan(ctx))) return rc;
+  if ((rc=wb_postscan(ctx))) return rc;
+  return wb_classify(ctx);
+}
+
+extern "C" int wb_get_stats(wb_ctx *ctx,wb_stats *out)
+{
+  if (!ctx || !out)
+    return WB_ERR_ARG;
+  *out=ctx->stats;
+  return WB_OK;
+}
+
+extern "C" int wb_sync(wb_ctx *ctx)
+{
+  if (!ctx)
+    return WB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  CK(cudaStreamSynchronize(ctx->st));
+  CK(cudaStreamSynchronize(ctx->stCopy));
+  return WB_OK;
+}
+
+// ============================================================================ host helpers
+
+extern "C" int wb_host_alloc(void **p,uint64_t bytes)
+{
+  if (!p)
+    return WB_ERR_ARG;
+  return cudaHostAlloc(p,(size_t)bytes,cudaHostAllocDefault)==cudaSuccess?WB_OK:WB_ERR_NOMEM;
+}
+
+extern "C" int wb_host_free(void *p)
+{
+  return cudaFreeHost(p)==cudaSuccess?WB_OK:WB_ERR_CUDA;
+}
+
+extern "C" int wb_size_fit(const double *corners,int n,double center[3],double *side)
+{
+  if (!corners || !center || !side)
+    return WB_ERR_ARG;
+  wbhost::sizeFit(corners,n,center,side);
+  return WB_OK;
+}
+
+extern "C" int wb_bbox_cube(const double *corners,int n,double cube[4])
+{
+  if (!corners || !cube)
+    return WB_ERR_ARG;
+  wbhost::bboxCube(corners,n,cube);
+  return WB_OK;
+}
+
+extern "C" int wb_snake_set_size(double cubeSide,double tileSize,double *spacing,int *lo,int *hi)
+{
+  if (!spacing || !lo || !hi)
+    return WB_ERR_ARG;
+  return wbhost::snakeSetSize(cubeSide,tileSize,spacing,lo,hi);
+}
+
+extern "C" int wb_ldecimal(double x,char *buf,int buflen)
+{
+  std::string s=wbhost::ldecimal(x);
+  if (!buf || (int)s.size()+1>buflen)
+    return WB_ERR_ARG;
+  memcpy(buf,s.c_str(),s.size()+1);
+  return (int)s.size();
+}
+
+extern "C" int wb_format_dump(const wb_leaf *leaves,uint64_t n,char *buf,uint64_t buflen)
+// OctStore::dump / OctBuffer::dump text (octree.cpp:673-689, 888-891); returns the length
+{
+  if ((!leaves && n) || !buf)
+    return WB_ERR_ARG;
+  std::string out;
+  out.reserve(n*64+64);
+  unsigned long long total=0;
+  for (uint64_t i=0;i<n;i++)
+  {
+    out+="("+wbhost::ldecimal(leaves[i].cx)+","+wbhost::ldecimal(leaves[i].cy)+","+wbhost::ldecimal(leaves[i].cz)+")\xc2\xb1";
+    out+=wbhost::ldecimal(leaves[i].half)+" "+std::to_string(leaves[i].count)+" points\n";
+    total+=leaves[i].count;
+  }
+  out+=std::to_string(total)+" total points\n";
+  if (out.size()+1>buflen)
+    return WB_ERR_ARG;
+  memcpy(buf,out.c_str(),out.size()+1);
+  return (int)out.size();
+}
