@@ -693,29 +693,33 @@ wb_postscan_kernel(const int *__restrict__ tNPoints,const uint8_t *__restrict__ 
 }
 
 // ============================================================================ K9: classify
+// classifyCylinder (classify.cpp:96-173) as a pure per-point function: label 1 iff the bearings
+// dir(P,Q) of every cloud point Q inside P's downward hyperboloid (dist_xy != 0) leave no
+// circular gap >= 144 degrees (surround(), classify.cpp:67-94), else 2.
+//
 // One warp owns one chunk of 32 consecutive points of the canonical order (spatial neighbours)
-// as its 32 QUERY points, one per lane.  The warp walks the bucket hierarchy once for all 32:
-// a node is entered if the downward hyperboloid of ANY of its queries can reach the node's
-// lowest point at the node's nearest xy; the same test per lane decides which queries look at a
-// chunk.  Candidate chunks are staged in shared memory and broadcast to the lanes.  Points found
-// inside a query's hyperboloid go to a per-warp queue of (query, dx, dy); whenever 32 are
-// queued, all lanes compute one atan2i each and fold the bearings into per-query angular bins
-// (16 bins of 22.5 degrees, min and max bearing per bin) from which "no gap >= 144 degrees" is
-// decided exactly (surround(), classify.cpp:67-94): gaps inside a bin are < 22.5 degrees, and
-// gaps between bins are max-of-previous-bin to min-of-next-bin.
+// as its 32 QUERY points.  The warp walks the bucket hierarchy once for all of them.
+//   * lane = query:  per visited node, can my hyperboloid reach it (lowest point at nearest xy),
+//                    and could it still tell me anything (see sectors below)?
+//   * lane = point:  per visited chunk, the 32 chunk points sit in registers, the interested
+//                    queries are broadcast one at a time from shared memory, every lane tests
+//                    its point, and the outcome is combined with warp reductions.
+// Bearings are first only binned into 64 sectors of 5.625 degrees (a few multiplies against
+// tan(k*5.625), exact atan2i only within 1e-7 of a sector edge).  144 degrees = 25.6 sectors, so
+//   longest empty run <= 23 sectors  =>  every gap < 25 sectors = 140.6 degrees: surrounded;
+//   longest empty run >= 26 sectors  =>  a gap  > 26 sectors = 146.2 degrees: not surrounded;
+// and a node whose angular extent lies inside already-occupied sectors cannot change the
+// occupancy and is skipped.  Only queries whose longest empty run is 24 or 25 sectors need exact
+// bearings: a second, much narrower walk computes atan2i for the points of the (at most four)
+// sectors that bound such runs and measures the gap exactly.
 
 #define WB_CL_WARPS 8
-#define WB_QCAP 64
 
 struct WbClassifyWarp
 {
   double qx[32],qy[32],qcz[32],qpor2[32];
-  double cx[32],cy[32],cz[32];
-  double pdx[WB_QCAP],pdy[WB_QCAP];
-  int pq[WB_QCAP];
-  uint32_t bmin[16][32],bmax[16][32];
-  uint32_t qmask[32],touched[32];
-  uint32_t stBase[8],stMask[8];
+  uint32_t keys[8][32];       // per stack entry: (squared distance | child) of the children still to visit
+  uint32_t stBase[8];
   int stLevel[8];
 };
 
@@ -733,49 +737,131 @@ __device__ __forceinline__ bool wb_reach(double gx0,double gx1,double gy0,double
   return zl*zl*(1+1e-12)-d2*(1-1e-12)>=por2*(1-1e-12);
 }
 
-__device__ __forceinline__ bool wb_surrounded(const WbClassifyWarp &w,int lane)
+__device__ __forceinline__ int wb_sector64(double dx,double dy)
+// Sector (0..63, 5.625 degrees each, counter-clockwise from +x) of the bearing whose binary angle
+// is u = atan2i(dy,dx) & 0x7fffffff, i.e. u >> 25; -1 if the direction is within 1e-7 (relative)
+// of a sector edge and the exact atan2i has to decide.
 {
-  uint32_t mask=w.qmask[lane];
-  if (mask==0)
-    return false;
-  int f=__ffs(mask)-1;
-  uint32_t firstMin=w.bmin[f][lane],prevMax=w.bmax[f][lane];
-  bool distinct=firstMin!=prevMax || (mask&(mask-1));
-  if (!distinct)
-    return false;
-  bool ok=true;
-  uint32_t m=mask&(mask-1);
-  while (m)
-  {
-    int b=__ffs(m)-1;
-    m&=m-1;
-    if (w.bmin[b][lane]-prevMax>=(uint32_t)WB_DEG144)
-      ok=false;
-    prevMax=w.bmax[b][lane];
-  }
-  if (((firstMin-prevMax)&0x7fffffffu)>=(uint32_t)WB_DEG144)
-    ok=false;
-  return ok;
+  const double T1=0.09849140335716425,T2=0.198912367379658,T3=0.3033466836073424,T4=0.41421356237309503,
+               T5=0.5345111359507916,T6=0.6681786379192989,T7=0.8206787908286602;
+  double ax=fabs(dx),ay=fabs(dy);
+  bool sw=ay>ax;
+  double lo=sw?ax:ay,hi=sw?ay:ax;
+  double c=hi*T4;
+  bool b1=lo>=c;
+  double m=fabs(lo-c);
+  c=hi*(b1?T6:T2);
+  bool b2=lo>=c;
+  m=fmin(m,fabs(lo-c));
+  c=hi*(b1?(b2?T7:T5):(b2?T3:T1));
+  bool b3=lo>=c;
+  m=fmin(m,fabs(lo-c));
+  m=fmin(m,fmin(lo,hi-lo));
+  if (!(m>1e-7*hi))                           // ~30 units of 2^-31 turn: atan2i rounds to integers
+    return -1;
+  int sub=(b1?4:0)+(b2?2:0)+(b3?1:0);
+  int s1=sw?15-sub:sub;
+  if (dy>=0)
+    return dx>=0?s1:31-s1;
+  return dx<0?32+s1:63-s1;
 }
 
-__device__ __forceinline__ void wb_drain(WbClassifyWarp &w,int lane,int cnt)
-// lanes 0..cnt-1 each turn one queued (query,dx,dy) into a bearing and fold it into the bins
+__device__ __forceinline__ int wb_sector64_exact(double dx,double dy,uint32_t &u)
 {
-  if (lane<cnt)
-  {
-    int q=w.pq[lane];
-    int a=wb_atan2i(w.pdy[lane],w.pdx[lane]);        // dir(P,Q)=atan2i(Q-P), point.cpp:194-197
-    uint32_t u=(uint32_t)a&0x7fffffffu;
-    uint32_t b=u>>27;
-    atomicMin(&w.bmin[b][q],u);
-    atomicMax(&w.bmax[b][q],u);
-    atomicOr(&w.qmask[q],1u<<b);
-    w.touched[q]=1;
-  }
-  __syncwarp();
+  u=(uint32_t)wb_atan2i(dy,dx)&0x7fffffffu;
+  return (int)(u>>25);
 }
 
-__global__ void __launch_bounds__(WB_CL_WARPS*32)
+__device__ __forceinline__ unsigned long long wb_rotl64(unsigned long long x,int r)
+{
+  r&=63;
+  return r?(x<<r)|(x>>(64-r)):x;
+}
+
+__device__ __forceinline__ unsigned long long wb_sector_mask(double mx,double my,float r2,float d2)
+// Conservative mask of the sectors of all bearings towards a disc of squared radius r2 whose
+// centre lies at (mx,my), d2 = mx^2+my^2.
+{
+  r2=r2*1.001f+1e-12f;
+  if (!(d2>r2*1.01f))
+    return ~0ull;
+  int sc=wb_sector64(mx,my);
+  int h=(int)sqrtf(256.0f*r2/d2)+2;            // asin(x) <= (pi/2) x: half width <= 16 r/d sectors
+  if (sc<0)
+  {
+    sc=wb_sector64(mx*1.0000001+my*1e-7,my*1.0000001-mx*1e-7);   // nudge off the edge; one more sector of slack
+    h++;
+    if (sc<0)
+      return ~0ull;
+  }
+  if (2*h+1>=64)
+    return ~0ull;
+  return wb_rotl64((1ull<<(2*h+1))-1,sc-h+64);
+}
+
+__device__ __forceinline__ unsigned long long wb_box_sectors(double px,double py,const WbBound &b)
+// Conservative mask of the sectors in which bearings from (px,py) to points of the box can fall.
+{
+  double mx=0.5*(b.xmin+b.xmax)-px,my=0.5*(b.ymin+b.ymax)-py;
+  double hx=0.5*(b.xmax-b.xmin),hy=0.5*(b.ymax-b.ymin);
+  return wb_sector_mask(mx,my,(float)(hx*hx+hy*hy),(float)(mx*mx+my*my));
+}
+
+__device__ __forceinline__ unsigned long long wb_runs_ge(unsigned long long empty,int len)
+// bit i set iff sectors i-len+1..i (circular) are all empty; len in {24,26}
+{
+  unsigned long long r=empty;
+  r&=wb_rotl64(r,1);
+  r&=wb_rotl64(r,2);
+  r&=wb_rotl64(r,4);
+  r&=wb_rotl64(r,8);                           // runs of 16
+  return r&wb_rotl64(r,len-16);
+}
+
+__device__ __forceinline__ unsigned long long wb_long_runs(unsigned long long occ)
+// Sectors that belong to an empty run of at least 24 sectors.  Only these can still decide the
+// outcome: shorter empty runs stay short whatever else turns up.
+{
+  unsigned long long x=wb_runs_ge(~occ,24);     // ends of such runs
+  x|=wb_rotl64(x,63);
+  x|=wb_rotl64(x,62);
+  x|=wb_rotl64(x,60);
+  x|=wb_rotl64(x,56);                           // each end spread back over 16 sectors
+  return x|wb_rotl64(x,56);                     // ... over 24
+}
+
+__device__ __forceinline__ bool wb_in_hyperboloid(double px,double py,double pcz,double ppor2,double s2,double maxSlope,
+                                                  double qx,double qy,double qz,double &ddx,double &ddy,bool &margin)
+// Hyperboloid::in (shape.cpp:127-135) for the hyperboloid of query P and cloud point Q, and
+// dist_xy(P,Q) != 0 (classify.cpp:150).  ddx,ddy = Q-P (the vector dir() takes the bearing of).
+{
+  double zd=__dsub_rn(pcz,qz);                      // centre.z - pnt.z
+  if (!(zd>0))
+    return false;
+  double dx=__dsub_rn(px,qx),dy=__dsub_rn(py,qy);
+  ddx=-dx;
+  ddy=-dy;
+  double zz=zd*zd,hs2=(dx*dx+dy*dy)*s2;
+  double diff=zz-hs2-ppor2,tol=1e-13*(zz+hs2+ppor2);
+  bool in;
+  if (diff>tol)
+    in=true;
+  else if (diff<-tol)
+    in=false;
+  else
+  {
+    // too close to call without the reference's exact expression
+    double d=wb_hypot(dx,dy);
+    double ds=__dmul_rn(d,maxSlope);
+    double lhs=__dsub_rn(__dmul_rn(zd,zd),__dmul_rn(ds,ds));
+    in=lhs>=ppor2;
+    if (fabs(lhs-ppor2)<=1e-12*(zz+ppor2) && (dx!=0 || dy!=0))
+      margin=true;
+  }
+  return in && (dx!=0 || dy!=0);
+}
+
+__global__ void __launch_bounds__(WB_CL_WARPS*32,3)
 wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,const double *__restrict__ sz,
                    unsigned long long n,uint32_t nChunks,
                    const WbBound *__restrict__ bounds,const uint32_t *__restrict__ levelOff,
@@ -783,10 +869,11 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
                    const uint32_t *__restrict__ winner,const double *__restrict__ tHyp,
                    double maxSlope,double thickness,
                    const uint8_t *__restrict__ clsIn,const uint32_t *__restrict__ perm,
+                   uint32_t ownFirst,uint32_t ownEnd,
                    uint8_t *__restrict__ labelSorted,unsigned long long *__restrict__ counters)
 {
-  extern __shared__ __align__(16) unsigned char smraw[];
-  WbClassifyWarp &w=reinterpret_cast<WbClassifyWarp *>(smraw)[threadIdx.x>>5];
+  __shared__ WbClassifyWarp wsh[WB_CL_WARPS];
+  WbClassifyWarp &w=wsh[threadIdx.x>>5];
   const int lane=threadIdx.x&31;
   const uint32_t chunk=blockIdx.x*WB_CL_WARPS+(threadIdx.x>>5);
   if (chunk>=nChunks)
@@ -795,13 +882,17 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
   const bool have=me<n;
   const double s2=maxSlope*maxSlope;
   double px=0,py=0,pcz=-INFINITY,ppor2=INFINITY;
-  bool done=true,untiled=false;
+  bool done=true,untiled=false,foreign=false;
   if (have)
   {
     px=sx[me];
     py=sy[me];
+    uint32_t src=perm[me];
+    foreign=src<ownFirst || src>=ownEnd;          // halo point of another GPU: not ours to label
     uint32_t wt=winner[me];
-    if (wt!=0xffffffffu)
+    if (foreign)
+      ;
+    else if (wt!=0xffffffffu)
     {
       double r=tHyp[wt];
       double por=__dmul_rn(r,__dmul_rn(maxSlope,maxSlope));       // Hyperboloid ctor, shape.cpp:119-125
@@ -813,195 +904,277 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
       untiled=true;
   }
   w.qx[lane]=px; w.qy[lane]=py; w.qcz[lane]=pcz; w.qpor2[lane]=ppor2;
-  w.qmask[lane]=0; w.touched[lane]=0;
-  #pragma unroll
-  for (int b=0;b<16;b++)
+  unsigned long long occ=0;                       // occupied sectors of my query
+  unsigned long long open=~0ull;                  // sectors of empty runs >= 24 (the only ones that matter)
+  uint32_t statNodes=0,statChunks=0,statPairs=0;  // work counters (warp-uniform)
+  bool margin=false,surrounded=false;
+  // second-walk state: up to two empty runs of 24/25 sectors, bounded below by sector k1 (we need
+  // the largest bearing in it) and above by k2 (the smallest bearing in it)
+  uint32_t wedge=0xffffffffu;                     // k1a | k2a<<8 | k1b<<16 | k2b<<24, 0xff = none
+  uint32_t maxLowA=0,minHighA=0xffffffffu,maxLowB=0,minHighB=0xffffffffu;
+  unsigned long long wedgeMask=0;
+  const int top=nLevels-1;
+  const uint32_t cntTop=levelCnt[top];
+  for (int pass=1;pass<=2;pass++)
   {
-    w.bmin[b][lane]=0xffffffffu;
-    w.bmax[b][lane]=0;
-  }
-  // group envelope: xy box of the queries, highest centre, smallest polar radius
-  double gx0=have&&!done?px:INFINITY,gx1=have&&!done?px:-INFINITY;
-  double gy0=have&&!done?py:INFINITY,gy1=have&&!done?py:-INFINITY;
-  double gcz=pcz,gpor2=ppor2;
-  #pragma unroll
-  for (int o=16;o;o>>=1)
-  {
-    gx0=fmin(gx0,__shfl_xor_sync(WB_FULL,gx0,o));
-    gx1=fmax(gx1,__shfl_xor_sync(WB_FULL,gx1,o));
-    gy0=fmin(gy0,__shfl_xor_sync(WB_FULL,gy0,o));
-    gy1=fmax(gy1,__shfl_xor_sync(WB_FULL,gy1,o));
-    gcz=fmax(gcz,__shfl_xor_sync(WB_FULL,gcz,o));
-    gpor2=fmin(gpor2,__shfl_xor_sync(WB_FULL,gpor2,o));
-  }
-  __syncwarp();
-  int sp=0,qcount=0;
-  bool margin=false;
-  if (!__all_sync(WB_FULL,done))
-  {
-    // root level: up to 32 nodes
-    const int top=nLevels-1;
-    uint32_t cntTop=levelCnt[top];
-    bool pass=false;
-    if ((uint32_t)lane<cntTop)
-      pass=wb_reach(gx0,gx1,gy0,gy1,gcz,gpor2,s2,bounds[levelOff[top]+lane]);
-    uint32_t m=__ballot_sync(WB_FULL,pass);
-    if (m)
+    bool live=pass==1?!done:wedgeMask!=0;
+    uint32_t liveMask=__ballot_sync(WB_FULL,live);
+    if (!liveMask)
+      break;
+    // group envelope over the live queries: xy box, highest centre, smallest polar radius,
+    // and the union of the sectors any of them still cares about
+    double gx0,gx1,gy0,gy1,gcz,gpor2,gmx,gmy;
+    float gr2;
+    unsigned long long needAny;
+    uint32_t envMask=0;
+    auto envelope=[&]()
     {
+      gx0=live?px:INFINITY; gx1=live?px:-INFINITY;
+      gy0=live?py:INFINITY; gy1=live?py:-INFINITY;
+      gcz=live?pcz:-INFINITY; gpor2=live?ppor2:INFINITY;
+      #pragma unroll
+      for (int o=16;o;o>>=1)
+      {
+        gx0=fmin(gx0,__shfl_xor_sync(WB_FULL,gx0,o));
+        gx1=fmax(gx1,__shfl_xor_sync(WB_FULL,gx1,o));
+        gy0=fmin(gy0,__shfl_xor_sync(WB_FULL,gy0,o));
+        gy1=fmax(gy1,__shfl_xor_sync(WB_FULL,gy1,o));
+        gcz=fmax(gcz,__shfl_xor_sync(WB_FULL,gcz,o));
+        gpor2=fmin(gpor2,__shfl_xor_sync(WB_FULL,gpor2,o));
+      }
+      gmx=0.5*(gx0+gx1); gmy=0.5*(gy0+gy1);
+      double hx=0.5*(gx1-gx0),hy=0.5*(gy1-gy0);
+      gr2=(float)(hx*hx+hy*hy);
+      envMask=liveMask;
+    };
+    auto needed=[&]()
+    {
+      unsigned long long mine=live?(pass==1?open:wedgeMask):0ull;
+      uint32_t lo=__reduce_or_sync(WB_FULL,(uint32_t)mine),hi=__reduce_or_sync(WB_FULL,(uint32_t)(mine>>32));
+      needAny=(unsigned long long)lo|((unsigned long long)hi<<32);
+    };
+    envelope();
+    needed();
+    // lanes = children of a node: can any live query reach it, and does any still need its sectors?
+    auto childTest=[&](const WbBound &cb,uint32_t &key)->bool
+    {
+      if (!wb_reach(gx0,gx1,gy0,gy1,gcz,gpor2,s2,cb))
+        return false;
+      double mx=0.5*(cb.xmin+cb.xmax)-gmx,my=0.5*(cb.ymin+cb.ymax)-gmy;
+      double hx=0.5*(cb.xmax-cb.xmin),hy=0.5*(cb.ymax-cb.ymin);
+      float d2=(float)(mx*mx+my*my);
+      float rr=sqrtf((float)(hx*hx+hy*hy))+sqrtf(gr2);
+      key=(__float_as_uint(d2)&0xffffffe0u)|(uint32_t)lane;
+      return (wb_sector_mask(mx,my,rr*rr,d2)&needAny)!=0;
+    };
+    int sp=0;
+    {
+      uint32_t key=0xffffffffu;
+      bool ok=false;
+      if ((uint32_t)lane<cntTop)
+        ok=childTest(bounds[levelOff[top]+lane],key);
+      w.keys[0][lane]=ok?key:0xffffffffu;
       if (lane==0)
       {
         w.stLevel[0]=top;
         w.stBase[0]=0;
-        w.stMask[0]=m;
       }
       sp=1;
-    }
-    __syncwarp();
-  }
-  while (sp>0)
-  {
-    // pop the lowest child of the top entry
-    int level=w.stLevel[sp-1];
-    uint32_t base=w.stBase[sp-1],mask=w.stMask[sp-1];
-    int bit=__ffs(mask)-1;
-    uint32_t node=base+bit;
-    __syncwarp();
-    mask&=mask-1;
-    if (mask)
-    {
-      if (lane==0)
-        w.stMask[sp-1]=mask;
-    }
-    else
-      sp--;
-    __syncwarp();
-    if (level>0)
-    {
-      // test the node's 32 children against the group envelope
-      uint32_t c=node*32+lane,cc=levelCnt[level-1];
-      bool pass=false;
-      if (c<cc)
-        pass=wb_reach(gx0,gx1,gy0,gy1,gcz,gpor2,s2,bounds[levelOff[level-1]+c]);
-      uint32_t m=__ballot_sync(WB_FULL,pass);
-      if (m)
-      {
-        if (lane==0)
-        {
-          w.stLevel[sp]=level-1;
-          w.stBase[sp]=node*32;
-          w.stMask[sp]=m;
-        }
-        sp++;
-      }
       __syncwarp();
-      continue;
     }
-    // ---- a candidate chunk: which of my queries can reach it?
-    WbBound cb=bounds[node];                        // level 0 offset is 0
-    bool lanePass=!done && wb_reach(px,px,py,py,pcz,ppor2,s2,cb);
-    if (!__any_sync(WB_FULL,lanePass))
-      continue;
+    while (sp>0)
     {
-      unsigned long long j=(unsigned long long)node*32+lane;
-      bool ok=j<n;
-      w.cx[lane]=ok?sx[j]:0.0;
-      w.cy[lane]=ok?sy[j]:0.0;
-      w.cz[lane]=ok?sz[j]:INFINITY;
-    }
-    __syncwarp();
-    #pragma unroll 2
-    for (int p=0;p<32;p++)
-    {
-      bool in=false;
-      double dx=0,dy=0;
-      if (lanePass)
+      // pop the nearest remaining child of the top entry
+      uint32_t best=__reduce_min_sync(WB_FULL,w.keys[sp-1][lane]);
+      if (best==0xffffffffu)
       {
-        double zd=__dsub_rn(pcz,w.cz[p]);          // centre.z - pnt.z, shape.cpp:130
-        if (zd>0)
-        {
-          dx=__dsub_rn(px,w.cx[p]);
-          dy=__dsub_rn(py,w.cy[p]);
-          double zz=zd*zd,hs2=(dx*dx+dy*dy)*s2;
-          double diff=zz-hs2-ppor2,tol=1e-13*(zz+hs2+ppor2);
-          if (diff>tol)
-            in=true;
-          else if (diff>=-tol)
-          {
-            // too close to call without the reference's exact expression (shape.cpp:127-135)
-            double d=wb_hypot(dx,dy);
-            double ds=__dmul_rn(d,maxSlope);
-            double lhs=__dsub_rn(__dmul_rn(zd,zd),__dmul_rn(ds,ds));
-            in=lhs>=ppor2;
-            if (fabs(lhs-ppor2)<=1e-12*(zz+ppor2) && (dx!=0 || dy!=0))
-              margin=true;
-          }
-          in=in && (dx!=0 || dy!=0);               // dist(...) != 0, classify.cpp:150
-        }
+        sp--;
+        continue;
       }
-      uint32_t bm=__ballot_sync(WB_FULL,in);
-      if (bm)
+      const int bit=best&31;
+      const int level=w.stLevel[sp-1];
+      const uint32_t node=w.stBase[sp-1]+bit;
+      if (lane==bit)
+        w.keys[sp-1][lane]=0xffffffffu;
+      __syncwarp();
+      // lane = query: does this node matter to me?
+      WbBound nb=bounds[levelOff[level]+node];
+      bool want=false;
+      if (live && wb_reach(px,px,py,py,pcz,ppor2,s2,nb))
       {
-        if (in)
+        unsigned long long bs=wb_box_sectors(px,py,nb);
+        want=pass==1?(bs&open)!=0:(bs&wedgeMask)!=0;
+      }
+      uint32_t qm=__ballot_sync(WB_FULL,want);
+      statNodes++;
+      if (!qm)
+        continue;
+      if (level>0)
+      {
+        uint32_t c=node*32+lane,cc=levelCnt[level-1];
+        uint32_t key=0xffffffffu;
+        bool ok=false;
+        if (c<cc)
+          ok=childTest(bounds[levelOff[level-1]+c],key);
+        if (__any_sync(WB_FULL,ok))
         {
-          int slot=qcount+__popc(bm&((1u<<lane)-1));
-          w.pq[slot]=lane;
-          w.pdx[slot]=-dx;                         // Q-P
-          w.pdy[slot]=-dy;
+          w.keys[sp][lane]=ok?key:0xffffffffu;
+          if (lane==0)
+          {
+            w.stLevel[sp]=level-1;
+            w.stBase[sp]=node*32;
+          }
+          sp++;
         }
-        qcount+=__popc(bm);
         __syncwarp();
-        if (qcount>=32)
+        continue;
+      }
+      // ---- a chunk: lane = point
+      unsigned long long j=(unsigned long long)node*32+lane;
+      const bool okp=j<n;
+      const double cxp=okp?sx[j]:0.0,cyp=okp?sy[j]:0.0,czp=okp?sz[j]:INFINITY;
+      statChunks++;
+      statPairs+=__popc(qm);
+      while (qm)
+      {
+        const int q=__ffs(qm)-1;
+        qm&=qm-1;
+        const double qx=w.qx[q],qy=w.qy[q],qcz=w.qcz[q],qpor2=w.qpor2[q];
+        double ddx=0,ddy=0;
+        bool mg=false;
+        bool in=wb_in_hyperboloid(qx,qy,qcz,qpor2,s2,maxSlope,cxp,cyp,czp,ddx,ddy,mg);
+        if (__any_sync(WB_FULL,mg) && lane==q)
+          margin=true;
+        if (pass==1)
         {
-          wb_drain(w,lane,32);
-          // move the tail down
-          int rest=qcount-32;
-          int tq=0; double tx=0,ty=0;
-          if (lane<rest)
+          int s=-2;
+          if (in)
           {
-            tq=w.pq[32+lane]; tx=w.pdx[32+lane]; ty=w.pdy[32+lane];
-          }
-          __syncwarp();
-          if (lane<rest)
-          {
-            w.pq[lane]=tq; w.pdx[lane]=tx; w.pdy[lane]=ty;
-          }
-          qcount=rest;
-          __syncwarp();
-          if (!done && w.touched[lane])
-          {
-            w.touched[lane]=0;
-            if (wb_surrounded(w,lane))
+            s=wb_sector64(ddx,ddy);
+            if (s<0)
             {
-              done=true;
-              lanePass=false;
+              uint32_t u;
+              s=wb_sector64_exact(ddx,ddy,u);
             }
           }
+          uint32_t lo=__reduce_or_sync(WB_FULL,(in && s<32)?1u<<s:0u);
+          uint32_t hi=__reduce_or_sync(WB_FULL,(in && s>=32)?1u<<(s-32):0u);
+          if (lane==q)
+            occ|=(unsigned long long)lo|((unsigned long long)hi<<32);
+        }
+        else
+        {
+          const uint32_t wq=__shfl_sync(WB_FULL,wedge,q);
+          uint32_t cMaxA=0,cMinA=0xffffffffu,cMaxB=0,cMinB=0xffffffffu;
+          if (in)
+          {
+            int s=wb_sector64(ddx,ddy);
+            int k1a=wq&255,k2a=(wq>>8)&255,k1b=(wq>>16)&255,k2b=wq>>24;
+            if (s<0 || s==k1a || s==k2a || s==k1b || s==k2b)
+            {
+              uint32_t u;
+              s=wb_sector64_exact(ddx,ddy,u);
+              if (s==k1a) cMaxA=u;
+              if (s==k2a) cMinA=u;
+              if (s==k1b) cMaxB=u;
+              if (s==k2b) cMinB=u;
+            }
+          }
+          cMaxA=__reduce_max_sync(WB_FULL,cMaxA);
+          cMinA=__reduce_min_sync(WB_FULL,cMinA);
+          cMaxB=__reduce_max_sync(WB_FULL,cMaxB);
+          cMinB=__reduce_min_sync(WB_FULL,cMinB);
+          if (lane==q)
+          {
+            maxLowA=max(maxLowA,cMaxA);
+            minHighA=min(minHighA,cMinA);
+            maxLowB=max(maxLowB,cMaxB);
+            minHighB=min(minHighB,cMinB);
+          }
+        }
+      }
+      if (pass==1)
+      {
+        // surrounded for sure once no empty run of 24 sectors is left
+        if (live)
+        {
+          open=wb_long_runs(occ);
+          if (!open)
+          {
+            surrounded=true;
+            done=true;
+            live=false;
+          }
+        }
+        liveMask=__ballot_sync(WB_FULL,live);
+        if (!liveMask)
+          break;
+        // shrink the envelope when queries have finished; refresh the needed sectors
+        if (liveMask!=envMask)
+          envelope();
+        needed();
+      }
+    }
+    if (pass==1)
+    {
+      // undecided queries: empty run of >= 26 sectors -> not surrounded; 24..25 -> exact second walk
+      if (!done)
+      {
+        unsigned long long empty=~occ;
+        unsigned long long r24=wb_runs_ge(empty,24);
+        if (r24 && !wb_runs_ge(empty,26))
+        {
+          // locate the runs: a run ends at sector e where r24 has a bit and sector e+1 is occupied
+          int nrun=0;
+          unsigned long long ends=r24&~wb_rotl64(empty,63);        // empty[e+1]==0  <=>  rotl(empty,63) bit e == 0
+          while (ends && nrun<2)
+          {
+            int e=__ffsll((long long)ends)-1;
+            ends&=ends-1;
+            int len=0;
+            while (len<64 && ((empty>>((e-len+64)&63))&1))
+              len++;
+            int k1=(e-len+64)&63,k2=(e+1)&63;
+            if (nrun==0)
+              wedge=(wedge&0xffff0000u)|(uint32_t)k1|((uint32_t)k2<<8);
+            else
+              wedge=(wedge&0x0000ffffu)|((uint32_t)k1<<16)|((uint32_t)k2<<24);
+            wedgeMask|=(1ull<<k1)|(1ull<<k2);
+            nrun++;
+          }
         }
       }
     }
-    __syncwarp();
-    if (__all_sync(WB_FULL,done))
-      break;
   }
-  // Entries still queued for finished queries are harmless: extra bearings can only split gaps.
-  if (qcount>0)
-    wb_drain(w,lane,qcount);
-  __syncwarp();
-  if (have)
+  if (wedgeMask)
+  {
+    // exact gaps of the 24/25-sector runs; every other gap is < 25 sectors < 144 degrees
+    bool gapA=(wedge&255)!=255 && ((minHighA-maxLowA)&0x7fffffffu)>=(uint32_t)WB_DEG144;
+    bool gapB=((wedge>>16)&255)!=255 && ((minHighB-maxLowB)&0x7fffffffu)>=(uint32_t)WB_DEG144;
+    surrounded=!(gapA || gapB);
+  }
+  if (have && !foreign)
   {
     uint8_t lab;
     if (untiled)
       lab=clsIn[perm[me]];                           // never visited by classifyCylinder
     else
-      lab=(done || wb_surrounded(w,lane))?1:2;       // classify.cpp:158-162
+      lab=surrounded?1:2;                            // classify.cpp:158-162
     labelSorted[me]=lab;
   }
-  unsigned mm=__ballot_sync(WB_FULL,margin && have);
+  else if (have)
+    labelSorted[me]=255;
+  unsigned mm=__ballot_sync(WB_FULL,margin);
   unsigned uu=__ballot_sync(WB_FULL,untiled);
+  unsigned aa=__ballot_sync(WB_FULL,wedgeMask!=0);
   if (lane==0)
   {
     if (mm) atomicAdd(&counters[0],(unsigned long long)__popc(mm));
     if (uu) atomicAdd(&counters[1],(unsigned long long)__popc(uu));
+    if (aa) atomicAdd(&counters[6],(unsigned long long)__popc(aa));
+    atomicAdd(&counters[8],(unsigned long long)statNodes);
+    atomicAdd(&counters[9],(unsigned long long)statChunks);
+    atomicAdd(&counters[10],(unsigned long long)statPairs);
   }
 }
 

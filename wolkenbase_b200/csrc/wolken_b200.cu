@@ -86,6 +86,7 @@ struct wb_ctx
   uint32_t *pairVals=nullptr;
   uint64_t nPairs=0;
   uint32_t nLeaves=0,nChunks=0;
+  uint32_t ownFirst=0,ownEnd=0xffffffffu;   // input-index range this GPU labels (the rest is halo)
   int nLevels=0;
   std::vector<uint32_t> hLevelOff,hLevelCnt;
   wb_stats stats{};
@@ -248,14 +249,12 @@ extern "C" int wb_create(int device,wb_ctx **out)
     cudaEventCreateWithFlags(&ctx->evCopy[i],cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->evDec[i],cudaEventDisableTiming);
   }
-  if (ctx->counters.ensure(8)!=cudaSuccess || ctx->dsegs.ensure(1)!=cudaSuccess)
+  if (ctx->counters.ensure(16)!=cudaSuccess || ctx->dsegs.ensure(1)!=cudaSuccess)
   {
     delete ctx;
     return WB_ERR_CUDA;
   }
-  cudaMemset(ctx->counters.p,0,8*sizeof(unsigned long long));
-  cudaFuncSetAttribute(wb_classify_kernel,cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       (int)(sizeof(WbClassifyWarp)*WB_CL_WARPS));
+  cudaMemset(ctx->counters.p,0,16*sizeof(unsigned long long));
   if (uploadTables(ctx)!=WB_OK)
   {
     delete ctx;
@@ -323,7 +322,7 @@ extern "C" int wb_clear(wb_ctx *ctx)
   uint64_t launches=ctx->stats.kernel_launches;
   memset(&ctx->stats,0,sizeof(ctx->stats));
   ctx->stats.kernel_launches=launches;
-  CK(cudaMemsetAsync(ctx->counters.p,0,8*sizeof(unsigned long long),ctx->st));
+  CK(cudaMemsetAsync(ctx->counters.p,0,16*sizeof(unsigned long long),ctx->st));
   return WB_OK;
 }
 
@@ -855,19 +854,25 @@ extern "C" int wb_classify(wb_ctx *ctx)
   cudaStream_t st=ctx->st;
   CK(cudaEventRecord(ctx->evA,st));
   CK(cudaMemsetAsync(ctx->counters.p,0,2*sizeof(unsigned long long),st));
+  CK(cudaMemsetAsync(ctx->counters.p+6,0,6*sizeof(unsigned long long),st));
   wb_init_labels_kernel<<<gridFor(ctx->n,256),256,0,st>>>(ctx->cls.p,ctx->n,ctx->labelIn.p);
   CK(cudaEventRecord(ctx->evC,st));
-  wb_classify_kernel<<<gridFor(ctx->nChunks,WB_CL_WARPS),WB_CL_WARPS*32,sizeof(WbClassifyWarp)*WB_CL_WARPS,st>>>(
+  wb_classify_kernel<<<gridFor(ctx->nChunks,WB_CL_WARPS),WB_CL_WARPS*32,0,st>>>(
       ctx->sx.p,ctx->sy.p,ctx->sz.p,nv,ctx->nChunks,ctx->bounds.p,ctx->levelOff.p,ctx->levelCnt.p,ctx->nLevels,
-      ctx->winner.p,ctx->tHyp.p,ctx->prm.maxSlope,ctx->prm.thickness,ctx->cls.p,ctx->perm,ctx->labelSorted.p,ctx->counters.p);
+      ctx->winner.p,ctx->tHyp.p,ctx->prm.maxSlope,ctx->prm.thickness,ctx->cls.p,ctx->perm,
+      ctx->ownFirst,ctx->ownEnd,ctx->labelSorted.p,ctx->counters.p);
   CK(cudaEventRecord(ctx->evD,st));
   wb_scatter_labels_kernel<<<gridFor(nv,256),256,0,st>>>(ctx->labelSorted.p,ctx->perm,nv,ctx->labelIn.p);
   ctx->stats.kernel_launches+=3;
   KCHECK();
   CK(cudaEventRecord(ctx->evB,st));
-  unsigned long long c[2]={0,0};
+  unsigned long long c[12]={0};
   CK(cudaMemcpyAsync(c,ctx->counters.p,sizeof(c),cudaMemcpyDeviceToHost,st));
   CK(cudaStreamSynchronize(st));
+  ctx->stats.n_second_walk=c[6];
+  ctx->stats.cl_nodes=c[8];
+  ctx->stats.cl_chunks=c[9];
+  ctx->stats.cl_pairs=c[10];
   ctx->stats.ms_classify=elapsed(ctx->evA,ctx->evB);
   ctx->stats.ms_classify_kernel=elapsed(ctx->evC,ctx->evD);
   ctx->stats.n_margin=c[0];
