@@ -224,7 +224,9 @@ def run_ours(args):
                    "untiled": int(st["n_untiled"])},
         "leaves": int(st["n_leaves"]), "tiles_nonempty": int(st["n_tiles_nonempty"]),
         "classify_work": {"nodes_per_point": st["cl_nodes"] * 32.0 / n, "chunks_per_point": st["cl_chunks"] * 32.0 / n,
-                          "pair_tests_per_point": st["cl_pairs"] * 32.0 / n, "second_walk_points": int(st["n_second_walk"])},
+                          "pair_tests_per_point": st["cl_pairs"] * 32.0 / n, "second_walk_points": int(st["n_second_walk"]),
+                          "second_walk": {"warps_frac": st["cl_warps2"] * 32.0 / n, "nodes": st["cl_nodes2"] * 32.0 / n,
+                                          "chunks": st["cl_chunks2"] * 32.0 / n, "pairs": st["cl_pairs2"] * 32.0 / n}},
         "gen_s": round(gen_s, 2),
     }
     if not args.no_cpu:

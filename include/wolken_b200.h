@@ -85,6 +85,7 @@ typedef struct wb_stats
   uint64_t n_untiled;               /* points in no tile cylinder (left unclassified) */
   uint64_t n_second_walk;           /* points whose widest gap was 135..152 degrees: exact bearings needed */
   uint64_t cl_nodes,cl_chunks,cl_pairs; /* classify work: hierarchy nodes visited, chunks opened, (query,chunk) pairs tested */
+  uint64_t cl_nodes2,cl_chunks2,cl_pairs2,cl_warps2; /* the same for the exact second walk, and warps that took it */
   uint64_t kernel_launches;         /* kernels launched by this context so far */
   double ms_h2d,ms_decode,ms_build,ms_scan,ms_postscan,ms_classify,ms_d2h;  /* last run, CUDA events */
   double ms_sort,ms_leaves,ms_hier,ms_pairs,ms_classify_kernel;

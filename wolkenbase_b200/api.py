@@ -31,7 +31,8 @@ class Geometry(C.Structure):
 class Stats(C.Structure):
     _fields_ = [(k, C.c_uint64) for k in ("n_points", "n_dropped", "n_leaves", "n_tiles_nonempty",
                                           "n_memberships", "n_margin", "n_untiled", "n_second_walk",
-                                          "cl_nodes", "cl_chunks", "cl_pairs", "kernel_launches")] + \
+                                          "cl_nodes", "cl_chunks", "cl_pairs", "cl_nodes2", "cl_chunks2",
+                                          "cl_pairs2", "cl_warps2", "kernel_launches")] + \
                [(k, C.c_double) for k in ("ms_h2d", "ms_decode", "ms_build", "ms_scan", "ms_postscan",
                                           "ms_classify", "ms_d2h", "ms_sort", "ms_leaves", "ms_hier",
                                           "ms_pairs", "ms_classify_kernel")]

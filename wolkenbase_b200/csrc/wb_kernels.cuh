@@ -719,6 +719,8 @@ struct WbClassifyWarp
 {
   double qx[32],qy[32],qcz[32],qpor2[32];
   uint32_t keys[8][32];       // per stack entry: (squared distance | child) of the children still to visit
+  uint32_t wants[32];         // chunks of the open level-0 entry: live queries that reach each chunk
+  unsigned long long cm[32];  // ... and the sectors the chunk can occupy, seen from anywhere in the group
   uint32_t stBase[8];
   int stLevel[8];
 };
@@ -805,6 +807,33 @@ __device__ __forceinline__ unsigned long long wb_box_sectors(double px,double py
   double mx=0.5*(b.xmin+b.xmax)-px,my=0.5*(b.ymin+b.ymax)-py;
   double hx=0.5*(b.xmax-b.xmin),hy=0.5*(b.ymax-b.ymin);
   return wb_sector_mask(mx,my,(float)(hx*hx+hy*hy),(float)(mx*mx+my*my));
+}
+
+__device__ __forceinline__ unsigned long long wb_span_mask(double dx0,double dx1,double dy0,double dy1)
+// Sectors of all bearings from the origin to the rectangle [dx0,dx1]x[dy0,dy1]: tight (the two
+// silhouette corners), widened by one sector only where a corner sits on a sector edge.
+{
+  const int L=dx0>0,R=dx1<0,B=dy0>0,T=dy1<0;
+  if (!(L|R|B|T))
+    return ~0ull;                                  // the origin is inside
+  // clockwise-most corner a, counter-clockwise-most corner b
+  double ax=B?dx1:(T?dx0:(L?dx0:dx1)),ay=L?dy0:(R?dy1:(B?dy0:dy1));
+  double bx=B?dx0:(T?dx1:(L?dx0:dx1)),by=L?dy1:(R?dy0:(B?dy0:dy1));
+  int sa=wb_sector64(ax,ay),sb=wb_sector64(bx,by);
+  if (sa<0)
+  {
+    uint32_t u;
+    sa=(wb_sector64_exact(ax,ay,u)+63)&63;
+  }
+  if (sb<0)
+  {
+    uint32_t u;
+    sb=(wb_sector64_exact(bx,by,u)+1)&63;
+  }
+  int len=((sb-sa)&63)+1;
+  if (len>40)                                      // cannot happen for a rectangle (< 180 degrees); be safe
+    return ~0ull;
+  return wb_rotl64((1ull<<len)-1,sa);
 }
 
 __device__ __forceinline__ unsigned long long wb_runs_ge(unsigned long long empty,int len)
@@ -906,7 +935,9 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
   w.qx[lane]=px; w.qy[lane]=py; w.qcz[lane]=pcz; w.qpor2[lane]=ppor2;
   unsigned long long occ=0;                       // occupied sectors of my query
   unsigned long long open=~0ull;                  // sectors of empty runs >= 24 (the only ones that matter)
-  uint32_t statNodes=0,statChunks=0,statPairs=0;  // work counters (warp-uniform)
+  uint32_t statNodes=0,statChunks=0,statPairs=0,statNodes2=0,statChunks2=0,statPairs2=0;  // work counters (warp-uniform)
+  long long tExpand=0,tPairs=0,tTotal=clock64(),tExpCount=0;
+  uint32_t statAnyIn=0,statNew=0,statEnvEmpty=0;
   bool margin=false,surrounded=false;
   // second-walk state: up to two empty runs of 24/25 sectors, bounded below by sector k1 (we need
   // the largest bearing in it) and above by k2 (the smallest bearing in it)
@@ -956,7 +987,7 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
     envelope();
     needed();
     // lanes = children of a node: can any live query reach it, and does any still need its sectors?
-    auto childTest=[&](const WbBound &cb,uint32_t &key)->bool
+    auto childTest=[&](const WbBound &cb,uint32_t &key,unsigned long long &cm)->bool
     {
       if (!wb_reach(gx0,gx1,gy0,gy1,gcz,gpor2,s2,cb))
         return false;
@@ -965,23 +996,64 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
       float d2=(float)(mx*mx+my*my);
       float rr=sqrtf((float)(hx*hx+hy*hy))+sqrtf(gr2);
       key=(__float_as_uint(d2)&0xffffffe0u)|(uint32_t)lane;
-      return (wb_sector_mask(mx,my,rr*rr,d2)&needAny)!=0;
+      (void)rr;
+      cm=wb_span_mask(cb.xmin-gx1,cb.xmax-gx0,cb.ymin-gy1,cb.ymax-gy0);   // valid for every query of the group
+      return (cm&needAny)!=0;
     };
+    // Push the children [base,base+32) of a node (level childLevel).  For chunks (childLevel 0)
+    // each child also gets the set of live queries whose hyperboloid reaches it, found with
+    // lanes = children and the queries broadcast one by one, so that popping a chunk is cheap.
     int sp=0;
+    auto expand=[&](int childLevel,uint32_t base)
     {
-      uint32_t key=0xffffffffu;
+      long long t0=clock64();
+      tExpCount++;
+      uint32_t c=base+lane,cc=levelCnt[childLevel];
+      uint32_t key=0xffffffffu,wants=0;
+      unsigned long long cm=0;
       bool ok=false;
-      if ((uint32_t)lane<cntTop)
-        ok=childTest(bounds[levelOff[top]+lane],key);
-      w.keys[0][lane]=ok?key:0xffffffffu;
+      WbBound cb;
+      if (c<cc)
+      {
+        cb=bounds[levelOff[childLevel]+c];
+        ok=childTest(cb,key,cm);
+      }
+      if (!__any_sync(WB_FULL,ok))
+      {
+        tExpand+=clock64()-t0;
+        return;
+      }
+      if (childLevel==0)
+      {
+        uint32_t lm=liveMask;
+        while (lm)
+        {
+          const int q=__ffs(lm)-1;
+          lm&=lm-1;
+          const double qx=w.qx[q],qy=w.qy[q],qcz=w.qcz[q],qpor2=w.qpor2[q];
+          if (ok && wb_reach(qx,qx,qy,qy,qcz,qpor2,s2,cb))
+            wants|=1u<<q;
+        }
+        ok=ok && wants!=0;
+        if (!__any_sync(WB_FULL,ok))
+        {
+          tExpand+=clock64()-t0;
+          return;
+        }
+        w.wants[lane]=wants;
+        w.cm[lane]=cm;
+      }
+      w.keys[sp][lane]=ok?key:0xffffffffu;
       if (lane==0)
       {
-        w.stLevel[0]=top;
-        w.stBase[0]=0;
+        w.stLevel[sp]=childLevel;
+        w.stBase[sp]=base;
       }
-      sp=1;
+      sp++;
       __syncwarp();
-    }
+      tExpand+=clock64()-t0;
+    };
+    expand(top,0);
     while (sp>0)
     {
       // pop the nearest remaining child of the top entry
@@ -997,54 +1069,71 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
       if (lane==bit)
         w.keys[sp-1][lane]=0xffffffffu;
       __syncwarp();
-      // lane = query: does this node matter to me?
-      WbBound nb=bounds[levelOff[level]+node];
+      if (pass==1) statNodes++; else statNodes2++;
+      // lane = query: does this node (still) matter to me?
       bool want=false;
-      if (live && wb_reach(px,px,py,py,pcz,ppor2,s2,nb))
-      {
-        unsigned long long bs=wb_box_sectors(px,py,nb);
-        want=pass==1?(bs&open)!=0:(bs&wedgeMask)!=0;
-      }
-      uint32_t qm=__ballot_sync(WB_FULL,want);
-      statNodes++;
-      if (!qm)
-        continue;
       if (level>0)
       {
-        uint32_t c=node*32+lane,cc=levelCnt[level-1];
-        uint32_t key=0xffffffffu;
-        bool ok=false;
-        if (c<cc)
-          ok=childTest(bounds[levelOff[level-1]+c],key);
-        if (__any_sync(WB_FULL,ok))
+        WbBound nb=bounds[levelOff[level]+node];
+        if (live && wb_reach(px,px,py,py,pcz,ppor2,s2,nb))
         {
-          w.keys[sp][lane]=ok?key:0xffffffffu;
-          if (lane==0)
-          {
-            w.stLevel[sp]=level-1;
-            w.stBase[sp]=node*32;
-          }
-          sp++;
+          unsigned long long bs=wb_span_mask(nb.xmin-px,nb.xmax-px,nb.ymin-py,nb.ymax-py);
+          want=pass==1?(bs&open)!=0:(bs&wedgeMask)!=0;
         }
-        __syncwarp();
+        if (__any_sync(WB_FULL,want))
+          expand(level-1,node*32);
         continue;
       }
+      {
+        const uint32_t wq=w.wants[bit];
+        const unsigned long long cmv=w.cm[bit];
+        want=live && ((wq>>lane)&1) && (cmv&(pass==1?open:wedgeMask))!=0;
+      }
+      if (!__any_sync(WB_FULL,want))
+        continue;
+      {
+        // the chunk's bearings as seen from my own query: tight silhouette span
+        WbBound nb=bounds[node];
+        if (want)
+          want=(wb_span_mask(nb.xmin-px,nb.xmax-px,nb.ymin-py,nb.ymax-py)&(pass==1?open:wedgeMask))!=0;
+      }
+      uint32_t qm=__ballot_sync(WB_FULL,want);
+      if (!qm)
+        continue;
       // ---- a chunk: lane = point
       unsigned long long j=(unsigned long long)node*32+lane;
       const bool okp=j<n;
       const double cxp=okp?sx[j]:0.0,cyp=okp?sy[j]:0.0,czp=okp?sz[j]:INFINITY;
-      statChunks++;
-      statPairs+=__popc(qm);
+      if (pass==1) { statChunks++; statPairs+=__popc(qm); } else { statChunks2++; statPairs2+=__popc(qm); }
+      long long tp0=clock64();
+      // Sectors each chunk point can occupy as seen from ANY query of the group (bearing from the
+      // group centre, widened by the group radius).  A query for which none of them is still of
+      // interest skips the chunk, and within the chunk only the points that can land in one of
+      // the query's interesting sectors are tested at all.
+      unsigned long long pmask=0;
+      if (okp)
+        pmask=wb_span_mask(cxp-gx1,cxp-gx0,cyp-gy1,cyp-gy0);
+      {
+        uint32_t lo=__reduce_or_sync(WB_FULL,(uint32_t)pmask),hi=__reduce_or_sync(WB_FULL,(uint32_t)(pmask>>32));
+        unsigned long long cme=(unsigned long long)lo|((unsigned long long)hi<<32);
+        qm&=__ballot_sync(WB_FULL,(cme&(pass==1?open:wedgeMask))!=0);
+      }
       while (qm)
       {
         const int q=__ffs(qm)-1;
         qm&=qm-1;
+        const unsigned long long mineq=pass==1?open:wedgeMask;
+        const unsigned long long oq=((unsigned long long)__shfl_sync(WB_FULL,(uint32_t)(mineq>>32),q)<<32)|
+                                    __shfl_sync(WB_FULL,(uint32_t)mineq,q);
+        const bool rel=(pmask&oq)!=0;
+        if (!__any_sync(WB_FULL,rel))
+          continue;
         const double qx=w.qx[q],qy=w.qy[q],qcz=w.qcz[q],qpor2=w.qpor2[q];
         double ddx=0,ddy=0;
-        bool mg=false;
-        bool in=wb_in_hyperboloid(qx,qy,qcz,qpor2,s2,maxSlope,cxp,cyp,czp,ddx,ddy,mg);
-        if (__any_sync(WB_FULL,mg) && lane==q)
-          margin=true;
+        bool in=rel && wb_in_hyperboloid(qx,qy,qcz,qpor2,s2,maxSlope,cxp,cyp,czp,ddx,ddy,margin);
+        if (!__any_sync(WB_FULL,in))
+          continue;
+        statAnyIn++;
         if (pass==1)
         {
           int s=-2;
@@ -1059,6 +1148,12 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
           }
           uint32_t lo=__reduce_or_sync(WB_FULL,(in && s<32)?1u<<s:0u);
           uint32_t hi=__reduce_or_sync(WB_FULL,(in && s>=32)?1u<<(s-32):0u);
+          {
+            unsigned long long add=(unsigned long long)lo|((unsigned long long)hi<<32);
+            unsigned long long oq=((unsigned long long)__shfl_sync(WB_FULL,(uint32_t)(occ>>32),q)<<32)|__shfl_sync(WB_FULL,(uint32_t)occ,q);
+            if (add&~oq)
+              statNew++;
+          }
           if (lane==q)
             occ|=(unsigned long long)lo|((unsigned long long)hi<<32);
         }
@@ -1093,6 +1188,7 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
           }
         }
       }
+      tPairs+=clock64()-tp0;
       if (pass==1)
       {
         // surrounded for sure once no empty run of 24 sectors is left
@@ -1175,6 +1271,17 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
     atomicAdd(&counters[8],(unsigned long long)statNodes);
     atomicAdd(&counters[9],(unsigned long long)statChunks);
     atomicAdd(&counters[10],(unsigned long long)statPairs);
+    atomicAdd(&counters[11],(unsigned long long)statNodes2);
+    atomicAdd(&counters[12],(unsigned long long)statChunks2);
+    atomicAdd(&counters[13],(unsigned long long)statPairs2);
+    if (statNodes2) atomicAdd(&counters[14],1ull);
+    atomicAdd(&counters[15],(unsigned long long)(clock64()-tTotal));
+    atomicAdd(&counters[16],(unsigned long long)tExpand);
+    atomicAdd(&counters[17],(unsigned long long)tPairs);
+    atomicAdd(&counters[18],(unsigned long long)tExpCount);
+    atomicAdd(&counters[19],(unsigned long long)statAnyIn);
+    atomicAdd(&counters[20],(unsigned long long)statNew);
+    atomicAdd(&counters[21],(unsigned long long)statEnvEmpty);
   }
 }
 

@@ -249,12 +249,12 @@ extern "C" int wb_create(int device,wb_ctx **out)
     cudaEventCreateWithFlags(&ctx->evCopy[i],cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->evDec[i],cudaEventDisableTiming);
   }
-  if (ctx->counters.ensure(16)!=cudaSuccess || ctx->dsegs.ensure(1)!=cudaSuccess)
+  if (ctx->counters.ensure(24)!=cudaSuccess || ctx->dsegs.ensure(1)!=cudaSuccess)
   {
     delete ctx;
     return WB_ERR_CUDA;
   }
-  cudaMemset(ctx->counters.p,0,16*sizeof(unsigned long long));
+  cudaMemset(ctx->counters.p,0,24*sizeof(unsigned long long));
   if (uploadTables(ctx)!=WB_OK)
   {
     delete ctx;
@@ -322,7 +322,7 @@ extern "C" int wb_clear(wb_ctx *ctx)
   uint64_t launches=ctx->stats.kernel_launches;
   memset(&ctx->stats,0,sizeof(ctx->stats));
   ctx->stats.kernel_launches=launches;
-  CK(cudaMemsetAsync(ctx->counters.p,0,16*sizeof(unsigned long long),ctx->st));
+  CK(cudaMemsetAsync(ctx->counters.p,0,24*sizeof(unsigned long long),ctx->st));
   return WB_OK;
 }
 
@@ -854,7 +854,7 @@ extern "C" int wb_classify(wb_ctx *ctx)
   cudaStream_t st=ctx->st;
   CK(cudaEventRecord(ctx->evA,st));
   CK(cudaMemsetAsync(ctx->counters.p,0,2*sizeof(unsigned long long),st));
-  CK(cudaMemsetAsync(ctx->counters.p+6,0,6*sizeof(unsigned long long),st));
+  CK(cudaMemsetAsync(ctx->counters.p+6,0,18*sizeof(unsigned long long),st));
   wb_init_labels_kernel<<<gridFor(ctx->n,256),256,0,st>>>(ctx->cls.p,ctx->n,ctx->labelIn.p);
   CK(cudaEventRecord(ctx->evC,st));
   wb_classify_kernel<<<gridFor(ctx->nChunks,WB_CL_WARPS),WB_CL_WARPS*32,0,st>>>(
@@ -866,13 +866,18 @@ extern "C" int wb_classify(wb_ctx *ctx)
   ctx->stats.kernel_launches+=3;
   KCHECK();
   CK(cudaEventRecord(ctx->evB,st));
-  unsigned long long c[12]={0};
+  unsigned long long c[24]={0};
   CK(cudaMemcpyAsync(c,ctx->counters.p,sizeof(c),cudaMemcpyDeviceToHost,st));
   CK(cudaStreamSynchronize(st));
   ctx->stats.n_second_walk=c[6];
   ctx->stats.cl_nodes=c[8];
   ctx->stats.cl_chunks=c[9];
   ctx->stats.cl_pairs=c[10];
+  ctx->stats.cl_nodes2=c[11];
+  ctx->stats.cl_chunks2=c[12];
+  ctx->stats.cl_pairs2=c[13];
+  ctx->stats.cl_warps2=c[14];
+  if (getenv("WB_TRACE")) fprintf(stderr,"classify cycles/warp: total %.0f expand %.0f pairs %.0f expansions %.1f\n",(double)c[15]/ctx->nChunks,(double)c[16]/ctx->nChunks,(double)c[17]/ctx->nChunks,(double)c[18]/ctx->nChunks),fprintf(stderr,"  per warp: pairs with a hit %.1f, pairs adding a sector %.1f, chunks empty for the envelope %.1f\n",(double)c[19]/ctx->nChunks,(double)c[20]/ctx->nChunks,(double)c[21]/ctx->nChunks);
   ctx->stats.ms_classify=elapsed(ctx->evA,ctx->evB);
   ctx->stats.ms_classify_kernel=elapsed(ctx->evC,ctx->evD);
   ctx->stats.n_margin=c[0];
