@@ -719,7 +719,8 @@ struct WbClassifyWarp
 {
   double qx[32],qy[32],qcz[32],qpor2[32];
   uint32_t keys[8][32];       // per stack entry: (squared distance | child) of the children still to visit
-  uint32_t wants[32];         // chunks of the open level-0 entry: live queries that reach each chunk
+  WbBound cb[32];             // bounds of the chunks of the open level-0 entry
+  uint32_t wants[32];         // ... live queries that reach each chunk
   unsigned long long cm[32];  // ... and the sectors the chunk can occupy, seen from anywhere in the group
   uint32_t stBase[8];
   int stLevel[8];
@@ -809,31 +810,35 @@ __device__ __forceinline__ unsigned long long wb_box_sectors(double px,double py
   return wb_sector_mask(mx,my,(float)(hx*hx+hy*hy),(float)(mx*mx+my*my));
 }
 
-__device__ __forceinline__ unsigned long long wb_span_mask(double dx0,double dx1,double dy0,double dy1)
-// Sectors of all bearings from the origin to the rectangle [dx0,dx1]x[dy0,dy1]: tight (the two
-// silhouette corners), widened by one sector only where a corner sits on a sector edge.
+__device__ __forceinline__ float wb_fast_angle(float x,float y)
+// Bearing of (x,y) in sector units [0,64], accurate to 0.04 sector (atan(q) ~ q(pi/4+0.273(1-q))).
+// Only used to build conservative masks; every decision about a real bearing uses wb_sector64.
 {
-  const int L=dx0>0,R=dx1<0,B=dy0>0,T=dy1<0;
-  if (!(L|R|B|T))
+  float ax=fabsf(x),ay=fabsf(y);
+  float mn=fminf(ax,ay),mx=fmaxf(ax,ay);
+  float q=__fdividef(mn,mx);
+  float a=q*(8.0f+2.781f*(1.0f-q));
+  if (ay>ax) a=16.0f-a;
+  if (x<0) a=32.0f-a;
+  if (y<0) a=64.0f-a;
+  return a;
+}
+
+__device__ __forceinline__ unsigned long long wb_span_mask(double dx0,double dx1,double dy0,double dy1)
+// Sectors of all bearings from the origin to the rectangle [dx0,dx1]x[dy0,dy1]: the two
+// silhouette corners, each widened by 0.06 sector for the approximate angle.
+{
+  const bool L=dx0>0,R=dx1<0,B=dy0>0,T=dy1<0;
+  if (!(L||R||B||T))
     return ~0ull;                                  // the origin is inside
   // clockwise-most corner a, counter-clockwise-most corner b
-  double ax=B?dx1:(T?dx0:(L?dx0:dx1)),ay=L?dy0:(R?dy1:(B?dy0:dy1));
-  double bx=B?dx0:(T?dx1:(L?dx0:dx1)),by=L?dy1:(R?dy0:(B?dy0:dy1));
-  int sa=wb_sector64(ax,ay),sb=wb_sector64(bx,by);
-  if (sa<0)
-  {
-    uint32_t u;
-    sa=(wb_sector64_exact(ax,ay,u)+63)&63;
-  }
-  if (sb<0)
-  {
-    uint32_t u;
-    sb=(wb_sector64_exact(bx,by,u)+1)&63;
-  }
+  float ax=(float)(B?dx1:(T?dx0:(L?dx0:dx1))),ay=(float)(L?dy0:(R?dy1:(B?dy0:dy1)));
+  float bx=(float)(B?dx0:(T?dx1:(L?dx0:dx1))),by=(float)(L?dy1:(R?dy0:(B?dy0:dy1)));
+  int sa=(int)floorf(wb_fast_angle(ax,ay)-0.06f),sb=(int)floorf(wb_fast_angle(bx,by)+0.06f);
   int len=((sb-sa)&63)+1;
-  if (len>40)                                      // cannot happen for a rectangle (< 180 degrees); be safe
+  if (len>40)                                      // a rectangle spans < 180 degrees; anything else is a wrap artefact
     return ~0ull;
-  return wb_rotl64((1ull<<len)-1,sa);
+  return wb_rotl64((1ull<<len)-1,sa&63);
 }
 
 __device__ __forceinline__ unsigned long long wb_runs_ge(unsigned long long empty,int len)
@@ -1004,7 +1009,7 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
     // each child also gets the set of live queries whose hyperboloid reaches it, found with
     // lanes = children and the queries broadcast one by one, so that popping a chunk is cheap.
     int sp=0;
-    auto expand=[&](int childLevel,uint32_t base)
+    auto expand=[&](int childLevel,uint32_t base,uint32_t askers)
     {
       long long t0=clock64();
       tExpCount++;
@@ -1025,7 +1030,7 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
       }
       if (childLevel==0)
       {
-        uint32_t lm=liveMask;
+        uint32_t lm=askers;
         while (lm)
         {
           const int q=__ffs(lm)-1;
@@ -1042,6 +1047,7 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
         }
         w.wants[lane]=wants;
         w.cm[lane]=cm;
+        w.cb[lane]=cb;
       }
       w.keys[sp][lane]=ok?key:0xffffffffu;
       if (lane==0)
@@ -1053,7 +1059,7 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
       __syncwarp();
       tExpand+=clock64()-t0;
     };
-    expand(top,0);
+    expand(top,0,liveMask);
     while (sp>0)
     {
       // pop the nearest remaining child of the top entry
@@ -1080,8 +1086,9 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
           unsigned long long bs=wb_span_mask(nb.xmin-px,nb.xmax-px,nb.ymin-py,nb.ymax-py);
           want=pass==1?(bs&open)!=0:(bs&wedgeMask)!=0;
         }
-        if (__any_sync(WB_FULL,want))
-          expand(level-1,node*32);
+        const uint32_t askers=__ballot_sync(WB_FULL,want);
+        if (askers)
+          expand(level-1,node*32,askers);
         continue;
       }
       {
@@ -1093,7 +1100,7 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
         continue;
       {
         // the chunk's bearings as seen from my own query: tight silhouette span
-        WbBound nb=bounds[node];
+        const WbBound nb=w.cb[bit];
         if (want)
           want=(wb_span_mask(nb.xmin-px,nb.xmax-px,nb.ymin-py,nb.ymax-py)&(pass==1?open:wedgeMask))!=0;
       }
