@@ -111,6 +111,15 @@ int wb_add_las(wb_ctx *ctx,const uint8_t *recs,uint64_t n,int fmt,int rec_len,
 /* Same, records already in device memory. */
 int wb_add_las_device(wb_ctx *ctx,const uint8_t *d_recs,uint64_t n,int fmt,int rec_len,
                       const double scale[3],const double offset[3],double unit);
+/* Already-decoded points in device memory (SoA int32 X,Y,Z + class byte), e.g. halo points
+ * received from another GPU; they become one more segment with its own scale/offset. */
+int wb_add_points_device(wb_ctx *ctx,const int32_t *d_x,const int32_t *d_y,const int32_t *d_z,const uint8_t *d_cls,
+                         uint64_t n,const double scale[3],const double offset[3],double unit);
+/* Copy the decoded columns of points [first,first+n) into caller-owned device buffers. */
+int wb_export_points_device(wb_ctx *ctx,uint64_t first,uint64_t n,int32_t *d_x,int32_t *d_y,int32_t *d_z,uint8_t *d_cls);
+/* Only points whose input index lies in [first,end) are labelled by wb_classify; the others
+ * (halo) take part in every query but keep label 255. */
+int wb_set_own_range(wb_ctx *ctx,uint64_t first,uint64_t end);
 /* Override the geometry derived from the extents (multi-GPU: every rank uses the global one). */
 int wb_set_geometry(wb_ctx *ctx,const double root_center[3],double root_side,const double cube[4]);
 int wb_get_geometry(wb_ctx *ctx,wb_geometry *out);
@@ -130,6 +139,17 @@ int wb_num_tiles(wb_ctx *ctx,uint64_t *n);                 /* non-empty tiles */
 int wb_get_tiles(wb_ctx *ctx,wb_tile *out,uint64_t cap);   /* ascending n */
 /* Replace hyperboloidSize of the listed tiles (classify parity independent of scan parity). */
 int wb_set_tiles(wb_ctx *ctx,const wb_tile *tiles,uint64_t n);
+
+/* Multi-GPU merge of the tile table.  Export writes, for every tile of the flowsnake range
+ * (wb_geometry.snake_lo..snake_hi, dense), nPoints, treeFlags and the bits of hyperboloidSize
+ * into caller-owned DEVICE buffers, zeroing tiles whose centre x is outside [x_lo,x_hi) — so
+ * that a sum over GPUs (ncclAllReduce) yields the global table; import loads it back. */
+int wb_export_tiles_device(wb_ctx *ctx,double x_lo,double x_hi,int32_t *d_npoints,int32_t *d_tree,int64_t *d_hyp_bits);
+int wb_import_tiles_device(wb_ctx *ctx,const int32_t *d_npoints,const int32_t *d_tree,const int64_t *d_hyp_bits,
+                           int postscanned /* the table already went through wb_postscan */);
+int wb_max_hyperboloid_size(wb_ctx *ctx,double *out);
+/* Tile membership only (which tile's parameters each point uses); implied by wb_scan. */
+int wb_assign(wb_ctx *ctx);
 
 /* ---- classify (TH_SPLIT) -------------------------------------------------- */
 int wb_classify(wb_ctx *ctx);

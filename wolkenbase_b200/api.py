@@ -62,6 +62,13 @@ def lib():
             "wb_add_extent": [vp, dp, dp],
             "wb_add_las": [vp, vp, u64, C.c_int, C.c_int, dp, dp, C.c_double],
             "wb_add_las_device": [vp, vp, u64, C.c_int, C.c_int, dp, dp, C.c_double],
+            "wb_add_points_device": [vp, vp, vp, vp, vp, u64, dp, dp, C.c_double],
+            "wb_export_points_device": [vp, u64, u64, vp, vp, vp, vp],
+            "wb_set_own_range": [vp, u64, u64],
+            "wb_export_tiles_device": [vp, C.c_double, C.c_double, vp, vp, vp],
+            "wb_import_tiles_device": [vp, vp, vp, vp, C.c_int],
+            "wb_max_hyperboloid_size": [vp, dp],
+            "wb_assign": [vp],
             "wb_set_geometry": [vp, dp, C.c_double, dp],
             "wb_get_geometry": [vp, C.POINTER(Geometry)],
             "wb_build": [vp],
@@ -105,7 +112,9 @@ EXPORTS = ["wb_create", "wb_destroy", "wb_last_error", "wb_reserve", "wb_clear",
            "wb_get_leaves", "wb_get_order", "wb_get_decoded", "wb_scan", "wb_postscan", "wb_num_tiles",
            "wb_get_tiles", "wb_set_tiles", "wb_classify", "wb_get_labels", "wb_count_classes", "wb_patch_records",
            "wb_run", "wb_get_stats", "wb_sync", "wb_host_alloc", "wb_host_free", "wb_size_fit", "wb_bbox_cube",
-           "wb_snake_set_size", "wb_ldecimal", "wb_format_dump"]
+           "wb_snake_set_size", "wb_ldecimal", "wb_format_dump", "wb_add_points_device", "wb_export_points_device",
+           "wb_set_own_range", "wb_export_tiles_device", "wb_import_tiles_device", "wb_max_hyperboloid_size",
+           "wb_assign"]
 
 
 def _d(v):
@@ -189,6 +198,29 @@ class Context:
         """Convenience for synth.Cloud: header corners + records."""
         self.add_extent([c * unit for c in cloud.min_corner], [c * unit for c in cloud.max_corner])
         self.add_las(cloud.records, cloud.fmt, cloud.scale, cloud.offset, unit)
+
+    def add_points_device(self, dx, dy, dz, dcls, n, scale, offset, unit=1.0):
+        self._ck(self._L.wb_add_points_device(self._h, dx, dy, dz, dcls, n, _d(scale), _d(offset), unit))
+
+    def export_points_device(self, first, n, dx, dy, dz, dcls):
+        self._ck(self._L.wb_export_points_device(self._h, first, n, dx, dy, dz, dcls))
+
+    def set_own_range(self, first, end):
+        self._ck(self._L.wb_set_own_range(self._h, first, end))
+
+    def export_tiles_device(self, x_lo, x_hi, d_np, d_tree, d_hyp):
+        self._ck(self._L.wb_export_tiles_device(self._h, x_lo, x_hi, d_np, d_tree, d_hyp))
+
+    def import_tiles_device(self, d_np, d_tree, d_hyp, postscanned=False):
+        self._ck(self._L.wb_import_tiles_device(self._h, d_np, d_tree, d_hyp, 1 if postscanned else 0))
+
+    def max_hyperboloid_size(self):
+        v = C.c_double()
+        self._ck(self._L.wb_max_hyperboloid_size(self._h, C.byref(v)))
+        return v.value
+
+    def assign(self):
+        self._ck(self._L.wb_assign(self._h))
 
     def set_geometry(self, root_center, root_side, cube):
         self._ck(self._L.wb_set_geometry(self._h, _d(root_center), root_side, _d(cube)))

@@ -1338,6 +1338,82 @@ wb_leaf_keys_kernel(const WbLeafDev *__restrict__ leaves,uint32_t nLeaves,const 
 }
 
 __global__ void __launch_bounds__(256)
+wb_copy_points_kernel(const int *__restrict__ x,const int *__restrict__ y,const int *__restrict__ z,
+                      const uint8_t *__restrict__ c,unsigned long long n,
+                      int *__restrict__ ox,int *__restrict__ oy,int *__restrict__ oz,uint8_t *__restrict__ oc,
+                      uint8_t *__restrict__ oret)
+{
+  unsigned long long i=(unsigned long long)blockIdx.x*blockDim.x+threadIdx.x;
+  if (i>=n)
+    return;
+  ox[i]=x[i]; oy[i]=y[i]; oz[i]=z[i];
+  oc[i]=c[i];
+  if (oret)
+    oret[i]=1;
+}
+
+__global__ void __launch_bounds__(256)
+wb_export_tiles_kernel(const int *__restrict__ tNPoints,const uint8_t *__restrict__ tTree,const double *__restrict__ tHyp,
+                       uint32_t nTiles,WbSnake snake,double xlo,double xhi,
+                       int *__restrict__ onp,int *__restrict__ otree,long long *__restrict__ ohyp)
+{
+  uint32_t t=blockIdx.x*blockDim.x+threadIdx.x;
+  if (t>=nTiles)
+    return;
+  int np=tNPoints[t],tr=0;
+  long long hb=0;
+  if (np)
+  {
+    int ex,ey;
+    double cx,cy;
+    wb_to_flowsnake((int)t+snake.lo,ex,ey);
+    wb_tile_center(ex,ey,snake,cx,cy);
+    if (cx>=xlo && cx<xhi)
+    {
+      tr=tTree[t];
+      hb=__double_as_longlong(tHyp[t]);
+    }
+    else
+      np=0;
+  }
+  onp[t]=np;
+  otree[t]=tr;
+  ohyp[t]=hb;
+}
+
+__global__ void __launch_bounds__(256)
+wb_import_tiles_kernel(const int *__restrict__ inp,const int *__restrict__ itree,const long long *__restrict__ ihyp,
+                       uint32_t nTiles,int *__restrict__ tNPoints,uint8_t *__restrict__ tTree,double *__restrict__ tHyp)
+{
+  uint32_t t=blockIdx.x*blockDim.x+threadIdx.x;
+  if (t>=nTiles)
+    return;
+  tNPoints[t]=inp[t];
+  tTree[t]=(uint8_t)itree[t];
+  tHyp[t]=__longlong_as_double(ihyp[t]);
+}
+
+__global__ void __launch_bounds__(256)
+wb_max_hyp_kernel(const int *__restrict__ tNPoints,const double *__restrict__ tHyp,uint32_t nTiles,
+                  unsigned long long *__restrict__ out)
+// hyperboloidSize is positive: its bit pattern orders like the value
+{
+  unsigned long long m=0;
+  for (uint32_t t=blockIdx.x*blockDim.x+threadIdx.x;t<nTiles;t+=gridDim.x*blockDim.x)
+    if (tNPoints[t])
+    {
+      double h=tHyp[t];
+      if (h>0 && h<INFINITY)
+        m=max(m,(unsigned long long)__double_as_longlong(h));
+    }
+  #pragma unroll
+  for (int o=16;o;o>>=1)
+    m=max(m,__shfl_xor_sync(WB_FULL,m,o));
+  if ((threadIdx.x&31)==0 && m)
+    atomicMax(out,m);
+}
+
+__global__ void __launch_bounds__(256)
 wb_compact_tiles_kernel(const int *__restrict__ tNPoints,uint32_t nTiles,uint32_t *__restrict__ flag)
 {
   uint32_t t=blockIdx.x*blockDim.x+threadIdx.x;

@@ -93,6 +93,8 @@ struct wb_ctx
   bool tablesUploaded=false;
 };
 
+static int ensureTileArrays(wb_ctx *ctx);
+
 namespace
 {
 
@@ -139,16 +141,34 @@ int uploadTables(wb_ctx *ctx)
   return WB_OK;
 }
 
+template <typename T> int growKeep(wb_ctx *ctx,DevBuf<T> &b,uint64_t keep,uint64_t n)
+// enlarge b to n elements, preserving the first `keep`
+{
+  if (n<=b.cap)
+    return WB_OK;
+  T *np=nullptr;
+  CK(cudaMalloc((void **)&np,(size_t)(n*sizeof(T))));
+  if (keep && b.p)
+    CK(cudaMemcpy(np,b.p,(size_t)(keep*sizeof(T)),cudaMemcpyDeviceToDevice));
+  if (b.p)
+    cudaFree(b.p);
+  b.p=np;
+  b.cap=n;
+  return WB_OK;
+}
+
 int ensurePointArrays(wb_ctx *ctx,uint64_t n)
 {
   if (n<=ctx->xi.cap)
     return WB_OK;
-  if (ctx->n)
-    return fail(ctx,WB_ERR_STATE,"point arrays too small (%llu > %llu): call wb_reserve before adding files",
-                (unsigned long long)n,(unsigned long long)ctx->xi.cap);
-  CK(ctx->xi.ensure(n)); CK(ctx->yi.ensure(n)); CK(ctx->zi.ensure(n));
-  CK(ctx->cls.ensure(n)); CK(ctx->ret.ensure(n));
-  ctx->reserved=n;
+  uint64_t want=ctx->n?std::max<uint64_t>(n,ctx->xi.cap*2):n;      // grow geometrically once files are in
+  int rc;
+  CK(cudaStreamSynchronize(ctx->st));
+  if ((rc=growKeep(ctx,ctx->xi,ctx->n,want)) || (rc=growKeep(ctx,ctx->yi,ctx->n,want)) ||
+      (rc=growKeep(ctx,ctx->zi,ctx->n,want)) || (rc=growKeep(ctx,ctx->cls,ctx->n,want)) ||
+      (rc=growKeep(ctx,ctx->ret,ctx->n,want)))
+    return rc;
+  ctx->reserved=want;
   return WB_OK;
 }
 
@@ -319,6 +339,8 @@ extern "C" int wb_clear(wb_ctx *ctx)
   ctx->phase=PH_EMPTY;
   ctx->nPairs=0;
   ctx->nLeaves=0;
+  ctx->ownFirst=0;
+  ctx->ownEnd=0xffffffffu;
   uint64_t launches=ctx->stats.kernel_launches;
   memset(&ctx->stats,0,sizeof(ctx->stats));
   ctx->stats.kernel_launches=launches;
@@ -447,6 +469,55 @@ extern "C" int wb_add_las(wb_ctx *ctx,const uint8_t *recs,uint64_t n,int fmt,int
   CK(cudaStreamSynchronize(ctx->st));
   ctx->stats.ms_h2d+=elapsed(ctx->evA,ctx->evB);       // copy and decode overlap: one figure for both
   return addSegment(ctx,n,scale,offset,unit);
+}
+
+extern "C" int wb_add_points_device(wb_ctx *ctx,const int32_t *dx,const int32_t *dy,const int32_t *dz,const uint8_t *dc,
+                                    uint64_t n,const double scale[3],const double offset[3],double unit)
+{
+  if (!ctx || (n && (!dx || !dy || !dz || !dc)) || !scale || !offset)
+    return WB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  if (ctx->phase>PH_LOADED)
+    return fail(ctx,WB_ERR_STATE,"cloud already built: wb_clear first");
+  int rc;
+  if ((rc=ensurePointArrays(ctx,ctx->n+n)))
+    return rc;
+  if (n)
+  {
+    wb_copy_points_kernel<<<gridFor(n,256),256,0,ctx->st>>>(dx,dy,dz,dc,n,ctx->xi.p+ctx->n,ctx->yi.p+ctx->n,
+                                                           ctx->zi.p+ctx->n,ctx->cls.p+ctx->n,ctx->ret.p+ctx->n);
+    ctx->stats.kernel_launches++;
+    KCHECK();
+    CK(cudaStreamSynchronize(ctx->st));
+  }
+  return addSegment(ctx,n,scale,offset,unit);
+}
+
+extern "C" int wb_export_points_device(wb_ctx *ctx,uint64_t first,uint64_t n,int32_t *dx,int32_t *dy,int32_t *dz,uint8_t *dc)
+{
+  if (!ctx || (n && (!dx || !dy || !dz || !dc)))
+    return WB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  if (first+n>ctx->n)
+    return fail(ctx,WB_ERR_ARG,"range outside the cloud");
+  if (n)
+  {
+    wb_copy_points_kernel<<<gridFor(n,256),256,0,ctx->st>>>(ctx->xi.p+first,ctx->yi.p+first,ctx->zi.p+first,ctx->cls.p+first,
+                                                           n,dx,dy,dz,dc,nullptr);
+    ctx->stats.kernel_launches++;
+    KCHECK();
+    CK(cudaStreamSynchronize(ctx->st));
+  }
+  return WB_OK;
+}
+
+extern "C" int wb_set_own_range(wb_ctx *ctx,uint64_t first,uint64_t end)
+{
+  if (!ctx || end<first)
+    return WB_ERR_ARG;
+  ctx->ownFirst=(uint32_t)first;
+  ctx->ownEnd=end>0xffffffffull?0xffffffffu:(uint32_t)end;
+  return WB_OK;
 }
 
 // ============================================================================ build
@@ -686,8 +757,11 @@ extern "C" int wb_scan(wb_ctx *ctx)
   const uint32_t T=ctx->nTiles;
   cudaStream_t st=ctx->st;
   CK(ctx->tilesOf.ensure(nv)); CK(ctx->winner.ensure(nv));
-  CK(ctx->tStart.ensure(T)); CK(ctx->tCount.ensure(T)); CK(ctx->tNPoints.ensure(T)); CK(ctx->tTree.ensure(T));
-  CK(ctx->tDensity.ensure(T)); CK(ctx->tHyp.ensure(T)); CK(ctx->tHeight.ensure(T));
+  {
+    int rc=ensureTileArrays(ctx);
+    if (rc)
+      return rc;
+  }
   CK(cudaEventRecord(ctx->evA,st));
   wb_member_count_kernel<<<gridFor(nv,128),128,0,st>>>(ctx->sx.p,ctx->sy.p,nv,ctx->snake,ctx->scr0.p,ctx->tilesOf.p,ctx->winner.p);
   ctx->stats.kernel_launches++;
@@ -733,6 +807,88 @@ extern "C" int wb_scan(wb_ctx *ctx)
   ctx->stats.n_tiles_nonempty=ne;
   ctx->stats.n_memberships=m;
   ctx->phase=PH_SCANNED;
+  return WB_OK;
+}
+
+static int ensureTileArrays(wb_ctx *ctx)
+{
+  const uint32_t T=ctx->nTiles;
+  CK(ctx->tStart.ensure(T)); CK(ctx->tCount.ensure(T)); CK(ctx->tNPoints.ensure(T)); CK(ctx->tTree.ensure(T));
+  CK(ctx->tDensity.ensure(T)); CK(ctx->tHyp.ensure(T)); CK(ctx->tHeight.ensure(T));
+  return WB_OK;
+}
+
+extern "C" int wb_assign(wb_ctx *ctx)
+{
+  if (!ctx)
+    return WB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  if (ctx->phase<PH_BUILT)
+    return fail(ctx,WB_ERR_STATE,"not built");
+  const uint64_t nv=ctx->nValid;
+  CK(ctx->tilesOf.ensure(nv)); CK(ctx->winner.ensure(nv));
+  wb_member_count_kernel<<<gridFor(nv,128),128,0,ctx->st>>>(ctx->sx.p,ctx->sy.p,nv,ctx->snake,ctx->scr0.p,ctx->tilesOf.p,ctx->winner.p);
+  ctx->stats.kernel_launches++;
+  KCHECK();
+  CK(cudaStreamSynchronize(ctx->st));
+  return WB_OK;
+}
+
+extern "C" int wb_export_tiles_device(wb_ctx *ctx,double xlo,double xhi,int32_t *dnp,int32_t *dtree,int64_t *dhyp)
+{
+  if (!ctx || !dnp || !dtree || !dhyp)
+    return WB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  if (ctx->phase<PH_SCANNED)
+    return fail(ctx,WB_ERR_STATE,"not scanned");
+  wb_export_tiles_kernel<<<gridFor(ctx->nTiles,256),256,0,ctx->st>>>(ctx->tNPoints.p,ctx->tTree.p,ctx->tHyp.p,ctx->nTiles,
+                                                                     ctx->snake,xlo,xhi,dnp,dtree,(long long *)dhyp);
+  ctx->stats.kernel_launches++;
+  KCHECK();
+  CK(cudaStreamSynchronize(ctx->st));
+  return WB_OK;
+}
+
+extern "C" int wb_import_tiles_device(wb_ctx *ctx,const int32_t *dnp,const int32_t *dtree,const int64_t *dhyp,int postscanned)
+{
+  if (!ctx || !dnp || !dtree || !dhyp)
+    return WB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  if (ctx->phase<PH_BUILT)
+    return fail(ctx,WB_ERR_STATE,"not built");
+  int rc=ensureTileArrays(ctx);
+  if (rc)
+    return rc;
+  wb_import_tiles_kernel<<<gridFor(ctx->nTiles,256),256,0,ctx->st>>>(dnp,dtree,(const long long *)dhyp,ctx->nTiles,
+                                                                     ctx->tNPoints.p,ctx->tTree.p,ctx->tHyp.p);
+  ctx->stats.kernel_launches++;
+  KCHECK();
+  CK(cudaStreamSynchronize(ctx->st));
+  if (postscanned)
+  {
+    if (ctx->phase<PH_POSTSCANNED)
+      ctx->phase=PH_POSTSCANNED;
+  }
+  else if (ctx->phase<PH_SCANNED || ctx->phase==PH_POSTSCANNED)
+    ctx->phase=PH_SCANNED;
+  return WB_OK;
+}
+
+extern "C" int wb_max_hyperboloid_size(wb_ctx *ctx,double *out)
+{
+  if (!ctx || !out)
+    return WB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  if (ctx->phase<PH_SCANNED)
+    return fail(ctx,WB_ERR_STATE,"not scanned");
+  CK(cudaMemsetAsync(ctx->counters.p+7,0,sizeof(unsigned long long),ctx->st));
+  wb_max_hyp_kernel<<<148*4,256,0,ctx->st>>>(ctx->tNPoints.p,ctx->tHyp.p,ctx->nTiles,ctx->counters.p+7);
+  ctx->stats.kernel_launches++;
+  KCHECK();
+  unsigned long long bits=0;
+  CK(cudaMemcpyAsync(&bits,ctx->counters.p+7,sizeof(bits),cudaMemcpyDeviceToHost,ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  memcpy(out,&bits,sizeof(double));
   return WB_OK;
 }
 
