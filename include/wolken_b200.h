@@ -129,6 +129,8 @@ int wb_num_leaves(wb_ctx *ctx,uint64_t *n);
 int wb_get_leaves(wb_ctx *ctx,wb_leaf *out,uint64_t cap);
 /* canonical order: order[k] = input index of the k-th point; keys[k] = its 63-bit Morton key */
 int wb_get_order(wb_ctx *ctx,uint32_t *order,uint64_t *keys);
+/* coordinates in canonical order, exactly the doubles the reference's LasPoint::location holds */
+int wb_get_points_sorted(wb_ctx *ctx,double *x,double *y,double *z);
 /* decoded SoA columns in input order (any pointer may be NULL) */
 int wb_get_decoded(wb_ctx *ctx,int32_t *x,int32_t *y,int32_t *z,uint8_t *cls);
 

@@ -1,0 +1,110 @@
+"""The reference-shaped C++ surface (wolkenbase_b200/host) end to end on the GPU: wolkencli's
+dump and classified LAS output against the oracle, and the OctStore query API against brute force."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import wb_oracle as O  # noqa: E402
+from wolkenbase_b200 import synth  # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "wolkenbase_b200", "host", "wolkencli")
+QUERY = os.path.join(ROOT, "wolkenbase_b200", "host", "wolkenquery")
+
+
+def _read_las(path):
+    raw = np.fromfile(path, dtype=np.uint8)
+    hs = int(raw[94:96].view("<u2")[0])
+    off = int(raw[96:100].view("<u4")[0])
+    fmt = int(raw[104])
+    ln = int(raw[105:107].view("<u2")[0])
+    n = int(raw[107:111].view("<u4")[0]) if fmt < 6 else int(raw[247:255].view("<u8")[0])
+    recs = raw[off:off + n * ln].reshape(n, ln)
+    return fmt, recs, raw[:hs]
+
+
+def test_cli_reference_mode_dump(tmp_path):
+    """Without -o the CLI does what the reference's does: header lines, cube, octree dump."""
+    cloud = synth.generate(2, 20000, seed=41)
+    las = str(tmp_path / "in.las")
+    cloud.write(las)
+    out = subprocess.run([CLI, "--dump", str(tmp_path / "dumpfile"), las], capture_output=True, text=True, check=True)
+    res = O.run([O.file_from_cloud(cloud)], classify=False)
+    assert "Version 1.2 %d points, format 1" % cloud.n in out.stdout
+    assert "All points in octree" in out.stdout and "Dumping octree" in out.stdout
+    cx, cy, cz = (O.ldecimal(v) for v in res.root_center)
+    assert "(%s,%s,%s)±%g" % (cx, cy, cz, res.root_side) in out.stdout
+    assert open(tmp_path / "dumpfile", encoding="utf-8").read() == res.dump
+
+
+def test_cli_classify_and_write(tmp_path):
+    cloud = synth.generate(5, 30000, seed=5)                     # format 3 (34 B), config 5's scene
+    las = str(tmp_path / "urban.las")
+    cloud.write(las)
+    res = O.run([O.file_from_cloud(cloud)])
+    # one file, class byte in place (config 1 style)
+    subprocess.run([CLI, "-o", str(tmp_path / "one"), "--separate-classes", "0", "--dump", str(tmp_path / "d1"), las],
+                   capture_output=True, text=True, check=True)
+    fmt, recs, hdr = _read_las(str(tmp_path / "one.las"))
+    assert fmt == 3 and recs.shape == cloud.records.shape
+    assert ((recs[:, 15] & 31) == res.labels).all()
+    other = np.delete(np.arange(recs.shape[1]), 15)
+    assert (recs[:, other] == cloud.records[:, other]).all()
+    assert bytes(hdr[26:38]) == b"MODIFICATION"
+    # split ground / nonground with a points-per-file limit (config 5 style)
+    r = subprocess.run([CLI, "-o", str(tmp_path / "split.las"), "--points-per-file", "10000", las],
+                       capture_output=True, text=True, check=True, cwd=str(tmp_path))
+    n_ground, n_non = int((res.labels == 2).sum()), int((res.labels == 1).sum())
+    assert "2 %d" % n_ground in r.stdout and "1 %d" % n_non in r.stdout
+    got = {1: [], 2: []}
+    for name in sorted(os.listdir(tmp_path)):
+        if name.startswith("split-"):
+            cls = 2 if "-ground-" in name else 1
+            f, rr, _ = _read_las(str(tmp_path / name))
+            assert rr.shape[0] <= 10000 and ((rr[:, 15] & 31) == cls).all()
+            got[cls].append(rr)
+    for cls, want_n in ((1, n_non), (2, n_ground)):
+        allr = np.concatenate(got[cls])
+        assert allr.shape[0] == want_n
+        # multiset of gpsTime equals the reference's selection
+        gps = np.sort(np.ascontiguousarray(allr[:, 20:28]).view("<f8").ravel())
+        want = np.sort(np.nonzero(res.labels == cls)[0].astype(np.float64))
+        assert (gps == want).all()
+    assert len(got[2]) == -(-n_ground // 10000)
+
+
+def test_octstore_queries(tmp_path):
+    """findBlocks / pointsIn / countPointsIn / hiLoPointsIn vs brute force (cf. testflat, wolkentest.cpp:143-167)."""
+    cloud = synth.generate(2, 40000, seed=43)
+    las = str(tmp_path / "q.las")
+    cloud.write(las)
+    res = O.run([O.file_from_cloud(cloud)], classify=False)
+    pts = res.points_sorted
+    c = [float(v) for v in pts.mean(axis=0)]
+    # cylinder
+    out = json.loads(subprocess.run([QUERY, las, "cyl", repr(c[0]), repr(c[1]), "3.5"], capture_output=True, text=True,
+                                    check=True).stdout.strip().splitlines()[-1])
+    inside = np.hypot(pts[:, 0] - c[0], pts[:, 1] - c[1]) <= 3.5
+    assert out["count"] == out["points"] == int(inside.sum()) and out["sorted"] == 1 and out["consistent"] == 1
+    assert out["lo"] == pts[inside, 2].min() and out["hi"] == pts[inside, 2].max()
+    assert out["total_points"] == cloud.n and out["total_blocks"] == len(res.leaves)
+    assert 0 < out["blocks"] < len(res.leaves)
+    # sphere
+    out = json.loads(subprocess.run([QUERY, las, "sph", repr(c[0]), repr(c[1]), repr(c[2]), "2.0"], capture_output=True,
+                                    text=True, check=True).stdout.strip().splitlines()[-1])
+    d = np.hypot(np.hypot(pts[:, 0] - c[0], pts[:, 1] - c[1]), pts[:, 2] - c[2])
+    assert out["count"] == int((d <= 2.0).sum())
+    # downward hyperboloid from 3 m above the centroid
+    v = (c[0], c[1], c[2] + 3.0)
+    out = json.loads(subprocess.run([QUERY, las, "hyp"] + [repr(x) for x in v] + ["0.5", "1"], capture_output=True,
+                                    text=True, check=True).stdout.strip().splitlines()[-1])
+    por = 0.5
+    zd = (v[2] + por) - pts[:, 2]
+    dd = np.hypot(v[0] - pts[:, 0], v[1] - pts[:, 1])
+    inside = (zd > 0) & (zd * zd - dd * dd >= por * por)
+    assert out["count"] == int(inside.sum()) and out["count"] > 10

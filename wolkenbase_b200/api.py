@@ -76,6 +76,7 @@ def lib():
             "wb_get_leaves": [vp, vp, u64],
             "wb_get_order": [vp, vp, vp],
             "wb_get_decoded": [vp, vp, vp, vp, vp],
+            "wb_get_points_sorted": [vp, vp, vp, vp],
             "wb_scan": [vp],
             "wb_postscan": [vp],
             "wb_num_tiles": [vp, C.POINTER(u64)],
@@ -114,7 +115,7 @@ EXPORTS = ["wb_create", "wb_destroy", "wb_last_error", "wb_reserve", "wb_clear",
            "wb_run", "wb_get_stats", "wb_sync", "wb_host_alloc", "wb_host_free", "wb_size_fit", "wb_bbox_cube",
            "wb_snake_set_size", "wb_ldecimal", "wb_format_dump", "wb_add_points_device", "wb_export_points_device",
            "wb_set_own_range", "wb_export_tiles_device", "wb_import_tiles_device", "wb_max_hyperboloid_size",
-           "wb_assign"]
+           "wb_assign", "wb_get_points_sorted"]
 
 
 def _d(v):
@@ -272,6 +273,11 @@ class Context:
         keys = np.empty(n, dtype=np.uint64)
         self._ck(self._L.wb_get_order(self._h, order.ctypes.data, keys.ctypes.data))
         return order, keys
+
+    def points_sorted(self, n):
+        x = np.empty(n); y = np.empty(n); z = np.empty(n)
+        self._ck(self._L.wb_get_points_sorted(self._h, x.ctypes.data, y.ctypes.data, z.ctypes.data))
+        return x, y, z
 
     def decoded(self, n):
         x = np.empty(n, dtype=np.int32)

@@ -730,6 +730,19 @@ extern "C" int wb_get_order(wb_ctx *ctx,uint32_t *order,uint64_t *keys)
   return WB_OK;
 }
 
+extern "C" int wb_get_points_sorted(wb_ctx *ctx,double *x,double *y,double *z)
+{
+  if (!ctx)
+    return WB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  if (ctx->phase<PH_BUILT)
+    return fail(ctx,WB_ERR_STATE,"not built");
+  if (x) CK(cudaMemcpy(x,ctx->sx.p,sizeof(double)*ctx->nValid,cudaMemcpyDeviceToHost));
+  if (y) CK(cudaMemcpy(y,ctx->sy.p,sizeof(double)*ctx->nValid,cudaMemcpyDeviceToHost));
+  if (z) CK(cudaMemcpy(z,ctx->sz.p,sizeof(double)*ctx->nValid,cudaMemcpyDeviceToHost));
+  return WB_OK;
+}
+
 extern "C" int wb_get_decoded(wb_ctx *ctx,int32_t *x,int32_t *y,int32_t *z,uint8_t *cls)
 {
   if (!ctx)

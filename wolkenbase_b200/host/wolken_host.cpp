@@ -1,0 +1,1013 @@
+// wolken_host.cpp — implementation of the reference-shaped C++ surface over the C ABI.
+#include <algorithm>
+#include <cassert>
+#include <climits>
+#include <cstdio>
+#include <cstring>
+#include <iostream>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include "wolken_host.h"
+
+using namespace std;
+
+Octree octRoot;
+OctStore octStore;
+Flowsnake snake;
+TileTable tiles;
+map<int,size_t> classTotals;
+double minHyperboloidSize=0.1,maxSlope=1,thickness=0,tileSize=1;
+
+namespace
+{
+wb_ctx *g_ctx=nullptr;
+int g_command=TH_WAIT;
+vector<LasHeader *> g_files;           // in read order: input index = concatenation of their records
+vector<size_t> g_fileFirst;
+vector<double> g_corners;
+Cube g_snakeCube;
+double g_snakeTile=1;
+bool g_built=false,g_scanned=false,g_postscanned=false,g_classified=false;
+// host mirrors, filled on demand
+bool g_haveStore=false;
+vector<wb_leaf> g_leaves;
+vector<uint64_t> g_leafLo;             // smallest key of each leaf's cube
+vector<double> g_x,g_y,g_z;
+vector<uint32_t> g_perm;
+vector<uint64_t> g_keys;
+vector<uint8_t> g_labels;
+deque<ThreadAction> g_results;
+
+void die(const char *what)
+{
+  cerr<<what<<": "<<(g_ctx?wb_last_error(g_ctx):"no context")<<endl;
+}
+
+void ensureContext()
+{
+  if (!g_ctx)
+  {
+    const char *d=getenv("WOLKEN_DEVICE");
+    if (wb_create(d?atoi(d):0,&g_ctx)!=WB_OK)
+    {
+      cerr<<"wolkenbase_b200: no usable CUDA device (there is no CPU path)\n";
+      exit(3);
+    }
+  }
+}
+
+uint64_t keyOf(xyz p)
+// 21 steps of Octree::findBlock's descent, octree.cpp:199-216
+{
+  xyz c=octRoot.getCenter();
+  double cx=c.getx(),cy=c.gety(),cz=c.getz(),q=octRoot.getSide()/4;
+  uint64_t key=0;
+  for (int l=0;l<WB_LEVELS;l++)
+  {
+    int xb=p.getx()>=cx,yb=p.gety()>=cy,zb=p.getz()>=cz;
+    key=(key<<3)|(uint64_t)(zb*4+yb*2+xb);
+    cx+=xb?q:-q; cy+=yb?q:-q; cz+=zb?q:-q;
+    q/=2;
+  }
+  return key;
+}
+
+void ensureBuilt()
+{
+  ensureContext();
+  if (g_built)
+    return;
+  double rc[3]={octRoot.getCenter().getx(),octRoot.getCenter().gety(),octRoot.getCenter().getz()};
+  double cube[4]={g_snakeCube.getCenter().getx(),g_snakeCube.getCenter().gety(),g_snakeCube.getCenter().getz(),g_snakeCube.getSide()};
+  wb_set_params(g_ctx,g_snakeTile,maxSlope,thickness,minHyperboloidSize);
+  if (octRoot.getSide()>0 && g_snakeCube.getSide()>0)
+    wb_set_geometry(g_ctx,rc,octRoot.getSide(),cube);
+  if (wb_build(g_ctx)!=WB_OK)
+  {
+    die("build");
+    exit(4);
+  }
+  g_built=true;
+  g_haveStore=false;
+}
+
+void ensureStore()
+{
+  ensureBuilt();
+  if (g_haveStore)
+    return;
+  uint64_t nl=0;
+  wb_num_leaves(g_ctx,&nl);
+  g_leaves.resize(nl);
+  if (nl)
+    wb_get_leaves(g_ctx,g_leaves.data(),nl);
+  wb_stats st;
+  wb_get_stats(g_ctx,&st);
+  size_t n=st.n_points;
+  g_x.resize(n); g_y.resize(n); g_z.resize(n); g_perm.resize(n); g_keys.resize(n);
+  wb_get_points_sorted(g_ctx,g_x.data(),g_y.data(),g_z.data());
+  wb_get_order(g_ctx,g_perm.data(),g_keys.data());
+  g_leafLo.resize(nl);
+  for (size_t i=0;i<nl;i++)
+  {
+    int s=3*(WB_LEVELS-g_leaves[i].depth);
+    g_leafLo[i]=s>=63?0:(g_keys[g_leaves[i].first]>>s)<<s;
+  }
+  g_haveStore=true;
+}
+
+void ensureLabels()
+{
+  if (!g_classified)
+    return;
+  size_t n=0;
+  for (auto f:g_files)
+    n+=f->numberPoints();
+  if (g_labels.size()!=n)
+  {
+    g_labels.resize(n);
+    wb_get_labels(g_ctx,g_labels.data());
+  }
+}
+
+LasPoint pointAt(size_t k)
+// k-th point of the canonical order, all attributes decoded from its original record
+{
+  uint32_t i=g_perm[k];
+  size_t f=upper_bound(g_fileFirst.begin(),g_fileFirst.end(),(size_t)i)-g_fileFirst.begin()-1;
+  LasPoint p=g_files[f]->readPoint(i-g_fileFirst[f]);
+  p.location=xyz(g_x[k],g_y[k],g_z[k]);
+  if (g_classified)
+  {
+    ensureLabels();
+    p.classification=g_labels[i];
+  }
+  return p;
+}
+
+Cube leafCube(size_t i)
+{
+  return Cube(xyz(g_leaves[i].cx,g_leaves[i].cy,g_leaves[i].cz),2*g_leaves[i].half);
+}
+
+void findBlocksRec(const Shape &sh,size_t lo,size_t hi,int depth,xyz c,double side,vector<int64_t> &out)
+// Octree::findBlocks (octree.cpp:234-251) over the leaf list: [lo,hi) are the leaves below the
+// node of centre c and side `side` at `depth`
+{
+  if (!sh.intersect(Cube(c,side)))
+    return;
+  for (int ch=0;ch<8;ch++)
+  {
+    int s=3*(WB_LEVELS-1-depth);
+    size_t a=lo;
+    while (a<hi && (int)((g_leafLo[a]>>s)&7)<ch) a++;
+    size_t b=a;
+    while (b<hi && (int)((g_leafLo[b]>>s)&7)==ch) b++;
+    if (a==b)
+      continue;
+    xyz cc(c.getx()+((ch&1)?side/4:-side/4),c.gety()+((ch&2)?side/4:-side/4),c.getz()+((ch&4)?side/4:-side/4));
+    if (b-a==1 && g_leaves[a].depth==depth+1)
+    {
+      if (sh.intersect(Cube(cc,side/2)))
+        out.push_back((int64_t)a);
+    }
+    else
+      findBlocksRec(sh,a,b,depth+1,cc,side/2,out);
+    lo=b;
+  }
+}
+} // namespace
+
+// ---------------------------------------------------------------- shapes (shape.cpp)
+bool Cube::in(xyz p) const
+{
+  return fabs(p.getx()-center.getx())<=side/2 && fabs(p.gety()-center.gety())<=side/2 && fabs(p.getz()-center.getz())<=side/2;
+}
+
+xyz Cube::corner(int n) const
+{
+  return xyz(center.getx()+((n&1)?side/2:-side/2),center.gety()+((n&2)?side/2:-side/2),center.getz()+((n&4)?side/2:-side/2));
+}
+
+bool Shape::in(Cube &cube) const
+{
+  bool ret=true;
+  for (int i=0;i<8;i++)
+    ret=ret && in(cube.corner(i));
+  return ret;
+}
+
+static double clampToward(double v,double c,double half)
+// the coordinate of the cube (centre c) nearest to v
+{
+  if (fabs(v-c)<half)
+    return v;
+  return v>c?c+half:c-half;
+}
+
+bool Paraboloid::in(xyz p) const
+{
+  double d=dist(xy(vertex),xy(p)),zd=vertex.getz()-p.getz();
+  if (radiusCurvature==0)
+    return d==0;
+  return 2*zd/radiusCurvature>=sqr(d/radiusCurvature);
+}
+
+xyz Paraboloid::closestPoint(Cube cube) const
+{
+  xyz c=cube.getCenter();
+  double h=cube.getSide()/2,z=c.getz();
+  if (radiusCurvature>0) z-=h;
+  if (radiusCurvature<0) z+=h;
+  return xyz(clampToward(vertex.getx(),c.getx(),h),clampToward(vertex.gety(),c.gety(),h),z);
+}
+
+Hyperboloid::Hyperboloid(xyz v,double r,double s)
+{
+  double por=r*sqr(s);
+  slope=s;
+  por2=sqr(por);
+  center=v+xyz(0,0,por);
+}
+
+bool Hyperboloid::in(xyz p) const
+{
+  double d=dist(xy(center),xy(p)),zd=center.getz()-p.getz();
+  if (slope>0)
+    return zd>0 && sqr(zd)-sqr(d*slope)>=por2;
+  return zd<0 && sqr(zd)-sqr(d*slope)>=por2;
+}
+
+xyz Hyperboloid::closestPoint(Cube cube) const
+{
+  xyz c=cube.getCenter();
+  double h=cube.getSide()/2,z=c.getz();
+  if (slope>0) z-=h;
+  if (slope<0) z+=h;
+  return xyz(clampToward(center.getx(),c.getx(),h),clampToward(center.gety(),c.gety(),h),z);
+}
+
+bool Sphere::in(xyz p) const
+{
+  return hypot(hypot(p.getx()-center.getx(),p.gety()-center.gety()),p.getz()-center.getz())<=radius;
+}
+
+xyz Sphere::closestPoint(Cube cube) const
+{
+  xyz c=cube.getCenter();
+  double h=cube.getSide()/2;
+  return xyz(clampToward(center.getx(),c.getx(),h),clampToward(center.gety(),c.gety(),h),clampToward(center.getz(),c.getz(),h));
+}
+
+bool Cylinder::in(xyz p) const
+{
+  return dist(center,xy(p))<=radius;
+}
+
+xyz Cylinder::closestPoint(Cube cube) const
+{
+  xyz c=cube.getCenter();
+  double h=cube.getSide()/2;
+  return xyz(clampToward(center.getx(),c.getx(),h),clampToward(center.gety(),c.gety(),h),c.getz());
+}
+
+// ---------------------------------------------------------------- LAS
+LasPoint::LasPoint()
+{
+  location=xyz(NAN,NAN,NAN);
+  intensity=returnNum=nReturns=classification=classificationFlags=0;
+  scannerChannel=userData=pointSource=nir=red=green=blue=0;
+  scanDirection=edgeLine=false;
+  scanAngle=0;
+  gpsTime=0;
+}
+
+LasHeader::LasHeader()
+{
+  map=nullptr;
+  mapLen=0;
+  versionMajor=versionMinor=0;
+  headerSize=pointOffset=0;
+  pointFormat=pointLength=0;
+  unit=1;
+  zipFlag=false;
+  for (auto &v:nPoints)
+    v=0;
+  xScale=yScale=zScale=xOffset=yOffset=zOffset=maxX=minX=maxY=minY=maxZ=minZ=0;
+}
+
+LasHeader::~LasHeader()
+{
+  close();
+}
+
+void LasHeader::close()
+{
+  if (map)
+    munmap(map,mapLen);
+  map=nullptr;
+  mapLen=0;
+}
+
+template <typename T> static T rd(const uint8_t *p)
+{
+  T v;
+  memcpy(&v,p,sizeof(T));
+  return v;
+}
+
+void LasHeader::openRead(string fileName)
+// Field layout and the "which point count is right" vote of las.cpp:299-428
+{
+  close();
+  filename=fileName;
+  versionMajor=versionMinor=0;
+  nPoints[0]=0;
+  int fd=open(fileName.c_str(),O_RDONLY);
+  if (fd<0)
+    return;
+  struct stat st;
+  if (fstat(fd,&st) || st.st_size<227)
+  {
+    ::close(fd);
+    return;
+  }
+  mapLen=st.st_size;
+  map=(uint8_t *)mmap(nullptr,mapLen,PROT_READ,MAP_PRIVATE,fd,0);
+  ::close(fd);
+  if (map==MAP_FAILED)
+  {
+    map=nullptr;
+    return;
+  }
+  if (memcmp(map,"LASF",4))
+    return;
+  const uint8_t *h=map;
+  versionMajor=h[24];
+  versionMinor=h[25];
+  headerSize=rd<uint16_t>(h+94);
+  pointOffset=rd<uint32_t>(h+96);
+  pointFormat=h[104];
+  pointLength=rd<uint16_t>(h+105);
+  unsigned legacy[6];
+  for (int i=0;i<6;i++)
+    legacy[i]=rd<uint32_t>(h+107+4*i);
+  xScale=rd<double>(h+131); yScale=rd<double>(h+139); zScale=rd<double>(h+147);
+  xOffset=rd<double>(h+155); yOffset=rd<double>(h+163); zOffset=rd<double>(h+171);
+  maxX=rd<double>(h+179); minX=rd<double>(h+187); maxY=rd<double>(h+195);
+  minY=rd<double>(h+203); maxZ=rd<double>(h+211); minZ=rd<double>(h+219);
+  for (auto &v:nPoints)
+    v=0;
+  if (headerSize>0xe3 && mapLen>=375)
+    for (int i=0;i<16;i++)
+      nPoints[i]=rd<uint64_t>(h+247+8*i);
+  int which=15;
+  size_t total=0;
+  for (int i=1;i<6;i++)
+  {
+    total+=legacy[i];
+    if (legacy[i]>legacy[0])
+      which&=~5;
+  }
+  if (total!=legacy[0]) which&=~1;
+  if (total!=0 || legacy[0]==0) which&=~4;
+  total=0;
+  for (int i=1;i<16;i++)
+  {
+    total+=nPoints[i];
+    if (nPoints[i]>nPoints[0])
+      which&=~10;
+  }
+  if (total!=nPoints[0]) which&=~2;
+  if (total!=0 || nPoints[0]==0) which&=~8;
+  for (int i=0;i<6;i++)
+  {
+    if (legacy[i]!=nPoints[i] && legacy[i]!=0) which&=~10;
+    if (nPoints[i]!=legacy[i] && nPoints[i]!=0) which&=~5;
+  }
+  if (which>0 && (which&3)==0)
+  {
+    cerr<<"Number of points by return are all 0. Setting first return to all points.\n";
+    nPoints[1]=nPoints[0];
+    legacy[1]=legacy[0];
+  }
+  if (which==1 || which==4)
+    for (int i=0;i<6;i++)
+      nPoints[i]=legacy[i];
+  if (which==0)
+    for (int i=0;i<6;i++)
+      nPoints[i]=0;
+  if (pointLength==0)
+    versionMajor=versionMinor=nPoints[0]=0;
+  if ((uint64_t)pointOffset+(uint64_t)nPoints[0]*pointLength>mapLen)
+    nPoints[0]=pointLength?(mapLen-pointOffset)/pointLength:0;   // truncated file: read what is there
+  zipFlag=pointOffset>=headerSize+8 && mapLen>=headerSize+8 && !memcmp(map+headerSize+2,"laszip",6);
+  if (zipFlag)
+    cout<<filename<<" is laszipped\n";
+}
+
+bool LasHeader::isValid() const
+{
+  return versionMajor>0 && versionMinor>0 && headerSize>0 && pointLength>0 && (headerSize>0xe3 || pointFormat<6);
+}
+
+static int degToBin(double deg)
+// degtobin -> rottobin, angle.cpp:233-251
+{
+  double ip=0,fp=2*modf(deg/360/2,&ip);
+  if (fp>=1) fp-=2;
+  if (fp<-1) fp+=2;
+  return (int)lrint(2147483648.*fp);
+}
+
+LasPoint LasHeader::readPoint(size_t num)
+// las.cpp:735-820
+{
+  LasPoint ret;
+  if (!map || num>=nPoints[0])
+    throw -1;
+  const uint8_t *r=map+pointOffset+num*pointLength;
+  int xi=rd<int32_t>(r),yi=rd<int32_t>(r+4),zi=rd<int32_t>(r+8),o;
+  ret.intensity=rd<uint16_t>(r+12);
+  if (pointFormat<6)
+  {
+    ret.returnNum=r[14]&7;
+    ret.nReturns=(r[14]>>3)&7;
+    ret.scanDirection=(r[14]>>6)&1;
+    ret.edgeLine=(r[14]>>7)&1;
+    ret.classification=r[15]&31;
+    ret.classificationFlags=(r[15]>>5)&7;
+    ret.scanAngle=degToBin((signed char)r[16]);
+    ret.userData=r[17];
+    ret.pointSource=rd<uint16_t>(r+18);
+    o=20;
+  }
+  else
+  {
+    ret.returnNum=r[14]&15;
+    ret.nReturns=(r[14]>>4)&15;
+    ret.classificationFlags=r[15]&15;
+    ret.scannerChannel=(r[15]>>4)&3;
+    ret.scanDirection=(r[15]>>6)&1;
+    ret.edgeLine=(r[15]>>7)&1;
+    ret.classification=r[16];
+    ret.userData=r[17];
+    ret.scanAngle=degToBin(rd<int16_t>(r+18)*0.006);
+    ret.pointSource=rd<uint16_t>(r+20);
+    o=22;
+  }
+  if ((1<<pointFormat)&0x7fa)
+  {
+    ret.gpsTime=rd<double>(r+o);
+    o+=8;
+  }
+  if ((1<<pointFormat)&0x5ac)
+  {
+    ret.red=rd<uint16_t>(r+o); ret.green=rd<uint16_t>(r+o+2); ret.blue=rd<uint16_t>(r+o+4);
+    o+=6;
+  }
+  if ((1<<pointFormat)&0x500)
+    ret.nir=rd<uint16_t>(r+o);
+  ret.location=xyz(xOffset+xScale*xi,yOffset+yScale*yi,zOffset+zScale*zi)*unit;
+  if (ret.location.getx()>maxX*unit || ret.location.getx()<minX*unit || ret.location.gety()>maxY*unit ||
+      ret.location.gety()<minY*unit || ret.location.getz()>maxZ*unit || ret.location.getz()<minZ*unit)
+    cerr<<"Point out of range\n";
+  return ret;
+}
+
+// ---------------------------------------------------------------- flowsnake / tiles
+Eisenstein toFlowsnake(int n)
+{
+  static const unsigned char tab[6][7]=
+  {
+    {0x52,0x05,0x06,0x24,0x33,0x40,0x01},{0x31,0x10,0x12,0x05,0x43,0x54,0x16},{0x46,0x24,0x21,0x10,0x53,0x35,0x22},
+    {0x31,0x10,0x03,0x54,0x36,0x35,0x22},{0x46,0x24,0x13,0x35,0x42,0x40,0x01},{0x52,0x05,0x23,0x40,0x51,0x54,0x16}
+  };
+  int dig[11],ori=0;
+  long long v=(long long)n+1235829214LL;
+  for (int i=0;i<11;i++) { dig[i]=(int)(v%7); v/=7; }
+  for (int i=10;i>=0;i--) { int t=tab[ori][dig[i]]; ori=t>>4; dig[i]=t&7; }
+  int x=0,y=0,px=1,py=0;
+  for (int i=0;i<11;i++)
+  {
+    int d=dig[i]-3,dy=(d+4)/3-1,dx=d-2*dy;
+    x+=dx*px-dy*py;
+    y+=dx*py+dy*px-dy*py;
+    int nx=2*px+py,ny=3*py-px;
+    px=nx; py=ny;
+  }
+  return Eisenstein(x,y);
+}
+
+void Flowsnake::setSize(Cube cube,double desiredSpacing)
+{
+  int lo,hi;
+  assert(desiredSpacing>0 && cube.getSide()>0);
+  wb_snake_set_size(cube.getSide(),desiredSpacing,&spacing,&lo,&hi);
+  center=xy(cube.getCenter());
+  startnum=counter=lo;
+  stopnum=hi;
+  g_snakeCube=cube;
+  g_snakeTile=desiredSpacing;
+  g_built=g_scanned=g_postscanned=g_classified=false;
+}
+
+Eisenstein Flowsnake::next()
+{
+  if (counter<=stopnum)
+    return toFlowsnake(counter++);
+  return Eisenstein(INT_MIN,INT_MIN);
+}
+
+Cylinder Flowsnake::cyl(Eisenstein e)
+{
+  double rad=spacing*41/71;
+  double re=(e.getx()-e.gety()/2.)*spacing,im=e.gety()*0.86602540378443864676372317*spacing;
+  if (e.getx()==INT_MIN)
+    rad=0;
+  return Cylinder(xy(re,im)+center,rad);
+}
+
+Tile &TileTable::operator[](Eisenstein e)
+{
+  auto it=byAddr.find(e);
+  if (it==byAddr.end())
+  {
+    Tile z;
+    memset(&z,0,sizeof(z));
+    it=byAddr.insert(make_pair(e,z)).first;
+  }
+  return it->second;
+}
+
+void refreshTiles()
+{
+  uint64_t n=0;
+  tiles.byAddr.clear();
+  if (wb_num_tiles(g_ctx,&n)!=WB_OK || !n)
+    return;
+  vector<wb_tile> t(n);
+  wb_get_tiles(g_ctx,t.data(),n);
+  for (auto &w:t)
+  {
+    Tile z;
+    memset(&z,0,sizeof(z));
+    z.nPoints=w.nPoints;
+    z.treeFlags=(short)w.treeFlags;
+    z.density=w.density;
+    z.hyperboloidSize=w.hyperboloidSize;
+    z.height=w.height;
+    tiles.byAddr[Eisenstein(w.ex,w.ey)]=z;
+  }
+}
+
+void initTiles()
+{
+  tiles.clear();
+}
+
+// ---------------------------------------------------------------- octree / store
+void Octree::sizeFit(vector<xyz> pnts)
+{
+  vector<double> c;
+  for (auto &p:pnts)
+  {
+    c.push_back(p.getx()); c.push_back(p.gety()); c.push_back(p.getz());
+  }
+  double ctr[3];
+  wb_size_fit(c.data(),(int)pnts.size(),ctr,&side);
+  center=xyz(ctr[0],ctr[1],ctr[2]);
+  g_corners=c;
+  g_built=false;
+}
+
+void Octree::clear()
+{
+  side=0;
+}
+
+int64_t Octree::findBlock(xyz pnt)
+{
+  ensureStore();
+  if (g_leaves.empty())
+    return -1;
+  uint64_t k=keyOf(pnt);
+  size_t i=upper_bound(g_leafLo.begin(),g_leafLo.end(),k)-g_leafLo.begin();
+  if (!i)
+    return -1;
+  i--;
+  int s=3*(WB_LEVELS-g_leaves[i].depth);
+  return (k>>s)==(g_leafLo[i]>>s)?(int64_t)i:-1;
+}
+
+Cube Octree::findCube(xyz pnt)
+{
+  int64_t b=findBlock(pnt);
+  if (b>=0)
+    return leafCube(b);
+  // an empty octant: descend as far as the populated tree goes (octree.cpp:218-232)
+  xyz c=center;
+  double s=side;
+  uint64_t k=keyOf(pnt);
+  size_t lo=0,hi=g_leaves.size();
+  for (int depth=0;depth<WB_LEVELS;depth++)
+  {
+    int ch=(int)((k>>(3*(WB_LEVELS-1-depth)))&7),sh=3*(WB_LEVELS-1-depth);
+    c=xyz(c.getx()+((ch&1)?s/4:-s/4),c.gety()+((ch&2)?s/4:-s/4),c.getz()+((ch&4)?s/4:-s/4));
+    s/=2;
+    size_t a=lo;
+    while (a<hi && (int)((g_leafLo[a]>>sh)&7)<ch) a++;
+    size_t b2=a;
+    while (b2<hi && (int)((g_leafLo[b2]>>sh)&7)==ch) b2++;
+    if (a==b2)
+      break;
+    lo=a; hi=b2;
+  }
+  return Cube(c,s);
+}
+
+vector<int64_t> Octree::findBlocks(const Shape &sh)
+{
+  vector<int64_t> out;
+  ensureStore();
+  if (!g_leaves.empty())
+    findBlocksRec(sh,0,g_leaves.size(),0,center,side,out);
+  return out;
+}
+
+size_t OctStore::getNumBlocks()
+{
+  ensureStore();
+  return g_leaves.size();
+}
+
+vector<LasPoint> OctStore::getAll(int64_t block)
+{
+  vector<LasPoint> ret;
+  ensureStore();
+  if (block<0 || (size_t)block>=g_leaves.size())
+    return ret;
+  for (size_t k=g_leaves[block].first;k<g_leaves[block].first+g_leaves[block].count;k++)
+    ret.push_back(pointAt(k));
+  return ret;
+}
+
+static bool lowerThan(const LasPoint &a,const LasPoint &b)
+{
+  return a.location.getz()<b.location.getz();
+}
+
+vector<LasPoint> OctStore::pointsIn(const Shape &sh,bool sorted)
+{
+  vector<LasPoint> ret;
+  for (int64_t b:octRoot.findBlocks(sh))
+  {
+    Cube cube=leafCube(b);
+    bool all=sh.in(cube);
+    for (size_t k=g_leaves[b].first;k<g_leaves[b].first+g_leaves[b].count;k++)
+      if (all || sh.in(xyz(g_x[k],g_y[k],g_z[k])))
+        ret.push_back(pointAt(k));
+  }
+  if (sorted)
+    sort(ret.begin(),ret.end(),lowerThan);
+  return ret;
+}
+
+uint64_t OctStore::countPointsIn(const Shape &sh)
+{
+  uint64_t ret=0;
+  for (int64_t b:octRoot.findBlocks(sh))
+  {
+    Cube cube=leafCube(b);
+    if (sh.in(cube))
+      ret+=g_leaves[b].count;
+    else
+      for (size_t k=g_leaves[b].first;k<g_leaves[b].first+g_leaves[b].count;k++)
+        ret+=sh.in(xyz(g_x[k],g_y[k],g_z[k]));
+  }
+  return ret;
+}
+
+array<double,2> OctStore::hiLoPointsIn(const Shape &sh)
+{
+  double hi=-INFINITY,lo=INFINITY;
+  for (int64_t b:octRoot.findBlocks(sh))
+    if (g_leaves[b].low<lo || g_leaves[b].high>hi)
+      for (size_t k=g_leaves[b].first;k<g_leaves[b].first+g_leaves[b].count;k++)
+        if (sh.in(xyz(g_x[k],g_y[k],g_z[k])))
+        {
+          hi=max(hi,g_z[k]);
+          lo=min(lo,g_z[k]);
+        }
+  return array<double,2>{lo,hi};
+}
+
+map<int,size_t> OctStore::countClasses(int64_t block)
+{
+  map<int,size_t> ret;
+  for (auto &p:getAll(block))
+    ret[p.classification]++;
+  return ret;
+}
+
+void OctStore::dump(ofstream &file)
+{
+  ensureStore();
+  vector<char> buf(g_leaves.size()*128+64);
+  int n=wb_format_dump(g_leaves.data(),g_leaves.size(),buf.data(),buf.size());
+  if (n>0)
+    file.write(buf.data(),n);
+}
+
+uint64_t OctStore::countPoints()
+{
+  ensureStore();
+  return g_x.size();
+}
+
+void OctStore::clear()
+{
+  if (g_ctx)
+    wb_clear(g_ctx);
+  g_files.clear();
+  g_fileFirst.clear();
+  g_built=g_scanned=g_postscanned=g_classified=g_haveStore=false;
+  g_labels.clear();
+}
+
+// ---------------------------------------------------------------- the phase protocol (threads.h)
+void startThreads(int)
+{
+  ensureContext();
+  g_command=TH_WAIT;
+}
+
+void joinThreads() {}
+int nThreads() { return 1; }
+double busyFraction() { return 0; }
+bool actionQueueEmpty() { return true; }
+bool resultQueueEmpty() { return g_results.empty(); }
+bool pointBufferEmpty() { return true; }
+size_t pointBufferSize() { return 0; }
+void setThreadCommand(int s) { waitForThreads(s); }
+int getThreadCommand() { return g_command; }
+int getThreadStatus() { return (g_command<<20)|g_command; }
+void fillTanTables() {}
+
+ThreadAction dequeueResult()
+{
+  ThreadAction a;
+  if (!g_results.empty())
+  {
+    a=g_results.front();
+    g_results.pop_front();
+  }
+  return a;
+}
+
+void enqueueAction(ThreadAction a)
+{
+  ensureContext();
+  switch (a.opcode)
+  {
+    case ACT_READ:
+    {
+      LasHeader *h=a.hdr;
+      if (!h || !h->isValid() || h->isZipped())
+      {
+        cerr<<"Error reading file\n";
+        break;
+      }
+      cout<<"Thread 0 reading "<<h->getFileName()<<endl;
+      if (g_files.empty())
+        for (size_t i=0;i+5<g_corners.size();i+=6)
+          wb_add_extent(g_ctx,&g_corners[i],&g_corners[i+3]);
+      double sc[3]={h->rawScale(0),h->rawScale(1),h->rawScale(2)},of[3]={h->rawOffset(0),h->rawOffset(1),h->rawOffset(2)};
+      if (wb_add_las(g_ctx,h->records(),h->numberPoints(),h->getPointFormat(),h->getPointLength(),sc,of,h->getUnit())!=WB_OK)
+      {
+        die("Error reading file");
+        break;
+      }
+      size_t first=g_fileFirst.empty()?0:g_fileFirst.back()+g_files.back()->numberPoints();
+      g_files.push_back(h);
+      g_fileFirst.push_back(first);
+      g_built=false;
+      break;
+    }
+    case ACT_COUNT:
+    {
+      uint64_t c[256];
+      if (g_classified && wb_count_classes(g_ctx,c)==WB_OK)
+        for (int i=0;i<256;i++)
+          if (c[i])
+            classTotals[i]+=c[i];
+      g_results.push_back(a);
+      break;
+    }
+    default:
+      break;
+  }
+}
+
+void waitForQueueEmpty()
+{
+  if (!g_files.empty())
+    ensureBuilt();
+}
+
+void waitForThreads(int newStatus)
+{
+  g_command=newStatus;
+  switch (newStatus)
+  {
+    case TH_SCAN:
+      ensureBuilt();
+      if (!g_scanned)
+      {
+        if (wb_scan(g_ctx)!=WB_OK) { die("scan"); exit(4); }
+        g_scanned=true;
+        refreshTiles();
+      }
+      break;
+    case TH_POSTSCAN:
+      waitForThreads(TH_SCAN);
+      g_command=TH_POSTSCAN;
+      if (!g_postscanned)
+      {
+        if (wb_postscan(g_ctx)!=WB_OK) { die("postscan"); exit(4); }
+        g_postscanned=true;
+        refreshTiles();
+      }
+      break;
+    case TH_SPLIT:
+      waitForThreads(TH_POSTSCAN);
+      g_command=TH_SPLIT;
+      if (!g_classified)
+      {
+        if (wb_classify(g_ctx)!=WB_OK) { die("classify"); exit(4); }
+        g_classified=true;
+        g_labels.clear();
+      }
+      break;
+    default:
+      break;
+  }
+}
+
+void scanCylinder(Eisenstein) { waitForThreads(TH_SCAN); }
+void postscanCylinder(Eisenstein) { waitForThreads(TH_POSTSCAN); }
+void classifyCylinder(Eisenstein) { waitForThreads(TH_SPLIT); }
+
+wb_ctx *wolkenContext() { ensureContext(); return g_ctx; }
+const char *wolkenLastError() { return g_ctx?wb_last_error(g_ctx):""; }
+
+vector<uint8_t> wolkenLabels()
+{
+  ensureLabels();
+  return g_labels;
+}
+
+// ---------------------------------------------------------------- writer (cloudoutput.cpp:119-246, reduced)
+static string className(int n)
+{
+  static const char *names[]={"raw","nonground","ground","lowveg","medveg","highveg","building","lownoise","",
+                              "water","rail","road","overlap","wireguard","conductor","tower","insulator","bridge",
+                              "highnoise","overhead","ignground","snow"};
+  if (n>=0 && n<22 && names[n][0])
+    return names[n];
+  return "class"+to_string(n);
+}
+
+namespace
+{
+struct OutFile
+{
+  string name;
+  FILE *f=nullptr;
+  uint64_t n=0,byReturn[16]={0};
+  int32_t mn[3]={INT32_MAX,INT32_MAX,INT32_MAX},mx[3]={INT32_MIN,INT32_MIN,INT32_MIN};
+};
+}
+
+int writeClassified(const deque<LasHeader> &inputs,const OutputOptions &opt,vector<string> *written)
+// One output (or one per class), optionally split every pointsPerFile points; file names
+// name[-class][-k].las with k zero-padded as the reference does (cloudoutput.cpp:135-160).
+// Records keep the inputs' format, scale and offset (all inputs must agree) with the class byte
+// replaced; the header is rewritten with the new counts and bounding box.
+{
+  if (inputs.empty() || !g_classified)
+    return -1;
+  const LasHeader &h0=inputs[0];
+  for (auto &h:inputs)
+    if (h.getPointFormat()!=h0.getPointFormat() || h.getPointLength()!=h0.getPointLength() ||
+        h.rawScale(0)!=h0.rawScale(0) || h.rawScale(1)!=h0.rawScale(1) || h.rawScale(2)!=h0.rawScale(2) ||
+        h.rawOffset(0)!=h0.rawOffset(0) || h.rawOffset(1)!=h0.rawOffset(1) || h.rawOffset(2)!=h0.rawOffset(2))
+    {
+      cerr<<"inputs differ in format, scale or offset: merging them needs re-quantisation, which is not implemented\n";
+      return -2;
+    }
+  ensureLabels();
+  const int fmt=h0.getPointFormat(),len=h0.getPointLength();
+  const unsigned hs=h0.headerLength();
+  uint64_t grand=g_labels.size();
+  int nDigits=0;
+  if (opt.pointsPerFile)
+  {
+    uint64_t quot=(grand+opt.pointsPerFile-1)/opt.pointsPerFile;
+    if (quot) quot--;
+    if (!quot) quot++;
+    while (quot) { quot/=10; nDigits++; }
+  }
+  map<int,vector<OutFile>> files;      // class (or -1 for all) -> sequence of files
+  auto fileFor=[&](int cls)->OutFile &
+  {
+    vector<OutFile> &v=files[cls];
+    if (v.empty() || (opt.pointsPerFile && v.back().n>=opt.pointsPerFile))
+    {
+      OutFile o;
+      char num[32]="";
+      if (opt.pointsPerFile)
+        snprintf(num,sizeof(num),"-%0*zu",nDigits,v.size());
+      o.name=opt.baseName+(cls>=0?"-"+className(cls):"")+num+".las";
+      o.f=fopen(o.name.c_str(),"wb");
+      if (o.f)
+        fwrite(h0.headerBytes(),1,hs,o.f);
+      v.push_back(o);
+    }
+    return v.back();
+  };
+  vector<uint8_t> rec(len);
+  size_t idx=0;
+  for (auto &h:inputs)
+  {
+    const uint8_t *r=h.records();
+    for (size_t i=0;i<h.numberPoints();i++,idx++,r+=len)
+    {
+      uint8_t lab=g_labels[idx];
+      OutFile &o=fileFor(opt.separateClasses?lab:-1);
+      if (!o.f)
+        return -3;
+      memcpy(rec.data(),r,len);
+      if (fmt<6)
+        rec[15]=(uint8_t)((rec[15]&0xe0)|(lab&31));     // writePoint, las.cpp:848
+      else
+        rec[16]=lab;                                     // las.cpp:857
+      fwrite(rec.data(),1,len,o.f);
+      o.n++;
+      int ret=fmt<6?(rec[14]&7):(rec[14]&15);
+      if (ret>0 && ret<16)
+        o.byReturn[ret]++;
+      for (int k=0;k<3;k++)
+      {
+        int32_t v=rd<int32_t>(rec.data()+4*k);
+        o.mn[k]=min(o.mn[k],v);
+        o.mx[k]=max(o.mx[k],v);
+      }
+    }
+  }
+  const char *sysId=opt.separateClasses?"EXTRACTION":(inputs.size()>1?"MERGE":"MODIFICATION");   // cloudoutput.cpp:127-132
+  for (auto &kv:files)
+    for (auto &o:kv.second)
+    {
+      vector<uint8_t> hd(h0.headerBytes(),h0.headerBytes()+hs);
+      memset(&hd[26],0,32);
+      memcpy(&hd[26],sysId,strlen(sysId));
+      memset(&hd[58],0,32);
+      memcpy(&hd[58],"wolkenbase_b200",15);
+      uint32_t off=hs,zero=0;
+      memcpy(&hd[96],&off,4);
+      memcpy(&hd[100],&zero,4);
+      bool legacyOk=o.n<=4294967295ull && fmt<6;
+      for (int i=0;i<6;i++)
+      {
+        uint32_t v=legacyOk?(uint32_t)(i?o.byReturn[i]:o.n):0;
+        memcpy(&hd[107+4*i],&v,4);
+      }
+      for (int k=0;k<3;k++)
+      {
+        double mx=h0.rawOffset(k)+h0.rawScale(k)*o.mx[k],mn=h0.rawOffset(k)+h0.rawScale(k)*o.mn[k];
+        memcpy(&hd[179+16*k],&mx,8);
+        memcpy(&hd[187+16*k],&mn,8);
+      }
+      if (hs>=375)
+      {
+        uint64_t z=0,evlr=hs+o.n*len;
+        memcpy(&hd[227],&z,8);
+        memcpy(&hd[235],&evlr,8);
+        memcpy(&hd[243],&zero,4);
+        for (int i=0;i<16;i++)
+        {
+          uint64_t v=i?o.byReturn[i]:o.n;
+          memcpy(&hd[247+8*i],&v,8);
+        }
+      }
+      fseek(o.f,0,SEEK_SET);
+      fwrite(hd.data(),1,hs,o.f);
+      fclose(o.f);
+      if (written)
+        written->push_back(o.name);
+    }
+  return 0;
+}

@@ -1,0 +1,354 @@
+// wolken_host.h — the reference's C++ surface for the ground-extraction path, on top of the
+// C ABI of libwolken_b200.so.  Same names, argument meaning and error behaviour as the
+// reference headers it stands in for:
+//   point.h (xy, xyz)            shape.h (Cube, Shape, Cylinder, Hyperboloid, Sphere, Paraboloid)
+//   las.h (LasPoint, LasHeader)  octree.h (Octree octRoot, OctStore octStore)
+//   eisenstein.h/flowsnake.h (Eisenstein, Flowsnake snake)   tile.h (Tile, tiles)
+//   scan.h / classify.h (scanCylinder, postscanCylinder, classifyCylinder, tuning globals)
+//   threads.h (startThreads, waitForThreads, enqueueAction, ... the phase protocol)
+// What differs is WHERE the work runs: waitForThreads(TH_x) launches the phase on the GPU and
+// returns when it is done, instead of flipping a command that worker threads poll.
+#ifndef WOLKEN_HOST_H
+#define WOLKEN_HOST_H
+#include <cmath>
+#include <cstdint>
+#include <array>
+#include <deque>
+#include <fstream>
+#include <map>
+#include <string>
+#include <vector>
+#include "../../include/wolken_b200.h"
+
+// ---------------------------------------------------------------- point.h
+class xyz;
+class xy
+{
+public:
+  xy(double e=0,double n=0): x(e),y(n) {}
+  xy(const xyz &p);
+  double getx() const { return x; }
+  double gety() const { return y; }
+  double east() const { return x; }
+  double north() const { return y; }
+  double length() const { return hypot(x,y); }
+  friend xy operator+(const xy &l,const xy &r) { return xy(l.x+r.x,l.y+r.y); }
+  friend xy operator-(const xy &l,const xy &r) { return xy(l.x-r.x,l.y-r.y); }
+  friend double dist(xy a,xy b) { return hypot(a.x-b.x,a.y-b.y); }
+private:
+  double x,y;
+  friend class xyz;
+};
+
+class xyz
+{
+public:
+  xyz(double e=0,double n=0,double h=0): x(e),y(n),z(h) {}
+  xyz(xy en,double h): x(en.getx()),y(en.gety()),z(h) {}
+  double getx() const { return x; }
+  double gety() const { return y; }
+  double getz() const { return z; }
+  double east() const { return x; }
+  double north() const { return y; }
+  double elev() const { return z; }
+  bool isnan() const { return std::isnan(x) || std::isnan(y) || std::isnan(z); }
+  bool isfinite() const { return std::isfinite(x) && std::isfinite(y) && std::isfinite(z); }
+  friend xyz operator+(const xyz &l,const xyz &r) { return xyz(l.x+r.x,l.y+r.y,l.z+r.z); }
+  friend xyz operator-(const xyz &l,const xyz &r) { return xyz(l.x-r.x,l.y-r.y,l.z-r.z); }
+  friend xyz operator*(const xyz &l,double r) { return xyz(l.x*r,l.y*r,l.z*r); }
+  friend bool operator==(const xyz &l,const xyz &r) { return l.x==r.x && l.y==r.y && l.z==r.z; }
+private:
+  double x,y,z;
+  friend class xy;
+};
+inline xy::xy(const xyz &p): x(p.x),y(p.y) {}
+inline double sqr(double v) { return v*v; }
+
+// ---------------------------------------------------------------- shape.h (shape.cpp:26-274)
+class Cube
+{
+public:
+  Cube(): side(0) {}
+  Cube(xyz c,double s): center(c),side(s) {}
+  bool in(xyz pnt) const;
+  xyz getCenter() const { return center; }
+  double getSide() const { return side; }
+  xyz corner(int n) const;
+private:
+  xyz center;
+  double side;
+};
+
+class Shape
+{
+public:
+  virtual ~Shape() {}
+  virtual bool in(xyz pnt) const=0;
+  virtual bool in(Cube &cube) const;               // all eight corners (convex shapes)
+  virtual xyz closestPoint(Cube cube) const=0;
+  virtual bool intersect(Cube cube) const { return in(closestPoint(cube)); }
+};
+
+class Paraboloid: public Shape
+{
+public:
+  Paraboloid(): radiusCurvature(0) {}
+  Paraboloid(xyz v,double r): vertex(v),radiusCurvature(r) {}
+  bool in(xyz pnt) const override;
+  xyz closestPoint(Cube cube) const override;
+  using Shape::in;
+private:
+  xyz vertex;
+  double radiusCurvature;
+};
+
+class Hyperboloid: public Shape
+{
+public:
+  Hyperboloid(): por2(0),slope(1) {}
+  Hyperboloid(xyz v,double r,double s);
+  bool in(xyz pnt) const override;
+  xyz closestPoint(Cube cube) const override;
+  using Shape::in;
+private:
+  xyz center;
+  double por2,slope;
+};
+
+class Sphere: public Shape
+{
+public:
+  Sphere(): radius(0) {}
+  Sphere(xyz c,double r): center(c),radius(r) {}
+  bool in(xyz pnt) const override;
+  xyz closestPoint(Cube cube) const override;
+  using Shape::in;
+private:
+  xyz center;
+  double radius;
+};
+
+class Cylinder: public Shape
+{
+public:
+  Cylinder(): radius(0) {}
+  Cylinder(xy c,double r): center(c),radius(r) {}
+  double getRadius() const { return radius; }
+  xy getCenter() const { return center; }
+  bool in(xyz pnt) const override;
+  xyz closestPoint(Cube cube) const override;
+  using Shape::in;
+private:
+  xy center;
+  double radius;
+};
+
+// ---------------------------------------------------------------- las.h
+class LasPoint
+{
+public:
+  xyz location;
+  unsigned short intensity,returnNum,nReturns;
+  bool scanDirection,edgeLine;
+  unsigned short classification,classificationFlags,scannerChannel,userData,pointSource;
+  int scanAngle;
+  double gpsTime;
+  unsigned short nir,red,green,blue;
+  LasPoint();
+  bool isEmpty() const { return location.isnan(); }
+};
+
+class LasHeader
+// Read side of las.cpp:299-428, 735-820 over a memory-mapped file (the records are handed to
+// the GPU as one span); write side: header + patched records (las.cpp:540-595).
+{
+public:
+  LasHeader();
+  ~LasHeader();
+  LasHeader(const LasHeader &)=delete;
+  LasHeader &operator=(const LasHeader &)=delete;
+  void openRead(std::string fileName);
+  bool isValid() const;
+  bool isZipped() const { return zipFlag; }
+  void close();
+  void setUnit(double u) { unit=u; }
+  double getUnit() const { return unit; }
+  std::string getFileName() const { return filename; }
+  size_t numberPoints(int r=0) const { return nPoints[r]; }
+  int getVersion() const { return (versionMajor<<8)+versionMinor; }
+  int getPointFormat() const { return pointFormat; }
+  int getPointLength() const { return pointLength; }
+  xyz getScale() const { return xyz(xScale*unit,yScale*unit,zScale*unit); }
+  xyz getOffset() const { return xyz(xOffset*unit,yOffset*unit,zOffset*unit); }
+  xyz minCorner() const { return xyz(minX*unit,minY*unit,minZ*unit); }
+  xyz maxCorner() const { return xyz(maxX*unit,maxY*unit,maxZ*unit); }
+  LasPoint readPoint(size_t num);                   // throws int -1 past the end, like the reference
+  const uint8_t *records() const { return map?map+pointOffset:nullptr; }
+  const uint8_t *headerBytes() const { return map; }
+  unsigned headerLength() const { return headerSize; }
+  double rawScale(int k) const { return k==0?xScale:(k==1?yScale:zScale); }
+  double rawOffset(int k) const { return k==0?xOffset:(k==1?yOffset:zOffset); }
+private:
+  std::string filename;
+  uint8_t *map;
+  size_t mapLen;
+  int versionMajor,versionMinor;
+  unsigned headerSize,pointOffset;
+  unsigned short pointFormat,pointLength;
+  double xScale,yScale,zScale,xOffset,yOffset,zOffset,maxX,minX,maxY,minY,maxZ,minZ,unit;
+  size_t nPoints[16];
+  bool zipFlag;
+};
+
+// ---------------------------------------------------------------- eisenstein.h / flowsnake.h / tile.h
+class Eisenstein
+{
+public:
+  Eisenstein(int xa=0,int ya=0): x(xa),y(ya) {}
+  int getx() const { return x; }
+  int gety() const { return y; }
+  friend bool operator<(const Eisenstein &a,const Eisenstein &b) { return a.y!=b.y?a.y<b.y:a.x<b.x; }
+private:
+  int x,y;
+};
+
+Eisenstein toFlowsnake(int n);                      // flowsnake.cpp:92-136
+
+class Flowsnake
+{
+public:
+  void setSize(Cube cube,double desiredSpacing);
+  void restart() { counter=startnum; }
+  Eisenstein next();                                // INT_MIN,INT_MIN when exhausted
+  Cylinder cyl(Eisenstein e);
+  double progress() { return 1; }                   // every phase is complete when its call returns
+  double getSpacing() const { return spacing; }
+  int first() const { return startnum; }
+  int last() const { return stopnum; }
+private:
+  xy center;
+  double spacing=0;
+  int startnum=0,counter=0,stopnum=-1;
+};
+
+struct Tile                                          // tile.h:27-35
+{
+  int nPoints,nGround;
+  short roofFlags,treeFlags;
+  double density,hyperboloidSize,height;
+};
+
+class TileTable                                      // stands in for harray<Tile> tiles
+{
+public:
+  Tile &operator[](Eisenstein e);                   // zero tile if absent, like harray
+  int count(Eisenstein e) { return byAddr.count(e); }
+  void clear() { byAddr.clear(); }
+  size_t size() const { return byAddr.size(); }
+private:
+  std::map<Eisenstein,Tile> byAddr;
+  friend void refreshTiles();
+};
+
+// ---------------------------------------------------------------- octree.h
+#define RECORDS WB_RECORDS
+
+class Octree
+{
+public:
+  void sizeFit(std::vector<xyz> pnts);              // octree.cpp:268-310
+  xyz getCenter() const { return center; }
+  double getSide() const { return side; }
+  Cube cube() const { return Cube(center,side); }
+  int64_t findBlock(xyz pnt);                       // leaf (= block) index in dump order, -1 if none
+  Cube findCube(xyz pnt);
+  std::vector<int64_t> findBlocks(const Shape &sh); // octree.cpp:234-251, same order
+  void clear();
+private:
+  xyz center;
+  double side=0;
+  friend class OctStore;
+};
+
+class OctStore
+{
+public:
+  size_t getNumBlocks();
+  std::vector<LasPoint> getAll(int64_t block);
+  std::vector<LasPoint> pointsIn(const Shape &sh,bool sorted=false);   // octree.cpp:1214-1242
+  uint64_t countPointsIn(const Shape &sh);
+  std::array<double,2> hiLoPointsIn(const Shape &sh);
+  std::map<int,size_t> countClasses(int64_t block);
+  void dump(std::ofstream &file);                   // octree.cpp:888-891
+  uint64_t countPoints();
+  void clear();
+  void disown() {}
+  void setIgnoreDupes(bool) {}
+  void shrink() {}
+};
+
+extern Octree octRoot;
+extern OctStore octStore;
+extern Flowsnake snake;
+extern TileTable tiles;
+extern std::map<int,size_t> classTotals;
+extern double minHyperboloidSize,maxSlope,thickness;  // scan.h:25
+extern double tileSize;                               // the GUI's setting, mainwindow.cpp:398-411
+
+// ---------------------------------------------------------------- threads.h
+#define TH_WAIT 1
+#define TH_READ 2
+#define TH_SCAN 3
+#define TH_POSTSCAN 4
+#define TH_SPLIT 5
+#define TH_PAUSE 6
+#define TH_STOP 7
+#define TH_ASLEEP 256
+#define ACT_READ 1
+#define ACT_COUNT 2
+#define ACT_WRITE 3
+
+struct ThreadAction
+{
+  int opcode=0;
+  int param0=0;
+  double param1=0,param2=0;
+  LasHeader *hdr=nullptr;                           // borrowed; must outlive the read
+  std::string filename;
+  int flags=0,result=0;
+};
+
+void startThreads(int n);                           // n is accepted and ignored: one GPU context
+void joinThreads();
+void enqueueAction(ThreadAction a);                 // ACT_READ runs at once; ACT_COUNT fills classTotals
+ThreadAction dequeueResult();
+bool actionQueueEmpty();
+bool resultQueueEmpty();
+bool pointBufferEmpty();
+size_t pointBufferSize();
+void setThreadCommand(int newStatus);
+int getThreadCommand();
+int getThreadStatus();                              // (command<<20)|command: "all threads in the commanded state"
+void waitForThreads(int newStatus);                 // runs the phase: TH_SCAN build+scan, TH_POSTSCAN, TH_SPLIT classify
+void waitForQueueEmpty();
+int nThreads();
+double busyFraction();
+void initTiles();
+
+void scanCylinder(Eisenstein cylAddress);           // scan.h:27 — first call runs the whole phase
+void postscanCylinder(Eisenstein cylAddress);
+void classifyCylinder(Eisenstein cylAddress);       // classify.h:24
+void fillTanTables();                               // uploaded by wb_create; kept for source compatibility
+
+// ---------------------------------------------------------------- the CLI's additions
+wb_ctx *wolkenContext();
+const char *wolkenLastError();
+std::vector<uint8_t> wolkenLabels();                // class byte per input record (files in read order)
+struct OutputOptions
+{
+  std::string baseName;
+  bool separateClasses=true;                        // mainwindow.cpp:398-411 defaults
+  size_t pointsPerFile=0;
+};
+int writeClassified(const std::deque<LasHeader> &inputs,const OutputOptions &opt,std::vector<std::string> *written);
+#endif

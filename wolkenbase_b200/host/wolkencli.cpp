@@ -1,0 +1,126 @@
+// wolkencli — the reference's command line (wolkencli.cpp:43-129: positional LAS inputs, header
+// lines, octree cube, "dumpfile") driving the GPU library through the reference-shaped C++
+// surface, extended with the GUI's classify-and-write sequence (wolkencanvas.cpp:469-625):
+//   wolkencli [options] input.las...
+//     -o, --output NAME          classify and write NAME[-class][-k].las
+//     --tile-size T  --max-slope S  --thickness K  --min-hyperboloid-size M   (QSettings keys, mainwindow.cpp:398-411)
+//     --points-per-file N        split outputs every N points (0 = no split)
+//     --separate-classes 0|1     one file per class (default 1, as the GUI)
+//     --threads N                accepted for compatibility, ignored
+//     --dump FILE                where to write the octree dump (default "dumpfile")
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <iostream>
+#include <fstream>
+#include "wolken_host.h"
+
+using namespace std;
+
+int main(int argc,char **argv)
+{
+  vector<string> inputFiles;
+  OutputOptions out;
+  string dumpName="dumpfile";
+  bool classify=false;
+  for (int i=1;i<argc;i++)
+  {
+    string a=argv[i];
+    auto val=[&]()->const char * { if (i+1>=argc) { cerr<<a<<" needs a value\n"; exit(2); } return argv[++i]; };
+    if (a=="-o" || a=="--output") { out.baseName=val(); classify=true; }
+    else if (a=="--tile-size") tileSize=atof(val());
+    else if (a=="--max-slope") maxSlope=atof(val());
+    else if (a=="--thickness") thickness=atof(val());
+    else if (a=="--min-hyperboloid-size") minHyperboloidSize=atof(val());
+    else if (a=="--points-per-file") out.pointsPerFile=strtoull(val(),nullptr,10);
+    else if (a=="--separate-classes") out.separateClasses=atoi(val())!=0;
+    else if (a=="--threads" || a=="--gpus") val();
+    else if (a=="--dump") dumpName=val();
+    else if (a.size() && a[0]=='-') { cerr<<"unknown option "<<a<<endl; return 2; }
+    else inputFiles.push_back(a);
+  }
+  if (out.baseName.size()>4 && out.baseName.substr(out.baseName.size()-4)==".las")
+    out.baseName.resize(out.baseName.size()-4);
+  deque<LasHeader> files(inputFiles.size());
+  vector<xyz> limits;
+  double mn[3]={INFINITY,INFINITY,INFINITY},mx[3]={-INFINITY,-INFINITY,-INFINITY};
+  for (size_t i=0;i<inputFiles.size();i++)
+  {
+    files[i].openRead(inputFiles[i]);
+    if (!files[i].isValid())
+    {
+      cerr<<inputFiles[i]<<": not a LAS file this program can read\n";
+      return 1;
+    }
+    limits.push_back(files[i].minCorner());
+    limits.push_back(files[i].maxCorner());
+    int ver=files[i].getVersion();
+    cout<<"Version "<<(ver>>8)<<'.'<<(ver&255)<<' ';
+    cout<<files[i].numberPoints()<<" points, format "<<files[i].getPointFormat()<<endl;
+  }
+  if (files.empty())
+  {
+    cerr<<"usage: wolkencli [options] input.las...\n";
+    return 2;
+  }
+  octRoot.sizeFit(limits);
+  xyz center=octRoot.getCenter();
+  char b0[64],b1[64],b2[64];
+  wb_ldecimal(center.getx(),b0,64); wb_ldecimal(center.gety(),b1,64); wb_ldecimal(center.getz(),b2,64);
+  cout<<'('<<b0<<','<<b1<<','<<b2<<")±"<<octRoot.getSide()<<endl;
+  // the cube handed to the flowsnake: bounding box of the header corners (wolkencanvas.cpp:502-519)
+  {
+    vector<double> c;
+    for (auto &p:limits) { c.push_back(p.getx()); c.push_back(p.gety()); c.push_back(p.getz()); }
+    double cube[4];
+    wb_bbox_cube(c.data(),(int)limits.size(),cube);
+    snake.setSize(Cube(xyz(cube[0],cube[1],cube[2]),cube[3]),tileSize);
+    initTiles();
+    (void)mn; (void)mx;
+  }
+  startThreads(1);
+  waitForThreads(TH_READ);
+  for (size_t i=0;i<files.size();i++)
+  {
+    ThreadAction ta;
+    ta.opcode=ACT_READ;
+    ta.hdr=&files[i];
+    enqueueAction(ta);
+    cout<<files[i].numberPoints()<<" points, "<<pointBufferSize()<<" points in buffer\n";
+  }
+  waitForQueueEmpty();
+  cout<<"All points in octree\n";
+  cout<<octStore.getNumBlocks()<<" blocks\n";
+  if (classify)
+  {
+    waitForThreads(TH_SCAN);
+    cout<<"Starting scan\n";
+    waitForThreads(TH_POSTSCAN);
+    cout<<"Starting postscan\n";
+    waitForThreads(TH_SPLIT);
+    cout<<"Starting classifying\n";
+    waitForThreads(TH_PAUSE);
+    cout<<"Counting points\n";
+    classTotals.clear();
+    ThreadAction ta;
+    ta.opcode=ACT_COUNT;
+    enqueueAction(ta);
+    cout<<"Classified points:\n";
+    for (auto &j:classTotals)
+      cout<<j.first<<' '<<j.second<<endl;
+    vector<string> written;
+    int rc=writeClassified(files,out,&written);
+    if (rc)
+      return 5;
+    for (auto &w:written)
+      cout<<"Wrote "<<w<<endl;
+  }
+  waitForThreads(TH_STOP);
+  cout<<"Dumping octree\n";
+  {
+    ofstream dumpFile(dumpName);
+    octStore.dump(dumpFile);
+  }
+  joinThreads();
+  return 0;
+}
