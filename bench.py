@@ -194,6 +194,13 @@ def run_ours(args):
     hist = ctx.count_classes()
 
     hbm, peak_src = peaks()
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["wb_classify_kernel"]
+        if abs(tj["points"] - n) <= 0.01 * n:
+            traffic = tj["dram_bytes_per_launch"]
+    except Exception:
+        pass
     ck_ms = phase.get("ms_classify_kernel", 0.0)
     alg_bytes = 13.0 * n                                     # 12 B read + 1 B written per point
     achieved = alg_bytes / (ck_ms * 1e-3) / 1e9 if ck_ms > 0 else 0.0
@@ -210,7 +217,7 @@ def run_ours(args):
                    "parallelism": "1 GPU"},
         "phases_ms": {k[3:]: round(v, 3) for k, v in sorted(phase.items())},
         "roofline": {"bound": "hbm", "kernel": "wb_classify_kernel", "achieved": achieved, "peak": hbm,
-                     "unit": "GB/s", "frac": achieved / hbm, "traffic": None, "peak_source": peak_src,
+                     "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic, "peak_source": peak_src,
                      "note": "algorithmic 13 B/point; the kernel is bound by its FP64/shared-memory inner loop "
                              "(SURVEY 8d), DRAM traffic from ncu is in profiles/"},
         "roofline_sort": {"bound": "hbm", "kernel": "radix sort (8 passes)", "achieved": sort_bytes / (sort_ms * 1e-3) / 1e9
