@@ -5,6 +5,7 @@
 // contracted).  Division and sqrt are IEEE-correct on the device.
 #pragma once
 #include <cstdint>
+#include <climits>
 #include <cuda_runtime.h>
 
 #define WB_DEG30  0x0aaaaaab   // angle.h:105

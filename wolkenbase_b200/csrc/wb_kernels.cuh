@@ -651,12 +651,58 @@ wb_scan_kernel(const uint32_t *__restrict__ tStart,uint32_t *__restrict__ tCount
 }
 
 // ============================================================================ K8: postscan
+// postscanCylinder (scan.cpp:142-179).  Reads only nPoints/treeFlags of other tiles, writes only
+// this tile's hyperboloidSize: no ordering hazard.  A tile outside the table has nPoints == 0.
+// The six ray walks step through Eisenstein addresses, so the populated tiles are first laid
+// out as a dense byte grid over (ex,ey) (0 empty, 1 populated, 2 populated tree tile): a step
+// is then one byte load instead of an inverse flowsnake numbering.
+
+__global__ void __launch_bounds__(256)
+wb_tile_extent_kernel(const int *__restrict__ tNPoints,uint32_t nTiles,WbSnake snake,int *__restrict__ ext)
+// ext = {min ex, min ey, max ex, max ey} over populated tiles
+{
+  uint32_t t=blockIdx.x*blockDim.x+threadIdx.x;
+  int x0=INT_MAX,y0=INT_MAX,x1=INT_MIN,y1=INT_MIN;
+  if (t<nTiles && tNPoints[t])
+  {
+    int ex,ey;
+    wb_to_flowsnake((int)t+snake.lo,ex,ey);
+    x0=x1=ex;
+    y0=y1=ey;
+  }
+  #pragma unroll
+  for (int o=16;o;o>>=1)
+  {
+    x0=min(x0,__shfl_xor_sync(WB_FULL,x0,o));
+    y0=min(y0,__shfl_xor_sync(WB_FULL,y0,o));
+    x1=max(x1,__shfl_xor_sync(WB_FULL,x1,o));
+    y1=max(y1,__shfl_xor_sync(WB_FULL,y1,o));
+  }
+  if ((threadIdx.x&31)==0 && x0!=INT_MAX)
+  {
+    atomicMin(&ext[0],x0);
+    atomicMin(&ext[1],y0);
+    atomicMax(&ext[2],x1);
+    atomicMax(&ext[3],y1);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+wb_tile_grid_kernel(const int *__restrict__ tNPoints,const uint8_t *__restrict__ tTree,uint32_t nTiles,WbSnake snake,
+                    const int *__restrict__ ext,uint8_t *__restrict__ grid)
+{
+  uint32_t t=blockIdx.x*blockDim.x+threadIdx.x;
+  if (t>=nTiles || !tNPoints[t])
+    return;
+  int ex,ey;
+  wb_to_flowsnake((int)t+snake.lo,ex,ey);
+  const long long W=(long long)ext[2]-ext[0]+1;
+  grid[(long long)(ey-ext[1])*W+(ex-ext[0])]=(uint8_t)(1+(tTree[t]&1));
+}
 
 __global__ void __launch_bounds__(128)
 wb_postscan_kernel(const int *__restrict__ tNPoints,const uint8_t *__restrict__ tTree,uint32_t nTiles,
-                   WbSnake snake,double *__restrict__ tHyp)
-// postscanCylinder (scan.cpp:142-179).  Reads only nPoints/treeFlags of other tiles, writes only
-// this tile's hyperboloidSize: no ordering hazard.  A tile outside the table has nPoints == 0.
+                   WbSnake snake,const int *__restrict__ ext,const uint8_t *__restrict__ grid,double *__restrict__ tHyp)
 {
   uint32_t t=blockIdx.x*blockDim.x+threadIdx.x;
   if (t>=nTiles || tNPoints[t]==0)
@@ -666,20 +712,23 @@ wb_postscan_kernel(const int *__restrict__ tNPoints,const uint8_t *__restrict__ 
   wb_to_flowsnake((int)t+snake.lo,ex,ey);
   if (tTree[t]&1)
   {
+    const int x0=ext[0],y0=ext[1],x1=ext[2],y1=ext[3];
+    const long long W=(long long)x1-x0+1;
     int i=1,ringcount,nontree;
     do
     {
       ringcount=nontree=0;
+      #pragma unroll
       for (int j=0;j<6;j++)
       {
-        long long n;
-        if (!wb_from_flowsnake(ex+rx[j]*i,ey+ry[j]*i,n) || n<snake.lo || n>snake.hi)
+        int nx=ex+rx[j]*i,ny=ey+ry[j]*i;
+        if (nx<x0 || nx>x1 || ny<y0 || ny>y1)
           continue;
-        uint32_t o=(uint32_t)(n-snake.lo);
-        if (tNPoints[o])
+        uint8_t c=grid[(long long)(ny-y0)*W+(nx-x0)];
+        if (c)
         {
           ringcount++;
-          if (tTree[o]&1)
+          if (c==2)
             count++;
           else
             nontree++;
@@ -941,8 +990,6 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
   unsigned long long occ=0;                       // occupied sectors of my query
   unsigned long long open=~0ull;                  // sectors of empty runs >= 24 (the only ones that matter)
   uint32_t statNodes=0,statChunks=0,statPairs=0,statNodes2=0,statChunks2=0,statPairs2=0;  // work counters (warp-uniform)
-  long long tExpand=0,tPairs=0,tTotal=clock64(),tExpCount=0;
-  uint32_t statAnyIn=0,statNew=0,statEnvEmpty=0;
   bool margin=false,surrounded=false;
   // second-walk state: up to two empty runs of 24/25 sectors, bounded below by sector k1 (we need
   // the largest bearing in it) and above by k2 (the smallest bearing in it)
@@ -1011,8 +1058,6 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
     int sp=0;
     auto expand=[&](int childLevel,uint32_t base,uint32_t askers)
     {
-      long long t0=clock64();
-      tExpCount++;
       uint32_t c=base+lane,cc=levelCnt[childLevel];
       uint32_t key=0xffffffffu,wants=0;
       unsigned long long cm=0;
@@ -1024,10 +1069,7 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
         ok=childTest(cb,key,cm);
       }
       if (!__any_sync(WB_FULL,ok))
-      {
-        tExpand+=clock64()-t0;
         return;
-      }
       if (childLevel==0)
       {
         uint32_t lm=askers;
@@ -1041,10 +1083,7 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
         }
         ok=ok && wants!=0;
         if (!__any_sync(WB_FULL,ok))
-        {
-          tExpand+=clock64()-t0;
           return;
-        }
         w.wants[lane]=wants;
         w.cm[lane]=cm;
         w.cb[lane]=cb;
@@ -1057,7 +1096,6 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
       }
       sp++;
       __syncwarp();
-      tExpand+=clock64()-t0;
     };
     expand(top,0,liveMask);
     while (sp>0)
@@ -1112,7 +1150,6 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
       const bool okp=j<n;
       const double cxp=okp?sx[j]:0.0,cyp=okp?sy[j]:0.0,czp=okp?sz[j]:INFINITY;
       if (pass==1) { statChunks++; statPairs+=__popc(qm); } else { statChunks2++; statPairs2+=__popc(qm); }
-      long long tp0=clock64();
       // Sectors each chunk point can occupy as seen from ANY query of the group (bearing from the
       // group centre, widened by the group radius).  A query for which none of them is still of
       // interest skips the chunk, and within the chunk only the points that can land in one of
@@ -1140,7 +1177,6 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
         bool in=rel && wb_in_hyperboloid(qx,qy,qcz,qpor2,s2,maxSlope,cxp,cyp,czp,ddx,ddy,margin);
         if (!__any_sync(WB_FULL,in))
           continue;
-        statAnyIn++;
         if (pass==1)
         {
           int s=-2;
@@ -1155,12 +1191,6 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
           }
           uint32_t lo=__reduce_or_sync(WB_FULL,(in && s<32)?1u<<s:0u);
           uint32_t hi=__reduce_or_sync(WB_FULL,(in && s>=32)?1u<<(s-32):0u);
-          {
-            unsigned long long add=(unsigned long long)lo|((unsigned long long)hi<<32);
-            unsigned long long oq=((unsigned long long)__shfl_sync(WB_FULL,(uint32_t)(occ>>32),q)<<32)|__shfl_sync(WB_FULL,(uint32_t)occ,q);
-            if (add&~oq)
-              statNew++;
-          }
           if (lane==q)
             occ|=(unsigned long long)lo|((unsigned long long)hi<<32);
         }
@@ -1195,7 +1225,6 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
           }
         }
       }
-      tPairs+=clock64()-tp0;
       if (pass==1)
       {
         // surrounded for sure once no empty run of 24 sectors is left
@@ -1282,13 +1311,6 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
     atomicAdd(&counters[12],(unsigned long long)statChunks2);
     atomicAdd(&counters[13],(unsigned long long)statPairs2);
     if (statNodes2) atomicAdd(&counters[14],1ull);
-    atomicAdd(&counters[15],(unsigned long long)(clock64()-tTotal));
-    atomicAdd(&counters[16],(unsigned long long)tExpand);
-    atomicAdd(&counters[17],(unsigned long long)tPairs);
-    atomicAdd(&counters[18],(unsigned long long)tExpCount);
-    atomicAdd(&counters[19],(unsigned long long)statAnyIn);
-    atomicAdd(&counters[20],(unsigned long long)statNew);
-    atomicAdd(&counters[21],(unsigned long long)statEnvEmpty);
   }
 }
 

@@ -1,6 +1,7 @@
 // wolken_b200.cu — C ABI of libwolken_b200.so (see include/wolken_b200.h): context, device
 // memory, phase drivers and timing around the kernels in wb_kernels.cuh.
 #include <cstdio>
+#include <climits>
 #include <cstdarg>
 #include <cstring>
 #include <string>
@@ -79,6 +80,8 @@ struct wb_ctx
   DevBuf<int> tNPoints;
   DevBuf<uint8_t> tTree;
   DevBuf<double> tDensity,tHyp,tHeight;
+  DevBuf<int> tileExt;
+  DevBuf<uint8_t> tileGrid;
   // results of build
   unsigned long long *keys=nullptr;   // sorted keys (keyA or keyB)
   uint32_t *perm=nullptr;             // sorted -> input
@@ -300,7 +303,7 @@ extern "C" void wb_destroy(wb_ctx *ctx)
   ctx->nodesA.release(); ctx->nodesB.release(); ctx->leaves.release(); ctx->bounds.release();
   ctx->levelOff.release(); ctx->levelCnt.release();
   ctx->tStart.release(); ctx->tCount.release(); ctx->tNPoints.release(); ctx->tTree.release();
-  ctx->tDensity.release(); ctx->tHyp.release(); ctx->tHeight.release();
+  ctx->tDensity.release(); ctx->tHyp.release(); ctx->tHeight.release(); ctx->tileExt.release(); ctx->tileGrid.release();
   cudaStreamDestroy(ctx->st); cudaStreamDestroy(ctx->stCopy);
   cudaEventDestroy(ctx->evA); cudaEventDestroy(ctx->evB); cudaEventDestroy(ctx->evC); cudaEventDestroy(ctx->evD);
   for (int i=0;i<2;i++)
@@ -914,8 +917,25 @@ extern "C" int wb_postscan(wb_ctx *ctx)
     return fail(ctx,WB_ERR_STATE,"postscan follows scan (and runs once)");
   cudaStream_t st=ctx->st;
   CK(cudaEventRecord(ctx->evA,st));
-  wb_postscan_kernel<<<gridFor(ctx->nTiles,128),128,0,st>>>(ctx->tNPoints.p,ctx->tTree.p,ctx->nTiles,ctx->snake,ctx->tHyp.p);
-  ctx->stats.kernel_launches++;
+  {
+    const int init[4]={INT_MAX,INT_MAX,INT_MIN,INT_MIN};
+    int ext[4];
+    CK(ctx->tileExt.ensure(4));
+    CK(cudaMemcpyAsync(ctx->tileExt.p,init,sizeof(init),cudaMemcpyHostToDevice,st));
+    wb_tile_extent_kernel<<<gridFor(ctx->nTiles,256),256,0,st>>>(ctx->tNPoints.p,ctx->nTiles,ctx->snake,ctx->tileExt.p);
+    CK(cudaMemcpyAsync(ext,ctx->tileExt.p,sizeof(ext),cudaMemcpyDeviceToHost,st));
+    CK(cudaStreamSynchronize(st));
+    uint64_t cells=1;
+    if (ext[0]<=ext[2])
+      cells=(uint64_t)((long long)ext[2]-ext[0]+1)*(uint64_t)((long long)ext[3]-ext[1]+1);
+    CK(ctx->tileGrid.ensure(cells));
+    CK(cudaMemsetAsync(ctx->tileGrid.p,0,cells,st));
+    wb_tile_grid_kernel<<<gridFor(ctx->nTiles,256),256,0,st>>>(ctx->tNPoints.p,ctx->tTree.p,ctx->nTiles,ctx->snake,
+                                                              ctx->tileExt.p,ctx->tileGrid.p);
+    wb_postscan_kernel<<<gridFor(ctx->nTiles,128),128,0,st>>>(ctx->tNPoints.p,ctx->tTree.p,ctx->nTiles,ctx->snake,
+                                                              ctx->tileExt.p,ctx->tileGrid.p,ctx->tHyp.p);
+    ctx->stats.kernel_launches+=3;
+  }
   KCHECK();
   CK(cudaEventRecord(ctx->evB,st));
   CK(cudaStreamSynchronize(st));
@@ -1046,7 +1066,6 @@ extern "C" int wb_classify(wb_ctx *ctx)
   ctx->stats.cl_chunks2=c[12];
   ctx->stats.cl_pairs2=c[13];
   ctx->stats.cl_warps2=c[14];
-  if (getenv("WB_TRACE")) fprintf(stderr,"classify cycles/warp: total %.0f expand %.0f pairs %.0f expansions %.1f\n",(double)c[15]/ctx->nChunks,(double)c[16]/ctx->nChunks,(double)c[17]/ctx->nChunks,(double)c[18]/ctx->nChunks),fprintf(stderr,"  per warp: pairs with a hit %.1f, pairs adding a sector %.1f, chunks empty for the envelope %.1f\n",(double)c[19]/ctx->nChunks,(double)c[20]/ctx->nChunks,(double)c[21]/ctx->nChunks);
   ctx->stats.ms_classify=elapsed(ctx->evA,ctx->evB);
   ctx->stats.ms_classify_kernel=elapsed(ctx->evC,ctx->evD);
   ctx->stats.n_margin=c[0];
