@@ -161,6 +161,11 @@ int wb_count_classes(wb_ctx *ctx,uint64_t counts[256]);
  * 6-10: las.cpp:754-756, 771, 848, 857) — host records, in place. */
 int wb_patch_records(wb_ctx *ctx,uint8_t *recs,uint64_t first_point,uint64_t n,int fmt,int rec_len);
 
+/* Device arithmetic exposed for known-answer tests (angle.cpp:117-155 atan2i, libm hypot as
+ * point.cpp:189-192 uses it, the 64-sector binning of the classifier; -1 = "ask atan2i"). */
+int wb_test_math(wb_ctx *ctx,uint64_t n,const double *y,const double *x,int32_t *atan2i_out,double *hypot_out,
+                 int32_t *sector_out);
+
 /* ---- whole pipeline -------------------------------------------------------- */
 int wb_run(wb_ctx *ctx);                                    /* build, scan, postscan, classify */
 int wb_get_stats(wb_ctx *ctx,wb_stats *out);

@@ -216,3 +216,52 @@ def test_size_independent_properties(ctx):
     # some, not all, of the scene is non-ground (the share depends on the tile spacing the snake picks)
     frac = hist[1] / n
     assert 0.05 < frac < 0.6
+
+
+@pytest.mark.parametrize("scene,n", [(1, 300000), (4, 300000), (5, 300000), (2, 400000)])
+def test_baseline_scenes_at_scale(ctx, scene, n):
+    """The four BASELINE scene models at a few hundred thousand points (deeper octrees, skewed
+    leaf occupancy for the terrestrial scene, stacked walls for the urban one): full parity."""
+    cloud = synth.generate(scene, n, seed=scene)
+    rep = _check_against_oracle(ctx, [cloud], {})
+    assert rep["mismatch"] == 0
+
+
+def test_device_math_known_answers(ctx):
+    """atan2i, hypot and the sector binning on the device against the oracle / libm."""
+    import ctypes
+    rng = np.random.default_rng(7)
+    n = 400000
+    x = rng.normal(size=n) * 10.0 ** rng.integers(-3, 3, size=n)
+    y = rng.normal(size=n) * 10.0 ** rng.integers(-3, 3, size=n)
+    # exact axes, diagonals, sector edges and the origin
+    special = np.array([[1, 0], [0, 1], [-1, 0], [0, -1], [1, 1], [-1, 1], [-1, -1], [1, -1], [0, 0], [3, 4],
+                        [1e-300, 1], [1, 1e-300], [-2.5, 1e-17]], dtype=np.float64)
+    x[:len(special)] = special[:, 0]
+    y[:len(special)] = special[:, 1]
+    a, h, s = ctx.test_math(y, x)
+    L = O.lib()
+    L.wbo_fill_tan_tables()
+    want_a = np.array([L.wbo_atan2i(float(yy), float(xx)) for yy, xx in zip(y[:60000], x[:60000])], dtype=np.int32)
+    assert (a[:60000] == want_a).all(), int((a[:60000] != want_a).sum())
+    libm = ctypes.CDLL("libm.so.6")
+    libm.hypot.restype = ctypes.c_double
+    libm.hypot.argtypes = [ctypes.c_double, ctypes.c_double]
+    want_h = np.array([libm.hypot(float(xx), float(yy)) for xx, yy in zip(x[:60000], y[:60000])])
+    assert (h[:60000].view(np.uint64) == want_h.view(np.uint64)).all()
+    # testintegertrig (wolkentest.cpp:122-132): atan2i(cossin(i)) folds back to i
+    ang = rng.integers(-2**31 + 100000, 2**31 - 100000, size=20000)
+    pi = np.arctan(np.longdouble(1)) * 4
+    th = ang.astype(np.longdouble) * pi / np.longdouble(1073741824.)
+    a2, _, _ = ctx.test_math(np.sin(th).astype(np.float64), np.cos(th).astype(np.float64))
+
+    def fold(v):
+        v = v.astype(np.int64) & 0xffffffff
+        return np.where(((v >> 30) % 3) != 0, v ^ 0x80000000, v)
+
+    assert (fold(a2) == fold(ang)).all()
+    # sectors: where the fast binning answers, it agrees with atan2i's own sector
+    u = a.astype(np.int64) & 0x7fffffff
+    ok = s >= 0
+    assert ok.mean() > 0.99
+    assert ((u[ok] >> 25) == s[ok]).all()

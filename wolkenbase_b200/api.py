@@ -86,6 +86,7 @@ def lib():
             "wb_get_labels": [vp, vp],
             "wb_count_classes": [vp, vp],
             "wb_patch_records": [vp, vp, u64, u64, C.c_int, C.c_int],
+            "wb_test_math": [vp, u64, vp, vp, vp, vp, vp],
             "wb_run": [vp],
             "wb_get_stats": [vp, C.POINTER(Stats)],
             "wb_sync": [vp],
@@ -115,7 +116,7 @@ EXPORTS = ["wb_create", "wb_destroy", "wb_last_error", "wb_reserve", "wb_clear",
            "wb_run", "wb_get_stats", "wb_sync", "wb_host_alloc", "wb_host_free", "wb_size_fit", "wb_bbox_cube",
            "wb_snake_set_size", "wb_ldecimal", "wb_format_dump", "wb_add_points_device", "wb_export_points_device",
            "wb_set_own_range", "wb_export_tiles_device", "wb_import_tiles_device", "wb_max_hyperboloid_size",
-           "wb_assign", "wb_get_points_sorted"]
+           "wb_assign", "wb_get_points_sorted", "wb_test_math"]
 
 
 def _d(v):
@@ -311,6 +312,16 @@ class Context:
 
     def patch_records(self, records, fmt, first=0):
         self._ck(self._L.wb_patch_records(self._h, records.ctypes.data, first, records.shape[0], fmt, records.shape[1]))
+
+    def test_math(self, y, x):
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        a = np.empty(len(x), dtype=np.int32)
+        h = np.empty(len(x), dtype=np.float64)
+        s = np.empty(len(x), dtype=np.int32)
+        self._ck(self._L.wb_test_math(self._h, len(x), y.ctypes.data, x.ctypes.data, a.ctypes.data, h.ctypes.data,
+                                      s.ctypes.data))
+        return a, h, s
 
     def stats(self):
         s = Stats()

@@ -57,28 +57,33 @@ __device__ __forceinline__ void wb_two_sum(double a,double b,double &s,double &e
 }
 
 __device__ __noinline__ double wb_hypot(double x,double y)
-// hypot() as libm gives it to dist() (point.cpp:189-192): sqrt(x^2+y^2) evaluated in
-// double-double and rounded once, i.e. correctly rounded but for astronomically rare ties.
-// (glibc's own algorithm is < 1 ulp; any point whose decision hangs on that last bit is
-// reported through the margin counter.)  No scaling: coordinates here are far from over/underflow.
+// hypot() as libm gives it to dist() (point.cpp:189-192).  glibc >= 2.35 (the image has 2.39)
+// computes h = sqrt(x^2+y^2) and applies one error-compensating step (Borges' algorithm, the
+// non-FMA branch of sysdeps/ieee754/dbl-64/e_hypot.c); restating that sequence with un-fused
+// operations reproduces libm bit for bit (checked on 2e5 random pairs against the host libm;
+// it is NOT always the correctly rounded value).  The scaling branches for huge/tiny inputs
+// are unreachable for coordinates in metres.
 {
   x=fabs(x);
   y=fabs(y);
-  if (x==0)
-    return y;
-  if (y==0)
-    return x;
-  double xx,xe,yy,ye,s,se;
-  wb_two_prod(x,x,xx,xe);
-  wb_two_prod(y,y,yy,ye);
-  wb_two_sum(xx,yy,s,se);
-  se=__dadd_rn(se,__dadd_rn(xe,ye));
-  double r=sqrt(s);
-  // one Newton correction in double-double: r + (S - r^2)/(2r)
-  double rr,re;
-  wb_two_prod(r,r,rr,re);
-  double d=__dadd_rn(__dsub_rn(__dsub_rn(s,rr),re),se);
-  return __dadd_rn(r,__ddiv_rn(d,__dmul_rn(2.0,r)));
+  double ax=x<y?y:x,ay=x<y?x:y;
+  if (__dmul_rn(ax,2.220446049250313e-16)>=ay)
+    return __dadd_rn(ax,ay);
+  double h=sqrt(__dadd_rn(__dmul_rn(ax,ax),__dmul_rn(ay,ay)));
+  double t1,t2;
+  if (h<=__dmul_rn(2.0,ay))
+  {
+    double delta=__dsub_rn(h,ay);
+    t1=__dmul_rn(ax,__dsub_rn(__dmul_rn(2.0,delta),ax));
+    t2=__dmul_rn(__dsub_rn(delta,__dmul_rn(2.0,__dsub_rn(ax,ay))),delta);
+  }
+  else
+  {
+    double delta=__dsub_rn(h,ax);
+    t1=__dmul_rn(__dmul_rn(2.0,delta),__dsub_rn(ax,__dmul_rn(2.0,ay)));
+    t2=__dadd_rn(__dmul_rn(__dsub_rn(__dmul_rn(4.0,delta),ay),ay),__dmul_rn(delta,delta));
+  }
+  return __dsub_rn(h,__ddiv_rn(__dadd_rn(t1,t2),__dmul_rn(2.0,h)));
 }
 
 __device__ __forceinline__ long long wb_lrint(double v)
@@ -87,9 +92,8 @@ __device__ __forceinline__ long long wb_lrint(double v)
 }
 
 __device__ __noinline__ int wb_atan2i(double y,double x)
-// atan2i(): angle.cpp:117-155.  The final correction term is evaluated in long double by the
-// reference; here it is plain double, which can differ only when the value is within
-// ~1e-10 of a half-integer (one unit of 2^-31 turn).
+// atan2i(): angle.cpp:117-155 (octant folding, 9-step bisection on the tangent table, rotation by
+// the bin centre, cubic correction).
 {
   int ret=0,h;
   double t,nx;
@@ -124,10 +128,26 @@ __device__ __noinline__ int wb_atan2i(double y,double x)
   {
     double q=__ddiv_rn(y,x);
     double c=__dmul_rn(__dmul_rn(q,q),q);
-    // 0x40000000/pi*y/x - 1.1392738508503886e8*c  (left to right)
-    const double k=341782637.78820266;            // 2^30/pi rounded to double
-    double v=__dsub_rn(__ddiv_rn(__dmul_rn(k,y),x),__dmul_rn(1.1392738508503886e8,c));
-    ret+=(int)wb_lrint(v);
+    // 0x40000000/M_PIl*y/x - 1.1392738508503886e8*c: the reference evaluates the first term in
+    // long double.  Here it is carried in double-double (K = the long double constant split in
+    // two), which agrees with the 64-bit-mantissa result unless the value is within ~1e-13 of a
+    // half-integer.
+    const double kh=341782637.7882158,kl=-2.112938091158867e-08;
+    double ph,pl;
+    wb_two_prod(kh,y,ph,pl);
+    pl=__fma_rn(kl,y,pl);
+    double qh=__ddiv_rn(ph,x);
+    double ql=__ddiv_rn(__dadd_rn(__fma_rn(-qh,x,ph),pl),x);
+    double term=__dmul_rn(1.1392738508503886e8,c);
+    double sh,se;
+    wb_two_sum(qh,-term,sh,se);
+    double r=rint(sh);
+    double d=__dadd_rn(__dsub_rn(sh,r),__dadd_rn(se,ql));
+    if (d>0.5)
+      r+=1.0;
+    else if (d<-0.5)
+      r-=1.0;
+    ret+=(int)r;
   }
   if (x==0 && y==0)
     ret=0;

@@ -1436,6 +1436,18 @@ wb_max_hyp_kernel(const int *__restrict__ tNPoints,const double *__restrict__ tH
 }
 
 __global__ void __launch_bounds__(256)
+wb_test_math_kernel(const double *__restrict__ y,const double *__restrict__ x,unsigned long long n,
+                    int *__restrict__ a,double *__restrict__ h,int *__restrict__ s)
+{
+  unsigned long long i=(unsigned long long)blockIdx.x*blockDim.x+threadIdx.x;
+  if (i>=n)
+    return;
+  a[i]=wb_atan2i(y[i],x[i]);
+  h[i]=wb_hypot(x[i],y[i]);
+  s[i]=wb_sector64(x[i],y[i]);
+}
+
+__global__ void __launch_bounds__(256)
 wb_compact_tiles_kernel(const int *__restrict__ tNPoints,uint32_t nTiles,uint32_t *__restrict__ flag)
 {
   uint32_t t=blockIdx.x*blockDim.x+threadIdx.x;

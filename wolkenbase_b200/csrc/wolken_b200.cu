@@ -1130,6 +1130,27 @@ extern "C" int wb_patch_records(wb_ctx *ctx,uint8_t *recs,uint64_t first,uint64_
   return WB_OK;
 }
 
+extern "C" int wb_test_math(wb_ctx *ctx,uint64_t n,const double *y,const double *x,int32_t *ao,double *ho,int32_t *so)
+{
+  if (!ctx || !y || !x || !ao || !ho || !so)
+    return WB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  DevBuf<double> dy,dx,dh;
+  DevBuf<int> da,ds;
+  CK(dy.ensure(n)); CK(dx.ensure(n)); CK(dh.ensure(n)); CK(da.ensure(n)); CK(ds.ensure(n));
+  CK(cudaMemcpy(dy.p,y,n*sizeof(double),cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dx.p,x,n*sizeof(double),cudaMemcpyHostToDevice));
+  wb_test_math_kernel<<<gridFor(n,256),256,0,ctx->st>>>(dy.p,dx.p,n,da.p,dh.p,ds.p);
+  ctx->stats.kernel_launches++;
+  KCHECK();
+  CK(cudaStreamSynchronize(ctx->st));
+  CK(cudaMemcpy(ao,da.p,n*sizeof(int),cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(ho,dh.p,n*sizeof(double),cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(so,ds.p,n*sizeof(int),cudaMemcpyDeviceToHost));
+  dy.release(); dx.release(); dh.release(); da.release(); ds.release();
+  return WB_OK;
+}
+
 extern "C" int wb_run(wb_ctx *ctx)
 {
   int rc;

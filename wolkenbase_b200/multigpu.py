@@ -263,16 +263,38 @@ def run_local(ranks, clouds):
     return [r.classify([sends[src][r.rank] for src in range(W)]) for r in ranks]
 
 
-def run_distributed(rank_obj, cloud, comm, dev_records=None, labels_out=None):
-    """One rank under torch.distributed."""
+def run_distributed(rank_obj, cloud, comm, dev_records=None, labels_out=None, timing=None):
+    """One rank under torch.distributed.  timing: optional dict that receives per-stage milliseconds."""
     r = rank_obj
+    t = [time.perf_counter()]
+
+    def lap(name):
+        if timing is not None:
+            torch.cuda.synchronize()
+            now = time.perf_counter()
+            timing[name] = timing.get(name, 0.0) + (now - t[0]) * 1e3
+            t[0] = now
+
     ext = comm.all_gather_doubles(r.load(cloud, dev_records), r.device)
     r.set_extents(ext)
-    recv = comm.all_to_all_rows(r.scan_sends())
-    comm.all_reduce_sum(r.scan(recv))
+    lap("load_decode")
+    sends = r.scan_sends()
+    lap("halo1_select")
+    recv = comm.all_to_all_rows(sends)
+    lap("halo1_exchange")
+    tabs = r.scan(recv)
+    lap("build_scan_export")
+    comm.all_reduce_sum(tabs)
+    lap("tile_allreduce")
     r.postscan()
-    recv = comm.all_to_all_rows(r.classify_sends())
-    return r.classify(recv, labels_out)
+    lap("postscan")
+    sends = r.classify_sends()
+    lap("halo2_select")
+    recv = comm.all_to_all_rows(sends)
+    lap("halo2_exchange")
+    out = r.classify(recv, labels_out)
+    lap("build_classify_labels")
+    return out
 
 
 # ---------------------------------------------------------------------------- bench (N > 1)
@@ -310,8 +332,10 @@ def bench(args, rank, world, local):
     dist.all_reduce(tot)
     n_total = int(tot.item())
 
-    def step(resident):
-        return run_distributed(R, cloud, comm, dev_recs if resident else None, labels_pin.array)
+    stage_ms = {}
+
+    def step(resident, timing=None):
+        return run_distributed(R, cloud, comm, dev_recs if resident else None, labels_pin.array, timing)
 
     for _ in range(args.warmup):
         step(True)
@@ -322,7 +346,7 @@ def bench(args, rank, world, local):
     comm.barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        step(True)
+        step(True, stage_ms)
     torch.cuda.synchronize()
     comm.barrier()
     dt = comm.all_reduce_max_scalar(time.perf_counter() - t0, dev)
@@ -360,6 +384,7 @@ def bench(args, rank, world, local):
                        "parallelism": "%d spatial strips, halo exchange + tile-table all-reduce" % world},
             "phases_ms_rank0": {"scan_stage_build": sa["ms_build"], "scan": sa["ms_scan"], "postscan": sa["ms_postscan"],
                                 "classify_stage_build": sb["ms_build"], "classify": sb["ms_classify"]},
+            "stages_ms_rank0": {k: round(v / args.steps, 2) for k, v in stage_ms.items()},
             "halo": {"scan_points": int(halo[0]), "classify_points": int(halo[1]),
                      "classify_fraction": float(halo[1]) / n_total, "por_max": R.por_max},
             "roofline": {"bound": "hbm", "kernel": "wb_classify_kernel (rank 0)", "achieved": achieved, "peak": hbm,
