@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libwolken_b200.so")
+LIB_PATH = os.environ.get("WB_LIB") or os.path.join(_HERE, "libwolken_b200.so")
 _LIB = None
 
 WB_RECORDS = 537

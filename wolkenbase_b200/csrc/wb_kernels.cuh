@@ -944,7 +944,10 @@ __device__ __forceinline__ bool wb_in_hyperboloid(double px,double py,double pcz
   return in && (dx!=0 || dy!=0);
 }
 
-__global__ void __launch_bounds__(WB_CL_WARPS*32,3)
+#ifndef WB_CL_MINBLOCKS
+#define WB_CL_MINBLOCKS 4      // 64 registers, 32 resident warps per SM: measured best of 2..6
+#endif
+__global__ void __launch_bounds__(WB_CL_WARPS*32,WB_CL_MINBLOCKS)
 wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,const double *__restrict__ sz,
                    unsigned long long n,uint32_t nChunks,
                    const WbBound *__restrict__ bounds,const uint32_t *__restrict__ levelOff,
@@ -997,7 +1000,6 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
   uint32_t maxLowA=0,minHighA=0xffffffffu,maxLowB=0,minHighB=0xffffffffu;
   unsigned long long wedgeMask=0;
   const int top=nLevels-1;
-  const uint32_t cntTop=levelCnt[top];
   for (int pass=1;pass<=2;pass++)
   {
     bool live=pass==1?!done:wedgeMask!=0;
