@@ -947,6 +947,7 @@ __device__ __forceinline__ bool wb_in_hyperboloid(double px,double py,double pcz
 #ifndef WB_CL_MINBLOCKS
 #define WB_CL_MINBLOCKS 4      // 64 registers, 32 resident warps per SM: measured best of 2..6
 #endif
+template <int PASS>
 __global__ void __launch_bounds__(WB_CL_WARPS*32,WB_CL_MINBLOCKS)
 wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,const double *__restrict__ sz,
                    unsigned long long n,uint32_t nChunks,
@@ -956,13 +957,19 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
                    double maxSlope,double thickness,
                    const uint8_t *__restrict__ clsIn,const uint32_t *__restrict__ perm,
                    uint32_t ownFirst,uint32_t ownEnd,
-                   uint8_t *__restrict__ labelSorted,unsigned long long *__restrict__ counters)
+                   uint8_t *__restrict__ labelSorted,unsigned long long *__restrict__ counters,
+                   uint32_t *__restrict__ wedgeBuf,uint8_t *__restrict__ chunkPending)
+// PASS 1: sector walk, decides every query whose longest empty run is not 24 or 25 sectors and
+//         leaves the bounding sectors of the others in wedgeBuf (chunkPending marks their chunks).
+// PASS 2: exact walk for the pending queries only.
 {
   __shared__ WbClassifyWarp wsh[WB_CL_WARPS];
   WbClassifyWarp &w=wsh[threadIdx.x>>5];
   const int lane=threadIdx.x&31;
   const uint32_t chunk=blockIdx.x*WB_CL_WARPS+(threadIdx.x>>5);
   if (chunk>=nChunks)
+    return;
+  if (PASS==2 && !chunkPending[chunk])
     return;
   const unsigned long long me=(unsigned long long)chunk*32+lane;
   const bool have=me<n;
@@ -1000,12 +1007,23 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
   uint32_t maxLowA=0,minHighA=0xffffffffu,maxLowB=0,minHighB=0xffffffffu;
   unsigned long long wedgeMask=0;
   const int top=nLevels-1;
-  for (int pass=1;pass<=2;pass++)
+  constexpr int pass=PASS;
+  if (PASS==2)
+  {
+    if (have && !done)
+      wedge=wedgeBuf[me];
+    for (int k=0;k<4;k++)
+    {
+      uint32_t sct=(wedge>>(8*k))&255;
+      if (sct!=255)
+        wedgeMask|=1ull<<sct;
+    }
+  }
   {
     bool live=pass==1?!done:wedgeMask!=0;
     uint32_t liveMask=__ballot_sync(WB_FULL,live);
     if (!liveMask)
-      break;
+      goto finish;
     // group envelope over the live queries: xy box, highest centre, smallest polar radius,
     // and the union of the sectors any of them still cares about
     double gx0,gx1,gy0,gy1,gcz,gpor2,gmx,gmy;
@@ -1280,24 +1298,38 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
       }
     }
   }
-  if (wedgeMask)
+finish:
+  if (PASS==1)
+  {
+    // hand the undecided queries to the second pass
+    if (have)
+      wedgeBuf[me]=wedge;
+    if (__any_sync(WB_FULL,wedgeMask!=0) && lane==0)
+      chunkPending[chunk]=1;
+  }
+  if (PASS==2 && wedgeMask)
   {
     // exact gaps of the 24/25-sector runs; every other gap is < 25 sectors < 144 degrees
     bool gapA=(wedge&255)!=255 && ((minHighA-maxLowA)&0x7fffffffu)>=(uint32_t)WB_DEG144;
     bool gapB=((wedge>>16)&255)!=255 && ((minHighB-maxLowB)&0x7fffffffu)>=(uint32_t)WB_DEG144;
     surrounded=!(gapA || gapB);
   }
-  if (have && !foreign)
+  if (PASS==1)
   {
-    uint8_t lab;
-    if (untiled)
-      lab=clsIn[perm[me]];                           // never visited by classifyCylinder
-    else
-      lab=surrounded?1:2;                            // classify.cpp:158-162
-    labelSorted[me]=lab;
+    if (have && !foreign)
+    {
+      uint8_t lab;
+      if (untiled)
+        lab=clsIn[perm[me]];                         // never visited by classifyCylinder
+      else
+        lab=surrounded?1:2;                          // classify.cpp:158-162 (pending ones are overwritten by pass 2)
+      labelSorted[me]=lab;
+    }
+    else if (have)
+      labelSorted[me]=255;
   }
-  else if (have)
-    labelSorted[me]=255;
+  else if (have && wedgeMask)
+    labelSorted[me]=surrounded?1:2;
   unsigned mm=__ballot_sync(WB_FULL,margin);
   unsigned uu=__ballot_sync(WB_FULL,untiled);
   unsigned aa=__ballot_sync(WB_FULL,wedgeMask!=0);

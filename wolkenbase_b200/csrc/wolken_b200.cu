@@ -81,6 +81,8 @@ struct wb_ctx
   DevBuf<uint8_t> tTree;
   DevBuf<double> tDensity,tHyp,tHeight;
   DevBuf<int> tileExt;
+  DevBuf<uint32_t> wedgeBuf;
+  DevBuf<uint8_t> chunkPending;
   DevBuf<uint8_t> tileGrid;
   // results of build
   unsigned long long *keys=nullptr;   // sorted keys (keyA or keyB)
@@ -303,7 +305,7 @@ extern "C" void wb_destroy(wb_ctx *ctx)
   ctx->nodesA.release(); ctx->nodesB.release(); ctx->leaves.release(); ctx->bounds.release();
   ctx->levelOff.release(); ctx->levelCnt.release();
   ctx->tStart.release(); ctx->tCount.release(); ctx->tNPoints.release(); ctx->tTree.release();
-  ctx->tDensity.release(); ctx->tHyp.release(); ctx->tHeight.release(); ctx->tileExt.release(); ctx->tileGrid.release();
+  ctx->tDensity.release(); ctx->tHyp.release(); ctx->tHeight.release(); ctx->tileExt.release(); ctx->tileGrid.release(); ctx->wedgeBuf.release(); ctx->chunkPending.release();
   cudaStreamDestroy(ctx->st); cudaStreamDestroy(ctx->stCopy);
   cudaEventDestroy(ctx->evA); cudaEventDestroy(ctx->evB); cudaEventDestroy(ctx->evC); cudaEventDestroy(ctx->evD);
   for (int i=0;i<2;i++)
@@ -1046,13 +1048,20 @@ extern "C" int wb_classify(wb_ctx *ctx)
   CK(cudaMemsetAsync(ctx->counters.p+6,0,18*sizeof(unsigned long long),st));
   wb_init_labels_kernel<<<gridFor(ctx->n,256),256,0,st>>>(ctx->cls.p,ctx->n,ctx->labelIn.p);
   CK(cudaEventRecord(ctx->evC,st));
-  wb_classify_kernel<<<gridFor(ctx->nChunks,WB_CL_WARPS),WB_CL_WARPS*32,0,st>>>(
+  CK(ctx->wedgeBuf.ensure(nv));
+  CK(ctx->chunkPending.ensure(ctx->nChunks));
+  CK(cudaMemsetAsync(ctx->chunkPending.p,0,ctx->nChunks,st));
+  wb_classify_kernel<1><<<gridFor(ctx->nChunks,WB_CL_WARPS),WB_CL_WARPS*32,0,st>>>(
       ctx->sx.p,ctx->sy.p,ctx->sz.p,nv,ctx->nChunks,ctx->bounds.p,ctx->levelOff.p,ctx->levelCnt.p,ctx->nLevels,
       ctx->winner.p,ctx->tHyp.p,ctx->prm.maxSlope,ctx->prm.thickness,ctx->cls.p,ctx->perm,
-      ctx->ownFirst,ctx->ownEnd,ctx->labelSorted.p,ctx->counters.p);
+      ctx->ownFirst,ctx->ownEnd,ctx->labelSorted.p,ctx->counters.p,ctx->wedgeBuf.p,ctx->chunkPending.p);
+  wb_classify_kernel<2><<<gridFor(ctx->nChunks,WB_CL_WARPS),WB_CL_WARPS*32,0,st>>>(
+      ctx->sx.p,ctx->sy.p,ctx->sz.p,nv,ctx->nChunks,ctx->bounds.p,ctx->levelOff.p,ctx->levelCnt.p,ctx->nLevels,
+      ctx->winner.p,ctx->tHyp.p,ctx->prm.maxSlope,ctx->prm.thickness,ctx->cls.p,ctx->perm,
+      ctx->ownFirst,ctx->ownEnd,ctx->labelSorted.p,ctx->counters.p,ctx->wedgeBuf.p,ctx->chunkPending.p);
   CK(cudaEventRecord(ctx->evD,st));
   wb_scatter_labels_kernel<<<gridFor(nv,256),256,0,st>>>(ctx->labelSorted.p,ctx->perm,nv,ctx->labelIn.p);
-  ctx->stats.kernel_launches+=3;
+  ctx->stats.kernel_launches+=4;
   KCHECK();
   CK(cudaEventRecord(ctx->evB,st));
   unsigned long long c[24]={0};
