@@ -762,7 +762,9 @@ wb_postscan_kernel(const int *__restrict__ tNPoints,const uint8_t *__restrict__ 
 // bearings: a second, much narrower walk computes atan2i for the points of the (at most four)
 // sectors that bound such runs and measures the gap exactly.
 
-#define WB_CL_WARPS 8
+#ifndef WB_CL_WARPS
+#define WB_CL_WARPS 1                    // one warp per CTA: a slow warp strands nothing (measured 8,4,2,1 warps: 1189,1115,1079,974 ms)
+#endif
 
 struct WbClassifyWarp
 {
@@ -945,7 +947,7 @@ __device__ __forceinline__ bool wb_in_hyperboloid(double px,double py,double pcz
 }
 
 #ifndef WB_CL_MINBLOCKS
-#define WB_CL_MINBLOCKS 4      // 64 registers, 32 resident warps per SM: measured best of 2..6
+#define WB_CL_MINBLOCKS (32/WB_CL_WARPS)   // 64 registers, 32 resident warps per SM: measured best of 16..48 warps
 #endif
 template <int PASS>
 __global__ void __launch_bounds__(WB_CL_WARPS*32,WB_CL_MINBLOCKS)

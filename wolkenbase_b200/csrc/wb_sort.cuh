@@ -147,7 +147,7 @@ wb_sort_upsweep_kernel(const uint64_t *__restrict__ keys,uint64_t n,int shift,
   table[(uint64_t)threadIdx.x*nBlocks+blockIdx.x]=hist[threadIdx.x];
 }
 
-__global__ void __launch_bounds__(WB_SORT_THREADS)
+__global__ void __launch_bounds__(WB_SORT_THREADS,3)
 wb_sort_downsweep_kernel(const uint64_t *__restrict__ keysIn,const uint32_t *__restrict__ valsIn,
                          uint64_t *__restrict__ keysOut,uint32_t *__restrict__ valsOut,
                          uint64_t n,int shift,const uint32_t *__restrict__ table,uint32_t nBlocks)
@@ -167,15 +167,12 @@ wb_sort_downsweep_kernel(const uint64_t *__restrict__ keysIn,const uint32_t *__r
     warpCnt[w][d]=0;
   __syncwarp();
   uint64_t key[WB_SORT_ITEMS];
-  uint32_t val[WB_SORT_ITEMS];
   uint16_t off[WB_SORT_ITEMS];
   #pragma unroll
   for (int r=0;r<WB_SORT_ITEMS;r++)
   {
     uint64_t j=warpBase+(uint64_t)r*32+lane;
-    bool ok=j<n;
-    key[r]=ok?keysIn[j]:~0ull;
-    val[r]=ok?valsIn[j]:0u;
+    key[r]=j<n?keysIn[j]:~0ull;
   }
   #pragma unroll
   for (int r=0;r<WB_SORT_ITEMS;r++)
@@ -224,7 +221,7 @@ wb_sort_downsweep_kernel(const uint64_t *__restrict__ keysIn,const uint32_t *__r
       uint32_t d=(uint32_t)((key[r]>>shift)&255);
       uint32_t p=digitBase[d]+warpCnt[w][d]+off[r];
       skeys[p]=key[r];
-      svals[p]=val[r];
+      svals[p]=valsIn[j];                           // values are only needed now: keeps 12 registers free during ranking
     }
   }
   __syncthreads();
