@@ -1168,7 +1168,7 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
       if (!qm)
         continue;
       // ---- a chunk: lane = point
-      unsigned long long j=(unsigned long long)node*32+lane;
+      const unsigned long long j=(unsigned long long)node*32+lane;
       const bool okp=j<n;
       const double cxp=okp?sx[j]:0.0,cyp=okp?sy[j]:0.0,czp=okp?sz[j]:INFINITY;
       if (pass==1) { statChunks++; statPairs+=__popc(qm); } else { statChunks2++; statPairs2+=__popc(qm); }
