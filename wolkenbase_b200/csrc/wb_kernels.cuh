@@ -552,6 +552,8 @@ wb_scan_kernel(const uint32_t *__restrict__ tStart,uint32_t *__restrict__ tCount
     return;
   }
   uint32_t start=tStart[t],cnt=end-start;
+  if (cnt>=(1u<<27))
+    cnt=(1u<<27)-1;                   // the pairwise-sum counter has 28 levels; a tile this full cannot occur (2^32 point limit / overlap)
   tCount[t]=cnt;
   atomicAdd(nNonEmpty,1ull);
   int ex,ey;
@@ -832,35 +834,6 @@ __device__ __forceinline__ unsigned long long wb_rotl64(unsigned long long x,int
   return r?(x<<r)|(x>>(64-r)):x;
 }
 
-__device__ __forceinline__ unsigned long long wb_sector_mask(double mx,double my,float r2,float d2)
-// Conservative mask of the sectors of all bearings towards a disc of squared radius r2 whose
-// centre lies at (mx,my), d2 = mx^2+my^2.
-{
-  r2=r2*1.001f+1e-12f;
-  if (!(d2>r2*1.01f))
-    return ~0ull;
-  int sc=wb_sector64(mx,my);
-  int h=(int)sqrtf(256.0f*r2/d2)+2;            // asin(x) <= (pi/2) x: half width <= 16 r/d sectors
-  if (sc<0)
-  {
-    sc=wb_sector64(mx*1.0000001+my*1e-7,my*1.0000001-mx*1e-7);   // nudge off the edge; one more sector of slack
-    h++;
-    if (sc<0)
-      return ~0ull;
-  }
-  if (2*h+1>=64)
-    return ~0ull;
-  return wb_rotl64((1ull<<(2*h+1))-1,sc-h+64);
-}
-
-__device__ __forceinline__ unsigned long long wb_box_sectors(double px,double py,const WbBound &b)
-// Conservative mask of the sectors in which bearings from (px,py) to points of the box can fall.
-{
-  double mx=0.5*(b.xmin+b.xmax)-px,my=0.5*(b.ymin+b.ymax)-py;
-  double hx=0.5*(b.xmax-b.xmin),hy=0.5*(b.ymax-b.ymin);
-  return wb_sector_mask(mx,my,(float)(hx*hx+hy*hy),(float)(mx*mx+my*my));
-}
-
 __device__ __forceinline__ float wb_fast_angle(float x,float y)
 // Bearing of (x,y) in sector units [0,64], accurate to 0.04 sector (atan(q) ~ q(pi/4+0.273(1-q))).
 // Only used to build conservative masks; every decision about a real bearing uses wb_sector64.
@@ -1029,7 +1002,6 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
     // group envelope over the live queries: xy box, highest centre, smallest polar radius,
     // and the union of the sectors any of them still cares about
     double gx0,gx1,gy0,gy1,gcz,gpor2,gmx,gmy;
-    float gr2;
     unsigned long long needAny;
     uint32_t envMask=0;
     auto envelope=[&]()
@@ -1048,8 +1020,6 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
         gpor2=fmin(gpor2,__shfl_xor_sync(WB_FULL,gpor2,o));
       }
       gmx=0.5*(gx0+gx1); gmy=0.5*(gy0+gy1);
-      double hx=0.5*(gx1-gx0),hy=0.5*(gy1-gy0);
-      gr2=(float)(hx*hx+hy*hy);
       envMask=liveMask;
     };
     auto needed=[&]()
@@ -1066,11 +1036,8 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
       if (!wb_reach(gx0,gx1,gy0,gy1,gcz,gpor2,s2,cb))
         return false;
       double mx=0.5*(cb.xmin+cb.xmax)-gmx,my=0.5*(cb.ymin+cb.ymax)-gmy;
-      double hx=0.5*(cb.xmax-cb.xmin),hy=0.5*(cb.ymax-cb.ymin);
       float d2=(float)(mx*mx+my*my);
-      float rr=sqrtf((float)(hx*hx+hy*hy))+sqrtf(gr2);
       key=(__float_as_uint(d2)&0xffffffe0u)|(uint32_t)lane;
-      (void)rr;
       cm=wb_span_mask(cb.xmin-gx1,cb.xmax-gx0,cb.ymin-gy1,cb.ymax-gy0);   // valid for every query of the group
       return (cm&needAny)!=0;
     };
@@ -1481,12 +1448,4 @@ wb_test_math_kernel(const double *__restrict__ y,const double *__restrict__ x,un
   a[i]=wb_atan2i(y[i],x[i]);
   h[i]=wb_hypot(x[i],y[i]);
   s[i]=wb_sector64(x[i],y[i]);
-}
-
-__global__ void __launch_bounds__(256)
-wb_compact_tiles_kernel(const int *__restrict__ tNPoints,uint32_t nTiles,uint32_t *__restrict__ flag)
-{
-  uint32_t t=blockIdx.x*blockDim.x+threadIdx.x;
-  if (t<nTiles)
-    flag[t]=tNPoints[t]!=0;
 }
