@@ -265,3 +265,40 @@ def test_device_math_known_answers(ctx):
     ok = s >= 0
     assert ok.mean() > 0.99
     assert ((u[ok] >> 25) == s[ok]).all()
+
+
+def test_error_behaviour(ctx):
+    """Every entry point reports instead of crashing: wrong phase order, unsupported formats,
+    missing extents (the reference asserts or prints; SURVEY.md §8b 'Error conventions')."""
+    cloud = synth.generate(2, 3000, seed=3)
+    ctx.clear()
+    ctx.set_params()
+    with pytest.raises(api.WolkenError, match="no points"):
+        ctx.build()
+    with pytest.raises(api.WolkenError, match="waveform|not supported"):
+        ctx.add_las(np.zeros((10, 57), dtype=np.uint8), 4, cloud.scale, cloud.offset)
+    with pytest.raises(api.WolkenError, match="shorter"):
+        ctx.add_las(np.zeros((10, 20), dtype=np.uint8), 1, cloud.scale, cloud.offset)
+    with pytest.raises(api.WolkenError, match="unknown"):
+        ctx.add_las(np.zeros((10, 28), dtype=np.uint8), 11, cloud.scale, cloud.offset)
+    ctx.add_las(cloud.records, cloud.fmt, cloud.scale, cloud.offset)
+    with pytest.raises(api.WolkenError, match="extent"):
+        ctx.build()                                               # no header corners given
+    ctx.add_extent(cloud.min_corner, cloud.max_corner)
+    with pytest.raises(api.WolkenError, match="not built"):
+        ctx.scan()
+    ctx.build()
+    with pytest.raises(api.WolkenError, match="postscan"):
+        ctx.classify()
+    with pytest.raises(api.WolkenError, match="not classified"):
+        ctx.labels(cloud.n)
+    with pytest.raises(api.WolkenError, match="already built"):
+        ctx.add_las(cloud.records, cloud.fmt, cloud.scale, cloud.offset)
+    ctx.scan()
+    ctx.postscan()
+    with pytest.raises(api.WolkenError, match="once"):
+        ctx.postscan()
+    ctx.classify()
+    assert ctx.labels(cloud.n).max() <= 2
+    with pytest.raises(api.WolkenError):
+        ctx.set_params(tile_size=-1.0)
