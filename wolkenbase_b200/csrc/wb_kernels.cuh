@@ -108,25 +108,42 @@ wb_decode_kernel(const uint8_t *__restrict__ recs,unsigned long long n,int fmt,i
 
 // ============================================================================ K2: Morton keys
 
+__device__ __forceinline__ uint32_t wb_cell21(double v,double c,double side)
+// Index (21 bits) of the cell of width side/2^21 that Octree::findBlock's descent
+// (octree.cpp:199-216: bit = coordinate >= centre, 21 times) ends in.  The descent is a binary
+// search for the cell [lo,lo+w) containing v, with every boundary a dyadic number that is exact in
+// FP64; so the cell is found by one scaled subtraction and then CHECKED against the exact
+// boundaries (and moved by one if the rounded quotient landed next door).  Coordinates outside
+// the root cube clamp to the first/last cell, as the comparison chain does.
+{
+  const double w=side*(1.0/2097152.0),lo0=c-0.5*side;     // exact: side is a power of two
+  double q=floor((v-lo0)/w);
+  q=fmin(fmax(q,0.0),2097151.0);
+  double lo=lo0+q*w;                                       // exact (dyadic, few significant bits)
+  if (v<lo && q>0.0)
+    q-=1.0;
+  else if (v>=lo+w && q<2097151.0)
+    q+=1.0;
+  return (uint32_t)q;
+}
+
+__device__ __forceinline__ unsigned long long wb_spread3(uint32_t v)
+// 21 bits -> every third bit of 63
+{
+  unsigned long long x=v&0x1fffffull;
+  x=(x|(x<<32))&0x1f00000000ffffull;
+  x=(x|(x<<16))&0x1f0000ff0000ffull;
+  x=(x|(x<<8))&0x100f00f00f00f00full;
+  x=(x|(x<<4))&0x10c30c30c30c30c3ull;
+  x=(x|(x<<2))&0x1249249249249249ull;
+  return x;
+}
+
 __device__ __forceinline__ unsigned long long wb_morton(double x,double y,double z,
                                                         double cx,double cy,double cz,double side)
-// 21 steps of Octree::findBlock's descent: bit = coordinate >= centre, child = z*4+y*2+x
-// (octree.cpp:199-216); child centre = centre +- side/4 (octree.cpp:335-337).  All centre
-// arithmetic is exact (dyadic), so no rounding mode matters here.
+// 63-bit key: per level (most significant first) the child index z*4+y*2+x of the descent.
 {
-  unsigned long long key=0;
-  double q=side*0.25;
-  #pragma unroll
-  for (int l=0;l<21;l++)
-  {
-    int xb=x>=cx,yb=y>=cy,zb=z>=cz;
-    key=(key<<3)|(unsigned long long)(zb*4+yb*2+xb);
-    cx+=xb?q:-q;
-    cy+=yb?q:-q;
-    cz+=zb?q:-q;
-    q*=0.5;
-  }
-  return key;
+  return wb_spread3(wb_cell21(x,cx,side))|(wb_spread3(wb_cell21(y,cy,side))<<1)|(wb_spread3(wb_cell21(z,cz,side))<<2);
 }
 
 __global__ void __launch_bounds__(256)
