@@ -991,6 +991,7 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
   w.qx[lane]=px; w.qy[lane]=py; w.qcz[lane]=pcz; w.qpor2[lane]=ppor2;
   unsigned long long occ=0;                       // occupied sectors of my query
   unsigned long long open=~0ull;                  // sectors of empty runs >= 24 (the only ones that matter)
+  bool changed=false;
   uint32_t statNodes=0,statChunks=0,statPairs=0,statNodes2=0,statChunks2=0,statPairs2=0;  // work counters (warp-uniform)
   bool margin=false,surrounded=false;
   // second-walk state: up to two empty runs of 24/25 sectors, bounded below by sector k1 (we need
@@ -1198,7 +1199,14 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
           uint32_t lo=__reduce_or_sync(WB_FULL,(in && s<32)?1u<<s:0u);
           uint32_t hi=__reduce_or_sync(WB_FULL,(in && s>=32)?1u<<(s-32):0u);
           if (lane==q)
-            occ|=(unsigned long long)lo|((unsigned long long)hi<<32);
+          {
+            unsigned long long add=((unsigned long long)lo|((unsigned long long)hi<<32))&open;   // only open sectors matter
+            if (add)
+            {
+              occ|=add;
+              changed=true;
+            }
+          }
         }
         else
         {
@@ -1234,8 +1242,11 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
       if (pass==1)
       {
         // surrounded for sure once no empty run of 24 sectors is left
-        if (live)
+        if (!__any_sync(WB_FULL,changed))
+          continue;                                 // nothing new for anybody: envelope and needs stand
+        if (changed)
         {
+          changed=false;
           open=wb_long_runs(occ);
           if (!open)
           {
