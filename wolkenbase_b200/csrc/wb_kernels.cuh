@@ -402,49 +402,31 @@ wb_member_fill_kernel(const uint32_t *__restrict__ cnt,const uint32_t *__restric
 
 __global__ void __launch_bounds__(256)
 wb_segment_kernel(const unsigned long long *__restrict__ pairKey,unsigned long long m,
-                  uint32_t *__restrict__ tStart,uint32_t *__restrict__ tCount)
+                  uint32_t *__restrict__ tStart,uint32_t *__restrict__ tCount,
+                  uint32_t *__restrict__ tileList,unsigned long long *__restrict__ nList)
+// start and count of every tile's run in the sorted (tile,point) pairs + the list of non-empty tiles
 {
   unsigned long long i=(unsigned long long)blockIdx.x*blockDim.x+threadIdx.x;
   if (i>=m)
     return;
   unsigned long long t=pairKey[i];
   if (i==0 || pairKey[i-1]!=t)
+  {
     tStart[t]=(uint32_t)i;
-  if (i+1==m || pairKey[i+1]!=t)
-    tCount[t]=(uint32_t)i+1;      // end for now; turned into a count by the scan kernel
+    unsigned long long lo=i+1,hi=m;  // first pair of the next tile: keys are sorted
+    while (lo<hi)
+    {
+      unsigned long long mid=(lo+hi)>>1;
+      if (pairKey[mid]<=t) lo=mid+1; else hi=mid;
+    }
+    tCount[t]=(uint32_t)(lo-i);
+    tileList[atomicAdd(nList,1ull)]=(uint32_t)t;
+  }
 }
 
 // ============================================================================ K7: tile scan
-// scanCylinder (scan.cpp:31-140), one thread per non-empty tile, streaming over the tile's
-// points in canonical order.  Pairwise sums keep the reference's association
-// (manysum.cpp:120-154): aligned power-of-two blocks summed as perfect trees, merged like a
-// binary counter, block totals added from the smallest block up.
-
-struct WbPairwise
-{
-  double lv[28];
-  __device__ void push(double v,uint32_t i)       // i = index of v (0-based)
-  {
-    // carry: merge with every level whose bit is set in i (they are complete blocks)
-    int l=0;
-    uint32_t m=i;
-    while (m&1)
-    {
-      v=__dadd_rn(lv[l],v);
-      m>>=1;
-      l++;
-    }
-    lv[l]=v;
-  }
-  __device__ double total(uint32_t n) const
-  {
-    double s=0;
-    for (int l=0;l<28;l++)
-      if ((n>>l)&1)
-        s=__dadd_rn(s,lv[l]);
-    return s;
-  }
-};
+// scanCylinder (scan.cpp:31-140).  The 3x3 Gauss-Jordan below restates matrix.cpp's rowop /
+// findpivot / gausselim; the kernel itself follows.
 
 struct WbMat3 { double a[3][3],b[3]; };
 
@@ -551,60 +533,128 @@ __device__ void wb_gausselim(WbMat3 &m)
       wb_rowop(m,i,j,i);
 }
 
-__global__ void __launch_bounds__(64)
-wb_scan_kernel(const uint32_t *__restrict__ tStart,uint32_t *__restrict__ tCount,uint32_t nTiles,
+#define WB_SCAN_WARPS 4
+
+__global__ void __launch_bounds__(WB_SCAN_WARPS*32)
+wb_scan_kernel(const uint32_t *__restrict__ tileList,uint32_t nList,
+               const uint32_t *__restrict__ tStart,const uint32_t *__restrict__ tCount,
                const uint32_t *__restrict__ pairVal,
                const double *__restrict__ sx,const double *__restrict__ sy,const double *__restrict__ sz,
                WbSnake snake,double minHyp,
                int *__restrict__ tNPoints,uint8_t *__restrict__ tTree,double *__restrict__ tDensity,
-               double *__restrict__ tHyp,double *__restrict__ tHeight,unsigned long long *nNonEmpty)
+               double *__restrict__ tHyp,double *__restrict__ tHeight)
+// scanCylinder (scan.cpp:31-140): ONE WARP PER NON-EMPTY TILE.  The tile's points (canonical order)
+// are taken 32 at a time, one per lane.  The eight normal-equation sums keep the reference's
+// association (pairwisesum, manysum.cpp:120-154 = perfect binary trees over aligned power-of-two
+// blocks, merged like a binary counter): inside a batch the tree is a butterfly of warp shuffles
+// (block sums of size 2^s are read off before step s for the tail of the last batch); across
+// batches lane j (j<8) carries quantity j's counter in shared memory.
 {
-  uint32_t t=blockIdx.x*blockDim.x+threadIdx.x;
-  if (t>=nTiles)
+  __shared__ double lvAll[WB_SCAN_WARPS][8][28];
+  __shared__ double totAll[WB_SCAN_WARPS][8];
+  const int lane=threadIdx.x&31,wi=threadIdx.x>>5;
+  const uint32_t widx=blockIdx.x*WB_SCAN_WARPS+wi;
+  if (widx>=nList)
     return;
-  uint32_t end=tCount[t];
-  if (end==0)
-  {
-    tNPoints[t]=0;
-    return;
-  }
-  uint32_t start=tStart[t],cnt=end-start;
+  double (*lv)[28]=lvAll[wi];
+  double *tot=totAll[wi];
+  const uint32_t t=tileList[widx];
+  const uint32_t start=tStart[t];
+  uint32_t cnt=tCount[t];
   if (cnt>=(1u<<27))
-    cnt=(1u<<27)-1;                   // the pairwise-sum counter has 28 levels; a tile this full cannot occur (2^32 point limit / overlap)
-  tCount[t]=cnt;
-  atomicAdd(nNonEmpty,1ull);
+    cnt=(1u<<27)-1;                   // 28 counter levels; unreachable below the 2^32-point limit
   int ex,ey;
   wb_to_flowsnake((int)t+snake.lo,ex,ey);
   double ccx,ccy;
   wb_tile_center(ex,ey,snake,ccx,ccy);
-  // normal equations: sums of x*x, x*y, y*y, x*1, y*1, x*z, y*z, 1*z  (1*1 sums to cnt exactly)
-  WbPairwise pxx,pxy,pyy,px,py,pxz,pyz,pz;
-  for (uint32_t i=0;i<cnt;i++)
+  const uint32_t nBatch=(cnt+31)>>5;
+  // ---- phase 1: pairwise sums of x*x, y*x, y*y, x, y, x*z, y*z, z  (1*1 sums to cnt exactly)
+  for (uint32_t b=0;b<nBatch;b++)
   {
-    uint32_t k=pairVal[start+i];
-    double x=__dsub_rn(sx[k],ccx),y=__dsub_rn(sy[k],ccy),z=sz[k];
-    pxx.push(__dmul_rn(x,x),i);
-    pxy.push(__dmul_rn(y,x),i);      // mt[1][k]*mt[0][k]
-    pyy.push(__dmul_rn(y,y),i);
-    px.push(x,i);                    // 1*x is exact
-    py.push(y,i);
-    pxz.push(__dmul_rn(x,z),i);
-    pyz.push(__dmul_rn(y,z),i);
-    pz.push(z,i);
+    const uint32_t i=b*32+lane;
+    const bool valid=i<cnt;
+    double v[8]={0,0,0,0,0,0,0,0};
+    if (valid)
+    {
+      const uint32_t k=pairVal[start+i];
+      const double x=__dsub_rn(sx[k],ccx),y=__dsub_rn(sy[k],ccy),z=sz[k];
+      v[0]=__dmul_rn(x,x);
+      v[1]=__dmul_rn(y,x);
+      v[2]=__dmul_rn(y,y);
+      v[3]=x;
+      v[4]=y;
+      v[5]=__dmul_rn(x,z);
+      v[6]=__dmul_rn(y,z);
+      v[7]=z;
+    }
+    const uint32_t r=min(32u,cnt-b*32);
+    #pragma unroll
+    for (int s=0;s<5;s++)
+    {
+      if (r<32 && ((r>>s)&1))
+      {
+        // the block of size 2^s of the tail starts where the higher bits of r end
+        const int pos=(int)(r&~((2u<<s)-1));
+        double mine=0;
+        #pragma unroll
+        for (int j=0;j<8;j++)
+        {
+          double e=__shfl_sync(WB_FULL,v[j],pos);
+          if (lane==j)
+            mine=e;
+        }
+        if (lane<8)
+          lv[lane][s]=mine;
+      }
+      #pragma unroll
+      for (int j=0;j<8;j++)
+        v[j]=__dadd_rn(v[j],__shfl_xor_sync(WB_FULL,v[j],1<<s));
+    }
+    if (r==32)
+    {
+      double mine=0;
+      #pragma unroll
+      for (int j=0;j<8;j++)
+        if (lane==j)
+          mine=v[j];
+      if (lane<8)
+      {
+        int l=5;
+        uint32_t m=b;
+        while (m&1)
+        {
+          mine=__dadd_rn(lv[lane][l],mine);
+          m>>=1;
+          l++;
+        }
+        lv[lane][l]=mine;
+      }
+    }
+    __syncwarp();
   }
+  if (lane<8)
+  {
+    double sum=0;
+    for (int l=0;l<28;l++)
+      if ((cnt>>l)&1)
+        sum=__dadd_rn(sum,lv[lane][l]);
+    tot[lane]=sum;
+  }
+  __syncwarp();
+  // ---- phase 2: 3x3 normal equations (every lane, same result)
   WbMat3 m;
-  m.a[0][0]=pxx.total(cnt);
-  m.a[1][0]=m.a[0][1]=pxy.total(cnt);
-  m.a[1][1]=pyy.total(cnt);
-  m.a[2][0]=m.a[0][2]=px.total(cnt);
-  m.a[2][1]=m.a[1][2]=py.total(cnt);
+  m.a[0][0]=tot[0];
+  m.a[1][0]=m.a[0][1]=tot[1];
+  m.a[1][1]=tot[2];
+  m.a[2][0]=m.a[0][2]=tot[3];
+  m.a[2][1]=m.a[1][2]=tot[4];
   m.a[2][2]=(double)cnt;
-  m.b[0]=pxz.total(cnt);
-  m.b[1]=pyz.total(cnt);
-  m.b[2]=pz.total(cnt);
+  m.b[0]=tot[5];
+  m.b[1]=tot[6];
+  m.b[2]=tot[7];
   wb_gausselim(m);
   double sl0=m.a[0][0]==0?NAN:m.b[0],sl1=m.a[1][1]==0?NAN:m.b[1];
-  double len=wb_hypot(sl0,sl1);
+  const double len=wb_hypot(sl0,sl1);
   if (len>1)
   {
     sl0=__ddiv_rn(sl0,len);
@@ -612,61 +662,109 @@ wb_scan_kernel(const uint32_t *__restrict__ tStart,uint32_t *__restrict__ tCount
   }
   if (isnan(sl0) || isnan(sl1))
     sl0=sl1=0;
-  double bottom=INFINITY,bottom2=INFINITY,top=-INFINITY;
-  for (uint32_t i=0;i<cnt;i++)
+  // ---- phase 3: bottom = lowest untilted z, f = its first position, top; then
+  //      bottom2 = lowest untilted z BEFORE position f (scan.cpp:78-87: the update only fires on a
+  //      strict new minimum), = bottom if there is none
+  double bestv=INFINITY,top=-INFINITY;
+  uint32_t besti=0xffffffffu;
+  for (uint32_t b=0;b<nBatch;b++)
   {
-    uint32_t k=pairVal[start+i];
-    double x=__dsub_rn(sx[k],ccx),y=__dsub_rn(sy[k],ccy);
-    double zt=__dadd_rn(__dmul_rn(sl1,y),__dmul_rn(sl0,x));      // dot(): a.y*b.y+a.x*b.x
-    double zu=__dsub_rn(sz[k],zt);
-    if (zu<bottom)
+    const uint32_t i=b*32+lane;
+    if (i<cnt)
     {
-      bottom2=bottom;
-      bottom=zu;
+      const uint32_t k=pairVal[start+i];
+      const double x=__dsub_rn(sx[k],ccx),y=__dsub_rn(sy[k],ccy);
+      const double zu=__dsub_rn(sz[k],__dadd_rn(__dmul_rn(sl1,y),__dmul_rn(sl0,x)));   // dot(): a.y*b.y+a.x*b.x
+      if (zu<bestv)
+      {
+        bestv=zu;
+        besti=i;
+      }
+      if (zu>top)
+        top=zu;
     }
-    if (zu>top)
-      top=zu;
   }
+  #pragma unroll
+  for (int o=16;o;o>>=1)
+  {
+    const double ov=__shfl_xor_sync(WB_FULL,bestv,o);
+    const uint32_t oi=__shfl_xor_sync(WB_FULL,besti,o);
+    if (ov<bestv || (ov==bestv && oi<besti))
+    {
+      bestv=ov;
+      besti=oi;
+    }
+    top=fmax(top,__shfl_xor_sync(WB_FULL,top,o));
+  }
+  const double bottom=bestv;
+  double bottom2=INFINITY;
+  for (uint32_t b=0;b*32<besti && b<nBatch;b++)
+  {
+    const uint32_t i=b*32+lane;
+    if (i<besti && i<cnt)
+    {
+      const uint32_t k=pairVal[start+i];
+      const double x=__dsub_rn(sx[k],ccx),y=__dsub_rn(sy[k],ccy);
+      const double zu=__dsub_rn(sz[k],__dadd_rn(__dmul_rn(sl1,y),__dmul_rn(sl0,x)));
+      bottom2=fmin(bottom2,zu);
+    }
+  }
+  #pragma unroll
+  for (int o=16;o;o>>=1)
+    bottom2=fmin(bottom2,__shfl_xor_sync(WB_FULL,bottom2,o));
   if (isinf(bottom2))
     bottom2=bottom;
+  // ---- phase 4: seven-sector histogram of the bottom layer
   int histo[7]={0,0,0,0,0,0,0};
   uint32_t nBottom=0;
   const double cut=__dadd_rn(bottom2,__dmul_rn(2.0,snake.radius));
   const double rin=__ddiv_rn(snake.radius,WB_SQRT7);
-  for (uint32_t i=0;i<cnt;i++)
+  for (uint32_t b=0;b<nBatch;b++)
   {
-    uint32_t k=pairVal[start+i];
-    double x=__dsub_rn(sx[k],ccx),y=__dsub_rn(sy[k],ccy);
-    double zt=__dadd_rn(__dmul_rn(sl1,y),__dmul_rn(sl0,x));
-    double zu=__dsub_rn(sz[k],zt);
-    if (zu<cut)
+    const uint32_t i=b*32+lane;
+    int sector=-1;
+    if (i<cnt)
     {
-      int sector=(int)wb_lrint(__ddiv_rn(__dmul_rn(atan2(y,x),3.0),WB_PI));
-      if (sector<0)
-        sector+=6;
-      sector=(sector%6)+1;
-      if (wb_hypot(x,y)<rin)
-        sector=0;
-      histo[sector]++;
-      nBottom++;
+      const uint32_t k=pairVal[start+i];
+      const double x=__dsub_rn(sx[k],ccx),y=__dsub_rn(sy[k],ccy);
+      const double zu=__dsub_rn(sz[k],__dadd_rn(__dmul_rn(sl1,y),__dmul_rn(sl0,x)));
+      if (zu<cut)
+      {
+        sector=(int)wb_lrint(__ddiv_rn(__dmul_rn(atan2(y,x),3.0),WB_PI));
+        if (sector<0)
+          sector+=6;
+        sector=(sector%6)+1;
+        if (wb_hypot(x,y)<rin)
+          sector=0;
+      }
+    }
+    #pragma unroll
+    for (int j=0;j<7;j++)
+    {
+      const int c=__popc(__ballot_sync(WB_FULL,sector==j));
+      histo[j]+=c;
+      nBottom+=c;
     }
   }
-  double density=0;
-  for (int j=0;j<7;j++)
-    density=__dadd_rn(density,(double)(histo[j]*histo[j]));
-  int tree=0;
-  if (cnt>nBottom && density<7)
-    tree=1;
-  density=__ddiv_rn(__ddiv_rn(__dmul_rn(sqrt(density),WB_SQRT7),__dmul_rn(snake.radius,snake.radius)),WB_PI);
-  if (cnt>nBottom && density<0.5)
-    tree=1;
-  if (__dsub_rn(top,bottom)>1.5)
-    tree=1;
-  tNPoints[t]=(int)cnt;
-  tTree[t]=(uint8_t)tree;
-  tDensity[t]=density;
-  tHyp[t]=sqrt(__dadd_rn(__ddiv_rn(1.0,density),__dmul_rn(minHyp,minHyp)));
-  tHeight[t]=__dsub_rn(top,bottom);
+  if (lane==0)
+  {
+    double density=0;
+    for (int j=0;j<7;j++)
+      density=__dadd_rn(density,(double)(histo[j]*histo[j]));
+    int tree=0;
+    if (cnt>nBottom && density<7)
+      tree=1;
+    density=__ddiv_rn(__ddiv_rn(__dmul_rn(sqrt(density),WB_SQRT7),__dmul_rn(snake.radius,snake.radius)),WB_PI);
+    if (cnt>nBottom && density<0.5)
+      tree=1;
+    if (__dsub_rn(top,bottom)>1.5)
+      tree=1;
+    tNPoints[t]=(int)cnt;
+    tTree[t]=(uint8_t)tree;
+    tDensity[t]=density;
+    tHyp[t]=sqrt(__dadd_rn(__ddiv_rn(1.0,density),__dmul_rn(minHyp,minHyp)));
+    tHeight[t]=__dsub_rn(top,bottom);
+  }
 }
 
 // ============================================================================ K8: postscan

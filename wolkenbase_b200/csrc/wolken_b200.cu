@@ -76,7 +76,7 @@ struct wb_ctx
   DevBuf<uint32_t> levelOff,levelCnt;
   // tiles
   uint32_t nTiles=0;
-  DevBuf<uint32_t> tStart,tCount;
+  DevBuf<uint32_t> tStart,tCount,tileList;
   DevBuf<int> tNPoints;
   DevBuf<uint8_t> tTree;
   DevBuf<double> tDensity,tHyp,tHeight;
@@ -304,7 +304,7 @@ extern "C" void wb_destroy(wb_ctx *ctx)
   ctx->staging[0].release(); ctx->staging[1].release(); ctx->dsegs.release();
   ctx->nodesA.release(); ctx->nodesB.release(); ctx->leaves.release(); ctx->bounds.release();
   ctx->levelOff.release(); ctx->levelCnt.release();
-  ctx->tStart.release(); ctx->tCount.release(); ctx->tNPoints.release(); ctx->tTree.release();
+  ctx->tStart.release(); ctx->tCount.release(); ctx->tileList.release(); ctx->tNPoints.release(); ctx->tTree.release();
   ctx->tDensity.release(); ctx->tHyp.release(); ctx->tHeight.release(); ctx->tileExt.release(); ctx->tileGrid.release(); ctx->wedgeBuf.release(); ctx->chunkPending.release();
   cudaStreamDestroy(ctx->st); cudaStreamDestroy(ctx->stCopy);
   cudaEventDestroy(ctx->evA); cudaEventDestroy(ctx->evB); cudaEventDestroy(ctx->evC); cudaEventDestroy(ctx->evD);
@@ -805,15 +805,21 @@ extern "C" int wb_scan(wb_ctx *ctx)
                    ctx->table.p,ctx->table.cap,ctx->blockSums.p,ctx->blockSums.cap,st,&inA,&ctx->stats.kernel_launches));
   ctx->pairKeys=(uint64_t *)(inA?ctx->pairKeyA.p:ctx->pairKeyB.p);
   ctx->pairVals=inA?ctx->pairValA.p:ctx->pairValB.p;
-  CK(cudaMemsetAsync(ctx->tStart.p,0,sizeof(uint32_t)*T,st));
-  CK(cudaMemsetAsync(ctx->tCount.p,0,sizeof(uint32_t)*T,st));
+  CK(cudaMemsetAsync(ctx->tNPoints.p,0,sizeof(int)*T,st));
   CK(cudaMemsetAsync(ctx->counters.p+3,0,sizeof(unsigned long long),st));
+  CK(ctx->tileList.ensure(std::min<uint64_t>(T,(uint64_t)m)+1));
   if (m)
-    wb_segment_kernel<<<gridFor(m,256),256,0,st>>>((const unsigned long long *)ctx->pairKeys,m,ctx->tStart.p,ctx->tCount.p);
+    wb_segment_kernel<<<gridFor(m,256),256,0,st>>>((const unsigned long long *)ctx->pairKeys,m,ctx->tStart.p,ctx->tCount.p,
+                                                   ctx->tileList.p,ctx->counters.p+3);
   CK(cudaEventRecord(ctx->evC,st));
-  wb_scan_kernel<<<gridFor(T,64),64,0,st>>>(ctx->tStart.p,ctx->tCount.p,T,ctx->pairVals,ctx->sx.p,ctx->sy.p,ctx->sz.p,
-                                            ctx->snake,ctx->prm.minHyp,ctx->tNPoints.p,ctx->tTree.p,ctx->tDensity.p,
-                                            ctx->tHyp.p,ctx->tHeight.p,ctx->counters.p+3);
+  unsigned long long nList=0;
+  CK(cudaMemcpyAsync(&nList,ctx->counters.p+3,sizeof(nList),cudaMemcpyDeviceToHost,st));
+  CK(cudaStreamSynchronize(st));
+  if (nList)
+    wb_scan_kernel<<<gridFor(nList,WB_SCAN_WARPS),WB_SCAN_WARPS*32,0,st>>>(ctx->tileList.p,(uint32_t)nList,ctx->tStart.p,ctx->tCount.p,
+                                              ctx->pairVals,ctx->sx.p,ctx->sy.p,ctx->sz.p,
+                                              ctx->snake,ctx->prm.minHyp,ctx->tNPoints.p,ctx->tTree.p,ctx->tDensity.p,
+                                              ctx->tHyp.p,ctx->tHeight.p);
   ctx->stats.kernel_launches+=2;
   KCHECK();
   CK(cudaEventRecord(ctx->evB,st));
