@@ -302,3 +302,45 @@ def test_error_behaviour(ctx):
     assert ctx.labels(cloud.n).max() <= 2
     with pytest.raises(api.WolkenError):
         ctx.set_params(tile_size=-1.0)
+
+
+def _shifted(cloud, dx_ticks, dy_ticks, new_scale=None):
+    """The same points expressed with another LAS offset (and optionally a coarser-looking scale
+    factor 1: ints divided is not possible in general, so only the offset moves)."""
+    recs = cloud.records.copy()
+    ints = np.ascontiguousarray(recs[:, :12]).view(np.int32).reshape(-1, 3).copy()
+    ints[:, 0] -= dx_ticks
+    ints[:, 1] -= dy_ticks
+    recs[:, :12] = ints.view(np.uint8).reshape(-1, 12)
+    d = synth.SynthDesc()
+    for f, _ in synth.SynthDesc._fields_:
+        setattr(d, f, getattr(cloud.desc, f))
+    d.offset[0] = cloud.desc.offset[0] + cloud.desc.scale * dx_ticks
+    d.offset[1] = cloud.desc.offset[1] + cloud.desc.scale * dy_ticks
+    bbox = cloud.bbox.copy()
+    bbox[0] -= dx_ticks; bbox[3] -= dx_ticks
+    bbox[1] -= dy_ticks; bbox[4] -= dy_ticks
+    return synth.Cloud(d, cloud.header, recs, bbox)
+
+
+def test_files_with_different_offsets_and_units(ctx):
+    """Per-file scale/offset (las.cpp:808 uses each header's own) and a length unit other than 1
+    (LasHeader::setUnit; mainwindow.cpp:398-411 'lengthUnit')."""
+    d = synth.describe(2, 50000)
+    half = d.grid_nx // 2
+    left = synth.generate(2, 50000, seed=29, region=(0, 0, half, d.grid_ny))
+    right = synth.generate(2, 50000, seed=29, region=(half, 0, d.grid_nx - half, d.grid_ny), gps_base=left.n)
+    right2 = _shifted(right, 20000, -7000)                          # same ground, different header offset
+    rep = _check_against_oracle(ctx, [left, right2], {})
+    assert rep["mismatch"] == 0
+    # unit: international foot
+    cloud = synth.generate(2, 20000, seed=30)
+    unit = 0.3048
+    ctx.clear()
+    ctx.set_params()
+    ctx.add_extent([c * unit for c in cloud.min_corner], [c * unit for c in cloud.max_corner])
+    ctx.add_las(cloud.records, cloud.fmt, cloud.scale, cloud.offset, unit)
+    ctx.run()
+    res = O.run([O.file_from_cloud(cloud)], unit=unit)
+    assert ctx.dump() == res.dump
+    assert (ctx.labels(cloud.n) == res.labels).all()
