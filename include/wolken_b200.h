@@ -177,6 +177,7 @@ int wb_host_free(void *p);
 /* host-side restatements used by the shims (no device work) */
 int wb_size_fit(const double *corners,int n_corners,double center[3],double *side);
 int wb_bbox_cube(const double *corners,int n_corners,double cube[4]);
+int wb_bound_rect(const double *corners,int n_corners,double box[6]);   /* BoundRect: left,bottom,low,right,top,high */
 int wb_snake_set_size(double cube_side,double tile_size,double *spacing,int *lo,int *hi);
 int wb_ldecimal(double x,char *buf,int buflen);
 int wb_format_dump(const wb_leaf *leaves,uint64_t n_leaves,char *buf,uint64_t buflen);

@@ -17,7 +17,11 @@
  * order (the scan phase is order dependent, scan.cpp:78-82).  Only meaningful with 1 thread.
  *
  * usage: ref_driver [-t threads] [-c] [-T tileSize] [-S maxSlope] [-K thickness]
- *                   [-M minHyperboloidSize] -o outprefix in1.las [in2.las ...]
+ *                   [-M minHyperboloidSize] [-w lasprefix [-s 0|1] [-p pointsPerFile]]
+ *                   -o outprefix in1.las [in2.las ...]
+ * -w writes the classified cloud with the reference's own LasHeader write path
+ * (las.cpp:456-514, 540-595, 636-673, 822-904), driven the way CloudOutput does it
+ * (cloudoutput.cpp:119-246; that class itself needs Qt, so its three loops are replayed here).
  */
 #include <cstdio>
 #include <cstdlib>
@@ -95,13 +99,14 @@ static void waitProgress()
 int main(int argc,char **argv)
 {
   int nthreads=1,opt;
-  bool canonical=false;
+  bool canonical=false,separateClasses=true;
   double tileSize=1;
-  string out="ref";
+  long pointsPerFile=0;
+  string out="ref",lasOut;
   maxSlope=1;
   thickness=0;
   minHyperboloidSize=0.1;
-  while ((opt=getopt(argc,argv,"t:cT:S:K:M:o:"))!=-1)
+  while ((opt=getopt(argc,argv,"t:cT:S:K:M:o:w:s:p:"))!=-1)
     switch (opt)
     {
       case 't': nthreads=atoi(optarg); break;
@@ -111,6 +116,9 @@ int main(int argc,char **argv)
       case 'K': thickness=atof(optarg); break;
       case 'M': minHyperboloidSize=atof(optarg); break;
       case 'o': out=optarg; break;
+      case 'w': lasOut=optarg; break;
+      case 's': separateClasses=atoi(optarg)!=0; break;
+      case 'p': pointsPerFile=atol(optarg); break;
       default: return 2;
     }
   if (nthreads<1)
@@ -250,6 +258,92 @@ int main(int argc,char **argv)
   {
     ofstream lf(out+".labels",ios::binary);
     lf.write((const char *)labels.data(),labels.size());
+  }
+  if (lasOut.size())
+  {
+    // WolkenCanvas::writeFile (wolkencanvas.cpp:582-625) + CloudOutput::openFiles/writeFiles/closeFiles
+    static const char *names[]={"raw","nonground","ground"};
+    vector<int> formats;
+    for (size_t i=0;i<headers.size();i++)
+      formats.push_back(headers[i].getPointFormat());
+    int pointFormat=joinPointFormat(formats);
+    xyz minCor(br.left(),br.bottom(),br.low()),maxCor(br.right(),br.top(),br.high());
+    xyz scale=combineScales(headers);
+    map<int,size_t> totals;
+    for (int64_t b=0;b<(int64_t)octStore.getNumBlocks();b++)
+    {
+      map<int,size_t> c=octStore.countClasses(b);
+      octStore.disown();
+      for (auto &j:c)
+        totals[j.first]+=j.second;
+    }
+    size_t grandTotal=0,quot;
+    int nDigits=0;
+    for (auto &j:totals)
+      grandTotal+=j.second;
+    int sysId=separateClasses?SI_EXTRACT:(headers.size()>1?SI_MERGE:SI_MODIFY);
+    if (pointsPerFile)
+    {
+      quot=(grandTotal+pointsPerFile-1)/pointsPerFile;
+      if (quot) quot--;
+      if (!quot) quot++;
+      while (quot) { quot/=10; nDigits++; }
+    }
+    map<int,deque<LasHeader> > outs;
+    auto openOne=[&](int cls,size_t i)
+    {
+      char num[32]="";
+      if (nDigits)
+        snprintf(num,sizeof(num),"%0*zu",nDigits,i);
+      string fn=lasOut+(cls>=0?string("-")+(cls<3?names[cls]:"other"):string())+(pointsPerFile?"-":"")+num+".las";
+      deque<LasHeader> &d=outs[cls<0?0:cls];
+      d.push_back(LasHeader());
+      d.back().openWrite(fn,sysId);
+      d.back().setUnit(1);
+      d.back().setScale(minCor,maxCor,scale);
+      d.back().setVersion(1,4);
+      d.back().setPointFormat(pointFormat);
+    };
+    if (separateClasses)
+      for (auto &j:totals)
+      {
+        quot=pointsPerFile?(j.second+pointsPerFile-1)/pointsPerFile:1;
+        for (size_t i=0;i<quot;i++)
+          openOne(j.first,i);
+      }
+    else
+    {
+      quot=pointsPerFile?(grandTotal+pointsPerFile-1)/pointsPerFile:1;
+      for (size_t i=0;i<quot;i++)
+        openOne(-1,i);
+    }
+    int nextBlocks[256];
+    for (int64_t b=0;b<(int64_t)octStore.getNumBlocks();b++)
+    {
+      for (auto &k:outs)
+      {
+        long long mn=grandTotal;
+        for (size_t j=0;j<k.second.size();j++)
+          if ((long long)k.second[j].numberPoints()<mn)
+          {
+            nextBlocks[k.first]=j;
+            mn=k.second[j].numberPoints();
+          }
+      }
+      vector<LasPoint> blk=octStore.getAll(b);
+      octStore.disown();
+      for (size_t j=0;j<blk.size();j++)
+      {
+        int cls=separateClasses?blk[j].classification:0;
+        outs[cls][nextBlocks[cls]].writePoint(blk[j]);
+      }
+    }
+    for (auto &k:outs)
+      for (size_t i=0;i<k.second.size();i++)
+      {
+        k.second[i].writeHeader();
+        k.second[i].close();
+      }
   }
   int sizeIndex=-1;
   for (int i=0;i<12;i++)

@@ -94,6 +94,7 @@ def lib():
             "wb_host_free": [vp],
             "wb_size_fit": [vp, C.c_int, dp, dp],
             "wb_bbox_cube": [vp, C.c_int, dp],
+            "wb_bound_rect": [vp, C.c_int, dp],
             "wb_snake_set_size": [C.c_double, C.c_double, dp, C.POINTER(C.c_int), C.POINTER(C.c_int)],
             "wb_ldecimal": [C.c_double, C.c_char_p, C.c_int],
             "wb_format_dump": [vp, u64, C.c_char_p, u64],
@@ -116,7 +117,7 @@ EXPORTS = ["wb_create", "wb_destroy", "wb_last_error", "wb_reserve", "wb_clear",
            "wb_run", "wb_get_stats", "wb_sync", "wb_host_alloc", "wb_host_free", "wb_size_fit", "wb_bbox_cube",
            "wb_snake_set_size", "wb_ldecimal", "wb_format_dump", "wb_add_points_device", "wb_export_points_device",
            "wb_set_own_range", "wb_export_tiles_device", "wb_import_tiles_device", "wb_max_hyperboloid_size",
-           "wb_assign", "wb_get_points_sorted", "wb_test_math"]
+           "wb_assign", "wb_get_points_sorted", "wb_test_math", "wb_bound_rect"]
 
 
 def _d(v):

@@ -75,6 +75,28 @@ inline void sizeFit(const double *c,int n,double center[3],double *sideOut)
   *sideOut=side;
 }
 
+inline void boundRect(const double *c,int n,double box[6])
+// BoundRect::include at orientation 0 (boundrect.cpp:60-73) over corners: {left,bottom,low,right,top,high}
+{
+  double b[6];
+  for (int k=0;k<6;k++)
+    b[k]=INFINITY;
+  for (int i=0;i<n;i++)
+  {
+    for (int k=0;k<4;k++)
+    {
+      int ang=(int)((unsigned)k*0x20000000u);
+      double s=(double)sinl(ang*M_PIl/1073741824.),co=(double)cosl(ang*M_PIl/1073741824.);
+      double v=c[3*i]*co+c[3*i+1]*s;
+      if (v<b[k]) b[k]=v;
+    }
+    if (c[3*i+2]<b[4]) b[4]=c[3*i+2];
+    if (-c[3*i+2]<b[5]) b[5]=-c[3*i+2];
+  }
+  box[0]=b[0]; box[1]=b[1]; box[2]=b[4];
+  box[3]=-b[2]; box[4]=-b[3]; box[5]=-b[5];
+}
+
 inline void bboxCube(const double *c,int n,double cube[4])
 // wolkencanvas.cpp:502-519: BoundRect over the header corners (boundrect.cpp:60-73, orientation 0;
 // xy::dirbound point.cpp:85-93 multiplies by the long-double-derived cos/sin of k*90 degrees),

@@ -1223,6 +1223,14 @@ extern "C" int wb_bbox_cube(const double *corners,int n,double cube[4])
   return WB_OK;
 }
 
+extern "C" int wb_bound_rect(const double *corners,int n,double box[6])
+{
+  if (!corners || !box)
+    return WB_ERR_ARG;
+  wbhost::boundRect(corners,n,box);
+  return WB_OK;
+}
+
 extern "C" int wb_snake_set_size(double cubeSide,double tileSize,double *spacing,int *lo,int *hi)
 {
   if (!spacing || !lo || !hi)

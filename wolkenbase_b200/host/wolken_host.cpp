@@ -15,6 +15,7 @@ using namespace std;
 
 Octree octRoot;
 OctStore octStore;
+CloudOutput cloudOutput;
 Flowsnake snake;
 TileTable tiles;
 map<int,size_t> classTotals;
@@ -293,9 +294,31 @@ LasHeader::LasHeader()
   pointFormat=pointLength=0;
   unit=1;
   zipFlag=false;
+  out=nullptr;
+  writePos=0;
   for (auto &v:nPoints)
     v=0;
   xScale=yScale=zScale=xOffset=yOffset=zOffset=maxX=minX=maxY=minY=maxZ=minZ=0;
+}
+
+LasHeader::LasHeader(const LasHeader &o)
+// member-wise, except that a copy never owns the mapping or the output stream
+{
+  filename=o.filename;
+  systemId=o.systemId;
+  map=nullptr;
+  mapLen=0;
+  out=nullptr;
+  versionMajor=o.versionMajor; versionMinor=o.versionMinor;
+  headerSize=o.headerSize; pointOffset=o.pointOffset;
+  pointFormat=o.pointFormat; pointLength=o.pointLength;
+  xScale=o.xScale; yScale=o.yScale; zScale=o.zScale;
+  xOffset=o.xOffset; yOffset=o.yOffset; zOffset=o.zOffset;
+  maxX=o.maxX; minX=o.minX; maxY=o.maxY; minY=o.minY; maxZ=o.maxZ; minZ=o.minZ;
+  unit=o.unit;
+  memcpy(nPoints,o.nPoints,sizeof(nPoints));
+  zipFlag=o.zipFlag;
+  writePos=o.writePos;
 }
 
 LasHeader::~LasHeader()
@@ -309,6 +332,9 @@ void LasHeader::close()
     munmap(map,mapLen);
   map=nullptr;
   mapLen=0;
+  if (out)
+    fclose(out);
+  out=nullptr;
 }
 
 template <typename T> static T rd(const uint8_t *p)
@@ -1009,5 +1035,423 @@ int writeClassified(const deque<LasHeader> &inputs,const OutputOptions &opt,vect
       if (written)
         written->push_back(o.name);
     }
+  return 0;
+}
+
+// ---------------------------------------------------------------- the reference's writer, restated
+static const short kPointLengths[]={20,28,26,34,57,63,30,36,38,59,67};           // las.cpp:38
+static const short kPointFeatures[]={0x0,0x1,0x2,0x3,0x9,0xb,0x101,0x103,0x107,0x109,0x10f};
+
+int joinPointFormat(vector<int> formats)
+{
+  int all=0,ret=0;
+  for (int f:formats)
+    if (f>=0 && f<11)
+      all|=kPointFeatures[f];
+  for (int i=0;i<11;i++)
+    if ((all|kPointFeatures[i])==kPointFeatures[i])
+    {
+      ret=i;
+      break;
+    }
+  return ret;
+}
+
+static double pairwiseSum(const vector<double> &a)
+// manysum.cpp:120-154: perfect trees over aligned power-of-two blocks, merged smallest block first
+{
+  double lv[32],sum=0;
+  size_t n=a.size();
+  for (size_t i=0;i<n;i++)
+  {
+    double v=a[i];
+    size_t m=i;
+    int l=0;
+    while (m&1) { v=lv[l]+v; m>>=1; l++; }
+    lv[l]=v;
+  }
+  for (int l=0;l<32;l++)
+    if ((n>>l)&1)
+      sum+=lv[l];
+  return sum;
+}
+
+static void bubbleUp(vector<double> &v)
+{
+  for (size_t i=0;i+1<v.size();i++)
+    if (v[i]>v[i+1])
+      swap(v[i],v[i+1]);
+}
+
+static void bubbleDown(vector<double> &v)
+{
+  for (int i=(int)v.size()-2;i>=0;i--)
+    if (v[i]>v[i+1])
+      swap(v[i],v[i+1]);
+}
+
+static double manyGcd(vector<double> numbers,double toler)
+// manygcd.cpp:41-76
+{
+  for (auto &x:numbers)
+    x=fabs(x);
+  if (numbers.empty())
+    return 0;
+  bubbleUp(numbers);
+  bubbleDown(numbers);
+  bubbleUp(numbers);
+  while (numbers.size() && numbers.back()>numbers[0]+toler)
+  {
+    size_t sz=numbers.size();
+    if (numbers[sz-1]-numbers[sz-2]>toler)
+    {
+      numbers[sz-1]-=numbers[sz-2];
+      bubbleDown(numbers);
+    }
+    else
+      numbers.resize(sz-1);
+    bubbleUp(numbers);
+  }
+  return numbers.size()?pairwiseSum(numbers)/numbers.size():0;
+}
+
+static double combine1Scale(vector<double> &scales,vector<double> &offsets)
+// las.cpp:906-925
+{
+  double toler=INFINITY,ret=0;
+  for (double s:scales)
+    if (fabs(s)<toler)
+      toler=fabs(s);
+  toler/=1e6;
+  double scalegcd=manyGcd(scales,toler),offsetgcd=manyGcd(offsets,toler);
+  if ((offsetgcd>10.5*scalegcd || offsetgcd==0) && fabs(offsetgcd/scalegcd-rint(offsetgcd/scalegcd))<1e-6)
+    ret=scalegcd;
+  for (int i=10;i>0;i--)
+    for (int j=10;j>0;j--)
+      if (fabs(scalegcd*i-offsetgcd*j)<toler)
+        ret=scalegcd/j;
+  return ret;
+}
+
+xyz combineScales(const deque<LasHeader> &headers)
+{
+  vector<double> xs,xo,ys,yo,zs,zo;
+  for (auto &h:headers)
+  {
+    xyz s=h.getScale(),o=h.getOffset();
+    xs.push_back(s.getx()); xo.push_back(o.getx());
+    ys.push_back(s.gety()); yo.push_back(o.gety());
+    zs.push_back(s.getz()); zo.push_back(o.getz());
+  }
+  return xyz(combine1Scale(xs,xo),combine1Scale(ys,yo),combine1Scale(zs,zo));
+}
+
+void LasHeader::openWrite(string fileName,int sysId)
+{
+  close();
+  filename=fileName;
+  out=fopen(fileName.c_str(),"wb+");
+  switch (sysId)
+  {
+    case SI_MERGE: systemId="MERGE"; break;
+    case SI_MODIFY: systemId="MODIFICATION"; break;
+    case SI_EXTRACT: systemId="EXTRACTION"; break;
+    case SI_TEST: systemId="TEST"; break;
+    default: systemId="OTHER";
+  }
+  versionMajor=1;
+  versionMinor=4;
+  xScale=yScale=zScale=0;
+  xOffset=yOffset=zOffset=NAN;
+  pointFormat=pointLength=0;
+  maxX=maxY=maxZ=-INFINITY;
+  minX=minY=minZ=INFINITY;
+  for (auto &v:nPoints)
+    v=0;
+}
+
+void LasHeader::setVersion(int major,int minor)
+{
+  versionMajor=major;
+  versionMinor=minor;
+  headerSize=major==1?(minor<4?0xe3:0x177):0;
+  writePos=pointOffset=headerSize;
+}
+
+void LasHeader::setPointFormat(int format)
+{
+  pointFormat=format;
+  pointLength=(format>=0 && format<11)?kPointLengths[format]:0;
+}
+
+void LasHeader::setScale(xyz minCor,xyz maxCor,xyz scale)
+// las.cpp:636-673
+{
+  auto one=[&](double mn,double mx,double sc,double &outScale,double &outOffset)
+  {
+    double minScale=(mx-mn)/4132485216.;
+    outOffset=(mn+mx)/2/unit;
+    if (sc>minScale && std::isfinite(sc))
+    {
+      outScale=sc/unit;
+      outOffset=rint(outOffset/outScale)*outScale;
+    }
+    else
+      outScale=minScale/unit;
+  };
+  one(minCor.getx(),maxCor.getx(),scale.getx(),xScale,xOffset);
+  one(minCor.gety(),maxCor.gety(),scale.gety(),yScale,yOffset);
+  one(minCor.getz(),maxCor.getz(),scale.getz(),zScale,zOffset);
+}
+
+static double binToDeg(int angle)
+{
+  return angle/2147483648.*360;
+}
+
+template <typename T> static void put(vector<uint8_t> &b,size_t o,T v)
+{
+  memcpy(&b[o],&v,sizeof(T));
+}
+
+void LasHeader::writePoint(const LasPoint &pnt)
+// las.cpp:822-904
+{
+  if (!out)
+    return;
+  vector<uint8_t> r(pointLength,0);
+  int xi=(int)lrint((pnt.location.getx()/unit-xOffset)/xScale);
+  int yi=(int)lrint((pnt.location.gety()/unit-yOffset)/yScale);
+  int zi=(int)lrint((pnt.location.getz()/unit-zOffset)/zScale);
+  put<int32_t>(r,0,xi); put<int32_t>(r,4,yi); put<int32_t>(r,8,zi);
+  double wx=xi*xScale+xOffset,wy=yi*yScale+yOffset,wz=zi*zScale+zOffset;
+  if (wx>maxX) maxX=wx;
+  if (wx<minX) minX=wx;
+  if (wy>maxY) maxY=wy;
+  if (wy<minY) minY=wy;
+  if (wz>maxZ) maxZ=wz;
+  if (wz<minZ) minZ=wz;
+  put<uint16_t>(r,12,pnt.intensity);
+  size_t o;
+  if (pointFormat<6)
+  {
+    r[14]=(uint8_t)((pnt.returnNum&7)+((pnt.nReturns&7)<<3)+((pnt.scanDirection&1)<<6)+((pnt.edgeLine&1)<<7));
+    r[15]=(uint8_t)((pnt.classification&31)+((pnt.classificationFlags&7)<<5));
+    r[16]=(uint8_t)lrint(binToDeg(pnt.scanAngle));
+    r[17]=(uint8_t)pnt.userData;
+    put<uint16_t>(r,18,pnt.pointSource);
+    o=20;
+  }
+  else
+  {
+    r[14]=(uint8_t)((pnt.returnNum&15)+((pnt.nReturns&15)<<4));
+    r[15]=(uint8_t)((pnt.classificationFlags&15)+((pnt.scannerChannel&3)<<4)+((pnt.scanDirection&1)<<6)+((pnt.edgeLine&1)<<7));
+    r[16]=(uint8_t)pnt.classification;
+    r[17]=(uint8_t)pnt.userData;
+    put<int16_t>(r,18,(int16_t)lrint(binToDeg(pnt.scanAngle)/0.006));
+    put<uint16_t>(r,20,pnt.pointSource);
+    o=22;
+  }
+  if ((1<<pointFormat)&0x7fa)
+  {
+    put<double>(r,o,pnt.gpsTime);
+    o+=8;
+  }
+  if ((1<<pointFormat)&0x5ac)
+  {
+    put<uint16_t>(r,o,pnt.red); put<uint16_t>(r,o+2,pnt.green); put<uint16_t>(r,o+4,pnt.blue);
+    o+=6;
+  }
+  if ((1<<pointFormat)&0x500)
+    put<uint16_t>(r,o,pnt.nir);
+  fseek(out,(long)writePos,SEEK_SET);
+  fwrite(r.data(),1,r.size(),out);
+  nPoints[0]++;
+  if (pnt.returnNum>0 && pnt.returnNum<16)
+    nPoints[pnt.returnNum]++;
+  writePos+=pointLength;
+}
+
+void LasHeader::writeHeader()
+// las.cpp:540-595.  Fields the reference never initialises on the write path (source id, global
+// encoding, GUID, start of waveform data) are written as zeros.
+{
+  if (!out)
+    return;
+  vector<uint8_t> h(headerSize,0);
+  memcpy(&h[0],"LASF",4);
+  h[24]=(uint8_t)versionMajor;
+  h[25]=(uint8_t)versionMinor;
+  memcpy(&h[26],systemId.c_str(),min<size_t>(32,systemId.size()));
+  const char *sw="wolkenbase_b200 (Wolkenbase 0.1.2~alpha)";
+  memcpy(&h[58],sw,min<size_t>(32,strlen(sw)));
+  time_t now=time(nullptr);
+  tm *ptm=gmtime(&now);
+  put<uint16_t>(h,90,(uint16_t)(ptm->tm_yday+1));
+  put<uint16_t>(h,92,(uint16_t)(ptm->tm_year+1900));
+  put<uint16_t>(h,94,(uint16_t)headerSize);
+  put<uint32_t>(h,96,pointOffset);
+  put<uint32_t>(h,100,0);
+  h[104]=(uint8_t)pointFormat;
+  put<uint16_t>(h,105,pointLength);
+  bool legacyValid=true;
+  for (int i=0;i<6;i++)
+    if (nPoints[i]>4294967295ull)
+      legacyValid=false;
+  for (int i=6;i<16;i++)
+    if (nPoints[i]>0)
+      legacyValid=false;
+  for (int i=0;i<6;i++)
+    put<uint32_t>(h,107+4*i,legacyValid?(uint32_t)nPoints[i]:0);
+  put<double>(h,131,xScale); put<double>(h,139,yScale); put<double>(h,147,zScale);
+  put<double>(h,155,xOffset); put<double>(h,163,yOffset); put<double>(h,171,zOffset);
+  put<double>(h,179,maxX); put<double>(h,187,minX); put<double>(h,195,maxY);
+  put<double>(h,203,minY); put<double>(h,211,maxZ); put<double>(h,219,minZ);
+  if (headerSize>0xe3)
+  {
+    put<uint64_t>(h,227,0);
+    put<uint64_t>(h,235,(uint64_t)writePos);
+    put<uint32_t>(h,243,0);
+    for (int i=0;i<16;i++)
+      put<uint64_t>(h,247+8*i,(uint64_t)nPoints[i]);
+  }
+  fseek(out,0,SEEK_SET);
+  fwrite(h.data(),1,h.size(),out);
+  fflush(out);
+}
+
+string CloudOutput::className(int n)
+{
+  return ::className(n);
+}
+
+static string nDecimal(long n,int dig)
+{
+  char buf[24]="";
+  if (dig)
+    snprintf(buf,sizeof(buf),"%0*ld",dig,n);
+  return buf;
+}
+
+void CloudOutput::openFiles(string name,map<int,size_t> totals)
+// cloudoutput.cpp:119-185
+{
+  int sysId=separateClasses?SI_EXTRACT:(nInputFiles>1?SI_MERGE:SI_MODIFY),nDigits=0;
+  size_t quot;
+  grandTotal=0;
+  written.clear();
+  for (auto &j:totals)
+    grandTotal+=j.second;
+  if (pointsPerFile)
+  {
+    quot=(grandTotal+pointsPerFile-1)/pointsPerFile;
+    if (quot) quot--;
+    if (!quot) quot++;
+    while (quot) { quot/=10; nDigits++; }
+  }
+  auto openOne=[&](int cls,size_t i)
+  {
+    string fn=name+(cls>=0?"-"+className(cls):string())+(pointsPerFile?"-":"")+nDecimal((long)i,nDigits)+".las";
+    deque<LasHeader> &d=headers[cls<0?0:cls];
+    d.emplace_back();
+    d.back().openWrite(fn,sysId);
+    d.back().setUnit(unit);
+    d.back().setScale(minCor,maxCor,scale);
+    d.back().setVersion(1,4);
+    d.back().setPointFormat(pointFormat);
+    written.push_back(fn);
+  };
+  if (separateClasses)
+    for (auto &j:totals)
+    {
+      quot=pointsPerFile?(j.second+pointsPerFile-1)/pointsPerFile:1;
+      for (size_t i=0;i<quot;i++)
+        openOne(j.first,i);
+    }
+  else
+  {
+    quot=pointsPerFile?(grandTotal+pointsPerFile-1)/pointsPerFile:1;
+    for (size_t i=0;i<quot;i++)
+      openOne(-1,i);
+  }
+}
+
+void CloudOutput::writeFiles()
+// cloudoutput.cpp:187-229: block by block, each class's points go to that class's least-full file
+{
+  int nextBlocks[256];
+  for (size_t i=0;i<octStore.getNumBlocks();i++)
+  {
+    for (auto &k:headers)
+    {
+      long long mn=(long long)grandTotal;
+      for (size_t j=0;j<k.second.size();j++)
+        if ((long long)k.second[j].numberPoints()<mn)
+        {
+          nextBlocks[k.first]=(int)j;
+          mn=(long long)k.second[j].numberPoints();
+        }
+    }
+    for (auto &p:octStore.getAll((int64_t)i))
+    {
+      int cls=separateClasses?p.classification:0;
+      auto it=headers.find(cls);
+      if (it!=headers.end() && !it->second.empty())
+        it->second[nextBlocks[cls]].writePoint(p);
+    }
+  }
+}
+
+void CloudOutput::closeFiles()
+{
+  for (auto &k:headers)
+  {
+    for (auto &h:k.second)
+    {
+      h.writeHeader();
+      h.close();
+    }
+    k.second.clear();
+  }
+  headers.clear();
+}
+
+int writeReferenceStyle(const deque<LasHeader> &inputs,const OutputOptions &opt,vector<string> *written)
+// WolkenCanvas::writeFile (wolkencanvas.cpp:582-625) without the GUI: joined point format, combined
+// scale, bounding box of the header corners, then CloudOutput open/write/close.
+{
+  if (inputs.empty() || !g_classified)
+    return -1;
+  vector<int> formats;
+  vector<double> c;
+  for (auto &h:inputs)
+  {
+    formats.push_back(h.getPointFormat());
+    xyz a=h.minCorner(),b=h.maxCorner();
+    c.push_back(a.getx()); c.push_back(a.gety()); c.push_back(a.getz());
+    c.push_back(b.getx()); c.push_back(b.gety()); c.push_back(b.getz());
+  }
+  double box[6];
+  wb_bound_rect(c.data(),(int)(c.size()/3),box);
+  cloudOutput.pointFormat=joinPointFormat(formats);
+  cloudOutput.minCor=xyz(box[0],box[1],box[2]);
+  cloudOutput.maxCor=xyz(box[3],box[4],box[5]);
+  cloudOutput.scale=combineScales(inputs);
+  cloudOutput.nInputFiles=(int)inputs.size();
+  cloudOutput.pointsPerFile=(int)opt.pointsPerFile;
+  cloudOutput.separateClasses=opt.separateClasses;
+  cloudOutput.unit=inputs[0].getUnit();
+  map<int,size_t> totals=classTotals;
+  if (totals.empty())
+  {
+    ensureLabels();
+    for (uint8_t l:g_labels)
+      totals[l]++;
+  }
+  cloudOutput.openFiles(opt.baseName,totals);
+  cloudOutput.writeFiles();
+  cloudOutput.closeFiles();
+  if (written)
+    *written=cloudOutput.written;
   return 0;
 }

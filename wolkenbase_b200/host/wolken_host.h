@@ -165,7 +165,7 @@ class LasHeader
 public:
   LasHeader();
   ~LasHeader();
-  LasHeader(const LasHeader &)=delete;
+  LasHeader(const LasHeader &o);                    // the reference copies headers into deques; only closed/unopened ones
   LasHeader &operator=(const LasHeader &)=delete;
   void openRead(std::string fileName);
   bool isValid() const;
@@ -182,6 +182,13 @@ public:
   xyz getOffset() const { return xyz(xOffset*unit,yOffset*unit,zOffset*unit); }
   xyz minCorner() const { return xyz(minX*unit,minY*unit,minZ*unit); }
   xyz maxCorner() const { return xyz(maxX*unit,maxY*unit,maxZ*unit); }
+  // write side (las.cpp:456-514, 540-595, 613-673, 822-904)
+  void openWrite(std::string fileName,int sysId);
+  void setVersion(int major,int minor);
+  void setPointFormat(int format);
+  void setScale(xyz minCor,xyz maxCor,xyz scale);
+  void writePoint(const LasPoint &pnt);
+  void writeHeader();
   LasPoint readPoint(size_t num);                   // throws int -1 past the end, like the reference
   const uint8_t *records() const { return map?map+pointOffset:nullptr; }
   const uint8_t *headerBytes() const { return map; }
@@ -198,7 +205,37 @@ private:
   double xScale,yScale,zScale,xOffset,yOffset,zOffset,maxX,minX,maxY,minY,maxZ,minZ,unit;
   size_t nPoints[16];
   bool zipFlag;
+  FILE *out;
+  size_t writePos;
+  std::string systemId;
 };
+
+#define SI_MERGE 0
+#define SI_MODIFY 1
+#define SI_EXTRACT 2
+#define SI_TEST 3
+int joinPointFormat(std::vector<int> formats);      // las.cpp:103-119
+xyz combineScales(const std::deque<LasHeader> &headers);   // las.cpp:906-944
+
+class CloudOutput                                    // cloudoutput.h:30-48, without Qt
+{
+public:
+  xyz minCor,maxCor,scale;
+  int nInputFiles=0;
+  size_t grandTotal=0;
+  int pointsPerFile=0;                               // 0 means no limit
+  int pointFormat=0;
+  bool separateClasses=true,writeLaz=false;
+  double unit=1;
+  std::string className(int n);
+  void openFiles(std::string name,std::map<int,size_t> classTotals);
+  void writeFiles();
+  void closeFiles();
+  std::vector<std::string> written;
+private:
+  std::map<int,std::deque<LasHeader> > headers;
+};
+extern CloudOutput cloudOutput;
 
 // ---------------------------------------------------------------- eisenstein.h / flowsnake.h / tile.h
 class Eisenstein
@@ -350,5 +387,8 @@ struct OutputOptions
   bool separateClasses=true;                        // mainwindow.cpp:398-411 defaults
   size_t pointsPerFile=0;
 };
+// Lossless writer: the inputs' own records with the class byte replaced (no re-quantisation).
 int writeClassified(const std::deque<LasHeader> &inputs,const OutputOptions &opt,std::vector<std::string> *written);
+// The reference's writer (CloudOutput: LAS 1.4, joined point format, combined scale, re-quantised XYZ).
+int writeReferenceStyle(const std::deque<LasHeader> &inputs,const OutputOptions &opt,std::vector<std::string> *written);
 #endif

@@ -8,6 +8,8 @@
 //     --separate-classes 0|1     one file per class (default 1, as the GUI)
 //     --threads N                accepted for compatibility, ignored
 //     --dump FILE                where to write the octree dump (default "dumpfile")
+//     --lossless                 keep the inputs' own records (format, scale, offset) and only replace the class
+//                                byte, instead of the reference's LAS 1.4 re-encoding (CloudOutput)
 #include <cstdlib>
 #include <cstring>
 #include <deque>
@@ -22,7 +24,7 @@ int main(int argc,char **argv)
   vector<string> inputFiles;
   OutputOptions out;
   string dumpName="dumpfile";
-  bool classify=false;
+  bool classify=false,lossless=false;
   for (int i=1;i<argc;i++)
   {
     string a=argv[i];
@@ -36,6 +38,7 @@ int main(int argc,char **argv)
     else if (a=="--separate-classes") out.separateClasses=atoi(val())!=0;
     else if (a=="--threads" || a=="--gpus") val();
     else if (a=="--dump") dumpName=val();
+    else if (a=="--lossless") lossless=true;
     else if (a.size() && a[0]=='-') { cerr<<"unknown option "<<a<<endl; return 2; }
     else inputFiles.push_back(a);
   }
@@ -109,7 +112,7 @@ int main(int argc,char **argv)
     for (auto &j:classTotals)
       cout<<j.first<<' '<<j.second<<endl;
     vector<string> written;
-    int rc=writeClassified(files,out,&written);
+    int rc=lossless?writeClassified(files,out,&written):writeReferenceStyle(files,out,&written);
     if (rc)
       return 5;
     for (auto &w:written)
