@@ -223,6 +223,11 @@ def run_ours(args):
         "roofline_sort": {"bound": "hbm", "kernel": "radix sort (8 passes)", "achieved": sort_bytes / (sort_ms * 1e-3) / 1e9
                           if sort_ms > 0 else 0.0, "peak": hbm, "unit": "GB/s",
                           "frac": (sort_bytes / (sort_ms * 1e-3) / 1e9 / hbm) if sort_ms > 0 else 0.0},
+        "roofline_decode": {"bound": "hbm", "kernel": "wb_decode_kernel", "achieved": (rec_len + 14.0) * n / (phase.get("ms_decode", 0.0) * 1e-3) / 1e9
+                            if phase.get("ms_decode", 0.0) > 0 else 0.0, "peak": hbm, "unit": "GB/s",
+                            "frac": ((rec_len + 14.0) * n / (phase.get("ms_decode", 0.0) * 1e-3) / 1e9 / hbm)
+                            if phase.get("ms_decode", 0.0) > 0 else 0.0,
+                            "note": "L+14 B/point: record read, 3 x int32 + class + return number written"},
         "e2e": {"value": n / dte, "unit": UNIT, "h2d_bytes_per_step": n * rec_len, "d2h_bytes_per_step": n,
                 "ms_per_step": dte * 1e3, "ms_h2d_decode": ste["ms_h2d"], "ms_d2h": ste["ms_d2h"]},
         "gpu_launches": int(launches),
