@@ -10,7 +10,12 @@
 #include <cuda_runtime.h>
 
 #define WB_SORT_THREADS 256
+#ifndef WB_SORT_ITEMS
 #define WB_SORT_ITEMS 12
+#endif
+#ifndef WB_SORT_MINBLOCKS
+#define WB_SORT_MINBLOCKS 4        // 64 registers: 4 CTAs/SM (measured 3 -> 4: 10.5 -> 8.8 ms for 8 passes over 1e8 pairs)
+#endif
 #define WB_SORT_TILE (WB_SORT_THREADS*WB_SORT_ITEMS)
 #define WB_SORT_WARPS (WB_SORT_THREADS/32)
 
@@ -147,7 +152,7 @@ wb_sort_upsweep_kernel(const uint64_t *__restrict__ keys,uint64_t n,int shift,
   table[(uint64_t)threadIdx.x*nBlocks+blockIdx.x]=hist[threadIdx.x];
 }
 
-__global__ void __launch_bounds__(WB_SORT_THREADS,3)
+__global__ void __launch_bounds__(WB_SORT_THREADS,WB_SORT_MINBLOCKS)
 wb_sort_downsweep_kernel(const uint64_t *__restrict__ keysIn,const uint32_t *__restrict__ valsIn,
                          uint64_t *__restrict__ keysOut,uint32_t *__restrict__ valsOut,
                          uint64_t n,int shift,const uint32_t *__restrict__ table,uint32_t nBlocks)
