@@ -78,6 +78,8 @@ typedef struct wb_stats
 {
   uint64_t n_points;                /* points in the store (after return-number-0 dropping) */
   uint64_t n_dropped;               /* records dropped by the return-number rule, threads.cpp:527-530 */
+  uint64_t n_duplicates;            /* records whose XYZ equals an earlier point's: not stored (octree.cpp:620-662);
+                                       they receive the stored point's class */
   uint64_t n_leaves;
   uint64_t n_tiles_nonempty;
   uint64_t n_memberships;           /* (point,tile) pairs = sum of tile nPoints */

@@ -28,6 +28,9 @@ CASES = [  # name, scene, n, seed, params
     ("terrestrial_40k", 4, 40000, 4, {}),
     ("aerial_30k_thick", 2, 30000, 7, {"thickness": 0.05, "max_slope": 0.7, "tile_size": 2.0,
                                        "min_hyperboloid_size": 0.2}),
+    # 400 records share their XYZ with another record: the reference keeps one point per location
+    # (octree.cpp:620-662); the lost records read 255 in ref_labels
+    ("aerial_20k_dups", 2, 20000, 77, {"dups": 400}),
 ]
 
 
@@ -47,6 +50,10 @@ def run_ref(las_paths, out_prefix, p):
 
 def compare(name, scene, n, seed, p, golden_dir=None):
     cloud = synth.generate(scene, n, seed=seed)
+    p = dict(p)
+    dups = p.pop("dups", 0)
+    if dups:
+        cloud = synth.with_duplicates(cloud, dups, seed)
     with tempfile.TemporaryDirectory() as td:
         las = os.path.join(td, name + ".las")
         cloud.write(las)
@@ -70,7 +77,10 @@ def compare(name, scene, n, seed, p, golden_dir=None):
             rep["tile_%s_bitexact" % fld] = int((a.view(np.uint64) != b.view(np.uint64)).sum())
     else:
         ok = False
-    mism = int((res.labels != rlabels).sum())
+    stored = rlabels != 255                      # lost duplicates were never stored
+    rep["duplicates"] = [int(res.n_duplicates), int(info["duplicates"]), int((~stored).sum())]
+    ok = ok and len(set(rep["duplicates"])) == 1
+    mism = int((res.labels[stored] != rlabels[stored]).sum())
     rep["label_mismatch"] = mism
     rep["labels_hist"] = np.bincount(rlabels, minlength=3)[:3].tolist()
     rep["margin_points"] = int(res.margin_count)
@@ -83,7 +93,7 @@ def compare(name, scene, n, seed, p, golden_dir=None):
     if golden_dir and ok:
         os.makedirs(golden_dir, exist_ok=True)
         np.savez_compressed(os.path.join(golden_dir, name + ".npz"),
-                            scene=scene, n=n, seed=seed, params=json.dumps(p),
+                            scene=scene, n=n, seed=seed, params=json.dumps(p), dups=dups,
                             ref_dump=np.frombuffer(rdump.encode("utf-8"), dtype=np.uint8),
                             ref_labels=rlabels, ref_tiles=rtiles,
                             ref_root=np.array(info["root_center"] + [info["root_side"]]),

@@ -160,10 +160,22 @@ def run(files, tile_size=1.0, max_slope=1.0, thickness=0.0, min_hyperboloid_size
         cls_list.append(cls[keep])
         corners.append([c * unit for c in f["min"]])
         corners.append([c * unit for c in f["max"]])
-    pts = np.ascontiguousarray(np.concatenate(pts_list)) if pts_list else np.zeros((0, 3))
+    pts_all = np.ascontiguousarray(np.concatenate(pts_list)) if pts_list else np.zeros((0, 3))
     corners = np.ascontiguousarray(np.array(corners, dtype=np.float64))
-    n = pts.shape[0]
     res = Result()
+    # OctBuffer::put (octree.cpp:620-662) overwrites a stored point whose location is identical:
+    # of several points with the same XYZ only one stays in the store (at the position of the first
+    # inserted, i.e. the lowest input index in canonical order).  The others are "lost"; here they
+    # simply inherit the survivor's label.
+    _, first_idx, inverse = np.unique(pts_all, axis=0, return_index=True, return_inverse=True)
+    inverse = inverse.reshape(-1)
+    rep = first_idx[inverse]                       # input index of each point's representative
+    is_rep = rep == np.arange(len(pts_all))
+    res.n_duplicates = int((~is_rep).sum())
+    res.representative = rep
+    rep_rank = np.cumsum(is_rep) - 1                # index among the kept points
+    pts = np.ascontiguousarray(pts_all[is_rep])
+    n = pts.shape[0]
     center = (C.c_double * 3)()
     side = C.c_double()
     L.wbo_size_fit(corners.ctypes.data, len(corners), center, C.byref(side))
@@ -179,6 +191,7 @@ def run(files, tile_size=1.0, max_slope=1.0, thickness=0.0, min_hyperboloid_size
     order = np.empty(n, dtype=np.uint32)
     L.wbo_sort(pts.ctypes.data, n, center, side.value, keys.ctypes.data, order.ctypes.data)
     res.keys, res.order = keys, order
+    res.order_input = np.nonzero(is_rep)[0][order]  # canonical order in terms of ORIGINAL input indices
     cap = max(16, n // 32 + 16)
     leaves = np.zeros(cap, dtype=LEAF_DTYPE)
     nl = L.wbo_leaves(keys.ctypes.data, n, center, side.value, leaves.ctypes.data, cap)
@@ -205,7 +218,8 @@ def run(files, tile_size=1.0, max_slope=1.0, thickness=0.0, min_hyperboloid_size
         labels = np.zeros(n, dtype=np.uint8)
         labels[order] = lab_sorted
         res.labels_sorted = lab_sorted
-        res.labels = labels
+        res.labels_kept = labels                    # one per distinct location
+        res.labels = labels[rep_rank[rep]]          # one per input point (duplicates share the survivor's)
         res.margin_count = margins.value
     return res
 

@@ -49,9 +49,11 @@ def _check_against_oracle(ctx, clouds, params, res=None):
     ints = np.concatenate([c.ints() for c in clouds])
     assert (x == ints[:, 0]).all() and (y == ints[:, 1]).all() and (z == ints[:, 2]).all()
     # K2/K3 order: bit-exact keys and permutation
-    order, keys = ctx.order(n)
+    nv = ctx.stats()["n_points"]              # stored points: records minus dropped and lost ones
+    assert nv == len(res.keys)
+    order, keys = (a[:nv] for a in ctx.order(n))
     assert (keys == res.keys).all()
-    assert (order == res.order).all()
+    assert (order == res.order_input).all()
     # K4 leaves: byte-identical dump
     assert ctx.dump() == res.dump
     lv = ctx.leaves()
@@ -88,6 +90,27 @@ def test_pipeline_matches_oracle(ctx, scene, n, seed):
     assert rep["mismatch"] == 0
 
 
+def test_identical_locations(ctx):
+    """OctBuffer::put (octree.cpp:620-662) keeps one point per XYZ: the dump, the order, the tile
+    counts and the labels follow the reference on clouds with pairs, longer chains and a file read twice."""
+    base = synth.generate(2, 20000, seed=31)
+    few = synth.with_duplicates(base, 300, 1)
+    rep = _check_against_oracle(ctx, [few], {})
+    assert rep["mismatch"] == 0 and 250 < rep["stats"]["n_duplicates"] <= 300
+    many = synth.with_duplicates(synth.with_duplicates(base, 15000, 2), 15000, 3)      # chains of 3 and more
+    rep = _check_against_oracle(ctx, [many], {})
+    assert rep["mismatch"] == 0 and rep["stats"]["n_duplicates"] > 9000         # multiplicities up to 10
+    assert rep["stats"]["n_points"] + rep["stats"]["n_duplicates"] == base.n
+    # the same file twice: every point of the second copy is lost, and gets the first copy's class
+    rep = _check_against_oracle(ctx, [base, base], {})
+    assert rep["mismatch"] == 0 and rep["stats"]["n_duplicates"] == base.n
+    lab = ctx.labels(2 * base.n)
+    assert (lab[:base.n] == lab[base.n:]).all()
+    # and the context is clean afterwards
+    rep = _check_against_oracle(ctx, [base], {})
+    assert rep["mismatch"] == 0 and rep["stats"]["n_duplicates"] == 0
+
+
 def test_nondefault_params(ctx):
     cloud = synth.generate(2, 30000, seed=7)
     p = {"thickness": 0.05, "max_slope": 0.7, "tile_size": 2.0, "min_hyperboloid_size": 0.2}
@@ -101,6 +124,9 @@ def test_matches_compiled_reference_fixture(ctx, case, golden_dir):
     g = np.load(os.path.join(golden_dir, case + ".npz"))
     p = json.loads(str(g["params"]))
     cloud = synth.generate(int(g["scene"]), int(g["n"]), seed=int(g["seed"]))
+    dups = int(g["dups"]) if "dups" in g else 0
+    if dups:
+        cloud = synth.with_duplicates(cloud, dups, int(g["seed"]))
     n = _run_gpu(ctx, [cloud], p)
     assert ctx.dump() == bytes(g["ref_dump"]).decode("utf-8")
     t, rt = ctx.tiles(), g["ref_tiles"]
@@ -109,7 +135,9 @@ def test_matches_compiled_reference_fixture(ctx, case, golden_dir):
         assert (t[f] == rt[f]).all(), f
     assert np.abs(t["hyperboloidSize"].view(np.int64) - rt["hyperboloidSize"].view(np.int64)).max() <= 4
     lab = ctx.labels(n)
-    mism = int((lab != g["ref_labels"]).sum())
+    stored = g["ref_labels"] != 255          # records the reference lost to an identical location
+    assert int((~stored).sum()) == ctx.stats()["n_duplicates"]
+    mism = int((lab[stored] != g["ref_labels"][stored]).sum())
     assert mism <= ctx.stats()["n_margin"], mism
 
 

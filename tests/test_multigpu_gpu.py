@@ -24,14 +24,17 @@ def _single(clouds, params):
     return lab, tiles
 
 
-@pytest.mark.parametrize("world,scene,n", [(2, 2, 60000), (3, 2, 90000), (4, 5, 60000)])
-def test_sharded_equals_single(world, scene, n):
+@pytest.mark.parametrize("world,scene,n,dups", [(2, 2, 60000, 0), (3, 2, 90000, 0), (4, 5, 60000, 0),
+                                                (2, 2, 40000, 2000)])
+def test_sharded_equals_single(world, scene, n, dups):
     d = synth.describe(scene, n)
     cuts = [d.grid_nx * k // world for k in range(world + 1)]
     clouds, base = [], 0
     for k in range(world):
         c = synth.generate(scene, n, seed=31, region=(cuts[k], 0, cuts[k + 1] - cuts[k], d.grid_ny), gps_base=base)
         base += c.n
+        if dups:                         # identical locations inside a strip (and so inside its halos)
+            c = synth.with_duplicates(c, dups, k)
         clouds.append(c)
     params = dict(tile_size=1.0, max_slope=1.0, thickness=0.0, min_hyperboloid_size=0.1)
     want, tiles = _single(clouds, params)

@@ -29,7 +29,7 @@ class Geometry(C.Structure):
 
 
 class Stats(C.Structure):
-    _fields_ = [(k, C.c_uint64) for k in ("n_points", "n_dropped", "n_leaves", "n_tiles_nonempty",
+    _fields_ = [(k, C.c_uint64) for k in ("n_points", "n_dropped", "n_duplicates", "n_leaves", "n_tiles_nonempty",
                                           "n_memberships", "n_margin", "n_untiled", "n_second_walk",
                                           "cl_nodes", "cl_chunks", "cl_pairs", "cl_nodes2", "cl_chunks2",
                                           "cl_pairs2", "cl_warps2", "kernel_launches")] + \

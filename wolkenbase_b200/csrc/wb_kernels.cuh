@@ -1443,6 +1443,86 @@ finish:
   }
 }
 
+// ============================================================================ K3b: identical locations
+// OctBuffer::put (octree.cpp:620-662) overwrites a stored point whose location equals the new one:
+// of several points with one XYZ a single point stays in the store, at the position of the first
+// inserted (lowest input index in canonical order).  Equal locations have equal keys, so the search
+// stays inside a run of equal keys.  The survivors keep the canonical order; the others are moved
+// behind them (key WB_KEY_DUP, stable re-sort) and later receive the survivor's label.
+#define WB_KEY_DUP 0xfffffffffffffffeull
+
+__global__ void __launch_bounds__(256)
+wb_dup_find_kernel(const unsigned long long *__restrict__ keys,const double *__restrict__ sx,
+                   const double *__restrict__ sy,const double *__restrict__ sz,unsigned long long nv,
+                   uint32_t *__restrict__ flag,uint32_t *__restrict__ prev,unsigned long long *__restrict__ count)
+{
+  unsigned long long j=(unsigned long long)blockIdx.x*blockDim.x+threadIdx.x;
+  if (j>=nv)
+    return;
+  uint32_t f=0,p=0;
+  if (j>0)
+  {
+    const unsigned long long k=keys[j];
+    if (keys[j-1]==k)
+    {
+      const double x=sx[j],y=sy[j],z=sz[j];
+      for (unsigned long long i=j;i>0 && keys[i-1]==k;)
+      {
+        i--;
+        if (sx[i]==x && sy[i]==y && sz[i]==z)
+        { // nearest earlier point at this location (may itself be a duplicate: resolved by wb_dup_jump)
+          f=1;
+          p=(uint32_t)i;
+          break;
+        }
+      }
+    }
+  }
+  flag[j]=f;
+  prev[j]=p;
+  if (f)
+    atomicAdd(count,1ull);
+}
+
+__global__ void __launch_bounds__(256)
+wb_dup_jump_kernel(const uint32_t *__restrict__ flag,uint32_t *prev,unsigned long long nv,
+                   unsigned long long *__restrict__ changed)
+// pointer jumping: prev[j] ends at the first point of its location (which is not flagged)
+{
+  unsigned long long j=(unsigned long long)blockIdx.x*blockDim.x+threadIdx.x;
+  if (j>=nv || !flag[j])
+    return;
+  uint32_t p=prev[j];
+  if (flag[p])
+  {
+    prev[j]=prev[p];
+    atomicAdd(changed,1ull);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+wb_dup_mark_kernel(const uint32_t *__restrict__ flag,const uint32_t *__restrict__ prev,
+                   const uint32_t *__restrict__ perm,unsigned long long nv,unsigned long long *keys,
+                   uint32_t *__restrict__ dupIn,uint32_t *__restrict__ dupRep,unsigned long long *__restrict__ slot)
+{
+  unsigned long long j=(unsigned long long)blockIdx.x*blockDim.x+threadIdx.x;
+  if (j>=nv || !flag[j])
+    return;
+  unsigned long long s=atomicAdd(slot,1ull);
+  dupIn[s]=perm[j];
+  dupRep[s]=perm[prev[j]];
+  keys[j]=WB_KEY_DUP;
+}
+
+__global__ void __launch_bounds__(256)
+wb_dup_labels_kernel(const uint32_t *__restrict__ dupIn,const uint32_t *__restrict__ dupRep,unsigned long long n,
+                     uint8_t *labelIn)
+{
+  unsigned long long u=(unsigned long long)blockIdx.x*blockDim.x+threadIdx.x;
+  if (u<n)
+    labelIn[dupIn[u]]=labelIn[dupRep[u]];
+}
+
 // ============================================================================ K10: labels back to input order
 
 __global__ void __launch_bounds__(256)

@@ -66,6 +66,8 @@ struct wb_ctx
   DevBuf<uint8_t> cls,ret,labelIn,labelSorted,leafDepth;
   DevBuf<unsigned long long> keyA,keyB,pairKeyA,pairKeyB,counters;
   DevBuf<uint32_t> idxA,idxB,scr0,scr1,winner,pairValA,pairValB,table,blockSums;
+  DevBuf<uint32_t> dupIn,dupRep;          // input indices of (lost duplicate, surviving point at the same XYZ)
+  uint64_t nDup=0;
   DevBuf<uint4> tilesOf;
   DevBuf<double> sx,sy,sz;
   DevBuf<uint8_t> staging[2];
@@ -338,6 +340,7 @@ extern "C" int wb_clear(wb_ctx *ctx)
   cudaSetDevice(ctx->device);
   CK(cudaStreamSynchronize(ctx->st));
   ctx->n=ctx->nValid=0;
+  ctx->nDup=0;
   ctx->segs.clear();
   ctx->corners.clear();
   ctx->geomOverride=false;
@@ -577,7 +580,7 @@ extern "C" int wb_build(wb_ctx *ctx)
   ctx->nValid=n-dropped;
   ctx->stats.n_dropped=dropped;
   ctx->stats.n_points=ctx->nValid;
-  const uint64_t nv=ctx->nValid;
+  uint64_t nv=ctx->nValid;
   if (!nv)
     return fail(ctx,WB_ERR_STATE,"every record was dropped");
   // ---- canonical-order coordinates
@@ -593,6 +596,57 @@ extern "C" int wb_build(wb_ctx *ctx)
                                                 ctx->sx.p,ctx->sy.p,ctx->sz.p);
   ctx->stats.kernel_launches++;
   KCHECK();
+  // ---- identical locations: one point per XYZ stays in the store (octree.cpp:620-662)
+  ctx->nDup=0;
+  {
+    unsigned long long *cnt=ctx->counters.p+4;
+    CK(cudaMemsetAsync(cnt,0,2*sizeof(unsigned long long),st));
+    wb_dup_find_kernel<<<gridFor(nv,256),256,0,st>>>(ctx->keys,ctx->sx.p,ctx->sy.p,ctx->sz.p,nv,
+                                                    ctx->scr0.p,ctx->scr1.p,cnt);
+    ctx->stats.kernel_launches++;
+    unsigned long long nDup=0;
+    CK(cudaMemcpyAsync(&nDup,cnt,sizeof(nDup),cudaMemcpyDeviceToHost,st));
+    CK(cudaStreamSynchronize(st));
+    if (nDup)
+    {
+      if (nDup>=nv)
+        return fail(ctx,WB_ERR_STATE,"internal: duplicate count");
+      CK(ctx->dupIn.ensure(nDup)); CK(ctx->dupRep.ensure(nDup));
+      for (int round=0;round<40;round++)
+      {
+        unsigned long long changed=0;
+        CK(cudaMemsetAsync(cnt+1,0,sizeof(unsigned long long),st));
+        wb_dup_jump_kernel<<<gridFor(nv,256),256,0,st>>>(ctx->scr0.p,ctx->scr1.p,nv,cnt+1);
+        ctx->stats.kernel_launches++;
+        CK(cudaMemcpyAsync(&changed,cnt+1,sizeof(changed),cudaMemcpyDeviceToHost,st));
+        CK(cudaStreamSynchronize(st));
+        if (!changed)
+          break;
+      }
+      CK(cudaMemsetAsync(cnt+1,0,sizeof(unsigned long long),st));
+      unsigned long long *curK=ctx->keys,*othK=(ctx->keys==ctx->keyA.p)?ctx->keyB.p:ctx->keyA.p;
+      uint32_t *curP=ctx->perm,*othP=(ctx->perm==ctx->idxA.p)?ctx->idxB.p:ctx->idxA.p;
+      wb_dup_mark_kernel<<<gridFor(nv,256),256,0,st>>>(ctx->scr0.p,ctx->scr1.p,curP,nv,curK,
+                                                      ctx->dupIn.p,ctx->dupRep.p,cnt+1);
+      ctx->stats.kernel_launches++;
+      KCHECK();
+      // stable re-sort: survivors keep their order, duplicates go behind them (before the dropped records)
+      bool inCur=true;
+      CK(wb_radix_sort((uint64_t *)curK,curP,(uint64_t *)othK,othP,n,0,64,ctx->table.p,ctx->table.cap,
+                       ctx->blockSums.p,ctx->blockSums.cap,st,&inCur,&ctx->stats.kernel_launches));
+      ctx->keys=inCur?curK:othK;
+      ctx->perm=inCur?curP:othP;
+      ctx->nDup=nDup;
+      ctx->nValid=nv-nDup;
+      ctx->stats.n_points=ctx->nValid;
+      wb_gather_kernel<<<gridFor(ctx->nValid,256),256,0,st>>>(ctx->perm,ctx->nValid,ctx->xi.p,ctx->yi.p,ctx->zi.p,
+                                                             ctx->dsegs.p,ctx->sx.p,ctx->sy.p,ctx->sz.p);
+      ctx->stats.kernel_launches++;
+      KCHECK();
+    }
+    ctx->stats.n_duplicates=ctx->nDup;
+    nv=ctx->nValid;
+  }
   // ---- leaves: level-synchronous top-down split
   CK(cudaEventRecord(ctx->evC,st));
   {
@@ -1068,6 +1122,11 @@ extern "C" int wb_classify(wb_ctx *ctx)
   CK(cudaEventRecord(ctx->evD,st));
   wb_scatter_labels_kernel<<<gridFor(nv,256),256,0,st>>>(ctx->labelSorted.p,ctx->perm,nv,ctx->labelIn.p);
   ctx->stats.kernel_launches+=4;
+  if (ctx->nDup)
+  { // records lost to an identical location take the class of the point that stayed in the store
+    wb_dup_labels_kernel<<<gridFor(ctx->nDup,256),256,0,st>>>(ctx->dupIn.p,ctx->dupRep.p,ctx->nDup,ctx->labelIn.p);
+    ctx->stats.kernel_launches++;
+  }
   KCHECK();
   CK(cudaEventRecord(ctx->evB,st));
   unsigned long long c[24]={0};

@@ -101,3 +101,14 @@ def generate(scene, n_points, seed=1, region=None, gps_base=0, out=None):
     hdr = np.zeros(375, dtype=np.uint8)
     size = L.wb_synth_header(C.byref(d), n, bbox.ctypes.data, hdr.ctypes.data)
     return Cloud(d, hdr[:size].copy(), recs, bbox)
+
+
+def with_duplicates(cloud, n_dup, seed=0):
+    """Copy of `cloud` in which n_dup records take the XYZ of other records (own attributes and
+    gpsTime kept): the reference stores one point per location (OctBuffer::put, octree.cpp:620-662)."""
+    recs = cloud.records.copy()
+    rng = np.random.default_rng(seed)
+    src = rng.integers(0, cloud.n, n_dup)
+    dst = rng.integers(0, cloud.n, n_dup)
+    recs[dst, :12] = recs[src, :12]
+    return Cloud(cloud.desc, cloud.header, recs, cloud.bbox)
