@@ -91,6 +91,7 @@ typedef struct wb_stats
   uint64_t kernel_launches;         /* kernels launched by this context so far */
   double ms_h2d,ms_decode,ms_build,ms_scan,ms_postscan,ms_classify,ms_d2h;  /* last run, CUDA events */
   double ms_sort,ms_leaves,ms_hier,ms_pairs,ms_classify_kernel;
+  double ms_encode,ms_encode_d2h;   /* wb_encode: kernel, copy of the records to the host */
 } wb_stats;
 
 /* ---- life cycle ---------------------------------------------------------- */
@@ -162,6 +163,41 @@ int wb_count_classes(wb_ctx *ctx,uint64_t counts[256]);
 /* Write each point's class into its record (byte 15 low 5 bits for formats 0-5, byte 16 for
  * 6-10: las.cpp:754-756, 771, 848, 857) — host records, in place. */
 int wb_patch_records(wb_ctx *ctx,uint8_t *recs,uint64_t first_point,uint64_t n,int fmt,int rec_len);
+
+/* ---- output records (ACT_WRITE) ------------------------------------------------
+ * CloudOutput::writeFiles (cloudoutput.cpp:187-229) walks the buckets in order and, for each class,
+ * appends the bucket's points of that class to the class's least-full file through
+ * LasHeader::writePoint (las.cpp:822-904): attributes as readPoint decoded them (las.cpp:735-820),
+ * the new class, XYZ re-quantised as lrint((x/unit-offset)/scale).  Here the caller keeps the
+ * sequential file choice (it needs only per-bucket class counts) and the device makes the records:
+ *   wb_keep_records(ctx,1)            before wb_add_las: keep the raw records in device memory
+ *   wb_leaf_class_counts              counts[leaf*K+k] = points of bucket `leaf` with class classes[k]
+ *                                     (K = n_classes, or 1 and every class when separate == 0)
+ *   wb_encode                         dest[leaf*K+k] = byte offset in `out` where that run of records
+ *                                     starts (even), file_of[leaf*K+k] = index of the file it belongs
+ *                                     to; out receives all records, stats[f] the header figures of
+ *                                     file f: per-return counts (n_points[0] = total) and the extremes
+ *                                     of the written integers (header min/max = i*scale+offset).
+ * Points whose class has no slot are not written (cloudoutput.cpp:212-214). */
+typedef struct wb_out_spec
+{
+  int32_t format,rec_len;           /* output point format (0-3, 6-8) and its record length, las.cpp:38 */
+  int32_t n_classes,separate;       /* CloudOutput::separateClasses */
+  double scale[3],offset[3],unit;   /* LasHeader::setScale (las.cpp:636-673) result, file units */
+  uint8_t classes[256];
+} wb_out_spec;
+typedef struct wb_file_stats
+{
+  uint64_t n_points[16];            /* LasHeader::nPoints: total, then by return number */
+  int32_t imin[3],imax[3],pad_[2];
+} wb_file_stats;
+int wb_keep_records(wb_ctx *ctx,int keep);
+int wb_leaf_class_counts(wb_ctx *ctx,const uint8_t *classes,int n_classes,int separate,uint32_t *counts);
+int wb_encode(wb_ctx *ctx,const wb_out_spec *spec,const uint64_t *dest,const uint32_t *file_of,uint32_t n_files,
+              uint8_t *out,uint64_t out_bytes,wb_file_stats *stats);
+/* Records lost to an identical XYZ (octree.cpp:620-662): input index of each and of the point that
+ * holds its place in the store; wb_stats.n_duplicates entries. */
+int wb_get_duplicates(wb_ctx *ctx,uint32_t *dup,uint32_t *rep,uint64_t cap);
 
 /* Device arithmetic exposed for known-answer tests (angle.cpp:117-155 atan2i, libm hypot as
  * point.cpp:189-192 uses it, the 64-sector binning of the classifier; -1 = "ask atan2i"). */

@@ -372,3 +372,67 @@ def test_files_with_different_offsets_and_units(ctx):
     res = O.run([O.file_from_cloud(cloud)], unit=unit)
     assert ctx.dump() == res.dump
     assert (ctx.labels(cloud.n) == res.labels).all()
+
+
+def test_encode_same_layout_returns_the_input_records(ctx):
+    """wb_encode (LasHeader::readPoint -> writePoint, las.cpp:735-904) with the input's own format,
+    scale and offset must give back the input records in canonical order with only the class
+    replaced; the header figures are the totals, per-return counts and integer extremes."""
+    cloud = synth.generate(5, 30000, seed=71)                      # format 3: gps + RGB
+    rng = np.random.default_rng(5)
+    recs = cloud.records.copy()
+    recs[:, 12:14] = rng.integers(0, 256, (cloud.n, 2), dtype=np.uint8)           # intensity
+    recs[:, 14] = rng.integers(1, 8, cloud.n, dtype=np.uint8) | (rng.integers(0, 32, cloud.n, dtype=np.uint8) << 3)
+    recs[:, 16:20] = rng.integers(0, 256, (cloud.n, 4), dtype=np.uint8)           # angle, user, source
+    recs[:, 16] = rng.integers(-90, 91, cloud.n).astype(np.int8).view(np.uint8)   # angles that survive deg->bin->deg
+    ctx.clear()
+    ctx.keep_records(True)
+    ctx.set_params()
+    ctx.add_extent(cloud.min_corner, cloud.max_corner)
+    ctx.add_las(recs, cloud.fmt, cloud.scale, cloud.offset)
+    ctx.run()
+    n = cloud.n
+    lab = ctx.labels(n)
+    order, _ = ctx.order(n)
+    cnt = ctx.leaf_class_counts()                                   # one slot: every class
+    lv = ctx.leaves()
+    assert (cnt[:, 0] == lv["count"]).all()
+    L = cloud.rec_len
+    dest = lv["first"].astype(np.uint64) * L
+    out, st = ctx.encode(cloud.fmt, L, cloud.scale, cloud.offset, dest, np.zeros(len(lv), np.uint32), 1, n * L)
+    want = recs[order].copy()
+    want[:, 15] = (want[:, 15] & 0xe0) | (lab[order] & 31)
+    got = out.reshape(n, L)
+    assert (got == want).all(), np.nonzero((got != want).any(axis=0))[0]
+    ints = cloud.ints()
+    assert st[0]["n_points"][0] == n and st[0]["imin"] == ints.min(axis=0).tolist() and st[0]["imax"] == ints.max(axis=0).tolist()
+    by_ret = np.bincount(recs[:, 14] & 7, minlength=16)
+    assert st[0]["n_points"][1:8] == by_ret[1:8].tolist()
+    # per class: one slot and one file per class present
+    classes = np.unique(lab).tolist()
+    K = len(classes)
+    cnt = ctx.leaf_class_counts(classes)
+    assert (cnt.sum(axis=1) == lv["count"]).all()
+    assert cnt.sum(axis=0).tolist() == [int((lab == c).sum()) for c in classes]
+    start = np.zeros_like(cnt, dtype=np.uint64)
+    start[1:] = np.cumsum(cnt, axis=0)[:-1]
+    tot = cnt.sum(axis=0).astype(np.uint64)
+    base = (np.concatenate([[0], np.cumsum(tot)[:-1]]) * L).astype(np.uint64)
+    dest = base[None, :] + start * L
+    file_of = np.tile(np.arange(K, dtype=np.uint32), (len(lv), 1))
+    out, st = ctx.encode(cloud.fmt, L, cloud.scale, cloud.offset, dest, file_of, K, n * L, classes=classes)
+    got = out.reshape(n, L)
+    lo = lab[order]
+    for k, c in enumerate(classes):
+        a = int(base[k]) // L
+        assert (got[a:a + int(tot[k])] == want[lo == c]).all(), c
+    assert [s["n_points"][0] for s in st] == tot.tolist()
+    ctx.clear()
+    ctx.keep_records(False)
+    # without the records the call must refuse, not invent them
+    ctx.add_extent(cloud.min_corner, cloud.max_corner)
+    ctx.add_las(recs, cloud.fmt, cloud.scale, cloud.offset)
+    ctx.run()
+    with pytest.raises(api.WolkenError):
+        ctx.encode(cloud.fmt, L, cloud.scale, cloud.offset, lv["first"].astype(np.uint64) * L,
+                   np.zeros(len(lv), np.uint32), 1, n * L)

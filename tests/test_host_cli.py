@@ -123,10 +123,12 @@ def _las14(path):
     return info, recs
 
 
+@pytest.mark.parametrize("writer", ["device", "host"])
 @pytest.mark.parametrize("scene,n,separate,ppf", [(5, 30000, 1, 8000), (2, 20000, 0, 0), (3, 15000, 1, 0)])
-def test_reference_style_writer_matches_reference(tmp_path, scene, n, separate, ppf):
+def test_reference_style_writer_matches_reference(tmp_path, scene, n, separate, ppf, writer):
     """CloudOutput + LasHeader::writePoint/writeHeader (cloudoutput.cpp:119-246, las.cpp:822-904):
-    our restatement against the reference's own write path (oracle/_ref/ref_driver -w).  Which of a
+    our writers (records made by wb_encode on the GPU, or by the C++ LasHeader::writePoint mirror with
+    --host-writer) against the reference's own write path (oracle/_ref/ref_driver -w).  Which of a
     class's files a bucket lands in depends on the reference's block numbering, so files are
     compared per class as multisets of records, plus the header fields that do not depend on it."""
     ref = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
@@ -141,7 +143,7 @@ def test_reference_style_writer_matches_reference(tmp_path, scene, n, separate, 
     subprocess.run([ref, "-t", "1", "-c", "-o", str(rdir / "r"), "-w", str(rdir / "out"), "-s", str(separate),
                     "-p", str(ppf), las], capture_output=True, text=True, check=True, cwd=str(rdir))
     cmd = [CLI, "-o", str(odir / "out"), "--separate-classes", str(separate), "--points-per-file", str(ppf),
-           "--dump", str(odir / "dump"), las]
+           "--dump", str(odir / "dump"), las] + (["--host-writer"] if writer == "host" else [])
     subprocess.run(cmd, capture_output=True, text=True, check=True, cwd=str(odir))
     rfiles = sorted(f for f in os.listdir(rdir) if f.startswith("out") and f.endswith(".las"))
     ofiles = sorted(f for f in os.listdir(odir) if f.startswith("out") and f.endswith(".las"))
@@ -177,3 +179,80 @@ def test_reference_style_writer_matches_reference(tmp_path, scene, n, separate, 
             np.array([x[0]["by_return"] for x in go[key]]).sum(axis=0).tolist()
         if ppf:
             assert all(x[0]["n"] <= ppf + 537 for x in go[key])
+
+
+def _scramble(cloud, seed):
+    """Random intensity, return/flag bits, scan angle, user data and source id (return number kept
+    non-zero) so that every field conversion of readPoint/writePoint is exercised."""
+    rng = np.random.default_rng(seed)
+    recs = cloud.records.copy()
+    n = cloud.n
+    last = 20 if cloud.fmt < 6 else 22
+    recs[:, 12:last] = rng.integers(0, 256, (n, last - 12), dtype=np.uint8)
+    if cloud.fmt < 6:
+        recs[:, 14] = (recs[:, 14] & 0xf8) | rng.integers(1, 8, n, dtype=np.uint8)
+    else:
+        recs[:, 14] = (recs[:, 14] & 0xf0) | rng.integers(1, 16, n, dtype=np.uint8)
+    return synth.Cloud(cloud.desc, cloud.header, recs, cloud.bbox)
+
+
+def _write_both(tmp_path, inputs, extra):
+    out = {}
+    for w in ("device", "host"):
+        d = tmp_path / w
+        d.mkdir()
+        cmd = [CLI, "-o", str(d / "out"), "--dump", str(d / "dump")] + extra + inputs + \
+            (["--host-writer"] if w == "host" else [])
+        r = subprocess.run(cmd, capture_output=True, text=True, cwd=str(d))
+        assert r.returncode == 0, r.stdout + r.stderr
+        out[w] = {f: open(str(d / f), "rb").read() for f in sorted(os.listdir(d)) if f.endswith(".las")}
+    return out
+
+
+@pytest.mark.parametrize("case", ["mixed_1_6", "mixed_3_6", "duplicates", "zero_returns", "split_one_class"])
+def test_device_writer_equals_host_writer(tmp_path, case):
+    """wb_encode (records made on the GPU) produces the same bytes as the C++ mirror of
+    LasHeader::readPoint/writePoint + CloudOutput::writeFiles — whole files, headers included — on
+    format conversion (legacy -> 1.4 layouts, scan angle, RGB), identical locations (the last
+    record's attributes in the first one's place), return number 0 (forced to 1) and file splitting."""
+    extra = []
+    if case.startswith("mixed"):
+        sa, sb = (2, 3) if case == "mixed_1_6" else (5, 3)            # formats 1+6 -> 6, 3+6 -> 7
+        d = synth.describe(sa, 20000)
+        a = synth.generate(sa, 20000, seed=61)
+        b = synth.generate(sb, 20000, seed=62, gps_base=a.n)
+        a, b = _scramble(a, 1), _scramble(b, 2)
+        clouds = [a, b]
+        assert {a.fmt, b.fmt} == ({1, 6} if case == "mixed_1_6" else {3, 6})
+        extra = ["--points-per-file", "9000"]
+    elif case == "duplicates":
+        clouds = [synth.with_duplicates(synth.with_duplicates(_scramble(synth.generate(2, 20000, seed=63), 3),
+                                                              6000, 1), 6000, 2)]
+    elif case == "zero_returns":
+        c = synth.generate(2, 20000, seed=64)
+        recs = c.records.copy()
+        recs[:, 14] &= 0xf8                                            # return number 0 everywhere: kept, written as 1
+        clouds = [synth.Cloud(c.desc, c.header, recs, c.bbox)]
+    else:
+        clouds = [_scramble(synth.generate(1, 30000, seed=65), 4)]
+        extra = ["--separate-classes", "0", "--points-per-file", "7000"]
+    inputs = []
+    for i, c in enumerate(clouds):
+        p = str(tmp_path / ("in%d.las" % i))
+        c.write(p)
+        inputs.append(p)
+    out = _write_both(tmp_path, inputs, extra)
+    assert list(out["device"].keys()) == list(out["host"].keys()) and len(out["device"]) >= 1
+    for f in out["device"]:
+        a, b = out["device"][f], out["host"][f]
+        assert len(a) == len(b), f
+        if a != b:
+            aa, bb = np.frombuffer(a, np.uint8), np.frombuffer(b, np.uint8)
+            bad = np.nonzero(aa != bb)[0]
+            raise AssertionError("%s differs at %d bytes, first at offset %d" % (f, len(bad), bad[0]))
+    if case == "zero_returns":
+        info, recs = _las14(str(tmp_path / "device" / sorted(out["device"])[0]))
+        assert ((recs[:, 14] & 7) == 1).all()
+    if case.startswith("mixed"):
+        info, recs = _las14(str(tmp_path / "device" / sorted(out["device"])[0]))
+        assert info["fmt"] == (6 if case == "mixed_1_6" else 7)

@@ -35,10 +35,21 @@ class Stats(C.Structure):
                                           "cl_pairs2", "cl_warps2", "kernel_launches")] + \
                [(k, C.c_double) for k in ("ms_h2d", "ms_decode", "ms_build", "ms_scan", "ms_postscan",
                                           "ms_classify", "ms_d2h", "ms_sort", "ms_leaves", "ms_hier",
-                                          "ms_pairs", "ms_classify_kernel")]
+                                          "ms_pairs", "ms_classify_kernel", "ms_encode", "ms_encode_d2h")]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class OutSpec(C.Structure):
+    _fields_ = [("format", C.c_int32), ("rec_len", C.c_int32), ("n_classes", C.c_int32), ("separate", C.c_int32),
+                ("scale", C.c_double * 3), ("offset", C.c_double * 3), ("unit", C.c_double),
+                ("classes", C.c_uint8 * 256)]
+
+
+class FileStats(C.Structure):
+    _fields_ = [("n_points", C.c_uint64 * 16), ("imin", C.c_int32 * 3), ("imax", C.c_int32 * 3),
+                ("pad_", C.c_int32 * 2)]
 
 
 class WolkenError(RuntimeError):
@@ -98,6 +109,10 @@ def lib():
             "wb_snake_set_size": [C.c_double, C.c_double, dp, C.POINTER(C.c_int), C.POINTER(C.c_int)],
             "wb_ldecimal": [C.c_double, C.c_char_p, C.c_int],
             "wb_format_dump": [vp, u64, C.c_char_p, u64],
+            "wb_keep_records": [vp, C.c_int],
+            "wb_leaf_class_counts": [vp, vp, C.c_int, C.c_int, vp],
+            "wb_encode": [vp, C.POINTER(OutSpec), vp, vp, C.c_uint32, vp, u64, vp],
+            "wb_get_duplicates": [vp, vp, vp, u64],
         }
         for name, args in sig.items():
             f = getattr(L, name)
@@ -117,7 +132,8 @@ EXPORTS = ["wb_create", "wb_destroy", "wb_last_error", "wb_reserve", "wb_clear",
            "wb_run", "wb_get_stats", "wb_sync", "wb_host_alloc", "wb_host_free", "wb_size_fit", "wb_bbox_cube",
            "wb_snake_set_size", "wb_ldecimal", "wb_format_dump", "wb_add_points_device", "wb_export_points_device",
            "wb_set_own_range", "wb_export_tiles_device", "wb_import_tiles_device", "wb_max_hyperboloid_size",
-           "wb_assign", "wb_get_points_sorted", "wb_test_math", "wb_bound_rect"]
+           "wb_assign", "wb_get_points_sorted", "wb_test_math", "wb_bound_rect", "wb_keep_records",
+           "wb_leaf_class_counts", "wb_encode", "wb_get_duplicates"]
 
 
 def _d(v):
@@ -269,6 +285,47 @@ class Context:
         if ln < 0:
             raise WolkenError("wb_format_dump failed")
         return buf.raw[:ln].decode("utf-8")
+
+    # ---- output records (ACT_WRITE)
+    def keep_records(self, keep=True):
+        """Before add_las: keep the raw records in device memory for encode()."""
+        self._ck(self._L.wb_keep_records(self._h, 1 if keep else 0))
+
+    def leaf_class_counts(self, classes=None):
+        """counts[leaf, k] = points of bucket `leaf` whose class is classes[k]; classes=None: all together."""
+        nl = len(self.leaves())
+        sep = classes is not None
+        cl = np.ascontiguousarray(classes if sep else [0], dtype=np.uint8)
+        out = np.zeros((nl, len(cl)), dtype=np.uint32)
+        self._ck(self._L.wb_leaf_class_counts(self._h, cl.ctypes.data, len(cl), 1 if sep else 0, out.ctypes.data))
+        return out
+
+    def encode(self, fmt, rec_len, scale, offset, dest, file_of, n_files, out_bytes, classes=None, unit=1.0):
+        """wb_encode: returns (records as a uint8 array of out_bytes, per-file stats)."""
+        spec = OutSpec()
+        spec.format, spec.rec_len = fmt, rec_len
+        spec.separate = 1 if classes is not None else 0
+        cl = list(classes) if classes is not None else [0]
+        spec.n_classes = len(cl)
+        for k, c in enumerate(cl):
+            spec.classes[k] = int(c)
+        for k in range(3):
+            spec.scale[k], spec.offset[k] = float(scale[k]), float(offset[k])
+        spec.unit = unit
+        dest = np.ascontiguousarray(dest, dtype=np.uint64)
+        file_of = np.ascontiguousarray(file_of, dtype=np.uint32)
+        out = np.zeros(out_bytes, dtype=np.uint8)
+        stats = (FileStats * n_files)()
+        self._ck(self._L.wb_encode(self._h, C.byref(spec), dest.ctypes.data, file_of.ctypes.data, n_files,
+                                   out.ctypes.data, out_bytes, stats))
+        return out, [{"n_points": list(s.n_points), "imin": list(s.imin), "imax": list(s.imax)} for s in stats]
+
+    def duplicates(self):
+        n = self.stats()["n_duplicates"]
+        dup = np.zeros(n, dtype=np.uint32)
+        rep = np.zeros(n, dtype=np.uint32)
+        self._ck(self._L.wb_get_duplicates(self._h, dup.ctypes.data, rep.ctypes.data, n))
+        return dup, rep
 
     def order(self, n):
         order = np.empty(n, dtype=np.uint32)

@@ -12,6 +12,7 @@
 #include "wb_host.h"
 #include "wb_kernels.cuh"
 #include "wb_sort.cuh"
+#include "wb_encode.cuh"
 
 namespace
 {
@@ -68,6 +69,15 @@ struct wb_ctx
   DevBuf<uint32_t> idxA,idxB,scr0,scr1,winner,pairValA,pairValB,table,blockSums;
   DevBuf<uint32_t> dupIn,dupRep;          // input indices of (lost duplicate, surviving point at the same XYZ)
   uint64_t nDup=0;
+  // raw records kept for wb_encode (one buffer per wb_add_las call)
+  bool keepRecords=false;
+  std::vector<uint8_t *> recBufs;
+  std::vector<WbRecSeg> recSegs;
+  DevBuf<WbRecSegs> drsegs;
+  DevBuf<uint8_t> outArena,encLut;
+  DevBuf<unsigned long long> encDest,encCount;
+  DevBuf<uint32_t> encFile,encCounts,attrSrc,invPerm;
+  DevBuf<int> encMinMax;
   DevBuf<uint4> tilesOf;
   DevBuf<double> sx,sy,sz;
   DevBuf<uint8_t> staging[2];
@@ -218,10 +228,16 @@ int decodeDevice(wb_ctx *ctx,const uint8_t *d,uint64_t first,uint64_t cnt,int fm
   return WB_OK;
 }
 
-int addSegment(wb_ctx *ctx,uint64_t n,const double scale[3],const double offset[3],double unit)
+int addSegment(wb_ctx *ctx,uint64_t n,const double scale[3],const double offset[3],double unit,
+               const uint8_t *keptRecs=nullptr,int fmt=-1,int recLen=0)
 {
   if (ctx->segs.size()>=WB_MAX_SEGMENTS)
     return fail(ctx,WB_ERR_ARG,"too many input files (max %d)",WB_MAX_SEGMENTS);
+  WbRecSeg rs;
+  rs.recs=keptRecs;
+  rs.fmt=fmt;
+  rs.recLen=recLen;
+  ctx->recSegs.push_back(rs);
   WbSegment s;
   s.first=ctx->n;
   s.count=n;
@@ -235,6 +251,14 @@ int addSegment(wb_ctx *ctx,uint64_t n,const double scale[3],const double offset[
   ctx->n+=n;
   ctx->phase=PH_LOADED;
   return WB_OK;
+}
+
+void freeKeptRecords(wb_ctx *ctx)
+{
+  for (uint8_t *b:ctx->recBufs)
+    cudaFree(b);
+  ctx->recBufs.clear();
+  ctx->recSegs.clear();
 }
 
 int checkFormat(wb_ctx *ctx,int fmt,int recLen)
@@ -308,6 +332,10 @@ extern "C" void wb_destroy(wb_ctx *ctx)
   ctx->levelOff.release(); ctx->levelCnt.release();
   ctx->tStart.release(); ctx->tCount.release(); ctx->tileList.release(); ctx->tNPoints.release(); ctx->tTree.release();
   ctx->tDensity.release(); ctx->tHyp.release(); ctx->tHeight.release(); ctx->tileExt.release(); ctx->tileGrid.release(); ctx->wedgeBuf.release(); ctx->chunkPending.release();
+  ctx->dupIn.release(); ctx->dupRep.release();
+  freeKeptRecords(ctx);
+  ctx->drsegs.release(); ctx->outArena.release(); ctx->encLut.release(); ctx->encDest.release(); ctx->encCount.release();
+  ctx->encFile.release(); ctx->encCounts.release(); ctx->attrSrc.release(); ctx->invPerm.release(); ctx->encMinMax.release();
   cudaStreamDestroy(ctx->st); cudaStreamDestroy(ctx->stCopy);
   cudaEventDestroy(ctx->evA); cudaEventDestroy(ctx->evB); cudaEventDestroy(ctx->evC); cudaEventDestroy(ctx->evD);
   for (int i=0;i<2;i++)
@@ -341,6 +369,8 @@ extern "C" int wb_clear(wb_ctx *ctx)
   CK(cudaStreamSynchronize(ctx->st));
   ctx->n=ctx->nValid=0;
   ctx->nDup=0;
+  freeKeptRecords(ctx);
+  ctx->outArena.release();            // sized by the last output; may be gigabytes
   ctx->segs.clear();
   ctx->corners.clear();
   ctx->geomOverride=false;
@@ -433,7 +463,15 @@ extern "C" int wb_add_las_device(wb_ctx *ctx,const uint8_t *d,uint64_t n,int fmt
   CK(cudaEventRecord(ctx->evB,ctx->st));
   CK(cudaStreamSynchronize(ctx->st));
   ctx->stats.ms_decode+=elapsed(ctx->evA,ctx->evB);
-  return addSegment(ctx,n,scale,offset,unit);
+  uint8_t *kept=nullptr;
+  if (ctx->keepRecords && n)
+  {
+    CK(cudaMalloc((void **)&kept,(size_t)(n*recLen+64)));
+    ctx->recBufs.push_back(kept);
+    CK(cudaMemcpyAsync(kept,d,(size_t)(n*recLen),cudaMemcpyDeviceToDevice,ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+  }
+  return addSegment(ctx,n,scale,offset,unit,kept,fmt,recLen);
 }
 
 extern "C" int wb_add_las(wb_ctx *ctx,const uint8_t *recs,uint64_t n,int fmt,int recLen,
@@ -453,20 +491,28 @@ extern "C" int wb_add_las(wb_ctx *ctx,const uint8_t *recs,uint64_t n,int fmt,int
   // double-buffered pipeline: copy chunk i+1 on the copy stream while chunk i is decoded
   const uint64_t chunkRecs=(uint64_t)1<<21;          // 2 Mi records (multiple of 16: chunks stay 16-byte aligned)
   const uint64_t chunkBytes=chunkRecs*recLen;
-  for (int b=0;b<2;b++)
-    CK(ctx->staging[b].ensure(std::min<uint64_t>(chunkBytes,n*recLen)+64));
+  uint8_t *kept=nullptr;
+  if (ctx->keepRecords && n)
+  { // the records stay resident for wb_encode: copy straight to their final place and decode there
+    CK(cudaMalloc((void **)&kept,(size_t)(n*recLen+64)));
+    ctx->recBufs.push_back(kept);
+  }
+  else
+    for (int b=0;b<2;b++)
+      CK(ctx->staging[b].ensure(std::min<uint64_t>(chunkBytes,n*recLen)+64));
   CK(cudaEventRecord(ctx->evA,ctx->st));
   uint64_t done=0;
   int b=0,used[2]={0,0};
   while (done<n)
   {
     uint64_t cnt=std::min(chunkRecs,n-done);
-    if (used[b])
+    uint8_t *dst=kept?kept+done*recLen:ctx->staging[b].p;
+    if (used[b] && !kept)
       CK(cudaStreamWaitEvent(ctx->stCopy,ctx->evDec[b],0));   // staging[b] free again?
-    CK(cudaMemcpyAsync(ctx->staging[b].p,recs+done*recLen,cnt*recLen,cudaMemcpyHostToDevice,ctx->stCopy));
+    CK(cudaMemcpyAsync(dst,recs+done*recLen,cnt*recLen,cudaMemcpyHostToDevice,ctx->stCopy));
     CK(cudaEventRecord(ctx->evCopy[b],ctx->stCopy));
     CK(cudaStreamWaitEvent(ctx->st,ctx->evCopy[b],0));
-    if ((rc=decodeDevice(ctx,ctx->staging[b].p,ctx->n+done,cnt,fmt,recLen,dropZeros,ctx->st)))
+    if ((rc=decodeDevice(ctx,dst,ctx->n+done,cnt,fmt,recLen,dropZeros,ctx->st)))
       return rc;
     CK(cudaEventRecord(ctx->evDec[b],ctx->st));
     used[b]=1;
@@ -476,7 +522,7 @@ extern "C" int wb_add_las(wb_ctx *ctx,const uint8_t *recs,uint64_t n,int fmt,int
   CK(cudaEventRecord(ctx->evB,ctx->st));
   CK(cudaStreamSynchronize(ctx->st));
   ctx->stats.ms_h2d+=elapsed(ctx->evA,ctx->evB);       // copy and decode overlap: one figure for both
-  return addSegment(ctx,n,scale,offset,unit);
+  return addSegment(ctx,n,scale,offset,unit,kept,fmt,recLen);
 }
 
 extern "C" int wb_add_points_device(wb_ctx *ctx,const int32_t *dx,const int32_t *dy,const int32_t *dz,const uint8_t *dc,
@@ -1179,6 +1225,175 @@ extern "C" int wb_count_classes(wb_ctx *ctx,uint64_t counts[256])
   CK(cudaMemcpyAsync(counts,d.p,256*sizeof(unsigned long long),cudaMemcpyDeviceToHost,ctx->st));
   CK(cudaStreamSynchronize(ctx->st));
   d.release();
+  return WB_OK;
+}
+
+// ============================================================================ output records (ACT_WRITE)
+
+extern "C" int wb_keep_records(wb_ctx *ctx,int keep)
+{
+  if (!ctx)
+    return WB_ERR_ARG;
+  if (ctx->n)
+    return fail(ctx,WB_ERR_STATE,"wb_keep_records comes before the first wb_add_las");
+  ctx->keepRecords=keep!=0;
+  return WB_OK;
+}
+
+extern "C" int wb_get_duplicates(wb_ctx *ctx,uint32_t *dup,uint32_t *rep,uint64_t cap)
+{
+  if (!ctx || (cap && (!dup || !rep)))
+    return WB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  if (ctx->phase<PH_BUILT)
+    return fail(ctx,WB_ERR_STATE,"not built");
+  if (cap<ctx->nDup)
+    return fail(ctx,WB_ERR_ARG,"duplicate buffers too small");
+  if (ctx->nDup)
+  {
+    CK(cudaMemcpy(dup,ctx->dupIn.p,sizeof(uint32_t)*ctx->nDup,cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(rep,ctx->dupRep.p,sizeof(uint32_t)*ctx->nDup,cudaMemcpyDeviceToHost));
+  }
+  return WB_OK;
+}
+
+namespace
+{
+int uploadClassLut(wb_ctx *ctx,const uint8_t *classes,int nClasses,int separate)
+{
+  uint8_t lut[256];
+  memset(lut,separate?255:0,sizeof(lut));
+  if (separate)
+    for (int k=0;k<nClasses;k++)
+    {
+      if (lut[classes[k]]!=255)
+        return fail(ctx,WB_ERR_ARG,"class %d listed twice",(int)classes[k]);
+      lut[classes[k]]=(uint8_t)k;
+    }
+  CK(ctx->encLut.ensure(256));
+  CK(cudaMemcpyAsync(ctx->encLut.p,lut,256,cudaMemcpyHostToDevice,ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  return WB_OK;
+}
+}
+
+extern "C" int wb_leaf_class_counts(wb_ctx *ctx,const uint8_t *classes,int nClasses,int separate,uint32_t *counts)
+{
+  if (!ctx || !counts || (separate && (!classes || nClasses<1 || nClasses>255)))
+    return WB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  if (ctx->phase<PH_CLASSIFIED)
+    return fail(ctx,WB_ERR_STATE,"not classified");
+  const int K=separate?nClasses:1;
+  int rc=uploadClassLut(ctx,classes,nClasses,separate);
+  if (rc)
+    return rc;
+  const uint64_t m=(uint64_t)ctx->nLeaves*K;
+  CK(ctx->encCounts.ensure(m+1));
+  wb_leaf_class_counts_kernel<<<gridFor((uint64_t)ctx->nLeaves*32,256),256,0,ctx->st>>>(
+      ctx->leaves.p,ctx->nLeaves,ctx->labelSorted.p,ctx->encLut.p,K,ctx->encCounts.p);
+  ctx->stats.kernel_launches++;
+  KCHECK();
+  CK(cudaMemcpyAsync(counts,ctx->encCounts.p,sizeof(uint32_t)*m,cudaMemcpyDeviceToHost,ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
+  return WB_OK;
+}
+
+extern "C" int wb_encode(wb_ctx *ctx,const wb_out_spec *spec,const uint64_t *dest,const uint32_t *fileOf,uint32_t nFiles,
+                         uint8_t *out,uint64_t outBytes,wb_file_stats *stats)
+{
+  if (!ctx || !spec || !dest || !fileOf || !nFiles || (!out && outBytes) || !stats)
+    return WB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  if (ctx->phase<PH_CLASSIFIED)
+    return fail(ctx,WB_ERR_STATE,"not classified");
+  static const int len[11]={20,28,26,34,57,63,30,36,38,59,67};
+  if (spec->format<0 || spec->format>10 || spec->rec_len!=len[spec->format] || spec->rec_len>WB_DEC_MAXLEN)
+    return fail(ctx,WB_ERR_FORMAT,"output format %d / record length %d not supported",spec->format,spec->rec_len);
+  if (spec->separate && (spec->n_classes<1 || spec->n_classes>255))
+    return fail(ctx,WB_ERR_ARG,"1..255 classes");
+  if (ctx->recSegs.size()!=ctx->segs.size())
+    return fail(ctx,WB_ERR_STATE,"internal: record segments");
+  for (size_t i=0;i<ctx->segs.size();i++)
+    if (ctx->segs[i].count && !ctx->recSegs[i].recs)
+      return fail(ctx,WB_ERR_STATE,"the records were not kept: call wb_keep_records(ctx,1) before wb_add_las");
+  if (outBytes&1)
+    return fail(ctx,WB_ERR_ARG,"odd output size");
+  cudaStream_t st=ctx->st;
+  const int K=spec->separate?spec->n_classes:1;
+  int rc=uploadClassLut(ctx,spec->classes,spec->n_classes,spec->separate);
+  if (rc)
+    return rc;
+  const uint64_t m=(uint64_t)ctx->nLeaves*K,nv=ctx->nValid;
+  CK(cudaEventRecord(ctx->evA,st));
+  CK(ctx->encDest.ensure(m+1)); CK(ctx->encFile.ensure(m+1));
+  CK(ctx->encMinMax.ensure((uint64_t)nFiles*6)); CK(ctx->encCount.ensure((uint64_t)nFiles*16));
+  CK(ctx->outArena.ensure(outBytes+64));
+  CK(cudaMemcpyAsync(ctx->encDest.p,dest,sizeof(uint64_t)*m,cudaMemcpyHostToDevice,st));
+  CK(cudaMemcpyAsync(ctx->encFile.p,fileOf,sizeof(uint32_t)*m,cudaMemcpyHostToDevice,st));
+  {
+    std::vector<int> mm((size_t)nFiles*6);
+    for (uint32_t f=0;f<nFiles;f++)
+      for (int k=0;k<6;k++)
+        mm[(size_t)f*6+k]=k<3?0x7fffffff:(int)0x80000000;
+    CK(cudaMemcpyAsync(ctx->encMinMax.p,mm.data(),sizeof(int)*mm.size(),cudaMemcpyHostToDevice,st));
+    CK(cudaMemsetAsync(ctx->encCount.p,0,sizeof(unsigned long long)*nFiles*16,st));
+    CK(cudaStreamSynchronize(st));
+  }
+  {
+    WbRecSegs hr;
+    memset(&hr,0,sizeof(hr));
+    for (size_t i=0;i<ctx->recSegs.size();i++)
+      hr.s[i]=ctx->recSegs[i];
+    CK(ctx->drsegs.ensure(1));
+    CK(cudaMemcpyAsync(ctx->drsegs.p,&hr,sizeof(hr),cudaMemcpyHostToDevice,st));
+    CK(cudaStreamSynchronize(st));
+  }
+  // whose attributes a stored point carries: its own record, or the last record at the same XYZ
+  const uint32_t *src=ctx->perm;
+  if (ctx->nDup)
+  {
+    CK(ctx->invPerm.ensure(ctx->n)); CK(ctx->attrSrc.ensure(nv));
+    wb_attr_source_kernel<<<gridFor(nv,256),256,0,st>>>(ctx->perm,nv,ctx->invPerm.p,ctx->attrSrc.p);
+    wb_attr_last_kernel<<<gridFor(ctx->nDup,256),256,0,st>>>(ctx->dupIn.p,ctx->dupRep.p,ctx->nDup,ctx->invPerm.p,ctx->attrSrc.p);
+    ctx->stats.kernel_launches+=2;
+    src=ctx->attrSrc.p;
+  }
+  WbOutSpec ds;
+  ds.fmt=spec->format; ds.recLen=spec->rec_len; ds.nClasses=spec->n_classes; ds.separate=spec->separate;
+  for (int k=0;k<3;k++)
+  {
+    ds.scale[k]=spec->scale[k];
+    ds.offset[k]=spec->offset[k];
+  }
+  ds.unit=spec->unit;
+  size_t smem=((nFiles<=WB_ENC_SMEM_FILES?(size_t)nFiles*WB_ENC_ACC:0)+(size_t)WB_ENC_WARPS*K)*sizeof(int);
+  wb_encode_kernel<<<(unsigned)wb_div_up(ctx->nLeaves,WB_ENC_WARPS),WB_ENC_WARPS*32,smem,st>>>(
+      ctx->leaves.p,ctx->nLeaves,ctx->sx.p,ctx->sy.p,ctx->sz.p,ctx->labelSorted.p,src,ctx->dsegs.p,ctx->drsegs.p,
+      ds,ctx->encLut.p,ctx->encDest.p,ctx->encFile.p,nFiles,ctx->outArena.p,ctx->encMinMax.p,ctx->encCount.p);
+  ctx->stats.kernel_launches++;
+  KCHECK();
+  CK(cudaEventRecord(ctx->evB,st));
+  CK(cudaMemcpyAsync(out,ctx->outArena.p,outBytes,cudaMemcpyDeviceToHost,st));
+  std::vector<int> mm((size_t)nFiles*6);
+  std::vector<unsigned long long> cnt((size_t)nFiles*16);
+  CK(cudaMemcpyAsync(mm.data(),ctx->encMinMax.p,sizeof(int)*mm.size(),cudaMemcpyDeviceToHost,st));
+  CK(cudaMemcpyAsync(cnt.data(),ctx->encCount.p,sizeof(unsigned long long)*cnt.size(),cudaMemcpyDeviceToHost,st));
+  CK(cudaEventRecord(ctx->evC,st));
+  CK(cudaStreamSynchronize(st));
+  for (uint32_t f=0;f<nFiles;f++)
+  {
+    for (int r=0;r<16;r++)
+      stats[f].n_points[r]=cnt[(size_t)f*16+r];
+    for (int k=0;k<3;k++)
+    {
+      stats[f].imin[k]=mm[(size_t)f*6+k];
+      stats[f].imax[k]=mm[(size_t)f*6+3+k];
+    }
+    stats[f].pad_[0]=stats[f].pad_[1]=0;
+  }
+  ctx->stats.ms_encode=elapsed(ctx->evA,ctx->evB);
+  ctx->stats.ms_encode_d2h=elapsed(ctx->evB,ctx->evC);
   return WB_OK;
 }
 

@@ -20,6 +20,7 @@ Flowsnake snake;
 TileTable tiles;
 map<int,size_t> classTotals;
 double minHyperboloidSize=0.1,maxSlope=1,thickness=0,tileSize=1;
+bool keepRecordsOnDevice=false;
 
 namespace
 {
@@ -39,6 +40,7 @@ vector<double> g_x,g_y,g_z;
 vector<uint32_t> g_perm;
 vector<uint64_t> g_keys;
 vector<uint8_t> g_labels;
+vector<uint32_t> g_attrSrc;           // canonical position -> input record whose attributes the stored point has
 deque<ThreadAction> g_results;
 
 void die(const char *what)
@@ -56,6 +58,7 @@ void ensureContext()
       cerr<<"wolkenbase_b200: no usable CUDA device (there is no CPU path)\n";
       exit(3);
     }
+    wb_keep_records(g_ctx,keepRecordsOnDevice?1:0);
   }
 }
 
@@ -116,6 +119,27 @@ void ensureStore()
     int s=3*(WB_LEVELS-g_leaves[i].depth);
     g_leafLo[i]=s>=63?0:(g_keys[g_leaves[i].first]>>s)<<s;
   }
+  // OctBuffer::put overwrites the stored point with a newcomer at the same XYZ (octree.cpp:626-644):
+  // the place is the first record's, the attributes the last one's
+  g_attrSrc=g_perm;
+  if (st.n_duplicates)
+  {
+    vector<uint32_t> dup(st.n_duplicates),rep(st.n_duplicates);
+    wb_get_duplicates(g_ctx,dup.data(),rep.data(),st.n_duplicates);
+    std::map<uint32_t,uint32_t> last;
+    for (size_t u=0;u<dup.size();u++)
+    {
+      uint32_t &l=last[rep[u]];
+      if (dup[u]>l)
+        l=dup[u];
+    }
+    for (size_t k=0;k<n;k++)
+    {
+      auto it=last.find(g_perm[k]);
+      if (it!=last.end())
+        g_attrSrc[k]=it->second;
+    }
+  }
   g_haveStore=true;
 }
 
@@ -136,9 +160,11 @@ void ensureLabels()
 LasPoint pointAt(size_t k)
 // k-th point of the canonical order, all attributes decoded from its original record
 {
-  uint32_t i=g_perm[k];
+  uint32_t i=g_attrSrc[k];
   size_t f=upper_bound(g_fileFirst.begin(),g_fileFirst.end(),(size_t)i)-g_fileFirst.begin()-1;
   LasPoint p=g_files[f]->readPoint(i-g_fileFirst[f]);
+  if (p.returnNum==0)
+    p.returnNum=1;                     // a stored point with return number 0: keep-zeros file, threads.cpp:527-528
   p.location=xyz(g_x[k],g_y[k],g_z[k]);
   if (g_classified)
   {
@@ -777,6 +803,14 @@ bool actionQueueEmpty() { return true; }
 bool resultQueueEmpty() { return g_results.empty(); }
 bool pointBufferEmpty() { return true; }
 size_t pointBufferSize() { return 0; }
+
+size_t duplicatePoints()
+{
+  ensureBuilt();
+  wb_stats st;
+  wb_get_stats(g_ctx,&st);
+  return st.n_duplicates;
+}
 void setThreadCommand(int s) { waitForThreads(s); }
 int getThreadCommand() { return g_command; }
 int getThreadStatus() { return (g_command<<20)|g_command; }
@@ -1272,6 +1306,27 @@ void LasHeader::writePoint(const LasPoint &pnt)
   writePos+=pointLength;
 }
 
+void LasHeader::writeEncoded(const uint8_t *recs,size_t nBytes,const wb_file_stats &st)
+// the effect of writePoint (las.cpp:822-904) for a run of records the device has already made
+{
+  if (!out || !st.n_points[0])
+    return;
+  fseek(out,(long)writePos,SEEK_SET);
+  fwrite(recs,1,nBytes,out);
+  writePos+=nBytes;
+  for (int i=0;i<16;i++)
+    nPoints[i]+=st.n_points[i];
+  // wx=xi*scale+offset is monotone in xi: the extremes of the integers give the extremes of wx
+  double lo[3]={st.imin[0]*xScale+xOffset,st.imin[1]*yScale+yOffset,st.imin[2]*zScale+zOffset};
+  double hi[3]={st.imax[0]*xScale+xOffset,st.imax[1]*yScale+yOffset,st.imax[2]*zScale+zOffset};
+  if (hi[0]>maxX) maxX=hi[0];
+  if (lo[0]<minX) minX=lo[0];
+  if (hi[1]>maxY) maxY=hi[1];
+  if (lo[1]<minY) minY=lo[1];
+  if (hi[2]>maxZ) maxZ=hi[2];
+  if (lo[2]<minZ) minZ=lo[2];
+}
+
 void LasHeader::writeHeader()
 // las.cpp:540-595.  Fields the reference never initialises on the write path (source id, global
 // encoding, GUID, start of waveform data) are written as zeros.
@@ -1402,6 +1457,93 @@ void CloudOutput::writeFiles()
   }
 }
 
+int CloudOutput::writeFilesDevice()
+// writeFiles with the per-point work on the GPU: the sequential part (which file a bucket's points
+// of one class go to, cloudoutput.cpp:197-206) stays here and needs only per-bucket class counts.
+{
+  ensureStore();
+  vector<int> keys;                                  // class slots in map order
+  vector<size_t> fileBase;                           // first global file index of each slot
+  vector<LasHeader *> fileHdr;
+  for (auto &k:headers)
+  {
+    keys.push_back(k.first);
+    fileBase.push_back(fileHdr.size());
+    for (auto &h:k.second)
+      fileHdr.push_back(&h);
+  }
+  const size_t K=keys.size(),nl=g_leaves.size(),nf=fileHdr.size();
+  if (!K || !nf || !nl)
+    return 0;
+  wb_out_spec spec;
+  memset(&spec,0,sizeof(spec));
+  spec.format=pointFormat;
+  spec.rec_len=fileHdr[0]->getPointLength();
+  spec.separate=separateClasses?1:0;
+  spec.n_classes=separateClasses?(int)K:1;
+  for (size_t k=0;k<K;k++)
+    spec.classes[k]=(uint8_t)keys[k];
+  for (int k=0;k<3;k++)
+  {
+    spec.scale[k]=fileHdr[0]->rawScale(k);
+    spec.offset[k]=fileHdr[0]->rawOffset(k);
+  }
+  spec.unit=unit;
+  vector<uint32_t> counts(nl*K);
+  if (wb_leaf_class_counts(g_ctx,spec.classes,spec.n_classes,spec.separate,counts.data())!=WB_OK)
+  {
+    die("leaf class counts");
+    return -1;
+  }
+  vector<uint64_t> filePts(nf,0),start(nl*K);
+  vector<uint32_t> fileOf(nl*K);
+  vector<int> next(K,0);
+  for (size_t i=0;i<nl;i++)
+  {
+    for (size_t k=0;k<K;k++)
+    {
+      long long mn=(long long)grandTotal;
+      size_t m=headers[keys[k]].size();
+      for (size_t j=0;j<m;j++)
+        if ((long long)filePts[fileBase[k]+j]<mn)
+        {
+          next[k]=(int)j;
+          mn=(long long)filePts[fileBase[k]+j];
+        }
+    }
+    for (size_t k=0;k<K;k++)
+    {
+      size_t f=fileBase[k]+next[k];
+      fileOf[i*K+k]=(uint32_t)f;
+      start[i*K+k]=filePts[f];
+      filePts[f]+=counts[i*K+k];
+    }
+  }
+  vector<uint64_t> fileOff(nf+1,0);
+  for (size_t f=0;f<nf;f++)
+    fileOff[f+1]=fileOff[f]+filePts[f]*(uint64_t)spec.rec_len;
+  vector<uint64_t> dest(nl*K);
+  for (size_t i=0;i<nl*K;i++)
+    dest[i]=fileOff[fileOf[i]]+start[i]*(uint64_t)spec.rec_len;
+  uint64_t total=fileOff[nf];
+  uint8_t *buf=nullptr;
+  if (total && wb_host_alloc((void **)&buf,total)!=WB_OK)
+  {
+    cerr<<"cannot allocate "<<total<<" bytes of pinned memory for the output records\n";
+    return -1;
+  }
+  vector<wb_file_stats> st(nf);
+  int rc=wb_encode(g_ctx,&spec,dest.data(),fileOf.data(),(uint32_t)nf,buf,total,st.data());
+  if (rc!=WB_OK)
+    die("encode");
+  else
+    for (size_t f=0;f<nf;f++)
+      fileHdr[f]->writeEncoded(buf+fileOff[f],(size_t)(fileOff[f+1]-fileOff[f]),st[f]);
+  if (buf)
+    wb_host_free(buf);
+  return rc==WB_OK?0:-1;
+}
+
 void CloudOutput::closeFiles()
 {
   for (auto &k:headers)
@@ -1449,8 +1591,14 @@ int writeReferenceStyle(const deque<LasHeader> &inputs,const OutputOptions &opt,
       totals[l]++;
   }
   cloudOutput.openFiles(opt.baseName,totals);
-  cloudOutput.writeFiles();
+  int rc=0;
+  if (keepRecordsOnDevice)
+    rc=cloudOutput.writeFilesDevice();
+  else
+    cloudOutput.writeFiles();
   cloudOutput.closeFiles();
+  if (rc)
+    return rc;
   if (written)
     *written=cloudOutput.written;
   return 0;

@@ -189,6 +189,7 @@ public:
   void setScale(xyz minCor,xyz maxCor,xyz scale);
   void writePoint(const LasPoint &pnt);
   void writeHeader();
+  void writeEncoded(const uint8_t *recs,size_t nBytes,const wb_file_stats &st);   // records made by wb_encode
   LasPoint readPoint(size_t num);                   // throws int -1 past the end, like the reference
   const uint8_t *records() const { return map?map+pointOffset:nullptr; }
   const uint8_t *headerBytes() const { return map; }
@@ -230,6 +231,7 @@ public:
   std::string className(int n);
   void openFiles(std::string name,std::map<int,size_t> classTotals);
   void writeFiles();
+  int writeFilesDevice();                           // the same files, records made by wb_encode
   void closeFiles();
   std::vector<std::string> written;
 private:
@@ -331,6 +333,8 @@ extern TileTable tiles;
 extern std::map<int,size_t> classTotals;
 extern double minHyperboloidSize,maxSlope,thickness;  // scan.h:25
 extern double tileSize;                               // the GUI's setting, mainwindow.cpp:398-411
+extern bool keepRecordsOnDevice;   // set before reading: the raw records stay in device memory and ACT_WRITE's
+                                   // records are made there (wb_encode) instead of by LasHeader::writePoint
 
 // ---------------------------------------------------------------- threads.h
 #define TH_WAIT 1
@@ -363,6 +367,7 @@ bool actionQueueEmpty();
 bool resultQueueEmpty();
 bool pointBufferEmpty();
 size_t pointBufferSize();
+size_t duplicatePoints();                           // alreadyInOctree.size() (octree.cpp:620-662): records lost to an identical XYZ
 void setThreadCommand(int newStatus);
 int getThreadCommand();
 int getThreadStatus();                              // (command<<20)|command: "all threads in the commanded state"

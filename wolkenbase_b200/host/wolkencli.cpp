@@ -8,6 +8,7 @@
 //     --separate-classes 0|1     one file per class (default 1, as the GUI)
 //     --threads N                accepted for compatibility, ignored
 //     --dump FILE                where to write the octree dump (default "dumpfile")
+//     --host-writer              make the output records on the CPU (LasHeader::writePoint) instead of on the GPU
 //     --lossless                 keep the inputs' own records (format, scale, offset) and only replace the class
 //                                byte, instead of the reference's LAS 1.4 re-encoding (CloudOutput)
 #include <cstdlib>
@@ -24,7 +25,7 @@ int main(int argc,char **argv)
   vector<string> inputFiles;
   OutputOptions out;
   string dumpName="dumpfile";
-  bool classify=false,lossless=false;
+  bool classify=false,lossless=false,hostWriter=false;
   for (int i=1;i<argc;i++)
   {
     string a=argv[i];
@@ -39,11 +40,13 @@ int main(int argc,char **argv)
     else if (a=="--threads" || a=="--gpus") val();
     else if (a=="--dump") dumpName=val();
     else if (a=="--lossless") lossless=true;
+    else if (a=="--host-writer") hostWriter=true;
     else if (a.size() && a[0]=='-') { cerr<<"unknown option "<<a<<endl; return 2; }
     else inputFiles.push_back(a);
   }
   if (out.baseName.size()>4 && out.baseName.substr(out.baseName.size()-4)==".las")
     out.baseName.resize(out.baseName.size()-4);
+  keepRecordsOnDevice=classify && !lossless && !hostWriter;
   deque<LasHeader> files(inputFiles.size());
   vector<xyz> limits;
   double mn[3]={INFINITY,INFINITY,INFINITY},mx[3]={-INFINITY,-INFINITY,-INFINITY};
@@ -93,6 +96,7 @@ int main(int argc,char **argv)
   }
   waitForQueueEmpty();
   cout<<"All points in octree\n";
+  cout<<duplicatePoints()<<" duplicate points\n";
   cout<<octStore.getNumBlocks()<<" blocks\n";
   if (classify)
   {
