@@ -111,6 +111,11 @@ int wb_add_extent(wb_ctx *ctx,const double min_corner[3],const double max_corner
  * on the device as they arrive.  fmt 0-3 and 6-8 (las.cpp:38). */
 int wb_add_las(wb_ctx *ctx,const uint8_t *recs,uint64_t n,int fmt,int rec_len,
                const double scale[3],const double offset[3],double unit);
+/* Same, straight from the file (LasHeader::readPoint's seek+read per point, las.cpp:735-745,
+ * becomes a pipeline): worker threads pread 1 Mi-record chunks starting at byte point_offset into a
+ * ring of pinned buffers while earlier chunks are copied and decoded.  A short file is an error. */
+int wb_add_las_file(wb_ctx *ctx,const char *path,uint64_t point_offset,uint64_t n,int fmt,int rec_len,
+                    const double scale[3],const double offset[3],double unit);
 /* Same, records already in device memory. */
 int wb_add_las_device(wb_ctx *ctx,const uint8_t *d_recs,uint64_t n,int fmt,int rec_len,
                       const double scale[3],const double offset[3],double unit);

@@ -436,3 +436,46 @@ def test_encode_same_layout_returns_the_input_records(ctx):
     with pytest.raises(api.WolkenError):
         ctx.encode(cloud.fmt, L, cloud.scale, cloud.offset, lv["first"].astype(np.uint64) * L,
                    np.zeros(len(lv), np.uint32), 1, n * L)
+
+
+def test_add_las_file_equals_add_las(ctx, tmp_path):
+    """The file reader pipeline (pread threads -> pinned ring -> H2D -> decode) delivers exactly what
+    wb_add_las gets from memory: several chunks, a ragged last one, kept records, and a file that
+    is shorter than its header says is an error, not a partial cloud."""
+    cloud = synth.generate(2, 2_600_000, seed=81)                  # 3 chunks of 1 Mi records
+    n = cloud.n
+    path = str(tmp_path / "big.las")
+    cloud.write(path)
+    hdr = len(cloud.header.tobytes())
+    _run_gpu(ctx, [cloud], {})
+    want_dec = [a.copy() for a in ctx.decoded(n)]
+    want_lab = ctx.labels(n).copy()
+    for keep in (False, True):
+        ctx.clear()
+        ctx.keep_records(keep)
+        ctx.set_params()
+        ctx.add_extent(cloud.min_corner, cloud.max_corner)
+        ctx.add_las_file(path, hdr, n, cloud.fmt, cloud.rec_len, cloud.scale, cloud.offset)
+        got = ctx.decoded(n)
+        for a, b in zip(got, want_dec):
+            assert (a == b).all()
+        ctx.run()
+        assert (ctx.labels(n) == want_lab).all()
+    ctx.clear()
+    ctx.keep_records(False)
+    ctx.add_extent(cloud.min_corner, cloud.max_corner)
+    with pytest.raises(api.WolkenError):
+        ctx.add_las_file(path, hdr, n + 1000, cloud.fmt, cloud.rec_len, cloud.scale, cloud.offset)
+    with pytest.raises(api.WolkenError):
+        ctx.add_las_file(str(tmp_path / "missing.las"), hdr, n, cloud.fmt, cloud.rec_len, cloud.scale, cloud.offset)
+    ctx.clear()
+    # a small file after a big one reuses the ring
+    small = synth.generate(1, 5000, seed=82)
+    p2 = str(tmp_path / "small.las")
+    small.write(p2)
+    ctx.set_params()
+    ctx.add_extent(small.min_corner, small.max_corner)
+    ctx.add_las_file(p2, len(small.header.tobytes()), small.n, small.fmt, small.rec_len, small.scale, small.offset)
+    ctx.run()
+    res = O.run([O.file_from_cloud(small)])
+    assert (ctx.labels(small.n) == res.labels).all()

@@ -73,6 +73,7 @@ def lib():
             "wb_add_extent": [vp, dp, dp],
             "wb_add_las": [vp, vp, u64, C.c_int, C.c_int, dp, dp, C.c_double],
             "wb_add_las_device": [vp, vp, u64, C.c_int, C.c_int, dp, dp, C.c_double],
+            "wb_add_las_file": [vp, C.c_char_p, u64, u64, C.c_int, C.c_int, dp, dp, C.c_double],
             "wb_add_points_device": [vp, vp, vp, vp, vp, u64, dp, dp, C.c_double],
             "wb_export_points_device": [vp, u64, u64, vp, vp, vp, vp],
             "wb_set_own_range": [vp, u64, u64],
@@ -133,7 +134,7 @@ EXPORTS = ["wb_create", "wb_destroy", "wb_last_error", "wb_reserve", "wb_clear",
            "wb_snake_set_size", "wb_ldecimal", "wb_format_dump", "wb_add_points_device", "wb_export_points_device",
            "wb_set_own_range", "wb_export_tiles_device", "wb_import_tiles_device", "wb_max_hyperboloid_size",
            "wb_assign", "wb_get_points_sorted", "wb_test_math", "wb_bound_rect", "wb_keep_records",
-           "wb_leaf_class_counts", "wb_encode", "wb_get_duplicates"]
+           "wb_leaf_class_counts", "wb_encode", "wb_get_duplicates", "wb_add_las_file"]
 
 
 def _d(v):
@@ -209,6 +210,11 @@ class Context:
         assert records.dtype == np.uint8 and records.ndim == 2 and records.flags.c_contiguous
         self._ck(self._L.wb_add_las(self._h, records.ctypes.data, records.shape[0], fmt, records.shape[1],
                                     _d(scale), _d(offset), unit))
+
+    def add_las_file(self, path, point_offset, n, fmt, rec_len, scale, offset, unit=1.0):
+        """ACT_READ from the file itself: pread on worker threads -> pinned ring -> H2D -> decode."""
+        self._ck(self._L.wb_add_las_file(self._h, os.fsencode(path), point_offset, n, fmt, rec_len,
+                                         _d(scale), _d(offset), unit))
 
     def add_las_device(self, dptr, n, fmt, rec_len, scale, offset, unit=1.0):
         self._ck(self._L.wb_add_las_device(self._h, dptr, n, fmt, rec_len, _d(scale), _d(offset), unit))

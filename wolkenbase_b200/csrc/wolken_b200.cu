@@ -9,6 +9,11 @@
 #include <algorithm>
 #include <cuda_runtime.h>
 #include "../../include/wolken_b200.h"
+#include <thread>
+#include <mutex>
+#include <condition_variable>
+#include <fcntl.h>
+#include <unistd.h>
 #include "wb_host.h"
 #include "wb_kernels.cuh"
 #include "wb_sort.cuh"
@@ -16,6 +21,8 @@
 
 namespace
 {
+
+#define WB_READ_THREADS 8          // pread workers = pinned buffers of wb_add_las_file (4: 17.7 GB/s from the page cache)
 
 template <typename T> struct DevBuf
 {
@@ -69,6 +76,10 @@ struct wb_ctx
   DevBuf<uint32_t> idxA,idxB,scr0,scr1,winner,pairValA,pairValB,table,blockSums;
   DevBuf<uint32_t> dupIn,dupRep;          // input indices of (lost duplicate, surviving point at the same XYZ)
   uint64_t nDup=0;
+  // pinned ring of the file reader (wb_add_las_file)
+  uint8_t *readBuf[WB_READ_THREADS]={};
+  uint64_t readBufBytes=0;
+  cudaEvent_t evRead[WB_READ_THREADS]={};
   // raw records kept for wb_encode (one buffer per wb_add_las call)
   bool keepRecords=false;
   std::vector<uint8_t *> recBufs;
@@ -334,6 +345,11 @@ extern "C" void wb_destroy(wb_ctx *ctx)
   ctx->tDensity.release(); ctx->tHyp.release(); ctx->tHeight.release(); ctx->tileExt.release(); ctx->tileGrid.release(); ctx->wedgeBuf.release(); ctx->chunkPending.release();
   ctx->dupIn.release(); ctx->dupRep.release();
   freeKeptRecords(ctx);
+  for (int i=0;i<WB_READ_THREADS;i++)
+  {
+    if (ctx->readBuf[i]) cudaFreeHost(ctx->readBuf[i]);
+    if (ctx->evRead[i]) cudaEventDestroy(ctx->evRead[i]);
+  }
   ctx->drsegs.release(); ctx->outArena.release(); ctx->encLut.release(); ctx->encDest.release(); ctx->encCount.release();
   ctx->encFile.release(); ctx->encCounts.release(); ctx->attrSrc.release(); ctx->invPerm.release(); ctx->encMinMax.release();
   cudaStreamDestroy(ctx->st); cudaStreamDestroy(ctx->stCopy);
@@ -522,6 +538,170 @@ extern "C" int wb_add_las(wb_ctx *ctx,const uint8_t *recs,uint64_t n,int fmt,int
   CK(cudaEventRecord(ctx->evB,ctx->st));
   CK(cudaStreamSynchronize(ctx->st));
   ctx->stats.ms_h2d+=elapsed(ctx->evA,ctx->evB);       // copy and decode overlap: one figure for both
+  return addSegment(ctx,n,scale,offset,unit,kept,fmt,recLen);
+}
+
+// ---- the reader pipeline: pread into a pinned ring on worker threads, H2D and decode behind it
+namespace
+{
+struct ReadRing
+{
+  std::mutex m;
+  std::condition_variable cv;
+  int state[WB_READ_THREADS]={};   // 0 free, 1 filled, -1 read error
+  bool stop=false;
+};
+}
+
+extern "C" int wb_add_las_file(wb_ctx *ctx,const char *path,uint64_t pointOffset,uint64_t n,int fmt,int recLen,
+                               const double scale[3],const double offset[3],double unit)
+{
+  if (!ctx || !path || !scale || !offset)
+    return WB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  int rc=checkFormat(ctx,fmt,recLen);
+  if (rc)
+    return rc;
+  if (ctx->phase>PH_LOADED)
+    return fail(ctx,WB_ERR_STATE,"cloud already built: wb_clear first");
+  int fd=open(path,O_RDONLY);
+  if (fd<0)
+    return fail(ctx,WB_ERR_ARG,"cannot open %s",path);
+  if ((rc=ensurePointArrays(ctx,ctx->n+n)))
+  {
+    close(fd);
+    return rc;
+  }
+  const int T=WB_READ_THREADS;
+  const uint64_t chunkRecs=(uint64_t)1<<20;          // 1 Mi records (multiple of 16: chunks stay 16-byte aligned)
+  const uint64_t chunkBytes=chunkRecs*recLen;
+  const uint64_t nChunks=wb_div_up(n,chunkRecs);
+  const uint64_t bufBytes=std::min<uint64_t>(chunkBytes,n*recLen)+64;
+  if (ctx->readBufBytes<bufBytes)
+  {
+    for (int i=0;i<T;i++)
+    {
+      if (ctx->readBuf[i])
+        cudaFreeHost(ctx->readBuf[i]);
+      ctx->readBuf[i]=nullptr;
+    }
+    ctx->readBufBytes=0;
+    for (int i=0;i<T && (uint64_t)i<nChunks;i++)
+      if (cudaHostAlloc((void **)&ctx->readBuf[i],bufBytes,cudaHostAllocDefault)!=cudaSuccess)
+      {
+        close(fd);
+        return fail(ctx,WB_ERR_NOMEM,"cannot pin %llu bytes for the reader",(unsigned long long)bufBytes);
+      }
+    if (nChunks>=(uint64_t)T)
+      ctx->readBufBytes=bufBytes;                    // the whole ring exists: reusable for any smaller file
+  }
+  for (int i=0;i<T;i++)
+  {
+    if (!ctx->evRead[i])
+      CK(cudaEventCreateWithFlags(&ctx->evRead[i],cudaEventDisableTiming));
+    if (!ctx->readBuf[i] && (uint64_t)i<nChunks)
+      CK(cudaHostAlloc((void **)&ctx->readBuf[i],bufBytes,cudaHostAllocDefault));
+  }
+  uint8_t *kept=nullptr;
+  if (ctx->keepRecords && n)
+  {
+    CK(cudaMalloc((void **)&kept,(size_t)(n*recLen+64)));
+    ctx->recBufs.push_back(kept);
+  }
+  else
+    for (int b=0;b<2;b++)
+      CK(ctx->staging[b].ensure(bufBytes));
+  ReadRing ring;
+  auto worker=[&](int t)
+  { // chunk k lives in buffer k%T and is read by thread k%T
+    for (uint64_t k=t;k<nChunks;k+=T)
+    {
+      {
+        std::unique_lock<std::mutex> lk(ring.m);
+        ring.cv.wait(lk,[&]{ return ring.state[t]==0 || ring.stop; });
+        if (ring.stop)
+          return;
+      }
+      uint64_t cnt=std::min(chunkRecs,n-k*chunkRecs),want=cnt*recLen,got=0;
+      off_t pos=(off_t)(pointOffset+k*chunkBytes);
+      while (got<want)
+      {
+        ssize_t r=pread(fd,ctx->readBuf[t]+got,want-got,pos+(off_t)got);
+        if (r<=0)
+          break;
+        got+=(uint64_t)r;
+      }
+      {
+        std::lock_guard<std::mutex> lk(ring.m);
+        ring.state[t]=got==want?1:-1;
+      }
+      ring.cv.notify_all();
+    }
+  };
+  std::vector<std::thread> threads;
+  for (int t=0;t<T && (uint64_t)t<nChunks;t++)
+    threads.emplace_back(worker,t);
+  auto finish=[&](int code)
+  {
+    {
+      std::lock_guard<std::mutex> lk(ring.m);
+      ring.stop=true;
+    }
+    ring.cv.notify_all();
+    for (auto &th:threads)
+      th.join();
+    close(fd);
+    return code;
+  };
+  cudaError_t ce=cudaEventRecord(ctx->evA,ctx->st);
+  int dropZeros=0,used[2]={0,0};
+  for (uint64_t k=0;k<nChunks && ce==cudaSuccess;k++)
+  {
+    const int t=(int)(k%T),b=(int)(k&1);
+    int stt;
+    {
+      std::unique_lock<std::mutex> lk(ring.m);
+      ring.cv.wait(lk,[&]{ return ring.state[t]!=0; });
+      stt=ring.state[t];
+    }
+    if (stt<0)
+      return finish(fail(ctx,WB_ERR_ARG,"%s: short read (the header promises %llu points)",path,(unsigned long long)n));
+    const uint64_t cnt=std::min(chunkRecs,n-k*chunkRecs);
+    const uint8_t *src=ctx->readBuf[t];
+    if (k==0)
+      dropZeros=(fmt<6?(src[14]&7):(src[14]&15))!=0;                 // threads.cpp:485-500: decided by record 0
+    uint8_t *dst=kept?kept+k*chunkBytes:ctx->staging[b].p;
+    if (used[b] && !kept)
+      ce=cudaStreamWaitEvent(ctx->stCopy,ctx->evDec[b],0);
+    if (ce==cudaSuccess) ce=cudaMemcpyAsync(dst,src,cnt*recLen,cudaMemcpyHostToDevice,ctx->stCopy);
+    if (ce==cudaSuccess) ce=cudaEventRecord(ctx->evRead[t],ctx->stCopy);
+    if (ce==cudaSuccess) ce=cudaStreamWaitEvent(ctx->st,ctx->evRead[t],0);
+    if (ce!=cudaSuccess)
+      break;
+    if ((rc=decodeDevice(ctx,dst,ctx->n+k*chunkRecs,cnt,fmt,recLen,dropZeros,ctx->st)))
+      return finish(rc);
+    ce=cudaEventRecord(ctx->evDec[b],ctx->st);
+    used[b]=1;
+    if (k>=1 && ce==cudaSuccess)
+    { // the previous chunk's copy is done by now or soon: hand its buffer back to its reader
+      const int tp=(int)((k-1)%T);
+      ce=cudaEventSynchronize(ctx->evRead[tp]);
+      {
+        std::lock_guard<std::mutex> lk(ring.m);
+        ring.state[tp]=0;
+      }
+      ring.cv.notify_all();
+    }
+  }
+  if (ce!=cudaSuccess)
+    return finish(fail(ctx,WB_ERR_CUDA,"%s",cudaGetErrorString(ce)));
+  ce=cudaEventRecord(ctx->evB,ctx->st);
+  if (ce==cudaSuccess) ce=cudaStreamSynchronize(ctx->stCopy);
+  if (ce==cudaSuccess) ce=cudaStreamSynchronize(ctx->st);
+  if (ce!=cudaSuccess)
+    return finish(fail(ctx,WB_ERR_CUDA,"%s",cudaGetErrorString(ce)));
+  finish(0);
+  ctx->stats.ms_h2d+=elapsed(ctx->evA,ctx->evB);       // file read, copy and decode overlap: one figure
   return addSegment(ctx,n,scale,offset,unit,kept,fmt,recLen);
 }
 

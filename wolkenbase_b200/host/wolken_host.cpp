@@ -845,7 +845,8 @@ void enqueueAction(ThreadAction a)
         for (size_t i=0;i+5<g_corners.size();i+=6)
           wb_add_extent(g_ctx,&g_corners[i],&g_corners[i+3]);
       double sc[3]={h->rawScale(0),h->rawScale(1),h->rawScale(2)},of[3]={h->rawOffset(0),h->rawOffset(1),h->rawOffset(2)};
-      if (wb_add_las(g_ctx,h->records(),h->numberPoints(),h->getPointFormat(),h->getPointLength(),sc,of,h->getUnit())!=WB_OK)
+      if (wb_add_las_file(g_ctx,h->getFileName().c_str(),h->getPointOffset(),h->numberPoints(),h->getPointFormat(),
+                          h->getPointLength(),sc,of,h->getUnit())!=WB_OK)
       {
         die("Error reading file");
         break;

@@ -178,6 +178,7 @@ public:
   int getVersion() const { return (versionMajor<<8)+versionMinor; }
   int getPointFormat() const { return pointFormat; }
   int getPointLength() const { return pointLength; }
+  size_t getPointOffset() const { return pointOffset; }
   xyz getScale() const { return xyz(xScale*unit,yScale*unit,zScale*unit); }
   xyz getOffset() const { return xyz(xOffset*unit,yOffset*unit,zOffset*unit); }
   xyz minCorner() const { return xyz(minX*unit,minY*unit,minZ*unit); }

@@ -9,6 +9,7 @@
 //     --threads N                accepted for compatibility, ignored
 //     --dump FILE                where to write the octree dump (default "dumpfile")
 //     --host-writer              make the output records on the CPU (LasHeader::writePoint) instead of on the GPU
+//     --timing                   print the wall time of each phase (seconds) as one JSON line at the end
 //     --lossless                 keep the inputs' own records (format, scale, offset) and only replace the class
 //                                byte, instead of the reference's LAS 1.4 re-encoding (CloudOutput)
 #include <cstdlib>
@@ -16,6 +17,7 @@
 #include <deque>
 #include <iostream>
 #include <fstream>
+#include <chrono>
 #include "wolken_host.h"
 
 using namespace std;
@@ -25,7 +27,9 @@ int main(int argc,char **argv)
   vector<string> inputFiles;
   OutputOptions out;
   string dumpName="dumpfile";
-  bool classify=false,lossless=false,hostWriter=false;
+  bool classify=false,lossless=false,hostWriter=false,timing=false;
+  auto now=[]{ return chrono::duration<double>(chrono::steady_clock::now().time_since_epoch()).count(); };
+  double t0=now(),tRead=0,tScan=0,tPost=0,tClass=0,tWrite=0,tDump=0,tOpen=0;
   for (int i=1;i<argc;i++)
   {
     string a=argv[i];
@@ -41,6 +45,7 @@ int main(int argc,char **argv)
     else if (a=="--dump") dumpName=val();
     else if (a=="--lossless") lossless=true;
     else if (a=="--host-writer") hostWriter=true;
+    else if (a=="--timing") timing=true;
     else if (a.size() && a[0]=='-') { cerr<<"unknown option "<<a<<endl; return 2; }
     else inputFiles.push_back(a);
   }
@@ -84,6 +89,8 @@ int main(int argc,char **argv)
     initTiles();
     (void)mn; (void)mx;
   }
+  tOpen=now()-t0;
+  double t=now();
   startThreads(1);
   waitForThreads(TH_READ);
   for (size_t i=0;i<files.size();i++)
@@ -98,13 +105,19 @@ int main(int argc,char **argv)
   cout<<"All points in octree\n";
   cout<<duplicatePoints()<<" duplicate points\n";
   cout<<octStore.getNumBlocks()<<" blocks\n";
+  tRead=now()-t;
   if (classify)
   {
+    // each transition runs the phase it names on the GPU and returns when it is done
+    t=now();
     waitForThreads(TH_SCAN);
+    tScan=now()-t; t=now();
     cout<<"Starting scan\n";
     waitForThreads(TH_POSTSCAN);
+    tPost=now()-t; t=now();
     cout<<"Starting postscan\n";
     waitForThreads(TH_SPLIT);
+    tClass=now()-t; t=now();
     cout<<"Starting classifying\n";
     waitForThreads(TH_PAUSE);
     cout<<"Counting points\n";
@@ -121,7 +134,9 @@ int main(int argc,char **argv)
       return 5;
     for (auto &w:written)
       cout<<"Wrote "<<w<<endl;
+    tWrite=now()-t;
   }
+  t=now();
   waitForThreads(TH_STOP);
   cout<<"Dumping octree\n";
   {
@@ -129,5 +144,10 @@ int main(int argc,char **argv)
     octStore.dump(dumpFile);
   }
   joinThreads();
+  tDump=now()-t;
+  if (timing)
+    cout<<"{\"open_s\": "<<tOpen<<", \"read_build_s\": "<<tRead<<", \"scan_s\": "<<tScan<<", \"postscan_s\": "<<tPost
+        <<", \"classify_s\": "<<tClass<<", \"count_write_s\": "<<tWrite<<", \"dump_s\": "<<tDump
+        <<", \"total_s\": "<<now()-t0<<"}\n";
   return 0;
 }
