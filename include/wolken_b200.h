@@ -180,7 +180,7 @@ int wb_patch_records(wb_ctx *ctx,uint8_t *recs,uint64_t first_point,uint64_t n,i
  *                                     (K = n_classes, or 1 and every class when separate == 0)
  *   wb_encode                         dest[leaf*K+k] = byte offset in `out` where that run of records
  *                                     starts (even), file_of[leaf*K+k] = index of the file it belongs
- *                                     to; out receives all records, stats[f] the header figures of
+ *                                     to; out (may be NULL) receives all records, stats[f] the header figures of
  *                                     file f: per-return counts (n_points[0] = total) and the extremes
  *                                     of the written integers (header min/max = i*scale+offset).
  * Points whose class has no slot are not written (cloudoutput.cpp:212-214). */
@@ -200,6 +200,10 @@ int wb_keep_records(wb_ctx *ctx,int keep);
 int wb_leaf_class_counts(wb_ctx *ctx,const uint8_t *classes,int n_classes,int separate,uint32_t *counts);
 int wb_encode(wb_ctx *ctx,const wb_out_spec *spec,const uint64_t *dest,const uint32_t *file_of,uint32_t n_files,
               uint8_t *out,uint64_t out_bytes,wb_file_stats *stats);
+/* wb_encode with out == NULL leaves the records in device memory; wb_write_encoded streams the span
+ * [arena_off, arena_off+bytes) of them into the open file descriptor at file_pos (D2H through a pinned
+ * ring, pwrite on worker threads). */
+int wb_write_encoded(wb_ctx *ctx,int fd,uint64_t file_pos,uint64_t arena_off,uint64_t bytes);
 /* Records lost to an identical XYZ (octree.cpp:620-662): input index of each and of the point that
  * holds its place in the store; wb_stats.n_duplicates entries. */
 int wb_get_duplicates(wb_ctx *ctx,uint32_t *dup,uint32_t *rep,uint64_t cap);

@@ -374,7 +374,7 @@ def test_files_with_different_offsets_and_units(ctx):
     assert (ctx.labels(cloud.n) == res.labels).all()
 
 
-def test_encode_same_layout_returns_the_input_records(ctx):
+def test_encode_same_layout_returns_the_input_records(ctx, tmp_path):
     """wb_encode (LasHeader::readPoint -> writePoint, las.cpp:735-904) with the input's own format,
     scale and offset must give back the input records in canonical order with only the class
     replaced; the header figures are the totals, per-return counts and integer extremes."""
@@ -404,6 +404,20 @@ def test_encode_same_layout_returns_the_input_records(ctx):
     want[:, 15] = (want[:, 15] & 0xe0) | (lab[order] & 31)
     got = out.reshape(n, L)
     assert (got == want).all(), np.nonzero((got != want).any(axis=0))[0]
+    # the same records streamed from device memory into a file, at an offset, in two spans
+    _, st2 = ctx.encode(cloud.fmt, L, cloud.scale, cloud.offset, dest, np.zeros(len(lv), np.uint32), 1, n * L,
+                        fetch=False)
+    assert st2 == st
+    with open(str(tmp_path / "spans.bin"), "wb") as f:
+        f.write(b"H" * 375)
+        f.flush()
+        half = (n // 2) * L
+        ctx.write_encoded(f.fileno(), 375 + half, half, n * L - half)
+        ctx.write_encoded(f.fileno(), 375, 0, half)
+    raw = np.fromfile(str(tmp_path / "spans.bin"), dtype=np.uint8)
+    assert len(raw) == 375 + n * L and (raw[:375] == ord("H")).all() and (raw[375:] == out).all()
+    with pytest.raises(api.WolkenError):
+        ctx.write_encoded(0, 0, n * L - 10, 100)
     ints = cloud.ints()
     assert st[0]["n_points"][0] == n and st[0]["imin"] == ints.min(axis=0).tolist() and st[0]["imax"] == ints.max(axis=0).tolist()
     by_ret = np.bincount(recs[:, 14] & 7, minlength=16)

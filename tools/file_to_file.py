@@ -1,6 +1,6 @@
 """File-to-file wall time of wolkencli (LAS in -> classified LAS 1.4 out), GPU writer and CPU writer.
 
-Usage (GPU box): python tools/file_to_file.py [points] [scene]
+Usage (GPU box): python tools/file_to_file.py [points] [scene] [writers, e.g. device,lossless]
 Writes the inputs under /tmp, prints one JSON line per writer.
 """
 import json
@@ -21,16 +21,20 @@ os.makedirs(work, exist_ok=True)
 cloud = synth.generate(scene, n, seed=scene)
 las = os.path.join(work, "in.las")
 cloud.write(las)
-for writer in ("device", "host", "lossless"):
+writers = sys.argv[3].split(",") if len(sys.argv) > 3 else ["device", "host", "lossless"]
+for writer in writers:
     d = os.path.join(work, writer)
     os.makedirs(d, exist_ok=True)
     cmd = [cli, "-o", os.path.join(d, "out"), "--dump", os.path.join(d, "dump"), "--timing", las]
+    env = dict(os.environ)
+    if writer == "device-mmap":
+        env["WB_WRITE_MODE"] = "mmap"
     if writer == "host":
         cmd.append("--host-writer")
     if writer == "lossless":
         cmd.append("--lossless")
     t = time.time()
-    r = subprocess.run(cmd, capture_output=True, text=True, cwd=d)
+    r = subprocess.run(cmd, capture_output=True, text=True, cwd=d, env=env)
     wall = time.time() - t
     if r.returncode != 0:
         print(writer, "failed", r.stdout[-500:], r.stderr[-500:])

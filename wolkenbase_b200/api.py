@@ -114,6 +114,7 @@ def lib():
             "wb_leaf_class_counts": [vp, vp, C.c_int, C.c_int, vp],
             "wb_encode": [vp, C.POINTER(OutSpec), vp, vp, C.c_uint32, vp, u64, vp],
             "wb_get_duplicates": [vp, vp, vp, u64],
+            "wb_write_encoded": [vp, C.c_int, u64, u64, u64],
         }
         for name, args in sig.items():
             f = getattr(L, name)
@@ -134,7 +135,7 @@ EXPORTS = ["wb_create", "wb_destroy", "wb_last_error", "wb_reserve", "wb_clear",
            "wb_snake_set_size", "wb_ldecimal", "wb_format_dump", "wb_add_points_device", "wb_export_points_device",
            "wb_set_own_range", "wb_export_tiles_device", "wb_import_tiles_device", "wb_max_hyperboloid_size",
            "wb_assign", "wb_get_points_sorted", "wb_test_math", "wb_bound_rect", "wb_keep_records",
-           "wb_leaf_class_counts", "wb_encode", "wb_get_duplicates", "wb_add_las_file"]
+           "wb_leaf_class_counts", "wb_encode", "wb_get_duplicates", "wb_add_las_file", "wb_write_encoded"]
 
 
 def _d(v):
@@ -306,7 +307,8 @@ class Context:
         self._ck(self._L.wb_leaf_class_counts(self._h, cl.ctypes.data, len(cl), 1 if sep else 0, out.ctypes.data))
         return out
 
-    def encode(self, fmt, rec_len, scale, offset, dest, file_of, n_files, out_bytes, classes=None, unit=1.0):
+    def encode(self, fmt, rec_len, scale, offset, dest, file_of, n_files, out_bytes, classes=None, unit=1.0,
+               fetch=True):
         """wb_encode: returns (records as a uint8 array of out_bytes, per-file stats)."""
         spec = OutSpec()
         spec.format, spec.rec_len = fmt, rec_len
@@ -320,11 +322,15 @@ class Context:
         spec.unit = unit
         dest = np.ascontiguousarray(dest, dtype=np.uint64)
         file_of = np.ascontiguousarray(file_of, dtype=np.uint32)
-        out = np.zeros(out_bytes, dtype=np.uint8)
+        out = np.zeros(out_bytes if fetch else 0, dtype=np.uint8)
         stats = (FileStats * n_files)()
         self._ck(self._L.wb_encode(self._h, C.byref(spec), dest.ctypes.data, file_of.ctypes.data, n_files,
-                                   out.ctypes.data, out_bytes, stats))
+                                   out.ctypes.data if fetch else None, out_bytes, stats))
         return out, [{"n_points": list(s.n_points), "imin": list(s.imin), "imax": list(s.imax)} for s in stats]
+
+    def write_encoded(self, fd, file_pos, arena_off, nbytes):
+        """Stream records left on the device by encode(..., fetch=False) into an open file."""
+        self._ck(self._L.wb_write_encoded(self._h, fd, file_pos, arena_off, nbytes))
 
     def duplicates(self):
         n = self.stats()["n_duplicates"]

@@ -9,6 +9,7 @@
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
+#include <chrono>
 #include "wolken_host.h"
 
 using namespace std;
@@ -21,6 +22,7 @@ TileTable tiles;
 map<int,size_t> classTotals;
 double minHyperboloidSize=0.1,maxSlope=1,thickness=0,tileSize=1;
 bool keepRecordsOnDevice=false;
+double hostTimes[4]={0,0,0,0};        // seconds in wb_create, wb_add_las_file, wb_build, wb_encode+write
 
 namespace
 {
@@ -33,7 +35,7 @@ Cube g_snakeCube;
 double g_snakeTile=1;
 bool g_built=false,g_scanned=false,g_postscanned=false,g_classified=false;
 // host mirrors, filled on demand
-bool g_haveStore=false;
+bool g_haveStore=false,g_haveLeaves=false;
 vector<wb_leaf> g_leaves;
 vector<uint64_t> g_leafLo;             // smallest key of each leaf's cube
 vector<double> g_x,g_y,g_z;
@@ -42,6 +44,14 @@ vector<uint64_t> g_keys;
 vector<uint8_t> g_labels;
 vector<uint32_t> g_attrSrc;           // canonical position -> input record whose attributes the stored point has
 deque<ThreadAction> g_results;
+
+struct Stopwatch
+{
+  double &acc;
+  std::chrono::steady_clock::time_point t0;
+  explicit Stopwatch(double &a):acc(a),t0(std::chrono::steady_clock::now()) {}
+  ~Stopwatch() { acc+=std::chrono::duration<double>(std::chrono::steady_clock::now()-t0).count(); }
+};
 
 void die(const char *what)
 {
@@ -53,6 +63,7 @@ void ensureContext()
   if (!g_ctx)
   {
     const char *d=getenv("WOLKEN_DEVICE");
+    Stopwatch sw(hostTimes[0]);
     if (wb_create(d?atoi(d):0,&g_ctx)!=WB_OK)
     {
       cerr<<"wolkenbase_b200: no usable CUDA device (there is no CPU path)\n";
@@ -88,25 +99,36 @@ void ensureBuilt()
   wb_set_params(g_ctx,g_snakeTile,maxSlope,thickness,minHyperboloidSize);
   if (octRoot.getSide()>0 && g_snakeCube.getSide()>0)
     wb_set_geometry(g_ctx,rc,octRoot.getSide(),cube);
+  Stopwatch sw(hostTimes[2]);
   if (wb_build(g_ctx)!=WB_OK)
   {
     die("build");
     exit(4);
   }
   g_built=true;
-  g_haveStore=false;
+  g_haveStore=g_haveLeaves=false;
 }
 
-void ensureStore()
+void ensureLeaves()
+// the bucket list alone (enough for getNumBlocks, dump and the device writer)
 {
   ensureBuilt();
-  if (g_haveStore)
+  if (g_haveLeaves)
     return;
   uint64_t nl=0;
   wb_num_leaves(g_ctx,&nl);
   g_leaves.resize(nl);
   if (nl)
     wb_get_leaves(g_ctx,g_leaves.data(),nl);
+  g_haveLeaves=true;
+}
+
+void ensureStore()
+{
+  ensureLeaves();
+  if (g_haveStore)
+    return;
+  uint64_t nl=g_leaves.size();
   wb_stats st;
   wb_get_stats(g_ctx,&st);
   size_t n=st.n_points;
@@ -582,8 +604,18 @@ Cylinder Flowsnake::cyl(Eisenstein e)
   return Cylinder(xy(re,im)+center,rad);
 }
 
+void TileTable::sync()
+{
+  if (stale)
+  {
+    stale=false;
+    refreshTiles();
+  }
+}
+
 Tile &TileTable::operator[](Eisenstein e)
 {
+  sync();
   auto it=byAddr.find(e);
   if (it==byAddr.end())
   {
@@ -691,7 +723,7 @@ vector<int64_t> Octree::findBlocks(const Shape &sh)
 
 size_t OctStore::getNumBlocks()
 {
-  ensureStore();
+  ensureLeaves();
   return g_leaves.size();
 }
 
@@ -766,7 +798,7 @@ map<int,size_t> OctStore::countClasses(int64_t block)
 
 void OctStore::dump(ofstream &file)
 {
-  ensureStore();
+  ensureLeaves();
   vector<char> buf(g_leaves.size()*128+64);
   int n=wb_format_dump(g_leaves.data(),g_leaves.size(),buf.data(),buf.size());
   if (n>0)
@@ -785,7 +817,7 @@ void OctStore::clear()
     wb_clear(g_ctx);
   g_files.clear();
   g_fileFirst.clear();
-  g_built=g_scanned=g_postscanned=g_classified=g_haveStore=false;
+  g_built=g_scanned=g_postscanned=g_classified=g_haveStore=g_haveLeaves=false;
   g_labels.clear();
 }
 
@@ -845,6 +877,7 @@ void enqueueAction(ThreadAction a)
         for (size_t i=0;i+5<g_corners.size();i+=6)
           wb_add_extent(g_ctx,&g_corners[i],&g_corners[i+3]);
       double sc[3]={h->rawScale(0),h->rawScale(1),h->rawScale(2)},of[3]={h->rawOffset(0),h->rawOffset(1),h->rawOffset(2)};
+      Stopwatch sw(hostTimes[1]);
       if (wb_add_las_file(g_ctx,h->getFileName().c_str(),h->getPointOffset(),h->numberPoints(),h->getPointFormat(),
                           h->getPointLength(),sc,of,h->getUnit())!=WB_OK)
       {
@@ -889,7 +922,7 @@ void waitForThreads(int newStatus)
       {
         if (wb_scan(g_ctx)!=WB_OK) { die("scan"); exit(4); }
         g_scanned=true;
-        refreshTiles();
+        tiles.invalidate();
       }
       break;
     case TH_POSTSCAN:
@@ -899,7 +932,7 @@ void waitForThreads(int newStatus)
       {
         if (wb_postscan(g_ctx)!=WB_OK) { die("postscan"); exit(4); }
         g_postscanned=true;
-        refreshTiles();
+        tiles.invalidate();
       }
       break;
     case TH_SPLIT:
@@ -1307,13 +1340,15 @@ void LasHeader::writePoint(const LasPoint &pnt)
   writePos+=pointLength;
 }
 
-void LasHeader::writeEncoded(const uint8_t *recs,size_t nBytes,const wb_file_stats &st)
-// the effect of writePoint (las.cpp:822-904) for a run of records the device has already made
+int LasHeader::writeEncoded(wb_ctx *ctx,uint64_t arenaOff,size_t nBytes,const wb_file_stats &st)
+// the effect of writePoint (las.cpp:822-904) for a run of records wb_encode has made on the device
 {
   if (!out || !st.n_points[0])
-    return;
-  fseek(out,(long)writePos,SEEK_SET);
-  fwrite(recs,1,nBytes,out);
+    return 0;
+  fflush(out);
+  int rc=wb_write_encoded(ctx,fileno(out),writePos,arenaOff,nBytes);
+  if (rc)
+    return rc;
   writePos+=nBytes;
   for (int i=0;i<16;i++)
     nPoints[i]+=st.n_points[i];
@@ -1326,6 +1361,7 @@ void LasHeader::writeEncoded(const uint8_t *recs,size_t nBytes,const wb_file_sta
   if (lo[1]<minY) minY=lo[1];
   if (hi[2]>maxZ) maxZ=hi[2];
   if (lo[2]<minZ) minZ=lo[2];
+  return 0;
 }
 
 void LasHeader::writeHeader()
@@ -1462,7 +1498,7 @@ int CloudOutput::writeFilesDevice()
 // writeFiles with the per-point work on the GPU: the sequential part (which file a bucket's points
 // of one class go to, cloudoutput.cpp:197-206) stays here and needs only per-bucket class counts.
 {
-  ensureStore();
+  ensureLeaves();
   vector<int> keys;                                  // class slots in map order
   vector<size_t> fileBase;                           // first global file index of each slot
   vector<LasHeader *> fileHdr;
@@ -1527,21 +1563,19 @@ int CloudOutput::writeFilesDevice()
   for (size_t i=0;i<nl*K;i++)
     dest[i]=fileOff[fileOf[i]]+start[i]*(uint64_t)spec.rec_len;
   uint64_t total=fileOff[nf];
-  uint8_t *buf=nullptr;
-  if (total && wb_host_alloc((void **)&buf,total)!=WB_OK)
-  {
-    cerr<<"cannot allocate "<<total<<" bytes of pinned memory for the output records\n";
-    return -1;
-  }
   vector<wb_file_stats> st(nf);
-  int rc=wb_encode(g_ctx,&spec,dest.data(),fileOf.data(),(uint32_t)nf,buf,total,st.data());
+  // the records stay on the device; each file's span is streamed into it (pinned ring + pwrite threads)
+  Stopwatch sw(hostTimes[3]);
+  int rc=wb_encode(g_ctx,&spec,dest.data(),fileOf.data(),(uint32_t)nf,nullptr,total,st.data());
   if (rc!=WB_OK)
     die("encode");
   else
-    for (size_t f=0;f<nf;f++)
-      fileHdr[f]->writeEncoded(buf+fileOff[f],(size_t)(fileOff[f+1]-fileOff[f]),st[f]);
-  if (buf)
-    wb_host_free(buf);
+    for (size_t f=0;f<nf && rc==WB_OK;f++)
+    {
+      rc=fileHdr[f]->writeEncoded(g_ctx,fileOff[f],(size_t)(fileOff[f+1]-fileOff[f]),st[f]);
+      if (rc!=WB_OK)
+        die("write");
+    }
   return rc==WB_OK?0:-1;
 }
 

@@ -190,7 +190,7 @@ public:
   void setScale(xyz minCor,xyz maxCor,xyz scale);
   void writePoint(const LasPoint &pnt);
   void writeHeader();
-  void writeEncoded(const uint8_t *recs,size_t nBytes,const wb_file_stats &st);   // records made by wb_encode
+  int writeEncoded(wb_ctx *ctx,uint64_t arenaOff,size_t nBytes,const wb_file_stats &st);   // records made by wb_encode
   LasPoint readPoint(size_t num);                   // throws int -1 past the end, like the reference
   const uint8_t *records() const { return map?map+pointOffset:nullptr; }
   const uint8_t *headerBytes() const { return map; }
@@ -278,14 +278,18 @@ struct Tile                                          // tile.h:27-35
   double density,hyperboloidSize,height;
 };
 
+void refreshTiles();
 class TileTable                                      // stands in for harray<Tile> tiles
 {
 public:
   Tile &operator[](Eisenstein e);                   // zero tile if absent, like harray
-  int count(Eisenstein e) { return byAddr.count(e); }
-  void clear() { byAddr.clear(); }
-  size_t size() const { return byAddr.size(); }
+  int count(Eisenstein e) { sync(); return byAddr.count(e); }
+  void clear() { byAddr.clear(); stale=false; }
+  size_t size() { sync(); return byAddr.size(); }
+  void invalidate() { stale=true; }                 // the device table changed: refill on next access
 private:
+  void sync();
+  bool stale=false;
   std::map<Eisenstein,Tile> byAddr;
   friend void refreshTiles();
 };
@@ -334,6 +338,7 @@ extern TileTable tiles;
 extern std::map<int,size_t> classTotals;
 extern double minHyperboloidSize,maxSlope,thickness;  // scan.h:25
 extern double tileSize;                               // the GUI's setting, mainwindow.cpp:398-411
+extern double hostTimes[4];        // seconds spent in wb_create, wb_add_las_file, wb_build, wb_encode+write
 extern bool keepRecordsOnDevice;   // set before reading: the raw records stay in device memory and ACT_WRITE's
                                    // records are made there (wb_encode) instead of by LasHeader::writePoint
 

@@ -145,9 +145,13 @@ int main(int argc,char **argv)
   }
   joinThreads();
   tDump=now()-t;
+  wb_stats gst;
+  memset(&gst,0,sizeof(gst));
+  wb_get_stats(wolkenContext(),&gst);
   if (timing)
     cout<<"{\"open_s\": "<<tOpen<<", \"read_build_s\": "<<tRead<<", \"scan_s\": "<<tScan<<", \"postscan_s\": "<<tPost
         <<", \"classify_s\": "<<tClass<<", \"count_write_s\": "<<tWrite<<", \"dump_s\": "<<tDump
-        <<", \"total_s\": "<<now()-t0<<"}\n";
+        <<", \"wb_create_s\": "<<hostTimes[0]<<", \"wb_add_las_file_s\": "<<hostTimes[1]<<", \"wb_build_s\": "<<hostTimes[2]
+        <<", \"wb_encode_write_s\": "<<hostTimes[3]<<", \"encode_kernel_ms\": "<<gst.ms_encode<<", \"total_s\": "<<now()-t0<<"}\n";
   return 0;
 }
