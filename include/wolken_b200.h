@@ -169,6 +169,24 @@ int wb_count_classes(wb_ctx *ctx,uint64_t counts[256]);
  * 6-10: las.cpp:754-756, 771, 848, 857) — host records, in place. */
 int wb_patch_records(wb_ctx *ctx,uint8_t *recs,uint64_t first_point,uint64_t n,int fmt,int rec_len);
 
+/* ---- store queries -----------------------------------------------------------
+ * OctStore::pointsIn / countPointsIn / hiLoPointsIn (octree.cpp:1214-1293) for the shapes of
+ * shape.cpp, on the device: the exact Shape::in predicates (same operations as shape.cpp:81-90,
+ * 127-135, 175-178, 215-219, 252-255) over the points a walk of the bounds hierarchy reaches.
+ * Shape parameters are the constructors' arguments:
+ *   WB_SPHERE      p = cx,cy,cz,radius            WB_PARABOLOID  p = vx,vy,vz,radiusCurvature
+ *   WB_HYPERBOLOID p = vx,vy,vz,r,slope           WB_CYLINDER    p = cx,cy,radius
+ *   WB_COLUMN      p = cx,cy,side
+ * wb_query_batch: one result per shape (count; lowest and highest z, +inf/-inf when empty — the
+ * per-pixel call of WolkenCanvas::pixelColorRead, wolkencanvas.cpp:92-108, for a whole raster).
+ * wb_query_points: the points in one shape, in the order pointsIn returns them (bucket order x
+ * in-bucket order); *n_out is the full count even when cap is smaller; any output may be NULL. */
+enum { WB_SPHERE=0,WB_PARABOLOID=1,WB_HYPERBOLOID=2,WB_CYLINDER=3,WB_COLUMN=4 };
+typedef struct wb_shape { int32_t type,pad_; double p[6]; } wb_shape;
+int wb_query_batch(wb_ctx *ctx,const wb_shape *shapes,uint64_t n,uint64_t *count,double *lo,double *hi);
+int wb_query_points(wb_ctx *ctx,const wb_shape *shape,uint64_t cap,uint64_t *n_out,uint32_t *pos,uint32_t *input_index,
+                    double *x,double *y,double *z);
+
 /* ---- output records (ACT_WRITE) ------------------------------------------------
  * CloudOutput::writeFiles (cloudoutput.cpp:187-229) walks the buckets in order and, for each class,
  * appends the bucket's points of that class to the class's least-full file through

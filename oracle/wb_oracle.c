@@ -123,6 +123,61 @@ int wbo_cylinder_intersects_cube(double cx,double cy,double r,const double c[3],
   return wbo_cylinder_in(cx,cy,r,x,y);
 }
 
+int wbo_shape_in(int type,const double q[6],const double p[3])
+/* Shape::in for every shape of shape.cpp; q = the constructor's arguments.
+ * 0 Sphere(c,r) 175-178 | 1 Paraboloid(v,rc) 81-90 | 2 Hyperboloid(v,r,s) 119-135 |
+ * 3 Cylinder(c,r) 215-219 | 4 Column(c,side) 252-255.  dist(): point.cpp:189-192, 383-386. */
+{
+  switch (type)
+  {
+    case 0:
+      return hypot(hypot(p[0]-q[0],p[1]-q[1]),p[2]-q[2])<=q[3];
+    case 1:
+    {
+      double xydist=hypot(q[0]-p[0],q[1]-p[1]),zdist=q[2]-p[2],r=q[3],t;
+      if (r==0)
+        return xydist==0;
+      t=xydist/r;
+      return 2*zdist/r>=t*t;
+    }
+    case 2:
+      return wbo_hyperboloid_in(q,q[3],q[4],p);
+    case 3:
+      return wbo_cylinder_in(q[0],q[1],q[2],p[0],p[1]);
+    case 4:
+      return fabs(q[0]-p[0])<=q[2]/2 && fabs(q[1]-p[1])<=q[2]/2;
+  }
+  return 0;
+}
+
+int wbo_shape_intersects_cube(int type,const double q[6],const double c[3],double side)
+/* Shape::intersect = in(closestPoint(cube)), shape.cpp:63-66 with the closestPoint of each shape
+ * (92-117, 137-159, 180-206, 220-238, 257-274) */
+{
+  double ax=q[0],ay=q[1],x=c[0],y=c[1],z=c[2],pt[3];
+  if (fabs(ax-x)<side/2) x=ax; else if (ax>x) x+=side/2; else x-=side/2;
+  if (fabs(ay-y)<side/2) y=ay; else if (ay>y) y+=side/2; else y-=side/2;
+  if (type==0)
+  {
+    if (fabs(q[2]-z)<side/2) z=q[2]; else if (q[2]>z) z+=side/2; else z-=side/2;
+  }
+  else if (type==1 || type==2)
+  {
+    double sgn=type==1?q[3]:q[4];
+    if (sgn>0) z-=side/2;
+    if (sgn<0) z+=side/2;
+  }
+  pt[0]=x; pt[1]=y; pt[2]=z;
+  return wbo_shape_in(type,q,pt);
+}
+
+void wbo_shape_filter(int type,const double q[6],const double *pts,uint64_t n,uint8_t *in)
+{
+  uint64_t i;
+  for (i=0;i<n;i++)
+    in[i]=(uint8_t)wbo_shape_in(type,q,pts+3*i);
+}
+
 /* ======================= flowsnake.cpp / eisenstein.cpp =================== */
 
 static const double squareSides[12]=

@@ -40,6 +40,9 @@ const double *wbo_sin_table(void);   /* 512 */
 int wbo_atan2i(double y,double x);
 int wbo_hyperboloid_in(const double v[3],double r,double s,const double p[3]);
 int wbo_cylinder_in(double cx,double cy,double r,double px,double py);
+int wbo_shape_in(int type,const double q[6],const double p[3]);
+int wbo_shape_intersects_cube(int type,const double q[6],const double c[3],double side);
+void wbo_shape_filter(int type,const double q[6],const double *pts,uint64_t n,uint8_t *in);
 int wbo_cylinder_intersects_cube(double cx,double cy,double r,const double cube_center[3],double side);
 void wbo_to_flowsnake(int n,int *ex,int *ey);
 int wbo_from_flowsnake(int ex,int ey,int64_t *n);   /* our inverse; returns 0 if representable */

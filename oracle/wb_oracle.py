@@ -74,6 +74,9 @@ def lib():
         L.wbo_postscan.argtypes = [C.c_void_p, C.c_int64, C.c_double]
         L.wbo_classify.argtypes = [C.c_void_p, C.c_uint64, dp, C.c_double, C.c_double, C.c_double,
                                    C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_uint64)]
+        L.wbo_shape_in.argtypes = [C.c_int, dp, dp]
+        L.wbo_shape_intersects_cube.argtypes = [C.c_int, dp, dp, C.c_double]
+        L.wbo_shape_filter.argtypes = [C.c_int, dp, C.c_void_p, C.c_uint64, C.c_void_p]
         L.wbo_tan_table.restype = dp
         L.wbo_cos_table.restype = dp
         L.wbo_sin_table.restype = dp
@@ -118,6 +121,25 @@ def least_squares(a, b):
     x = np.zeros(a.shape[1])
     lib().wbo_least_squares(a.ctypes.data, b.ctypes.data, a.shape[0], a.shape[1], x.ctypes.data)
     return x
+
+
+def shape_in(kind, params, p):
+    q = list(params) + [0.0] * (6 - len(params))
+    return bool(lib().wbo_shape_in(kind, _d3(q), _d3(p)))
+
+
+def shape_intersects_cube(kind, params, center, side):
+    q = list(params) + [0.0] * (6 - len(params))
+    return bool(lib().wbo_shape_intersects_cube(kind, _d3(q), _d3(center), side))
+
+
+def shape_filter(kind, params, pts):
+    """Shape::in over an (n,3) array -> bool mask."""
+    q = list(params) + [0.0] * (6 - len(params))
+    pts = np.ascontiguousarray(pts, dtype=np.float64)
+    out = np.zeros(len(pts), dtype=np.uint8)
+    lib().wbo_shape_filter(kind, _d3(q), pts.ctypes.data, len(pts), out.ctypes.data)
+    return out.astype(bool)
 
 
 def surround(dirs):

@@ -493,3 +493,59 @@ def test_add_las_file_equals_add_las(ctx, tmp_path):
     ctx.run()
     res = O.run([O.file_from_cloud(small)])
     assert (ctx.labels(small.n) == res.labels).all()
+
+
+def test_store_queries_on_device(ctx):
+    """OctStore::countPointsIn / hiLoPointsIn / pointsIn (octree.cpp:1214-1293) on the device for
+    every shape of shape.cpp against the oracle's Shape::in over the canonical-order points:
+    same counts, same z range, same points in the same order — including shapes that miss, that
+    swallow the cloud, that open upward, and degenerate ones."""
+    cloud = synth.generate(5, 40000, seed=91)
+    n = _run_gpu(ctx, [cloud], {})
+    x, y, z = ctx.points_sorted(n)
+    pts = np.stack([x, y, z], axis=1)
+    order, _ = ctx.order(n)
+    rng = np.random.default_rng(7)
+    c = pts[rng.integers(0, n, 64)]                                # centres on the cloud
+    ext = pts.max(axis=0) - pts.min(axis=0)
+    cases = []
+    for i in range(12):
+        p = c[i]
+        cases.append((api.SPHERE, [p[0], p[1], p[2], [0.0, 0.3, 2.0, 15.0, 1e4][i % 5]]))
+        cases.append((api.PARABOLOID, [p[0], p[1], p[2] + [0.0, 1.0, 5.0][i % 3], [0.5, 13.0, -2.0, 0.0][i % 4]]))
+        cases.append((api.HYPERBOLOID, [p[0], p[1], p[2] + [0.0, 2.0][i % 2], [0.1, 0.5, 20.0][i % 3], [1.0, 0.3, 2.0, -1.0][i % 4]]))
+        cases.append((api.CYLINDER, [p[0], p[1], [0.0, 0.58, 7.0, 1e4][i % 4]]))
+        cases.append((api.COLUMN, [p[0], p[1], [0.01, 1.0, 30.0][i % 3]]))
+    cases.append((api.SPHERE, [pts[:, 0].min() - 500, pts[:, 1].min() - 500, 0, 10]))       # misses everything
+    cases.append((api.CYLINDER, [pts[:, 0].mean(), pts[:, 1].mean(), float(ext[:2].max())]))  # swallows everything
+    shp = np.concatenate([api.shapes(k, p) for k, p in cases])
+    count, lo, hi = ctx.query_batch(shp)
+    hits = 0
+    for i, (k, p) in enumerate(cases):
+        m = O.shape_filter(k, p, pts)
+        assert int(count[i]) == int(m.sum()), (i, k, p)
+        if m.any():
+            assert lo[i] == z[m].min() and hi[i] == z[m].max(), (i, k, p)
+            hits += 1
+        else:
+            assert lo[i] == np.inf and hi[i] == -np.inf
+        total, pos, idx, got = ctx.query_points(shp[i:i + 1])
+        assert total == int(m.sum()) and (pos == np.nonzero(m)[0]).all() and (idx == order[m]).all()
+        assert (got == pts[m]).all()
+    assert hits > 40 and int(count[-1]) == n and int(count[-2]) == 0
+    # a raster of columns (WolkenCanvas::pixelColorRead for every pixel) in one call
+    gx, gy = np.meshgrid(np.linspace(pts[:, 0].min(), pts[:, 0].max(), 64), np.linspace(pts[:, 1].min(), pts[:, 1].max(), 48))
+    side = 2.5
+    cols = api.shapes(api.COLUMN, np.stack([gx.ravel(), gy.ravel(), np.full(gx.size, side)], axis=1))
+    count, lo, hi = ctx.query_batch(cols)
+    for i in rng.integers(0, len(cols), 60):
+        m = O.shape_filter(api.COLUMN, [gx.ravel()[i], gy.ravel()[i], side], pts)
+        assert int(count[i]) == int(m.sum())
+        if m.any():
+            assert lo[i] == z[m].min() and hi[i] == z[m].max()
+    assert int(count.sum()) > n // 2
+    # capped output reports the full count
+    total, pos, idx, got = ctx.query_points(shp[-1:], cap=100)
+    assert total == n and len(pos) == 100 and (pos == np.arange(100)).all()
+    with pytest.raises(api.WolkenError):
+        ctx.query_batch(api.shapes(9, [0, 0, 0]))

@@ -78,8 +78,11 @@ def test_cli_classify_and_write(tmp_path):
     assert len(got[2]) == -(-n_ground // 10000)
 
 
-def test_octstore_queries(tmp_path):
-    """findBlocks / pointsIn / countPointsIn / hiLoPointsIn vs brute force (cf. testflat, wolkentest.cpp:143-167)."""
+@pytest.mark.parametrize("mode", ["device", "host"])
+def test_octstore_queries(tmp_path, mode):
+    """findBlocks / pointsIn / countPointsIn / hiLoPointsIn vs brute force (cf. testflat, wolkentest.cpp:143-167),
+    with the queries on the GPU (wb_query_*) and on the CPU mirror of the octree walk (--host)."""
+    host = ["--host"] if mode == "host" else []
     cloud = synth.generate(2, 40000, seed=43)
     las = str(tmp_path / "q.las")
     cloud.write(las)
@@ -87,7 +90,7 @@ def test_octstore_queries(tmp_path):
     pts = res.points_sorted
     c = [float(v) for v in pts.mean(axis=0)]
     # cylinder
-    out = json.loads(subprocess.run([QUERY, las, "cyl", repr(c[0]), repr(c[1]), "3.5"], capture_output=True, text=True,
+    out = json.loads(subprocess.run([QUERY, las, "cyl", repr(c[0]), repr(c[1]), "3.5"] + host, capture_output=True, text=True,
                                     check=True).stdout.strip().splitlines()[-1])
     inside = np.hypot(pts[:, 0] - c[0], pts[:, 1] - c[1]) <= 3.5
     assert out["count"] == out["points"] == int(inside.sum()) and out["sorted"] == 1 and out["consistent"] == 1
@@ -95,19 +98,27 @@ def test_octstore_queries(tmp_path):
     assert out["total_points"] == cloud.n and out["total_blocks"] == len(res.leaves)
     assert 0 < out["blocks"] < len(res.leaves)
     # sphere
-    out = json.loads(subprocess.run([QUERY, las, "sph", repr(c[0]), repr(c[1]), repr(c[2]), "2.0"], capture_output=True,
+    out = json.loads(subprocess.run([QUERY, las, "sph", repr(c[0]), repr(c[1]), repr(c[2]), "2.0"] + host, capture_output=True,
                                     text=True, check=True).stdout.strip().splitlines()[-1])
     d = np.hypot(np.hypot(pts[:, 0] - c[0], pts[:, 1] - c[1]), pts[:, 2] - c[2])
     assert out["count"] == int((d <= 2.0).sum())
     # downward hyperboloid from 3 m above the centroid
     v = (c[0], c[1], c[2] + 3.0)
-    out = json.loads(subprocess.run([QUERY, las, "hyp"] + [repr(x) for x in v] + ["0.5", "1"], capture_output=True,
+    out = json.loads(subprocess.run([QUERY, las, "hyp"] + [repr(x) for x in v] + ["0.5", "1"] + host, capture_output=True,
                                     text=True, check=True).stdout.strip().splitlines()[-1])
     por = 0.5
     zd = (v[2] + por) - pts[:, 2]
     dd = np.hypot(v[0] - pts[:, 0], v[1] - pts[:, 1])
     inside = (zd > 0) & (zd * zd - dd * dd >= por * por)
     assert out["count"] == int(inside.sum()) and out["count"] > 10
+    # paraboloid and column against the oracle's Shape::in
+    for kind, code, prm in (("par", 1, [c[0], c[1], c[2] + 2.0, 6.0]), ("col", 4, [c[0], c[1], 3.0])):
+        out = json.loads(subprocess.run([QUERY, las, kind] + [repr(x) for x in prm] + host, capture_output=True,
+                                        text=True, check=True).stdout.strip().splitlines()[-1])
+        m = O.shape_filter(code, prm, pts)
+        assert out["count"] == out["points"] == int(m.sum()) and out["count"] > 5, kind
+        assert out["lo"] == pts[m, 2].min() and out["hi"] == pts[m, 2].max()
+        assert out["sorted"] == 1 and out["consistent"] == 1
 
 
 def _las14(path):

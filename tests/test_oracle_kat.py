@@ -33,6 +33,27 @@ def test_cylinder_kat():
     assert not cube((-11, -7, 2), 1 / 32.)
 
 
+def test_paraboloid_sphere_column_kat():
+    # testparaboloid, wolkentest.cpp:188-202: Paraboloid((0,0,13),13)
+    par = (0, 0, 13, 13)
+    v, a, b, c, d, e = (0, 0, 13), (5, 0, 12), (5, 2, 12), (13, 13, 0), (-14, -12, 0), (9, 16, 0)
+    assert O.shape_in(1, par, v) and O.shape_in(1, par, a) and not O.shape_in(1, par, b)
+    assert O.shape_in(1, par, c) and not O.shape_in(1, par, d) and O.shape_in(1, par, e)
+    assert O.shape_intersects_cube(1, par, v, 1) and not O.shape_intersects_cube(1, par, b, 0.1)
+    # testsphere, wolkentest.cpp:204-221: 89^2 = 15^2+36^2+80^2 = 39^2+48^2+64^2
+    sph = (100, 200, 300, 89)
+    for p, want in [((100, 200, 300), True), ((115, 164, 220), True), ((115, 163, 220), False), ((36, 239, 252), True),
+                    ((36, 240, 252), False), ((64, 120, 315), True), ((63, 120, 315), False), ((164, 248, 339), True),
+                    ((164, 248, 340), False)]:
+        assert O.shape_in(0, sph, p) == want, p
+    # the generic entry agrees with the dedicated ones (testhyperboloid, testcylinder)
+    assert O.shape_in(2, (100, 200, 300, 72, 1), (118, 176, 294)) and not O.shape_in(2, (100, 200, 300, 72, 1), (118, 176, 295))
+    assert O.shape_in(3, (0, 0, 13), (5, 12, 0)) and not O.shape_in(3, (0, 0, 13), (5, 13, 4))
+    assert O.shape_intersects_cube(3, (0, 0, 13), (-11, -7, 2), 1 / 16.) and not O.shape_intersects_cube(3, (0, 0, 13), (-11, -7, 2), 1 / 32.)
+    # Column, shape.cpp:252-255: inclusive on both sides
+    assert O.shape_in(4, (10, 20, 2), (11, 19, 5)) and O.shape_in(4, (10, 20, 2), (9, 21, -3)) and not O.shape_in(4, (10, 20, 2), (11.0001, 20, 0))
+
+
 def test_least_squares_kat():
     # testleastsquares, wolkentest.cpp:744-760
     x = O.least_squares([[1, 3], [2, 4], [1, 6]], [4, 1, 3])

@@ -52,6 +52,19 @@ class FileStats(C.Structure):
                 ("pad_", C.c_int32 * 2)]
 
 
+SHAPE_DTYPE = np.dtype([("type", "<i4"), ("pad_", "<i4"), ("p", "<f8", (6,))])
+SPHERE, PARABOLOID, HYPERBOLOID, CYLINDER, COLUMN = range(5)
+
+
+def shapes(kind, params):
+    """(n, k) parameter rows -> wb_shape array (parameters = the reference constructors' arguments)."""
+    params = np.atleast_2d(np.asarray(params, dtype=np.float64))
+    out = np.zeros(len(params), dtype=SHAPE_DTYPE)
+    out["type"] = kind
+    out["p"][:, :params.shape[1]] = params
+    return out
+
+
 class WolkenError(RuntimeError):
     pass
 
@@ -115,6 +128,8 @@ def lib():
             "wb_encode": [vp, C.POINTER(OutSpec), vp, vp, C.c_uint32, vp, u64, vp],
             "wb_get_duplicates": [vp, vp, vp, u64],
             "wb_write_encoded": [vp, C.c_int, u64, u64, u64],
+            "wb_query_batch": [vp, vp, u64, vp, vp, vp],
+            "wb_query_points": [vp, vp, u64, C.POINTER(u64), vp, vp, vp, vp, vp],
         }
         for name, args in sig.items():
             f = getattr(L, name)
@@ -135,7 +150,8 @@ EXPORTS = ["wb_create", "wb_destroy", "wb_last_error", "wb_reserve", "wb_clear",
            "wb_snake_set_size", "wb_ldecimal", "wb_format_dump", "wb_add_points_device", "wb_export_points_device",
            "wb_set_own_range", "wb_export_tiles_device", "wb_import_tiles_device", "wb_max_hyperboloid_size",
            "wb_assign", "wb_get_points_sorted", "wb_test_math", "wb_bound_rect", "wb_keep_records",
-           "wb_leaf_class_counts", "wb_encode", "wb_get_duplicates", "wb_add_las_file", "wb_write_encoded"]
+           "wb_leaf_class_counts", "wb_encode", "wb_get_duplicates", "wb_add_las_file", "wb_write_encoded", "wb_query_batch",
+           "wb_query_points"]
 
 
 def _d(v):
@@ -331,6 +347,31 @@ class Context:
     def write_encoded(self, fd, file_pos, arena_off, nbytes):
         """Stream records left on the device by encode(..., fetch=False) into an open file."""
         self._ck(self._L.wb_write_encoded(self._h, fd, file_pos, arena_off, nbytes))
+
+    # ---- store queries (OctStore::countPointsIn / hiLoPointsIn / pointsIn)
+    def query_batch(self, shp):
+        shp = np.ascontiguousarray(shp, dtype=SHAPE_DTYPE)
+        n = len(shp)
+        count = np.zeros(n, dtype=np.uint64)
+        lo = np.zeros(n)
+        hi = np.zeros(n)
+        self._ck(self._L.wb_query_batch(self._h, shp.ctypes.data, n, count.ctypes.data, lo.ctypes.data, hi.ctypes.data))
+        return count, lo, hi
+
+    def query_points(self, shp, cap=None):
+        shp = np.ascontiguousarray(shp, dtype=SHAPE_DTYPE)
+        assert len(shp) == 1
+        n = C.c_uint64()
+        if cap is None:
+            self._ck(self._L.wb_query_points(self._h, shp.ctypes.data, 0, C.byref(n), None, None, None, None, None))
+            cap = n.value
+        pos = np.zeros(cap, dtype=np.uint32)
+        idx = np.zeros(cap, dtype=np.uint32)
+        x, y, z = np.zeros(cap), np.zeros(cap), np.zeros(cap)
+        self._ck(self._L.wb_query_points(self._h, shp.ctypes.data, cap, C.byref(n), pos.ctypes.data, idx.ctypes.data,
+                                         x.ctypes.data, y.ctypes.data, z.ctypes.data))
+        m = min(cap, n.value)
+        return n.value, pos[:m], idx[:m], np.stack([x[:m], y[:m], z[:m]], axis=1)
 
     def duplicates(self):
         n = self.stats()["n_duplicates"]

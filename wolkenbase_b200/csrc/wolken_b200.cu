@@ -20,6 +20,7 @@
 #include "wb_kernels.cuh"
 #include "wb_sort.cuh"
 #include "wb_encode.cuh"
+#include "wb_query.cuh"
 
 namespace
 {
@@ -1412,6 +1413,96 @@ extern "C" int wb_count_classes(wb_ctx *ctx,uint64_t counts[256])
   CK(cudaMemcpyAsync(counts,d.p,256*sizeof(unsigned long long),cudaMemcpyDeviceToHost,ctx->st));
   CK(cudaStreamSynchronize(ctx->st));
   d.release();
+  return WB_OK;
+}
+
+// ============================================================================ store queries (OctStore)
+
+namespace
+{
+int checkShapes(wb_ctx *ctx,const wb_shape *sh,uint64_t n)
+{
+  for (uint64_t i=0;i<n;i++)
+    if (sh[i].type<WB_SHAPE_SPHERE || sh[i].type>WB_SHAPE_COLUMN)
+      return fail(ctx,WB_ERR_ARG,"shape %llu: unknown type %d",(unsigned long long)i,sh[i].type);
+  return WB_OK;
+}
+}
+
+extern "C" int wb_query_batch(wb_ctx *ctx,const wb_shape *shapes,uint64_t n,uint64_t *count,double *lo,double *hi)
+{
+  if (!ctx || (n && !shapes))
+    return WB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  if (ctx->phase<PH_BUILT)
+    return fail(ctx,WB_ERR_STATE,"not built");
+  if (!n)
+    return WB_OK;
+  int rc=checkShapes(ctx,shapes,n);
+  if (rc)
+    return rc;
+  static_assert(sizeof(wb_shape)==sizeof(WbShapeDev),"shape layout");
+  DevBuf<WbShapeDev> ds;
+  DevBuf<unsigned long long> dc;
+  DevBuf<double> dl,dh;
+  cudaStream_t st=ctx->st;
+  CK(ds.ensure(n)); CK(dc.ensure(n)); CK(dl.ensure(n)); CK(dh.ensure(n));
+  CK(cudaMemcpyAsync(ds.p,shapes,sizeof(wb_shape)*n,cudaMemcpyHostToDevice,st));
+  wb_query_kernel<<<(unsigned)wb_div_up(n,WB_Q_WARPS),WB_Q_WARPS*32,0,st>>>(ds.p,n,ctx->sx.p,ctx->sy.p,ctx->sz.p,ctx->nValid,
+      ctx->bounds.p,ctx->levelOff.p,ctx->levelCnt.p,ctx->nLevels,dc.p,dl.p,dh.p);
+  ctx->stats.kernel_launches++;
+  KCHECK();
+  if (count) CK(cudaMemcpyAsync(count,dc.p,sizeof(uint64_t)*n,cudaMemcpyDeviceToHost,st));
+  if (lo) CK(cudaMemcpyAsync(lo,dl.p,sizeof(double)*n,cudaMemcpyDeviceToHost,st));
+  if (hi) CK(cudaMemcpyAsync(hi,dh.p,sizeof(double)*n,cudaMemcpyDeviceToHost,st));
+  CK(cudaStreamSynchronize(st));
+  ds.release(); dc.release(); dl.release(); dh.release();
+  return WB_OK;
+}
+
+extern "C" int wb_query_points(wb_ctx *ctx,const wb_shape *shape,uint64_t cap,uint64_t *nOut,uint32_t *pos,uint32_t *idx,
+                               double *x,double *y,double *z)
+{
+  if (!ctx || !shape || !nOut)
+    return WB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  if (ctx->phase<PH_BUILT)
+    return fail(ctx,WB_ERR_STATE,"not built");
+  int rc=checkShapes(ctx,shape,1);
+  if (rc)
+    return rc;
+  const uint64_t nv=ctx->nValid;
+  cudaStream_t st=ctx->st;
+  // scr0/scr1 are free between the phases (each phase that uses them fills them first)
+  WbShapeDev s;
+  memcpy(&s,shape,sizeof(s));
+  wb_query_flag_kernel<<<gridFor(nv,256),256,0,st>>>(s,ctx->sx.p,ctx->sy.p,ctx->sz.p,nv,ctx->scr0.p);
+  ctx->stats.kernel_launches++;
+  CK(wb_exclusive_scan(ctx->scr0.p,ctx->scr1.p,nv,ctx->blockSums.p,ctx->blockSums.cap,st,&ctx->stats.kernel_launches));
+  uint32_t lastPos=0,lastFlag=0;
+  CK(cudaMemcpyAsync(&lastPos,ctx->scr1.p+nv-1,sizeof(uint32_t),cudaMemcpyDeviceToHost,st));
+  CK(cudaMemcpyAsync(&lastFlag,ctx->scr0.p+nv-1,sizeof(uint32_t),cudaMemcpyDeviceToHost,st));
+  CK(cudaStreamSynchronize(st));
+  const uint64_t total=(uint64_t)lastPos+lastFlag;
+  *nOut=total;
+  const uint64_t m=std::min(total,cap);
+  if (m && (pos || idx || x || y || z))
+  {
+    DevBuf<uint32_t> dp,di;
+    DevBuf<double> dx,dy,dz;
+    CK(dp.ensure(m)); CK(di.ensure(m)); CK(dx.ensure(m)); CK(dy.ensure(m)); CK(dz.ensure(m));
+    wb_query_emit_kernel<<<gridFor(nv,256),256,0,st>>>(ctx->scr0.p,ctx->scr1.p,nv,ctx->perm,ctx->sx.p,ctx->sy.p,ctx->sz.p,
+                                                      m,dp.p,di.p,dx.p,dy.p,dz.p);
+    ctx->stats.kernel_launches++;
+    KCHECK();
+    if (pos) CK(cudaMemcpyAsync(pos,dp.p,sizeof(uint32_t)*m,cudaMemcpyDeviceToHost,st));
+    if (idx) CK(cudaMemcpyAsync(idx,di.p,sizeof(uint32_t)*m,cudaMemcpyDeviceToHost,st));
+    if (x) CK(cudaMemcpyAsync(x,dx.p,sizeof(double)*m,cudaMemcpyDeviceToHost,st));
+    if (y) CK(cudaMemcpyAsync(y,dy.p,sizeof(double)*m,cudaMemcpyDeviceToHost,st));
+    if (z) CK(cudaMemcpyAsync(z,dz.p,sizeof(double)*m,cudaMemcpyDeviceToHost,st));
+    CK(cudaStreamSynchronize(st));
+    dp.release(); di.release(); dx.release(); dy.release(); dz.release();
+  }
   return WB_OK;
 }
 

@@ -22,6 +22,7 @@ TileTable tiles;
 map<int,size_t> classTotals;
 double minHyperboloidSize=0.1,maxSlope=1,thickness=0,tileSize=1;
 bool keepRecordsOnDevice=false;
+bool hostQueries=false;
 double hostTimes[4]={0,0,0,0};        // seconds in wb_create, wb_add_las_file, wb_build, wb_encode+write
 
 namespace
@@ -279,6 +280,33 @@ Hyperboloid::Hyperboloid(xyz v,double r,double s)
   slope=s;
   por2=sqr(por);
   center=v+xyz(0,0,por);
+  vertex0=v;
+  r0=r;
+}
+
+static bool fillShape(wb_shape &s,int type,double a,double b,double c,double d,double e)
+{
+  memset(&s,0,sizeof(s));
+  s.type=type;
+  s.p[0]=a; s.p[1]=b; s.p[2]=c; s.p[3]=d; s.p[4]=e;
+  return true;
+}
+bool Paraboloid::abi(wb_shape &s) const { return fillShape(s,WB_PARABOLOID,vertex.getx(),vertex.gety(),vertex.getz(),radiusCurvature,0); }
+bool Hyperboloid::abi(wb_shape &s) const { return fillShape(s,WB_HYPERBOLOID,vertex0.getx(),vertex0.gety(),vertex0.getz(),r0,slope); }
+bool Sphere::abi(wb_shape &s) const { return fillShape(s,WB_SPHERE,center.getx(),center.gety(),center.getz(),radius,0); }
+bool Cylinder::abi(wb_shape &s) const { return fillShape(s,WB_CYLINDER,center.getx(),center.gety(),radius,0,0); }
+bool Column::abi(wb_shape &s) const { return fillShape(s,WB_COLUMN,center.getx(),center.gety(),side,0,0); }
+
+bool Column::in(xyz p) const
+{
+  return fabs(center.getx()-p.getx())<=side/2 && fabs(center.gety()-p.gety())<=side/2;
+}
+
+xyz Column::closestPoint(Cube cube) const
+{
+  xyz c=cube.getCenter();
+  double h=cube.getSide()/2;
+  return xyz(clampToward(center.getx(),c.getx(),h),clampToward(center.gety(),c.gety(),h),c.getz());
 }
 
 bool Hyperboloid::in(xyz p) const
@@ -743,9 +771,73 @@ static bool lowerThan(const LasPoint &a,const LasPoint &b)
   return a.location.getz()<b.location.getz();
 }
 
+static LasPoint pointFromInput(uint32_t inputIdx,double x,double y,double z)
+// the stored point at (x,y,z) whose first record is inputIdx, without the host copy of the store
+{
+  static std::map<uint32_t,uint32_t> last;           // survivor -> last record at its location
+  static bool haveLast=false;
+  if (!haveLast)
+  {
+    wb_stats st;
+    wb_get_stats(g_ctx,&st);
+    if (st.n_duplicates)
+    {
+      vector<uint32_t> dup(st.n_duplicates),rep(st.n_duplicates);
+      wb_get_duplicates(g_ctx,dup.data(),rep.data(),st.n_duplicates);
+      for (size_t u=0;u<dup.size();u++)
+      {
+        uint32_t &l=last[rep[u]];
+        if (dup[u]>l)
+          l=dup[u];
+      }
+    }
+    haveLast=true;
+  }
+  uint32_t i=inputIdx;
+  auto it=last.find(i);
+  if (it!=last.end())
+    i=it->second;
+  size_t f=upper_bound(g_fileFirst.begin(),g_fileFirst.end(),(size_t)i)-g_fileFirst.begin()-1;
+  LasPoint p=g_files[f]->readPoint(i-g_fileFirst[f]);
+  if (p.returnNum==0)
+    p.returnNum=1;
+  p.location=xyz(x,y,z);
+  if (g_classified)
+  {
+    ensureLabels();
+    p.classification=g_labels[inputIdx];
+  }
+  return p;
+}
+
 vector<LasPoint> OctStore::pointsIn(const Shape &sh,bool sorted)
 {
   vector<LasPoint> ret;
+  wb_shape ws;
+  if (!hostQueries && sh.abi(ws))
+  { // on the device: exact predicate over the whole store, results in bucket order
+    ensureBuilt();
+    uint64_t n=0;
+    if (wb_query_points(g_ctx,&ws,0,&n,nullptr,nullptr,nullptr,nullptr,nullptr)!=WB_OK)
+    {
+      die("query");
+      return ret;
+    }
+    vector<uint32_t> idx(n);
+    vector<double> x(n),y(n),z(n);
+    if (n && wb_query_points(g_ctx,&ws,n,&n,nullptr,idx.data(),x.data(),y.data(),z.data())!=WB_OK)
+    {
+      die("query");
+      return ret;
+    }
+    ret.reserve(n);
+    for (size_t k=0;k<n;k++)
+      ret.push_back(pointFromInput(idx[k],x[k],y[k],z[k]));
+    if (sorted)
+      sort(ret.begin(),ret.end(),lowerThan);
+    return ret;
+  }
+  ensureStore();
   for (int64_t b:octRoot.findBlocks(sh))
   {
     Cube cube=leafCube(b);
@@ -762,6 +854,15 @@ vector<LasPoint> OctStore::pointsIn(const Shape &sh,bool sorted)
 uint64_t OctStore::countPointsIn(const Shape &sh)
 {
   uint64_t ret=0;
+  wb_shape ws;
+  if (!hostQueries && sh.abi(ws))
+  {
+    ensureBuilt();
+    if (wb_query_batch(g_ctx,&ws,1,&ret,nullptr,nullptr)!=WB_OK)
+      die("query");
+    return ret;
+  }
+  ensureStore();
   for (int64_t b:octRoot.findBlocks(sh))
   {
     Cube cube=leafCube(b);
@@ -777,6 +878,15 @@ uint64_t OctStore::countPointsIn(const Shape &sh)
 array<double,2> OctStore::hiLoPointsIn(const Shape &sh)
 {
   double hi=-INFINITY,lo=INFINITY;
+  wb_shape ws;
+  if (!hostQueries && sh.abi(ws))
+  {
+    ensureBuilt();
+    if (wb_query_batch(g_ctx,&ws,1,nullptr,&lo,&hi)!=WB_OK)
+      die("query");
+    return array<double,2>{lo,hi};
+  }
+  ensureStore();
   for (int64_t b:octRoot.findBlocks(sh))
     if (g_leaves[b].low<lo || g_leaves[b].high>hi)
       for (size_t k=g_leaves[b].first;k<g_leaves[b].first+g_leaves[b].count;k++)

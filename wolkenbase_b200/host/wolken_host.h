@@ -87,6 +87,7 @@ public:
   virtual bool in(Cube &cube) const;               // all eight corners (convex shapes)
   virtual xyz closestPoint(Cube cube) const=0;
   virtual bool intersect(Cube cube) const { return in(closestPoint(cube)); }
+  virtual bool abi(wb_shape &) const { return false; } // constructor arguments for the device queries; false = CPU only
 };
 
 class Paraboloid: public Shape
@@ -97,6 +98,7 @@ public:
   bool in(xyz pnt) const override;
   xyz closestPoint(Cube cube) const override;
   using Shape::in;
+  bool abi(wb_shape &s) const override;
 private:
   xyz vertex;
   double radiusCurvature;
@@ -105,14 +107,15 @@ private:
 class Hyperboloid: public Shape
 {
 public:
-  Hyperboloid(): por2(0),slope(1) {}
+  Hyperboloid(): por2(0),slope(1),r0(0) {}
   Hyperboloid(xyz v,double r,double s);
   bool in(xyz pnt) const override;
   xyz closestPoint(Cube cube) const override;
   using Shape::in;
+  bool abi(wb_shape &s) const override;
 private:
-  xyz center;
-  double por2,slope;
+  xyz center,vertex0;
+  double por2,slope,r0;
 };
 
 class Sphere: public Shape
@@ -123,6 +126,7 @@ public:
   bool in(xyz pnt) const override;
   xyz closestPoint(Cube cube) const override;
   using Shape::in;
+  bool abi(wb_shape &s) const override;
 private:
   xyz center;
   double radius;
@@ -138,9 +142,24 @@ public:
   bool in(xyz pnt) const override;
   xyz closestPoint(Cube cube) const override;
   using Shape::in;
+  bool abi(wb_shape &s) const override;
 private:
   xy center;
   double radius;
+};
+
+class Column: public Shape                          // shape.cpp:240-274
+{
+public:
+  Column(): side(0) {}
+  Column(xy c,double s): center(c),side(s) {}
+  bool in(xyz pnt) const override;
+  xyz closestPoint(Cube cube) const override;
+  using Shape::in;
+  bool abi(wb_shape &s) const override;
+private:
+  xy center;
+  double side;
 };
 
 // ---------------------------------------------------------------- las.h
@@ -339,6 +358,7 @@ extern std::map<int,size_t> classTotals;
 extern double minHyperboloidSize,maxSlope,thickness;  // scan.h:25
 extern double tileSize;                               // the GUI's setting, mainwindow.cpp:398-411
 extern double hostTimes[4];        // seconds spent in wb_create, wb_add_las_file, wb_build, wb_encode+write
+extern bool hostQueries;           // true: OctStore queries run on the CPU mirror (the checker) instead of the GPU
 extern bool keepRecordsOnDevice;   // set before reading: the raw records stay in device memory and ACT_WRITE's
                                    // records are made there (wb_encode) instead of by LasHeader::writePoint
 

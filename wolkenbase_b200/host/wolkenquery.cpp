@@ -1,7 +1,8 @@
 // wolkenquery — exercises the OctStore query surface (findBlock, findBlocks, pointsIn,
 // countPointsIn, hiLoPointsIn; octree.cpp:199-251, 1214-1293) on a LAS file, like the reference's
 // testflat (wolkentest.cpp:143-167) does for a cylinder.  Used by tests/test_host_cli.py.
-//   wolkenquery in.las cyl cx cy r | sph cx cy cz r | hyp vx vy vz r s
+//   wolkenquery in.las cyl cx cy r | sph cx cy cz r | hyp vx vy vz r s | par vx vy vz rc | col cx cy side [--host]
+// Queries run on the GPU (wb_query_*); --host runs the CPU mirror of the octree walk instead (the checker).
 #include <cstdlib>
 #include <cstring>
 #include <deque>
@@ -13,6 +14,11 @@ int main(int argc,char **argv)
 {
   if (argc<4)
     return 2;
+  if (!strcmp(argv[argc-1],"--host"))
+  {
+    hostQueries=true;
+    argc--;
+  }
   deque<LasHeader> files(1);
   files[0].openRead(argv[1]);
   if (!files[0].isValid())
@@ -39,6 +45,10 @@ int main(int argc,char **argv)
     sh=new Sphere(xyz(atof(argv[3]),atof(argv[4]),atof(argv[5])),atof(argv[6]));
   else if (kind=="hyp" && argc>=8)
     sh=new Hyperboloid(xyz(atof(argv[3]),atof(argv[4]),atof(argv[5])),atof(argv[6]),atof(argv[7]));
+  else if (kind=="par" && argc>=7)
+    sh=new Paraboloid(xyz(atof(argv[3]),atof(argv[4]),atof(argv[5])),atof(argv[6]));
+  else if (kind=="col" && argc>=6)
+    sh=new Column(xy(atof(argv[3]),atof(argv[4])),atof(argv[5]));
   else
     return 2;
   vector<int64_t> blocks=octRoot.findBlocks(*sh);
