@@ -164,15 +164,18 @@ def run_ours(args):
     phase = {}
     torch.cuda.synchronize()
     t0 = time.perf_counter()
+    ctx.mark(0)                       # CUDA events on the library's own stream bracket the K steps
     for _ in range(args.steps):
         step_resident()
         st = ctx.stats()
         for k, v in st.items():
             if k.startswith("ms_"):
                 phase[k] = phase.get(k, 0.0) + v
+    ctx.mark(1)
+    dt = ctx.mark_elapsed(0, 1) * 1e-3
     ctx.sync()
     torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
+    dt_wall = time.perf_counter() - t0
     clocks = sampler.stop()
     st = ctx.stats()
     launches = (st["kernel_launches"] - launches0) // max(1, args.steps)
@@ -186,10 +189,13 @@ def run_ours(args):
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     e2e_steps = max(1, min(args.steps, 3))
+    ctx.mark(2)
     for _ in range(e2e_steps):
         step_e2e()
+    ctx.mark(3)
+    dte = ctx.mark_elapsed(2, 3) * 1e-3 / e2e_steps
     torch.cuda.synchronize()
-    dte = (time.perf_counter() - t0) / e2e_steps
+    dte_wall = (time.perf_counter() - t0) / e2e_steps
     ste = ctx.stats()
     hist = ctx.count_classes()
 
@@ -208,7 +214,9 @@ def run_ours(args):
     sort_bytes = 32.0 * 8 * n                                # 8 passes x (8 read + 12 read + 12 written)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_step, "ms_per_step_wall": dt_wall / args.steps * 1e3,
+        "timer": "CUDA events on the library's compute stream around the K steps (wb_mark); wall clock alongside",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": "%s: %d points, LAS format %d (%d B records), scene %d seed %d; "
                                "tileSize 1 maxSlope 1 thickness 0 minHyperboloidSize 0.1" %
@@ -229,7 +237,7 @@ def run_ours(args):
                             if phase.get("ms_decode", 0.0) > 0 else 0.0,
                             "note": "L+14 B/point: record read, 3 x int32 + class + return number written"},
         "e2e": {"value": n / dte, "unit": UNIT, "h2d_bytes_per_step": n * rec_len, "d2h_bytes_per_step": n,
-                "ms_per_step": dte * 1e3, "ms_h2d_decode": ste["ms_h2d"], "ms_d2h": ste["ms_d2h"]},
+                "ms_per_step": dte * 1e3, "ms_per_step_wall": dte_wall * 1e3, "ms_h2d_decode": ste["ms_h2d"], "ms_d2h": ste["ms_d2h"]},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "labels": {"ground": int(hist[2]), "nonground": int(hist[1]), "margin_points": int(st["n_margin"]),
@@ -281,10 +289,15 @@ def cpu_baseline(scene, sample_points, bounded=True, threads=None):
 
 
 def run_reference(args):
+    """The reference's own CPU implementation of the path (oracle/_ref, all host threads) on a
+    bounded sample of OUR arm's workload: same config, metric, unit."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    scene = args.scene or (2 if args.gpus == 1 else 3)
+    from wolkenbase_b200 import synth
+    world = max(1, args.gpus)
+    scene, d, per_gpu, wname = workload(args, world)
+    rec_len = synth.lib().wb_synth_record_length(d.fmt)
     vals, last = [], None
     for i in range(args.warmup + args.steps):
         last = cpu_baseline(scene, args.cpu_points)
@@ -298,7 +311,11 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
             "steps": len(vals), "warmup": args.warmup, "ms_per_step": last["seconds"] * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "reference CPU path on a %s" % last["sample"], "points": args.cpu_points},
+            "config": {"workload": "%s: %d points, LAS format %d (%d B records), scene %d seed %d; "
+                                   "tileSize 1 maxSlope 1 thickness 0 minHyperboloidSize 0.1" %
+                                   (wname, per_gpu * world, d.fmt, rec_len, scene, scene),
+                       "points": per_gpu * world,
+                       "sample": "each step = the reference's CPU path over a %s" % last["sample"]},
             "cpu_baseline": dict(last, value=v),
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))

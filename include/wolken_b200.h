@@ -111,6 +111,10 @@ int wb_add_extent(wb_ctx *ctx,const double min_corner[3],const double max_corner
  * on the device as they arrive.  fmt 0-3 and 6-8 (las.cpp:38). */
 int wb_add_las(wb_ctx *ctx,const uint8_t *recs,uint64_t n,int fmt,int rec_len,
                const double scale[3],const double offset[3],double unit);
+/* ACT_READ drops records whose return number is 0 when the file's first record has a non-zero return number
+ * (threads.cpp:485-500, 527-530) — the default here, decided per wb_add_las* call.  keep_all = 1 stores every
+ * record, as a caller that feeds embufferPoint itself does (wolkencli.cpp:104-108). */
+int wb_set_return_zero_rule(wb_ctx *ctx,int keep_all);
 /* Same, straight from the file (LasHeader::readPoint's seek+read per point, las.cpp:735-745,
  * becomes a pipeline): worker threads pread 1 Mi-record chunks starting at byte point_offset into a
  * ring of pinned buffers while earlier chunks are copied and decoded.  A short file is an error. */
@@ -235,6 +239,13 @@ int wb_test_math(wb_ctx *ctx,uint64_t n,const double *y,const double *x,int32_t 
 int wb_run(wb_ctx *ctx);                                    /* build, scan, postscan, classify */
 int wb_get_stats(wb_ctx *ctx,wb_stats *out);
 int wb_sync(wb_ctx *ctx);
+/* Timing marks: wb_mark records CUDA event `slot` (0..WB_MARKS-1) on the stream the kernels are launched
+ * on, behind all work issued so far; wb_mark_elapsed waits for mark `to` and returns the device time
+ * between two marks.  (The reference times phases with wall clocks around waitForThreads,
+ * wolkencanvas.cpp:341-354; a caller of this library cannot see its private stream otherwise.) */
+#define WB_MARKS 8
+int wb_mark(wb_ctx *ctx,int slot);
+int wb_mark_elapsed(wb_ctx *ctx,int from,int to,double *ms);
 
 /* ---- host helpers --------------------------------------------------------- */
 int wb_host_alloc(void **p,uint64_t bytes);                 /* pinned host memory */

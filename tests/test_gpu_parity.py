@@ -189,6 +189,15 @@ def test_return_number_zero_rule(ctx):
     sub2 = synth.Cloud(cloud.desc, cloud.header, recs2, cloud.bbox)
     n = _run_gpu(ctx, [sub2], {})
     assert ctx.stats()["n_dropped"] == 0
+    # a caller that embuffers every point itself (wolkencli.cpp:104-108) keeps them all
+    ctx.set_return_zero_rule(True)
+    try:
+        n = _run_gpu(ctx, [sub], {})
+        st = ctx.stats()
+        assert st["n_dropped"] == 0 and st["n_points"] == sub.n
+        assert (ctx.labels(n) == O.run([O.file_from_cloud(cloud)]).labels).all()   # same XYZ as the untouched cloud
+    finally:
+        ctx.set_return_zero_rule(False)
 
 
 def test_injected_tile_table(ctx):

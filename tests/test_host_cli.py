@@ -42,6 +42,30 @@ def test_cli_reference_mode_dump(tmp_path):
     assert open(tmp_path / "dumpfile", encoding="utf-8").read() == res.dump
 
 
+def test_cli_embuffer_flow_equals_act_read(tmp_path):
+    """The reference's wolkencli feeds the pool point by point (readPoint + embufferPoint, wolkencli.cpp:104-108);
+    the shim turns those calls into runs of records for the device.  Two files, one with zero return numbers
+    (which this flow keeps: nothing filters the points the caller embuffers)."""
+    a = synth.generate(2, 12000, seed=43)
+    b = synth.generate(2, 9000, seed=44)
+    rb = b.records.copy()
+    rb[3::5, 14] &= 0xf8
+    b = synth.Cloud(b.desc, b.header, rb, b.bbox)
+    la, lb = str(tmp_path / "a.las"), str(tmp_path / "b.las")
+    a.write(la)
+    b.write(lb)
+    out = subprocess.run([CLI, "--embuffer", "-o", str(tmp_path / "o"), "--lossless", "--separate-classes", "0",
+                          "--dump", str(tmp_path / "d"), la, lb], capture_output=True, text=True, check=True)
+    assert "%d points, %d points in buffer" % (a.n, a.n) in out.stdout
+    assert "%d points, %d points in buffer" % (b.n, a.n + b.n) in out.stdout
+    keep_all = synth.Cloud(b.desc, b.header, synth.generate(2, 9000, seed=44).records, b.bbox)
+    res = O.run([O.file_from_cloud(a), O.file_from_cloud(keep_all)])
+    assert open(tmp_path / "d", encoding="utf-8").read() == res.dump
+    fmt, recs, _ = _read_las(str(tmp_path / "o.las"))
+    assert recs.shape[0] == a.n + b.n
+    assert ((recs[:, 15] & 31) == res.labels).all()
+
+
 def test_cli_classify_and_write(tmp_path):
     cloud = synth.generate(5, 30000, seed=5)                     # format 3 (34 B), config 5's scene
     las = str(tmp_path / "urban.las")

@@ -115,6 +115,9 @@ def lib():
             "wb_run": [vp],
             "wb_get_stats": [vp, C.POINTER(Stats)],
             "wb_sync": [vp],
+            "wb_mark": [vp, C.c_int],
+            "wb_set_return_zero_rule": [vp, C.c_int],
+            "wb_mark_elapsed": [vp, C.c_int, C.c_int, dp],
             "wb_host_alloc": [C.POINTER(vp), u64],
             "wb_host_free": [vp],
             "wb_size_fit": [vp, C.c_int, dp, dp],
@@ -151,7 +154,7 @@ EXPORTS = ["wb_create", "wb_destroy", "wb_last_error", "wb_reserve", "wb_clear",
            "wb_set_own_range", "wb_export_tiles_device", "wb_import_tiles_device", "wb_max_hyperboloid_size",
            "wb_assign", "wb_get_points_sorted", "wb_test_math", "wb_bound_rect", "wb_keep_records",
            "wb_leaf_class_counts", "wb_encode", "wb_get_duplicates", "wb_add_las_file", "wb_write_encoded", "wb_query_batch",
-           "wb_query_points"]
+           "wb_query_points", "wb_mark", "wb_mark_elapsed", "wb_set_return_zero_rule"]
 
 
 def _d(v):
@@ -291,6 +294,16 @@ class Context:
     def sync(self):
         self._ck(self._L.wb_sync(self._h))
 
+    def mark(self, slot):
+        """CUDA event `slot` on the library's compute stream, behind all work issued so far."""
+        self._ck(self._L.wb_mark(self._h, slot))
+
+    def mark_elapsed(self, a, b):
+        """Device milliseconds between marks a and b (waits for b)."""
+        ms = C.c_double()
+        self._ck(self._L.wb_mark_elapsed(self._h, a, b, C.byref(ms)))
+        return ms.value
+
     # ---- results
     def leaves(self):
         n = C.c_uint64()
@@ -310,6 +323,10 @@ class Context:
         return buf.raw[:ln].decode("utf-8")
 
     # ---- output records (ACT_WRITE)
+    def set_return_zero_rule(self, keep_all):
+        """keep_all=True: store records with return number 0 too (wolkencli.cpp:104-108 callers)."""
+        self._ck(self._L.wb_set_return_zero_rule(self._h, 1 if keep_all else 0))
+
     def keep_records(self, keep=True):
         """Before add_las: keep the raw records in device memory for encode()."""
         self._ck(self._L.wb_keep_records(self._h, 1 if keep else 0))

@@ -63,6 +63,7 @@ struct wb_ctx
   std::string err;
   cudaStream_t st=nullptr,stCopy=nullptr;
   cudaEvent_t evA=nullptr,evB=nullptr,evC=nullptr,evD=nullptr,evCopy[2]={nullptr,nullptr},evDec[2]={nullptr,nullptr};
+  cudaEvent_t evMark[WB_MARKS]={},evJoin=nullptr;     // wb_mark: caller-placed timing events on the compute stream
   WbParams prm{1,1,0,0.1};
   Phase phase=PH_EMPTY;
   // cloud
@@ -85,6 +86,7 @@ struct wb_ctx
   cudaEvent_t evRead[WB_READ_THREADS]={};
   // raw records kept for wb_encode (one buffer per wb_add_las call)
   bool keepRecords=false;
+  bool keepZeroReturns=false;          // wb_set_return_zero_rule(ctx,1)
   std::vector<uint8_t *> recBufs;
   std::vector<WbRecSeg> recSegs;
   DevBuf<WbRecSegs> drsegs;
@@ -363,6 +365,9 @@ extern "C" void wb_destroy(wb_ctx *ctx)
     cudaEventDestroy(ctx->evCopy[i]);
     cudaEventDestroy(ctx->evDec[i]);
   }
+  for (int i=0;i<WB_MARKS;i++)
+    if (ctx->evMark[i]) cudaEventDestroy(ctx->evMark[i]);
+  if (ctx->evJoin) cudaEventDestroy(ctx->evJoin);
   delete ctx;
 }
 
@@ -478,6 +483,8 @@ extern "C" int wb_add_las_device(wb_ctx *ctx,const uint8_t *d,uint64_t n,int fmt
     CK(cudaStreamSynchronize(ctx->st));
     dropZeros=(fmt<6?(b14&7):(b14&15))!=0;          // threads.cpp:485-500: decided by record 0
   }
+  if (ctx->keepZeroReturns)
+    dropZeros=0;
   CK(cudaEventRecord(ctx->evA,ctx->st));
   if ((rc=decodeDevice(ctx,d,ctx->n,n,fmt,recLen,dropZeros,ctx->st)))
     return rc;
@@ -509,6 +516,8 @@ extern "C" int wb_add_las(wb_ctx *ctx,const uint8_t *recs,uint64_t n,int fmt,int
   if ((rc=ensurePointArrays(ctx,ctx->n+n)))
     return rc;
   int dropZeros=n?((fmt<6?(recs[14]&7):(recs[14]&15))!=0):0;
+  if (ctx->keepZeroReturns)
+    dropZeros=0;
   // double-buffered pipeline: copy chunk i+1 on the copy stream while chunk i is decoded
   const uint64_t chunkRecs=(uint64_t)1<<21;          // 2 Mi records (multiple of 16: chunks stay 16-byte aligned)
   const uint64_t chunkBytes=chunkRecs*recLen;
@@ -677,7 +686,7 @@ extern "C" int wb_add_las_file(wb_ctx *ctx,const char *path,uint64_t pointOffset
     const uint64_t cnt=std::min(chunkRecs,n-k*chunkRecs);
     const uint8_t *src=ctx->readBuf[t];
     if (k==0)
-      dropZeros=(fmt<6?(src[14]&7):(src[14]&15))!=0;                 // threads.cpp:485-500: decided by record 0
+      dropZeros=!ctx->keepZeroReturns && (fmt<6?(src[14]&7):(src[14]&15))!=0;   // threads.cpp:485-500: decided by record 0
     uint8_t *dst=kept?kept+k*chunkBytes:ctx->staging[b].p;
     if (used[b] && !kept)
       ce=cudaStreamWaitEvent(ctx->stCopy,ctx->evDec[b],0);
@@ -1508,6 +1517,14 @@ extern "C" int wb_query_points(wb_ctx *ctx,const wb_shape *shape,uint64_t cap,ui
 
 // ============================================================================ output records (ACT_WRITE)
 
+extern "C" int wb_set_return_zero_rule(wb_ctx *ctx,int keep_all)
+{
+  if (!ctx)
+    return WB_ERR_ARG;
+  ctx->keepZeroReturns=keep_all!=0;
+  return WB_OK;
+}
+
 extern "C" int wb_keep_records(wb_ctx *ctx,int keep)
 {
   if (!ctx)
@@ -1868,6 +1885,37 @@ extern "C" int wb_sync(wb_ctx *ctx)
   cudaSetDevice(ctx->device);
   CK(cudaStreamSynchronize(ctx->st));
   CK(cudaStreamSynchronize(ctx->stCopy));
+  return WB_OK;
+}
+
+extern "C" int wb_mark(wb_ctx *ctx,int slot)
+// A timing event on the compute stream, behind everything issued so far (both streams: the copy
+// stream is joined first, so a mark after wb_add_las also covers its transfers).
+{
+  if (!ctx || slot<0 || slot>=WB_MARKS)
+    return WB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  if (!ctx->evMark[slot])
+    CK(cudaEventCreate(&ctx->evMark[slot]));
+  if (!ctx->evJoin)
+    CK(cudaEventCreateWithFlags(&ctx->evJoin,cudaEventDisableTiming));
+  CK(cudaEventRecord(ctx->evJoin,ctx->stCopy));
+  CK(cudaStreamWaitEvent(ctx->st,ctx->evJoin,0));
+  CK(cudaEventRecord(ctx->evMark[slot],ctx->st));
+  return WB_OK;
+}
+
+extern "C" int wb_mark_elapsed(wb_ctx *ctx,int from,int to,double *ms)
+{
+  if (!ctx || !ms || from<0 || from>=WB_MARKS || to<0 || to>=WB_MARKS)
+    return WB_ERR_ARG;
+  if (!ctx->evMark[from] || !ctx->evMark[to])
+    return fail(ctx,WB_ERR_STATE,"wb_mark_elapsed: mark %d or %d was never recorded",from,to);
+  cudaSetDevice(ctx->device);
+  CK(cudaEventSynchronize(ctx->evMark[to]));
+  float f=0;
+  CK(cudaEventElapsedTime(&f,ctx->evMark[from],ctx->evMark[to]));
+  *ms=f;
   return WB_OK;
 }
 

@@ -29,8 +29,15 @@ namespace
 {
 wb_ctx *g_ctx=nullptr;
 int g_command=TH_WAIT;
-vector<LasHeader *> g_files;           // in read order: input index = concatenation of their records
-vector<size_t> g_fileFirst;
+struct InputSeg { LasHeader *h; size_t firstRec,count; };   // a run of records of one open file
+vector<InputSeg> g_files;              // in read order: input index = concatenation of these runs
+vector<size_t> g_fileFirst;            // input index of each run's first record
+// embufferPoint: records waiting to be handed to the device (runs of consecutive readPoint results)
+vector<InputSeg> g_pending;
+size_t g_pendingPoints=0;
+thread_local LasHeader *t_lastHdr=nullptr;      // the most recent readPoint on this thread: header, record, location
+thread_local size_t t_lastNum=0;
+thread_local double t_lastLoc[3]={0,0,0};
 vector<double> g_corners;
 Cube g_snakeCube;
 double g_snakeTile=1;
@@ -45,6 +52,8 @@ vector<uint64_t> g_keys;
 vector<uint8_t> g_labels;
 vector<uint32_t> g_attrSrc;           // canonical position -> input record whose attributes the stored point has
 deque<ThreadAction> g_results;
+
+void flushPointBuffer();
 
 struct Stopwatch
 {
@@ -93,6 +102,7 @@ uint64_t keyOf(xyz p)
 void ensureBuilt()
 {
   ensureContext();
+  flushPointBuffer();
   if (g_built)
     return;
   double rc[3]={octRoot.getCenter().getx(),octRoot.getCenter().gety(),octRoot.getCenter().getz()};
@@ -171,8 +181,8 @@ void ensureLabels()
   if (!g_classified)
     return;
   size_t n=0;
-  for (auto f:g_files)
-    n+=f->numberPoints();
+  for (auto &f:g_files)
+    n+=f.count;
   if (g_labels.size()!=n)
   {
     g_labels.resize(n);
@@ -185,7 +195,7 @@ LasPoint pointAt(size_t k)
 {
   uint32_t i=g_attrSrc[k];
   size_t f=upper_bound(g_fileFirst.begin(),g_fileFirst.end(),(size_t)i)-g_fileFirst.begin()-1;
-  LasPoint p=g_files[f]->readPoint(i-g_fileFirst[f]);
+  LasPoint p=g_files[f].h->readPoint(g_files[f].firstRec+(i-g_fileFirst[f]));
   if (p.returnNum==0)
     p.returnNum=1;                     // a stored point with return number 0: keep-zeros file, threads.cpp:527-528
   p.location=xyz(g_x[k],g_y[k],g_z[k]);
@@ -573,6 +583,9 @@ LasPoint LasHeader::readPoint(size_t num)
   if ((1<<pointFormat)&0x500)
     ret.nir=rd<uint16_t>(r+o);
   ret.location=xyz(xOffset+xScale*xi,yOffset+yScale*yi,zOffset+zScale*zi)*unit;
+  t_lastHdr=this;                       // embufferPoint hands this very record to the device
+  t_lastNum=num;
+  t_lastLoc[0]=ret.location.getx(); t_lastLoc[1]=ret.location.gety(); t_lastLoc[2]=ret.location.getz();
   if (ret.location.getx()>maxX*unit || ret.location.getx()<minX*unit || ret.location.gety()>maxY*unit ||
       ret.location.gety()<minY*unit || ret.location.getz()>maxZ*unit || ret.location.getz()<minZ*unit)
     cerr<<"Point out of range\n";
@@ -798,7 +811,7 @@ static LasPoint pointFromInput(uint32_t inputIdx,double x,double y,double z)
   if (it!=last.end())
     i=it->second;
   size_t f=upper_bound(g_fileFirst.begin(),g_fileFirst.end(),(size_t)i)-g_fileFirst.begin()-1;
-  LasPoint p=g_files[f]->readPoint(i-g_fileFirst[f]);
+  LasPoint p=g_files[f].h->readPoint(g_files[f].firstRec+(i-g_fileFirst[f]));
   if (p.returnNum==0)
     p.returnNum=1;
   p.location=xyz(x,y,z);
@@ -927,6 +940,8 @@ void OctStore::clear()
     wb_clear(g_ctx);
   g_files.clear();
   g_fileFirst.clear();
+  g_pending.clear();
+  g_pendingPoints=0;
   g_built=g_scanned=g_postscanned=g_classified=g_haveStore=g_haveLeaves=false;
   g_labels.clear();
 }
@@ -943,8 +958,8 @@ int nThreads() { return 1; }
 double busyFraction() { return 0; }
 bool actionQueueEmpty() { return true; }
 bool resultQueueEmpty() { return g_results.empty(); }
-bool pointBufferEmpty() { return true; }
-size_t pointBufferSize() { return 0; }
+bool pointBufferEmpty() { return g_pendingPoints==0; }
+size_t pointBufferSize() { return g_pendingPoints; }
 
 size_t duplicatePoints()
 {
@@ -969,6 +984,84 @@ ThreadAction dequeueResult()
   return a;
 }
 
+namespace
+{
+void sendExtents()
+{
+  if (g_files.empty())
+    for (size_t i=0;i+5<g_corners.size();i+=6)
+      wb_add_extent(g_ctx,&g_corners[i],&g_corners[i+3]);
+}
+
+void addInputRun(LasHeader *h,size_t firstRec,size_t count)
+{
+  size_t first=g_fileFirst.empty()?0:g_fileFirst.back()+g_files.back().count;
+  g_files.push_back(InputSeg{h,firstRec,count});
+  g_fileFirst.push_back(first);
+  g_built=g_scanned=g_postscanned=g_classified=false;
+}
+
+void flushPointBuffer()
+// The embuffered records go to the device as they lie in their files (runs of consecutive records).
+{
+  if (g_pending.empty())
+    return;
+  ensureContext();
+  wb_set_return_zero_rule(g_ctx,1);     // the caller chose the points: none is dropped (wolkencli.cpp:104-108)
+  for (auto &r:g_pending)
+  {
+    LasHeader *h=r.h;
+    sendExtents();
+    double sc[3]={h->rawScale(0),h->rawScale(1),h->rawScale(2)},of[3]={h->rawOffset(0),h->rawOffset(1),h->rawOffset(2)};
+    Stopwatch sw(hostTimes[1]);
+    if (wb_add_las(g_ctx,h->records()+r.firstRec*h->getPointLength(),r.count,h->getPointFormat(),h->getPointLength(),
+                   sc,of,h->getUnit())!=WB_OK)
+    {
+      die("Error storing points");
+      break;
+    }
+    addInputRun(h,r.firstRec,r.count);
+  }
+  wb_set_return_zero_rule(g_ctx,0);
+  g_pending.clear();
+  g_pendingPoints=0;
+}
+} // namespace
+
+void embufferPoint(LasPoint point,bool fromFile)
+// threads.cpp:201-229.  The device store keeps the file's own integers, so the point must be the one the last
+// readPoint on this thread returned (the reference's callers, wolkencli.cpp:104-108 and threads.cpp:525-531,
+// do exactly that); anything else is refused aloud.
+{
+  (void)fromFile;
+  if (point.isEmpty())
+    return;
+  if (!t_lastHdr || point.location.getx()!=t_lastLoc[0] || point.location.gety()!=t_lastLoc[1] ||
+      point.location.getz()!=t_lastLoc[2])
+  {
+    cerr<<"embufferPoint: not the point readPoint just returned; ignored (the GPU store holds LAS records)\n";
+    return;
+  }
+  if (!g_pending.empty() && g_pending.back().h==t_lastHdr && g_pending.back().firstRec+g_pending.back().count==t_lastNum)
+    g_pending.back().count++;
+  else
+    g_pending.push_back(InputSeg{t_lastHdr,t_lastNum,1});
+  g_pendingPoints++;
+}
+
+void embufferPoints(vector<LasPoint> points,int)
+// threads.cpp:231-246 re-embuffers the 537 points of a split block; there are no such splits here.
+{
+  if (!points.empty())
+    cerr<<"embufferPoints: nothing to re-insert, buckets are split on the device\n";
+}
+
+LasPoint debufferPoint(int) { return LasPoint(); }   // empty point = "buffer is empty", threads.cpp:248-264
+void sleepDead(int) {}
+int thisThread() { return -1; }                      // the caller's thread, threads.cpp:414-417
+bool tileDoneQueueEmpty() { return true; }
+Eisenstein dequeueTileDone() { return Eisenstein(INT_MIN,INT_MIN); }
+
 void enqueueAction(ThreadAction a)
 {
   ensureContext();
@@ -983,9 +1076,8 @@ void enqueueAction(ThreadAction a)
         break;
       }
       cout<<"Thread 0 reading "<<h->getFileName()<<endl;
-      if (g_files.empty())
-        for (size_t i=0;i+5<g_corners.size();i+=6)
-          wb_add_extent(g_ctx,&g_corners[i],&g_corners[i+3]);
+      flushPointBuffer();
+      sendExtents();
       double sc[3]={h->rawScale(0),h->rawScale(1),h->rawScale(2)},of[3]={h->rawOffset(0),h->rawOffset(1),h->rawOffset(2)};
       Stopwatch sw(hostTimes[1]);
       if (wb_add_las_file(g_ctx,h->getFileName().c_str(),h->getPointOffset(),h->numberPoints(),h->getPointFormat(),
@@ -994,10 +1086,7 @@ void enqueueAction(ThreadAction a)
         die("Error reading file");
         break;
       }
-      size_t first=g_fileFirst.empty()?0:g_fileFirst.back()+g_files.back()->numberPoints();
-      g_files.push_back(h);
-      g_fileFirst.push_back(first);
-      g_built=false;
+      addInputRun(h,0,h->numberPoints());
       break;
     }
     case ACT_COUNT:
@@ -1017,6 +1106,7 @@ void enqueueAction(ThreadAction a)
 
 void waitForQueueEmpty()
 {
+  flushPointBuffer();
   if (!g_files.empty())
     ensureBuilt();
 }

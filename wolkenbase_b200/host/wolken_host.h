@@ -374,6 +374,7 @@ extern bool keepRecordsOnDevice;   // set before reading: the raw records stay i
 #define ACT_READ 1
 #define ACT_COUNT 2
 #define ACT_WRITE 3
+#define ACT_LOAD 4                                  // accepted, no-op: there is no block file to load (threads.cpp:591-628)
 
 struct ThreadAction
 {
@@ -391,8 +392,18 @@ void enqueueAction(ThreadAction a);                 // ACT_READ runs at once; AC
 ThreadAction dequeueResult();
 bool actionQueueEmpty();
 bool resultQueueEmpty();
+Eisenstein dequeueTileDone();                       // always (INT_MIN,INT_MIN): phases complete as a whole, no per-tile repaint queue
+bool tileDoneQueueEmpty();
+// The reference's wolkencli feeds the pool itself: readPoint, then embufferPoint (wolkencli.cpp:104-108).  Here the
+// records such points came from wait as runs of consecutive records and reach the GPU in waitForQueueEmpty (or any
+// phase change); a point that is not the one the last readPoint on this thread returned is refused with a message.
+void embufferPoint(LasPoint point,bool fromFile);
+void embufferPoints(std::vector<LasPoint> points,int thread);   // split re-insertion (octree.cpp:1332): never needed here
+LasPoint debufferPoint(int thread);                 // always the empty point
 bool pointBufferEmpty();
-size_t pointBufferSize();
+size_t pointBufferSize();                           // embuffered points not yet on the device
+void sleepDead(int thread);
+int thisThread();                                   // -1 = the calling (main) thread, threads.cpp:414-417
 size_t duplicatePoints();                           // alreadyInOctree.size() (octree.cpp:620-662): records lost to an identical XYZ
 void setThreadCommand(int newStatus);
 int getThreadCommand();

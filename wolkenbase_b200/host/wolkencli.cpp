@@ -10,6 +10,8 @@
 //     --dump FILE                where to write the octree dump (default "dumpfile")
 //     --host-writer              make the output records on the CPU (LasHeader::writePoint) instead of on the GPU
 //     --timing                   print the wall time of each phase (seconds) as one JSON line at the end
+//     --embuffer                 feed the store the way the reference's wolkencli does (readPoint + embufferPoint per
+//                                point, wolkencli.cpp:104-108) instead of one ACT_READ per file
 //     --lossless                 keep the inputs' own records (format, scale, offset) and only replace the class
 //                                byte, instead of the reference's LAS 1.4 re-encoding (CloudOutput)
 #include <cstdlib>
@@ -27,7 +29,7 @@ int main(int argc,char **argv)
   vector<string> inputFiles;
   OutputOptions out;
   string dumpName="dumpfile";
-  bool classify=false,lossless=false,hostWriter=false,timing=false;
+  bool classify=false,lossless=false,hostWriter=false,timing=false,perPoint=false;
   auto now=[]{ return chrono::duration<double>(chrono::steady_clock::now().time_since_epoch()).count(); };
   double t0=now(),tRead=0,tScan=0,tPost=0,tClass=0,tWrite=0,tDump=0,tOpen=0;
   for (int i=1;i<argc;i++)
@@ -46,6 +48,7 @@ int main(int argc,char **argv)
     else if (a=="--lossless") lossless=true;
     else if (a=="--host-writer") hostWriter=true;
     else if (a=="--timing") timing=true;
+    else if (a=="--embuffer") perPoint=true;
     else if (a.size() && a[0]=='-') { cerr<<"unknown option "<<a<<endl; return 2; }
     else inputFiles.push_back(a);
   }
@@ -95,10 +98,16 @@ int main(int argc,char **argv)
   waitForThreads(TH_READ);
   for (size_t i=0;i<files.size();i++)
   {
-    ThreadAction ta;
-    ta.opcode=ACT_READ;
-    ta.hdr=&files[i];
-    enqueueAction(ta);
+    if (perPoint)
+      for (size_t j=0;j<files[i].numberPoints();j++)
+        embufferPoint(files[i].readPoint(j),true);
+    else
+    {
+      ThreadAction ta;
+      ta.opcode=ACT_READ;
+      ta.hdr=&files[i];
+      enqueueAction(ta);
+    }
     cout<<files[i].numberPoints()<<" points, "<<pointBufferSize()<<" points in buffer\n";
   }
   waitForQueueEmpty();
