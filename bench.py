@@ -249,10 +249,59 @@ def run_ours(args):
                                           "chunks": st["cl_chunks2"] * 32.0 / n, "pairs": st["cl_pairs2"] * 32.0 / n}},
         "gen_s": round(gen_s, 2),
     }
+    if not args.no_scaling_base and not args.points and not args.scene:
+        try:
+            line["weak_scaling_base"] = scaling_base(ctx, args)
+        except Exception as e:                      # an auxiliary figure must never cost the bench line
+            line["weak_scaling_base"] = {"error": "%s: %s" % (type(e).__name__, e)}
+            ctx.close()
+            ctx = api.Context(local)
     if not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(scene, args.cpu_points, bounded=True)
     ctx.close()
     print(json.dumps(line))
+
+
+def scaling_base(ctx, args):
+    """The N>1 runs shard BASELINE configs[2] (C3, 125 M points per GPU, LAS format 6) while the N=1 line is
+    configs[1] (C2), whose tile spacing and hyperboloid sizes make a point several times dearer.  So that
+    N-GPU values can be set against a like-for-like single-GPU figure, the N=1 line also carries one GPU's
+    throughput on ONE GPU'S SHARE of the 8-GPU scene: rank 0's x-strip of the 1 B-point cloud, with the whole
+    scene's geometry (same root cube, same tile lattice), no halo and no exchange.  Records resident in HBM,
+    CUDA events on the library's stream, 1 warm-up + 2 timed passes."""
+    import torch
+    from wolkenbase_b200 import synth
+    per_gpu, world = 125_000_000, 8
+    d = synth.describe(3, per_gpu * world)
+    cloud = synth.generate(3, per_gpu * world, seed=3, region=(0, 0, d.grid_nx // world, d.grid_ny))
+    n = cloud.n
+    lo = (d.offset[0], d.offset[1], cloud.min_corner[2])
+    hi = (d.offset[0] + d.scale * d.extent_ticks, d.offset[1] + d.scale * d.extent_ticks, cloud.max_corner[2])
+    dev = torch.from_numpy(cloud.records.reshape(-1)).cuda()
+    torch.cuda.synchronize()
+
+    def step():
+        ctx.clear()
+        ctx.add_extent(cloud.min_corner, cloud.max_corner)
+        ctx.add_extent(lo, hi)                     # the other seven strips' corners: the scene's full xy extent
+        ctx.add_las_device(dev.data_ptr(), n, cloud.fmt, cloud.rec_len, cloud.scale, cloud.offset)
+        ctx.run()
+
+    step()
+    steps = 2
+    ctx.mark(4)
+    for _ in range(steps):
+        step()
+    ctx.mark(5)
+    ms = ctx.mark_elapsed(4, 5) / steps
+    st = ctx.stats()
+    g = ctx.geometry()
+    del dev
+    return {"workload": "C3 multi-tile aerial scene, rank 0's strip of the 8-GPU run: %d points, LAS format %d "
+                        "(%d B records), the 1 B-point scene's geometry (tile spacing %.3f m), no halo"
+                        % (n, cloud.fmt, cloud.rec_len, g.spacing),
+            "value": n / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps, "warmup": 1,
+            "classify_kernel_ms": st["ms_classify_kernel"]}
 
 
 def cpu_baseline(scene, sample_points, bounded=True, threads=None):
@@ -331,6 +380,8 @@ def main():
     ap.add_argument("--scene", type=int, default=0)
     ap.add_argument("--cpu-points", type=int, default=400_000)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-scaling-base", action="store_true",
+                    help="skip the single-GPU run of the multi-GPU workload (weak_scaling_base)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

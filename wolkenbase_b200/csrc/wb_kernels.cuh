@@ -883,9 +883,27 @@ wb_postscan_kernel(const int *__restrict__ tNPoints,const uint8_t *__restrict__ 
 #define WB_CL_WARPS 1                    // one warp per CTA: a slow warp strands nothing (measured 8,4,2,1 warps: 1189,1115,1079,974 ms)
 #endif
 
+// Single-precision shortcuts (both leave every decision to the exact double code when in doubt; the error
+// bounds are pinned by tests/test_float_filters.py): sector binning of the bearings, and the
+// (chunk, query) reach test at expansion.  0 = the double-precision originals.
+#ifndef WB_CL_FSECTOR
+#define WB_CL_FSECTOR 1
+#endif
+#ifndef WB_CL_FREACH
+#define WB_CL_FREACH 1
+#endif
+#ifndef WB_CL_FSPAN
+#define WB_CL_FSPAN 1
+#endif
+
 struct WbClassifyWarp
 {
   double qx[32],qy[32],qcz[32],qpor2[32];
+#if WB_CL_FREACH
+  float fx[32],fy[32],fh[32],f2p[32];   // the same queries relative to the warp's origin: xy, vertex height, 2*por
+  double org[3];                        // that origin (the warp's first query)
+  float fgh,fzq;                        // bounds of |fx|,|fy| and of |fh| over the warp's queries
+#endif
   uint32_t keys[8][32];       // per stack entry: (squared distance | child) of the children still to visit
   WbBound cb[32];             // bounds of the chunks of the open level-0 entry
   uint32_t wants[32];         // ... live queries that reach each chunk
@@ -937,6 +955,37 @@ __device__ __forceinline__ int wb_sector64(double dx,double dy)
   return dx<0?32+s1:63-s1;
 }
 
+__device__ __forceinline__ int wb_sector64f(double dxd,double dyd)
+// wb_sector64 with the three tangent comparisons in single precision (half the instructions: a
+// double select is two moves).  The inputs lose 2^-24 each in the conversion and every product
+// another 2^-24, so a comparison lo >= hi*T is off by at most 2.5e-7*hi; anything within 4e-6*hi
+// of a sector edge returns -1 and the exact atan2i decides, as before.  Quadrants come from the
+// signs of the doubles.
+{
+  const float T1=0.09849140335716425f,T2=0.198912367379658f,T3=0.3033466836073424f,T4=0.41421356237309503f,
+              T5=0.5345111359507916f,T6=0.6681786379192989f,T7=0.8206787908286602f;
+  const float ax=fabsf((float)dxd),ay=fabsf((float)dyd);
+  const bool sw=ay>ax;
+  const float lo=sw?ax:ay,hi=sw?ay:ax;
+  float c=hi*T4;
+  const bool b1=lo>=c;
+  float m=fabsf(lo-c);
+  c=hi*(b1?T6:T2);
+  const bool b2=lo>=c;
+  m=fminf(m,fabsf(lo-c));
+  c=hi*(b1?(b2?T7:T5):(b2?T3:T1));
+  const bool b3=lo>=c;
+  m=fminf(m,fabsf(lo-c));
+  m=fminf(m,fminf(lo,hi-lo));
+  if (!(m>4e-6f*hi) || !(hi>1e-30f) || !(hi<1e30f))     // near an edge, or outside the range where float keeps the ratio
+    return -1;
+  const int sub=(b1?4:0)+(b2?2:0)+(b3?1:0);
+  const int s1=sw?15-sub:sub;
+  if (dyd>=0)
+    return dxd>=0?s1:31-s1;
+  return dxd<0?32+s1:63-s1;
+}
+
 __device__ __forceinline__ int wb_sector64_exact(double dx,double dy,uint32_t &u)
 {
   u=(uint32_t)wb_atan2i(dy,dx)&0x7fffffffu;
@@ -967,12 +1016,23 @@ __device__ __forceinline__ unsigned long long wb_span_mask(double dx0,double dx1
 // Sectors of all bearings from the origin to the rectangle [dx0,dx1]x[dy0,dy1]: the two
 // silhouette corners, each widened by 0.06 sector for the approximate angle.
 {
+#if WB_CL_FSPAN
+  // the corners are only ever used as floats: convert first, so that the selects move one register, not two
+  // (the conversion keeps signs; a difference that underflows to 0 makes the rectangle touch the origin: wider mask)
+  const float x0=(float)dx0,x1=(float)dx1,y0=(float)dy0,y1=(float)dy1;
+  const bool L=x0>0,R=x1<0,B=y0>0,T=y1<0;
+  if (!(L||R||B||T))
+    return ~0ull;                                  // the origin is inside
+  const float ax=B?x1:(T?x0:(L?x0:x1)),ay=L?y0:(R?y1:(B?y0:y1));
+  const float bx=B?x0:(T?x1:(L?x0:x1)),by=L?y1:(R?y0:(B?y0:y1));
+#else
   const bool L=dx0>0,R=dx1<0,B=dy0>0,T=dy1<0;
   if (!(L||R||B||T))
     return ~0ull;                                  // the origin is inside
   // clockwise-most corner a, counter-clockwise-most corner b
   float ax=(float)(B?dx1:(T?dx0:(L?dx0:dx1))),ay=(float)(L?dy0:(R?dy1:(B?dy0:dy1)));
   float bx=(float)(B?dx0:(T?dx1:(L?dx0:dx1))),by=(float)(L?dy1:(R?dy0:(B?dy0:dy1)));
+#endif
   int sa=(int)floorf(wb_fast_angle(ax,ay)-0.06f),sb=(int)floorf(wb_fast_angle(bx,by)+0.06f);
   int len=((sb-sa)&63)+1;
   if (len>40)                                      // a rectangle spans < 180 degrees; anything else is a wrap artefact
@@ -1087,6 +1147,24 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
       untiled=true;
   }
   w.qx[lane]=px; w.qy[lane]=py; w.qcz[lane]=pcz; w.qpor2[lane]=ppor2;
+#if WB_CL_FREACH
+  // Single-precision copies for the (chunk, query) reach test at expansion: coordinates relative to the
+  // first query of the warp, so that the conversion error is 2^-24 of a distance, not of an easting.
+  {
+    const double ox=__shfl_sync(WB_FULL,px,0),oy=__shfl_sync(WB_FULL,py,0),oz=__shfl_sync(WB_FULL,have?sz[me]:0.0,0);
+    const bool q=have && !done;
+    const double por=q?sqrt(ppor2):0.0;
+    const float fx=q?(float)(px-ox):0.0f,fy=q?(float)(py-oy):0.0f,fh=q?(float)((pcz-por)-oz):0.0f;
+    w.fx[lane]=fx; w.fy[lane]=fy; w.fh[lane]=fh; w.f2p[lane]=fminf((float)(2*por),1e30f);
+    const float gh=__uint_as_float(__reduce_max_sync(WB_FULL,__float_as_uint(fmaxf(fabsf(fx),fabsf(fy)))));
+    const float zq=__uint_as_float(__reduce_max_sync(WB_FULL,__float_as_uint(fabsf(fh))));
+    if (lane==0)
+    {
+      w.org[0]=ox; w.org[1]=oy; w.org[2]=oz;
+      w.fgh=gh; w.fzq=zq;
+    }
+  }
+#endif
   unsigned long long occ=0;                       // occupied sectors of my query
   unsigned long long open=~0ull;                  // sectors of empty runs >= 24 (the only ones that matter)
   bool changed=false;
@@ -1178,6 +1256,30 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
       if (childLevel==0)
       {
         uint32_t lm=askers;
+#if WB_CL_FREACH
+        // Conservative single-precision form of wb_reach(query, chunk box): with a = vertex height - lowest z,
+        // (a+por)^2 - d^2 s^2 >= por^2  <=>  a (a + 2 por) >= d^2 s^2  (a >= 0).  Every rounding is covered: the
+        // distances shrink by ed, the drop grows by ez (8x the worst conversion + subtraction error), the
+        // products carry 4e-6 (their own roundings stay below 1e-6).  It only has to admit every pair the double test admits; the chunk's points are
+        // tested exactly later.
+        const double ox=w.org[0],oy=w.org[1],oz=w.org[2];
+        const float x0=(float)(cb.xmin-ox),x1=(float)(cb.xmax-ox),y0=(float)(cb.ymin-oy),y1=(float)(cb.ymax-oy),
+                    z0=(float)(cb.zmin-oz);
+        const float ed=9.5367431640625e-7f*(fmaxf(fmaxf(fabsf(x0),fabsf(x1)),fmaxf(fabsf(y0),fabsf(y1)))+w.fgh);
+        const float ez=9.5367431640625e-7f*(fabsf(z0)+w.fzq)+1e-6f;
+        const float fs2=(float)s2*0.999998f;
+        while (lm)
+        {
+          const int q=__ffs(lm)-1;
+          lm&=lm-1;
+          const float qx=w.fx[q],qy=w.fy[q],qh=w.fh[q],q2p=w.f2p[q];
+          const float dx=fmaxf(0.0f,fmaxf(x0-qx,qx-x1)-ed);
+          const float dy=fmaxf(0.0f,fmaxf(y0-qy,qy-y1)-ed);
+          const float a=(qh-z0)+ez;
+          if (ok && a>=0.0f && a*(a+q2p)*1.000002f>=(dx*dx+dy*dy)*fs2)
+            wants|=1u<<q;
+        }
+#else
         while (lm)
         {
           const int q=__ffs(lm)-1;
@@ -1186,6 +1288,7 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
           if (ok && wb_reach(qx,qx,qy,qy,qcz,qpor2,s2,cb))
             wants|=1u<<q;
         }
+#endif
         ok=ok && wants!=0;
         if (!__any_sync(WB_FULL,ok))
           return;
@@ -1287,7 +1390,7 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
           int s=-2;
           if (in)
           {
-            s=wb_sector64(ddx,ddy);
+            s=WB_CL_FSECTOR?wb_sector64f(ddx,ddy):wb_sector64(ddx,ddy);
             if (s<0)
             {
               uint32_t u;
@@ -1312,7 +1415,7 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
           uint32_t cMaxA=0,cMinA=0xffffffffu,cMaxB=0,cMinB=0xffffffffu;
           if (in)
           {
-            int s=wb_sector64(ddx,ddy);
+            int s=WB_CL_FSECTOR?wb_sector64f(ddx,ddy):wb_sector64(ddx,ddy);
             int k1a=wq&255,k2a=(wq>>8)&255,k1b=(wq>>16)&255,k2b=wq>>24;
             if (s<0 || s==k1a || s==k2a || s==k1b || s==k2b)
             {

@@ -52,6 +52,8 @@ vector<uint64_t> g_keys;
 vector<uint8_t> g_labels;
 vector<uint32_t> g_attrSrc;           // canonical position -> input record whose attributes the stored point has
 deque<ThreadAction> g_results;
+std::map<uint32_t,uint32_t> g_lastAtLocation;   // duplicates: surviving record -> last record at the same XYZ (valid per build)
+bool g_haveLastAtLocation=false;
 
 void flushPointBuffer();
 
@@ -117,7 +119,7 @@ void ensureBuilt()
     exit(4);
   }
   g_built=true;
-  g_haveStore=g_haveLeaves=false;
+  g_haveStore=g_haveLeaves=g_haveLastAtLocation=false;
 }
 
 void ensureLeaves()
@@ -787,10 +789,10 @@ static bool lowerThan(const LasPoint &a,const LasPoint &b)
 static LasPoint pointFromInput(uint32_t inputIdx,double x,double y,double z)
 // the stored point at (x,y,z) whose first record is inputIdx, without the host copy of the store
 {
-  static std::map<uint32_t,uint32_t> last;           // survivor -> last record at its location
-  static bool haveLast=false;
-  if (!haveLast)
+  std::map<uint32_t,uint32_t> &last=g_lastAtLocation;   // survivor -> last record at its location
+  if (!g_haveLastAtLocation)
   {
+    last.clear();
     wb_stats st;
     wb_get_stats(g_ctx,&st);
     if (st.n_duplicates)
@@ -804,7 +806,7 @@ static LasPoint pointFromInput(uint32_t inputIdx,double x,double y,double z)
           l=dup[u];
       }
     }
-    haveLast=true;
+    g_haveLastAtLocation=true;
   }
   uint32_t i=inputIdx;
   auto it=last.find(i);
