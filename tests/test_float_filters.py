@@ -112,125 +112,3 @@ def test_float_reach_admits_everything_the_double_test_admits():
         extra += int((f & ~d).sum())
     assert extra < 0.25 * total                              # and it still prunes (these inputs sit ON the surface)
 
-
-def _in_hyperboloid_double(px, py, pcz, ppor2, s, qx, qy, qz):
-    """wb_in_hyperboloid (wb_kernels.cuh), i.e. Hyperboloid::in (shape.cpp:127-135) and dist_xy != 0."""
-    s2 = s * s
-    zd = pcz - qz
-    dx, dy = px - qx, py - qy
-    zz, hs2 = zd * zd, (dx * dx + dy * dy) * s2
-    diff, tol = zz - hs2 - ppor2, 1e-13 * (zz + hs2 + ppor2)
-    ds = np.hypot(dx, dy) * s
-    exact = zd * zd - ds * ds >= ppor2
-    res = np.where(diff > tol, True, np.where(diff < -tol, False, exact))
-    return (zd > 0) & res & ((dx != 0) | (dy != 0))
-
-
-def _pair_float(px, py, pcz, ppor2, s, qx, qy, qz, org):
-    """The single-precision first try (WB_CL_FPAIR): returns (decided_in, decided_out)."""
-    ox, oy, oz = org
-    por = np.sqrt(ppor2)
-    fqx, fqy = (px - ox).astype(f32), (py - oy).astype(f32)
-    fqh = ((pcz - por) - oz).astype(f32)
-    fq2p = np.minimum((2 * por).astype(f32), f32(1e30))
-    fgh = f32(np.max(np.maximum(np.abs(fqx), np.abs(fqy))))
-    fzq = f32(np.max(np.abs(fqh)))
-    xf, yf, zf = (qx - ox).astype(f32), (qy - oy).astype(f32), (qz - oz).astype(f32)
-    c = f32(2.384185791015625e-7)
-    exy = c * (np.maximum(np.abs(xf), np.abs(yf)) + fgh)
-    ea = c * (np.abs(zf) + fzq)
-    fs2 = f32(s * s)
-    k1, k2 = f32(2) * ea, f32(2) * fs2 * exy
-    k3 = f32(2) * fs2 * exy * exy + f32(1e-30)
-    dxf, dyf, fa = xf - fqx, yf - fqy, fqh - zf
-    t1, t2 = fa * (fa + fq2p), (dxf * dxf + dyf * dyf) * fs2
-    diff = t1 - t2
-    E = k1 * (np.abs(fa) + fq2p) + (k2 * (np.abs(dxf) + np.abs(dyf)) + (f32(4e-7) * (np.abs(t1) + t2) + k3))
-    din = (diff > E) & (fa > 0) & ((np.abs(dxf) > exy) | (np.abs(dyf) > exy))
-    dout = diff < -E
-    return din, dout, dxf, dyf, exy
-
-
-def sector64ff(dx, dy, eabs):
-    t = [f32(v) for v in T]
-    ax, ay = np.abs(dx), np.abs(dy)
-    sw = ay > ax
-    lo, hi = np.where(sw, ax, ay), np.where(sw, ay, ax)
-    c = hi * t[3]
-    b1 = lo >= c
-    m = np.abs(lo - c)
-    c = hi * np.where(b1, t[5], t[1])
-    b2 = lo >= c
-    m = np.minimum(m, np.abs(lo - c))
-    c = hi * np.where(b1, np.where(b2, t[6], t[4]), np.where(b2, t[2], t[0]))
-    b3 = lo >= c
-    m = np.minimum(m, np.abs(lo - c))
-    m = np.minimum(m, np.minimum(lo, hi - lo))
-    undecided = ~(m > f32(4e-6) * hi + f32(2) * eabs) | ~(hi < f32(1e30))
-    sub = b1 * 4 + b2 * 2 + b3 * 1
-    s1 = np.where(sw, 15 - sub, sub)
-    s = np.where(dy >= 0, np.where(dx >= 0, s1, 31 - s1), np.where(dx < 0, 32 + s1, 63 - s1))
-    return np.where(undecided, -1, s)
-
-
-def test_float_pair_test_never_contradicts_the_double_test():
-    rng = np.random.default_rng(7)
-    L = O.lib()
-    total = decided = 0
-    for trial in range(150):
-        base = rng.choice([0.0, 1e3, 5e5, 4.2e6])
-        span = rng.choice([5.0, 50.0, 2000.0, 50000.0])
-        n = 20000
-        org = (base + rng.uniform(0, span), base * 0.7 + rng.uniform(0, span), rng.uniform(-50, 3000))
-        s = rng.choice([0.1, 0.5, 1.0, 2.0, 7.0])
-        por = 10 ** rng.uniform(-1, 3.2, n) * s * s
-        # queries within a few metres of the origin, on the LAS grid (multiples of 1 mm) like real points
-        px = np.round(org[0] + rng.uniform(-3, 3, n), 3)
-        py = np.round(org[1] + rng.uniform(-3, 3, n), 3)
-        pz = np.round(org[2] + rng.uniform(-10, 10, n), 3)
-        pcz, ppor2 = pz + por, por * por
-        r = span * 10 ** rng.uniform(-4, 0, n)
-        r[: n // 10] = 0.0                                       # same xy (points stacked in z)
-        th = rng.uniform(0, 2 * np.pi, n)
-        qx, qy = np.round(px + r * np.cos(th), 3), np.round(py + r * np.sin(th), 3)
-        d2 = (qx - px) ** 2 + (qy - py) ** 2
-        surf = pcz - np.sqrt(ppor2 + d2 * s * s)
-        eps = rng.choice([0, 1e-12, 1e-9, 1e-6, 1e-4, 1e-2, 1.0, 100.0], n) * rng.uniform(-1, 1, n)
-        qz = surf + eps
-        qz[::3] = np.round(qz[::3], 3)
-        truth = _in_hyperboloid_double(px, py, pcz, ppor2, s, qx, qy, qz)
-        din, dout, dxf, dyf, exy = _pair_float(px, py, pcz, ppor2, s, qx, qy, qz, org)
-        assert not (din & dout).any()
-        assert truth[din].all(), "float said in, double says out"
-        assert not truth[dout].any(), "float said out, double says in"
-        total += n
-        decided += int((din | dout).sum())
-        # bearings from the float differences: exact or undecided
-        sel = np.nonzero(din)[0][:300]
-        sec = sector64ff(dxf[sel], dyf[sel], exy[sel])
-        for k, sk in zip(sel, sec):
-            if sk >= 0:
-                u = L.wbo_atan2i(float(qy[k] - py[k]), float(qx[k] - px[k])) & 0x7fffffff
-                assert sk == u >> 25
-    assert decided > 0.3 * total        # adversarial inputs: on the surface to 1e-12, a tenth with the same xy
-
-
-def test_float_pair_test_decides_nearly_always_on_a_real_neighbourhood():
-    """UTM-sized coordinates, 1 mm grid, neighbours within 60 m, relief of metres: the double test is needed for
-    a few points in ten thousand (so a warp rarely diverges into it)."""
-    rng = np.random.default_rng(11)
-    n = 400000
-    org = (512345.678, 4212345.678, 123.456)
-    px = np.round(org[0] + rng.uniform(-1, 1, n), 3)
-    py = np.round(org[1] + rng.uniform(-1, 1, n), 3)
-    pz = np.round(org[2] + rng.uniform(-0.5, 0.5, n), 3)
-    por = np.full(n, 68.0)
-    r = 60 * np.sqrt(rng.uniform(0, 1, n))
-    th = rng.uniform(0, 2 * np.pi, n)
-    qx, qy = np.round(px + r * np.cos(th), 3), np.round(py + r * np.sin(th), 3)
-    qz = np.round(pz + 0.15 * r * np.cos(th) + rng.normal(0, 0.02, n) - r * r / 136 * rng.uniform(0, 2, n), 3)
-    truth = _in_hyperboloid_double(px, py, pz + por, por * por, 1.0, qx, qy, qz)
-    din, dout, _, _, _ = _pair_float(px, py, pz + por, por * por, 1.0, qx, qy, qz, org)
-    assert truth[din].all() and not truth[dout].any()
-    assert 0.2 < truth.mean() < 0.8
-    assert (din | dout).mean() > 0.999

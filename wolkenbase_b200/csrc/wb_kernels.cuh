@@ -895,9 +895,6 @@ wb_postscan_kernel(const int *__restrict__ tNPoints,const uint8_t *__restrict__ 
 #ifndef WB_CL_FSPAN
 #define WB_CL_FSPAN 1
 #endif
-#ifndef WB_CL_FPAIR
-#define WB_CL_FPAIR 0                   // single-precision first try of Hyperboloid::in per (query, point); needs WB_CL_FREACH
-#endif
 
 struct WbClassifyWarp
 {
@@ -987,35 +984,6 @@ __device__ __forceinline__ int wb_sector64f(double dxd,double dyd)
   if (dyd>=0)
     return dxd>=0?s1:31-s1;
   return dxd<0?32+s1:63-s1;
-}
-
-__device__ __forceinline__ int wb_sector64ff(float dx,float dy,float eabs)
-// The same from single-precision differences that are each off by at most eabs/2 (coordinates relative to the
-// warp's origin): a comparison lo >= hi*T is then off by at most eabs + 2.5e-7*hi.  Decided only when every
-// comparison clears 2*eabs + 4e-6*hi, which also makes both signs certain (lo > 2*eabs).
-{
-  const float T1=0.09849140335716425f,T2=0.198912367379658f,T3=0.3033466836073424f,T4=0.41421356237309503f,
-              T5=0.5345111359507916f,T6=0.6681786379192989f,T7=0.8206787908286602f;
-  const float ax=fabsf(dx),ay=fabsf(dy);
-  const bool sw=ay>ax;
-  const float lo=sw?ax:ay,hi=sw?ay:ax;
-  float c=hi*T4;
-  const bool b1=lo>=c;
-  float m=fabsf(lo-c);
-  c=hi*(b1?T6:T2);
-  const bool b2=lo>=c;
-  m=fminf(m,fabsf(lo-c));
-  c=hi*(b1?(b2?T7:T5):(b2?T3:T1));
-  const bool b3=lo>=c;
-  m=fminf(m,fabsf(lo-c));
-  m=fminf(m,fminf(lo,hi-lo));
-  if (!(m>fmaf(4e-6f,hi,2.0f*eabs)) || !(hi<1e30f))
-    return -1;
-  const int sub=(b1?4:0)+(b2?2:0)+(b3?1:0);
-  const int s1=sw?15-sub:sub;
-  if (dy>=0)
-    return dx>=0?s1:31-s1;
-  return dx<0?32+s1:63-s1;
 }
 
 __device__ __forceinline__ int wb_sector64_exact(double dx,double dy,uint32_t &u)
@@ -1389,15 +1357,6 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
       const unsigned long long j=(unsigned long long)node*32+lane;
       const bool okp=j<n;
       const double cxp=okp?sx[j]:0.0,cyp=okp?sy[j]:0.0,czp=okp?sz[j]:INFINITY;
-#if WB_CL_FPAIR
-      // The chunk's points relative to the warp's origin, in single precision, with the bounds of what the
-      // conversions and subtractions below can lose: exy for an xy difference (twice the worst case), ea for a drop.
-      const float xf=(float)(cxp-w.org[0]),yf=(float)(cyp-w.org[1]),zf=okp?(float)(czp-w.org[2]):0.0f;
-      const float exy=2.384185791015625e-7f*(fmaxf(fabsf(xf),fabsf(yf))+w.fgh);      // 2^-22
-      const float ea=2.384185791015625e-7f*(fabsf(zf)+w.fzq);
-      const float fs2p=(float)s2;
-      const float k1=2.0f*ea,k2=2.0f*fs2p*exy,k3=2.0f*fs2p*exy*exy+1e-30f;
-#endif
       if (pass==1) { statChunks++; statPairs+=__popc(qm); } else { statChunks2++; statPairs2+=__popc(qm); }
       // Sectors each chunk point can occupy as seen from ANY query of the group (bearing from the
       // group centre, widened by the group radius).  A query for which none of them is still of
@@ -1421,45 +1380,17 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
         const bool rel=(pmask&oq)!=0;
         if (!__any_sync(WB_FULL,rel))
           continue;
-#if WB_CL_FPAIR
-        // Hyperboloid::in, first in single precision: with a = vertex height - z and d the xy distance,
-        // (a+por)^2 - (d s)^2 >= por^2  <=>  a (a + 2 por) - d^2 s^2 >= 0 and a > 0.  E bounds everything the
-        // float evaluation can be off by (tests/test_float_filters.py mirrors it); inside +-E, or when the xy
-        // distance could be zero, the double-precision test below decides as before.
-        const float fqx=w.fx[q],fqy=w.fy[q],fqh=w.fh[q],fq2p=w.f2p[q];
-        const float dxf=xf-fqx,dyf=yf-fqy,fa=fqh-zf;
-        const float t1=fa*(fa+fq2p),t2=(dxf*dxf+dyf*dyf)*fs2p;
-        const float fdiff=t1-t2;
-        const float E=fmaf(k1,fabsf(fa)+fq2p,fmaf(k2,fabsf(dxf)+fabsf(dyf),fmaf(4e-7f,fabsf(t1)+t2,k3)));
-        bool in=rel && fdiff>E && fa>0.0f && (fabsf(dxf)>exy || fabsf(dyf)>exy);
-        double ddx=0,ddy=0;
-        if (rel && !in && !(fdiff<-E))
-          in=wb_in_hyperboloid(w.qx[q],w.qy[q],w.qcz[q],w.qpor2[q],s2,maxSlope,cxp,cyp,czp,ddx,ddy,margin);
-        if (!__any_sync(WB_FULL,in))
-          continue;
-#else
         const double qx=w.qx[q],qy=w.qy[q],qcz=w.qcz[q],qpor2=w.qpor2[q];
         double ddx=0,ddy=0;
         bool in=rel && wb_in_hyperboloid(qx,qy,qcz,qpor2,s2,maxSlope,cxp,cyp,czp,ddx,ddy,margin);
         if (!__any_sync(WB_FULL,in))
           continue;
-#endif
         if (pass==1)
         {
           int s=-2;
           if (in)
           {
-#if WB_CL_FPAIR
-            s=wb_sector64ff(dxf,dyf,exy);
-            if (s<0)
-            {
-              ddx=__dsub_rn(cxp,w.qx[q]);
-              ddy=__dsub_rn(cyp,w.qy[q]);
-              s=wb_sector64f(ddx,ddy);
-            }
-#else
             s=WB_CL_FSECTOR?wb_sector64f(ddx,ddy):wb_sector64(ddx,ddy);
-#endif
             if (s<0)
             {
               uint32_t u;
@@ -1484,19 +1415,11 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
           uint32_t cMaxA=0,cMinA=0xffffffffu,cMaxB=0,cMinB=0xffffffffu;
           if (in)
           {
-#if WB_CL_FPAIR
-            int s=wb_sector64ff(dxf,dyf,exy);
-#else
             int s=WB_CL_FSECTOR?wb_sector64f(ddx,ddy):wb_sector64(ddx,ddy);
-#endif
             int k1a=wq&255,k2a=(wq>>8)&255,k1b=(wq>>16)&255,k2b=wq>>24;
             if (s<0 || s==k1a || s==k2a || s==k1b || s==k2b)
             {
               uint32_t u;
-#if WB_CL_FPAIR
-              ddx=__dsub_rn(cxp,w.qx[q]);
-              ddy=__dsub_rn(cyp,w.qy[q]);
-#endif
               s=wb_sector64_exact(ddx,ddy,u);
               if (s==k1a) cMaxA=u;
               if (s==k2a) cMinA=u;
