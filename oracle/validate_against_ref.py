@@ -31,6 +31,11 @@ CASES = [  # name, scene, n, seed, params
     # 400 records share their XYZ with another record: the reference keeps one point per location
     # (octree.cpp:620-662); the lost records read 255 in ref_labels
     ("aerial_20k_dups", 2, 20000, 77, {"dups": 400}),
+    # LAS 1.4 format 6 (30 B records): the reference's other readPoint branch (las.cpp:759-781)
+    ("multitile_fmt6_40k", 3, 40000, 3, {}),
+    ("urban_40k_slope2", 5, 40000, 9, {"max_slope": 2.0, "thickness": 0.1}),
+    ("street_30k_tile3", 1, 30000, 4, {"tile_size": 3.0}),
+    ("terrestrial_30k_slope05", 4, 30000, 6, {"max_slope": 0.5, "min_hyperboloid_size": 1.0}),
 ]
 
 
