@@ -1096,6 +1096,39 @@ static int cmp_tile_n(const void *a,const void *b)
   return (x->n>y->n)-(x->n<y->n);
 }
 
+int wbo_point_hyperboloid_sizes(const double *pts,uint64_t n,const double cube[4],double tile_size,
+                                const wbo_tile *tiles,int64_t n_tiles,double *out)
+/* The hyperboloidSize classifyCylinder uses for each point (classify.cpp:121-131): that of the LAST tile in
+ * flowsnake order whose cylinder contains it; NaN for a point in no tile.  Lets a test drive the classify
+ * step alone. */
+{
+  snake_t s;
+  wbo_tile *byn;
+  uint64_t i;
+  snake_init(&s,cube,tile_size);
+  byn=(wbo_tile *)malloc(sizeof(wbo_tile)*(n_tiles?n_tiles:1));
+  memcpy(byn,tiles,sizeof(wbo_tile)*n_tiles);
+  qsort(byn,n_tiles,sizeof(wbo_tile),cmp_tile_n);
+  for (i=0;i<n;i++)
+  {
+    int64_t ns[19],best=LLONG_MIN;
+    int exs[19],eys[19],c=covering_tiles(&s,pts[3*i],pts[3*i+1],ns,exs,eys),j;
+    const wbo_tile *t=NULL;
+    for (j=0;j<c;j++)
+      if (ns[j]>best)
+        best=ns[j];
+    if (c)
+    {
+      wbo_tile key;
+      key.n=(int32_t)best;
+      t=(const wbo_tile *)bsearch(&key,byn,n_tiles,sizeof(wbo_tile),cmp_tile_n);
+    }
+    out[i]=t?t->hyperboloidSize:NAN;
+  }
+  free(byn);
+  return 0;
+}
+
 int wbo_classify(const double *pts,uint64_t n,const double cube[4],double tile_size,
                  double max_slope,double thickness,const wbo_tile *tiles,int64_t n_tiles,
                  uint8_t *labels,uint64_t *margin_count)

@@ -77,6 +77,10 @@ int wbo_classify(const double *pts_sorted,uint64_t n,const double cube[4],double
                  double max_slope,double thickness,const wbo_tile *tiles,int64_t n_tiles,
                  uint8_t *labels,uint64_t *margin_count);
 
+/* hyperboloidSize of the tile that classifies each point (NaN: in no tile); same arguments as wbo_classify */
+int wbo_point_hyperboloid_sizes(const double *pts_sorted,uint64_t n,const double cube[4],double tile_size,
+                                const wbo_tile *tiles,int64_t n_tiles,double *out);
+
 #ifdef __cplusplus
 }
 #endif

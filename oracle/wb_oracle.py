@@ -246,6 +246,18 @@ def run(files, tile_size=1.0, max_slope=1.0, thickness=0.0, min_hyperboloid_size
     return res
 
 
+def point_hyperboloid_sizes(res, tile_size=1.0):
+    """Per point of res.points_sorted: hyperboloidSize of the tile that classifies it (NaN = in no tile)."""
+    L = lib()
+    n = len(res.points_sorted)
+    out = np.empty(n, dtype=np.float64)
+    tiles = np.ascontiguousarray(res.tiles)
+    cube = (C.c_double * 4)(*res.cube)
+    L.wbo_point_hyperboloid_sizes(res.points_sorted.ctypes.data, C.c_uint64(n), cube, C.c_double(tile_size),
+                                  tiles.ctypes.data, C.c_int64(len(tiles)), out.ctypes.data)
+    return out
+
+
 def file_from_cloud(cloud):
     """Adapter from wolkenbase_b200.synth.Cloud to the dict `run` takes."""
     return {"records": cloud.records, "fmt": cloud.fmt, "scale": cloud.scale, "offset": cloud.offset,

@@ -1,0 +1,55 @@
+"""ctypes front end of the SIMT emulator build of the classify kernels (tests/simt/classify_emul.cpp).
+TEST INFRASTRUCTURE ONLY."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def build(variant="", out="libwb_simt.so"):
+    subprocess.check_call(["make", "-s", "-C", _HERE, "OUT=" + out, "VARIANT=" + variant])
+    return os.path.join(_HERE, out)
+
+
+_LIBS = {}
+
+
+def lib(variant="", out="libwb_simt.so"):
+    key = (variant, out)
+    if key not in _LIBS:
+        L = C.CDLL(build(variant, out))
+        from oracle import wb_oracle as O
+        OL = O.lib()
+        OL.wbo_fill_tan_tables()
+        for f in ("wbo_tan_table", "wbo_cos_table", "wbo_sin_table"):
+            getattr(OL, f).restype = C.c_void_p
+        L.simt_set_tables(C.c_void_p(OL.wbo_tan_table()), C.c_void_p(OL.wbo_cos_table()), C.c_void_p(OL.wbo_sin_table()))
+        L.simt_classify.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_double, C.c_double,
+                                    C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+        _LIBS[key] = L
+    return _LIBS[key]
+
+
+def classify(points_sorted, hyp, max_slope=1.0, thickness=0.0, chunks=None, variant="", out="libwb_simt.so"):
+    """Labels (canonical order) for the queries of chunks [chunks[0], chunks[1]) — all by default; 254 elsewhere,
+    0 for points in no tile.  Also returns the kernel's work counters and the number of warp-wide intrinsics."""
+    L = lib(variant, out)
+    n = len(points_sorted)
+    sx = np.ascontiguousarray(points_sorted[:, 0])
+    sy = np.ascontiguousarray(points_sorted[:, 1])
+    sz = np.ascontiguousarray(points_sorted[:, 2])
+    hyp = np.ascontiguousarray(hyp, dtype=np.float64)
+    lab = np.zeros(n, dtype=np.uint8)
+    counters = np.zeros(24, dtype=np.uint64)
+    coll = C.c_ulonglong()
+    c0, c1 = chunks if chunks else (0, 0xffffffff)
+    L.simt_classify(sx.ctypes.data, sy.ctypes.data, sz.ctypes.data, n, hyp.ctypes.data, max_slope, thickness,
+                    c0, c1, lab.ctypes.data, counters.ctypes.data, C.byref(coll))
+    work = {"margin": int(counters[0]), "untiled": int(counters[1]), "second_walk_points": int(counters[6]),
+            "nodes": int(counters[8]), "chunks": int(counters[9]), "pairs": int(counters[10]),
+            "nodes2": int(counters[11]), "chunks2": int(counters[12]), "pairs2": int(counters[13]),
+            "collectives": coll.value}
+    return lab, work

@@ -1,0 +1,225 @@
+// simt.h — a warp of 32 fibers in lock step: just enough of the SIMT execution model to run the warp-synchronous
+// kernels of wolkenbase_b200/csrc on a CPU, for tests.  TEST INFRASTRUCTURE ONLY.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#if defined(__x86_64__)
+#define SIMT_ASM_SWITCH 1
+#else
+#include <ucontext.h>
+#endif
+
+namespace simt
+{
+#ifdef SIMT_ASM_SWITCH
+// A fiber switch that saves what the System V ABI makes the callee keep (rbx, rbp, r12-r15, the stack pointer, the
+// x87 and SSE control words) and nothing else: ~20x cheaper than swapcontext, which also makes a signal-mask syscall.
+struct ucontext_t { void *sp; };
+extern "C" void simt_switch(void **from_sp,void *to_sp);
+asm(R"(
+.text
+.globl simt_switch
+.type simt_switch,@function
+simt_switch:
+  pushq %rbp
+  pushq %rbx
+  pushq %r12
+  pushq %r13
+  pushq %r14
+  pushq %r15
+  subq $8,%rsp
+  stmxcsr (%rsp)
+  fnstcw 4(%rsp)
+  movq %rsp,(%rdi)
+  movq %rsi,%rsp
+  ldmxcsr (%rsp)
+  fldcw 4(%rsp)
+  addq $8,%rsp
+  popq %r15
+  popq %r14
+  popq %r13
+  popq %r12
+  popq %rbx
+  popq %rbp
+  ret
+.size simt_switch,.-simt_switch
+)");
+inline void swapcontext(ucontext_t *from,ucontext_t *to) { simt_switch(&from->sp,to->sp); }
+inline void make_fiber(ucontext_t *c,char *stack,size_t bytes,void (*entry)())
+{
+  // initial frame: [mxcsr|fpucw] r15 r14 r13 r12 rbx rbp <entry> <pad>; after `ret` rsp is 16n+8 as at a call
+  uintptr_t top=((uintptr_t)(stack+bytes))&~(uintptr_t)15;
+  void **sp=(void **)top;
+  *--sp=nullptr;                   // pad: keeps (rsp+8)%16==0 inside entry
+  *--sp=(void *)entry;             // return address
+  for (int i=0;i<6;i++)
+    *--sp=nullptr;                 // rbp rbx r12 r13 r14 r15
+  unsigned cw[2];
+  asm volatile("stmxcsr %0" : "=m"(cw[0]));
+  unsigned short fcw;
+  asm volatile("fnstcw %0" : "=m"(fcw));
+  cw[1]=fcw;
+  *--sp=nullptr;
+  memcpy(sp,cw,8);
+  c->sp=sp;
+}
+#else
+inline void make_fiber(ucontext_t *c,char *stack,size_t bytes,void (*entry)())
+{
+  getcontext(c);
+  c->uc_stack.ss_sp=stack;
+  c->uc_stack.ss_size=bytes;
+  c->uc_link=nullptr;
+  makecontext(c,entry,0);
+}
+#endif
+
+struct dim3_ { unsigned x=1,y=1,z=1; };
+enum Op { OP_NONE=0,OP_SYNC,OP_BALLOT,OP_OR,OP_MINU,OP_MAXU,OP_SHFL,OP_MATCH };
+
+struct Lane
+{
+  dim3_ tid,bid,bdim,gdim;
+  ucontext_t ctx;
+  char *stack=nullptr;
+  bool finished=true;
+  // pending collective
+  int op=OP_NONE,site=0;
+  unsigned long long val=0,result=0;
+  unsigned aux=0,mask=0;
+};
+
+struct Warp
+{
+  Lane lane[32];
+  ucontext_t sched;
+  int current=-1;
+  std::function<void()> body;
+  unsigned long long collectives=0;
+};
+
+inline Warp *&warp_ptr() { static thread_local Warp *w=nullptr; return w; }
+inline Lane *cur() { Warp *w=warp_ptr(); return &w->lane[w->current]; }
+
+inline unsigned long long collective(int op,int site,unsigned long long val,unsigned aux,unsigned mask)
+// Called by a lane: park until every live lane of the warp has arrived at the same call site, then return this
+// lane's result.
+{
+  Warp *w=warp_ptr();
+  Lane *l=&w->lane[w->current];
+  l->op=op; l->site=site; l->val=val; l->aux=aux; l->mask=mask;
+  swapcontext(&l->ctx,&w->sched);
+  return l->result;
+}
+
+inline void lane_entry()
+{
+  Warp *w=warp_ptr();
+  w->body();
+  w->lane[w->current].finished=true;
+  w->lane[w->current].op=OP_NONE;
+  swapcontext(&w->lane[w->current].ctx,&w->sched);
+}
+
+inline void resolve(Warp *w)
+// all live lanes are parked: check uniformity, compute the results
+{
+  int op=OP_NONE,site=0,first=-1;
+  for (int i=0;i<32;i++)
+    if (!w->lane[i].finished)
+    {
+      if (first<0) { first=i; op=w->lane[i].op; site=w->lane[i].site; }
+      else if (w->lane[i].op!=op || w->lane[i].site!=site)
+      {
+        fprintf(stderr,"simt: divergent collective: lane %d at line %d (op %d), lane %d at line %d (op %d)\n",
+                first,site,op,i,w->lane[i].site,w->lane[i].op);
+        abort();
+      }
+    }
+  if (first<0)
+    return;
+  w->collectives++;
+  unsigned ballot=0;
+  unsigned long long acc_or=0,acc_min=~0ull,acc_max=0;
+  for (int i=0;i<32;i++)
+    if (!w->lane[i].finished)
+    {
+      if (w->lane[i].val) ballot|=1u<<i;
+      acc_or|=w->lane[i].val;
+      if (w->lane[i].val<acc_min) acc_min=w->lane[i].val;
+      if (w->lane[i].val>acc_max) acc_max=w->lane[i].val;
+    }
+  for (int i=0;i<32;i++)
+  {
+    Lane &l=w->lane[i];
+    if (l.finished)
+      continue;
+    switch (op)
+    {
+      case OP_SYNC: l.result=0; break;
+      case OP_BALLOT: l.result=ballot&l.mask; break;
+      case OP_OR: l.result=acc_or; break;
+      case OP_MINU: l.result=acc_min; break;
+      case OP_MAXU: l.result=acc_max; break;
+      case OP_SHFL:
+      {
+        const Lane &s=w->lane[l.aux&31];
+        l.result=s.finished?l.val:s.val;      // reading an exited lane is undefined on the GPU; keep own value
+        break;
+      }
+      case OP_MATCH:
+      {
+        unsigned m=0;
+        for (int j=0;j<32;j++)
+          if (!w->lane[j].finished && w->lane[j].val==l.val)
+            m|=1u<<j;
+        l.result=m;
+        break;
+      }
+      default: l.result=0;
+    }
+  }
+}
+
+// Run `body` once per lane of one warp.  The lanes see threadIdx.x = firstThread..firstThread+31.
+inline unsigned long long run_warp(const std::function<void()> &body,unsigned firstThread,unsigned block,unsigned blockDim,
+                                   unsigned gridDim,size_t stackBytes=256*1024)
+{
+  static thread_local Warp *w=nullptr;
+  if (!w)
+  {
+    w=new Warp;
+    for (int i=0;i<32;i++)
+      w->lane[i].stack=(char *)malloc(stackBytes);
+  }
+  warp_ptr()=w;
+  w->body=body;
+  w->collectives=0;
+  for (int i=0;i<32;i++)
+  {
+    Lane &l=w->lane[i];
+    l.tid.x=firstThread+i; l.bid.x=block; l.bdim.x=blockDim; l.gdim.x=gridDim;
+    l.finished=false;
+    l.op=OP_NONE;
+    make_fiber(&l.ctx,l.stack,stackBytes,lane_entry);
+  }
+  while (true)
+  {
+    bool any=false;
+    for (int i=0;i<32;i++)
+      if (!w->lane[i].finished)
+      {
+        any=true;
+        w->current=i;
+        swapcontext(&w->sched,&w->lane[i].ctx);     // runs until the lane parks at a collective or finishes
+      }
+    if (!any)
+      break;
+    resolve(w);
+  }
+  return w->collectives;
+}
+} // namespace simt

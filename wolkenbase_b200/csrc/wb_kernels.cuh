@@ -895,6 +895,11 @@ wb_postscan_kernel(const int *__restrict__ tNPoints,const uint8_t *__restrict__ 
 #ifndef WB_CL_FSPAN
 #define WB_CL_FSPAN 1
 #endif
+// Round-2 candidate, written without a GPU at hand and therefore off until it has been through the parity suite
+// and an A/B on the bench workload ("next"): bulk re-filter of a chunk entry's waiting children.
+#ifndef WB_CL_REFILTER
+#define WB_CL_REFILTER 0
+#endif
 
 struct WbClassifyWarp
 {
@@ -1463,6 +1468,14 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
         if (liveMask!=envMask)
           envelope();
         needed();
+#if WB_CL_REFILTER
+        // The siblings still waiting in this entry: drop at once those no live query can want any more — the
+        // necessary half of the test every pop makes (a reaching query that is still live, a sector some live
+        // query still needs), for all 32 children in one step instead of one rejected pop each.
+        if (!((w.wants[lane]&liveMask) && (w.cm[lane]&needAny)))
+          w.keys[sp-1][lane]=0xffffffffu;
+        __syncwarp();
+#endif
       }
     }
     if (pass==1)
