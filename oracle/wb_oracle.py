@@ -72,6 +72,8 @@ def lib():
         L.wbo_scan.argtypes = [C.c_void_p, C.c_uint64, dp, C.c_double, C.c_double, C.c_void_p, C.c_int64]
         L.wbo_scan.restype = C.c_int64
         L.wbo_postscan.argtypes = [C.c_void_p, C.c_int64, C.c_double]
+        L.wbo_point_hyperboloid_sizes.argtypes = [C.c_void_p, C.c_uint64, dp, C.c_double, C.c_void_p, C.c_int64,
+                                                  C.c_void_p]
         L.wbo_classify.argtypes = [C.c_void_p, C.c_uint64, dp, C.c_double, C.c_double, C.c_double,
                                    C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_uint64)]
         L.wbo_shape_in.argtypes = [C.c_int, dp, dp]
@@ -253,8 +255,8 @@ def point_hyperboloid_sizes(res, tile_size=1.0):
     out = np.empty(n, dtype=np.float64)
     tiles = np.ascontiguousarray(res.tiles)
     cube = (C.c_double * 4)(*res.cube)
-    L.wbo_point_hyperboloid_sizes(res.points_sorted.ctypes.data, C.c_uint64(n), cube, C.c_double(tile_size),
-                                  tiles.ctypes.data, C.c_int64(len(tiles)), out.ctypes.data)
+    L.wbo_point_hyperboloid_sizes(res.points_sorted.ctypes.data, n, cube, tile_size, tiles.ctypes.data, len(tiles),
+                                  out.ctypes.data)
     return out
 
 

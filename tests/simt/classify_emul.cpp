@@ -19,6 +19,9 @@ extern "C" int simt_set_tables(const double *tanTable,const double *cosTable,con
   return 0;
 }
 
+static bool g_reset=true;
+extern "C" void simt_reset() { g_reset=true; }   // the caller's arrays changed: forget the cached hierarchy
+
 template <typename F> static unsigned long long launch(unsigned nBlocks,unsigned blockThreads,F body)
 // every block = blockThreads/32 independent warps (none of the kernels run here uses __syncthreads)
 {
@@ -52,22 +55,71 @@ extern "C" int simt_classify(const double *sx,const double *sy,const double *sz,
     c=(c+31)/32;
   }
   const int nLevels=(int)levelCnt.size();
-  std::vector<WbBound> bounds(total);
+  // The hierarchy is kept between calls on the same arrays (a caller sampling warps of a large cloud).  Small
+  // clouds go through the emulated wb_chunk_bounds_kernel / wb_node_bounds_kernel; large ones through plain loops
+  // that take the same minima and maxima.
+  static std::vector<WbBound> bounds;
+  static const double *boundsOf=nullptr;
+  static uint64_t boundsN=0;
   levelOff.resize(16); levelCnt.resize(16);
   unsigned long long coll=0;
-  coll+=launch((nChunks*32+255)/256,256,[&]{ wb_chunk_bounds_kernel(sx,sy,sz,n,bounds.data(),nChunks); });
-  for (int l=1;l<nLevels;l++)
-    coll+=launch((levelCnt[l]*32+255)/256,256,[&]{ wb_node_bounds_kernel(bounds.data()+levelOff[l-1],levelCnt[l-1],
-                                                                           bounds.data()+levelOff[l],levelCnt[l]); });
-  // one "tile" per point: winner = own index (or none), tHyp = its hyperboloidSize
-  std::vector<uint32_t> winner(n),perm(n),wedge(n,0xffffffffu);
-  std::vector<uint8_t> clsIn(n,0),pending(nChunks,0);
-  for (uint64_t i=0;i<n;i++)
+  if (g_reset || boundsOf!=sx || boundsN!=n)
   {
-    winner[i]=std::isnan(hyp[i])?0xffffffffu:(uint32_t)i;
-    perm[i]=(uint32_t)i;
+    bounds.assign(total,WbBound());
+    if (n<=(1u<<20))
+    {
+      coll+=launch((nChunks*32+255)/256,256,[&]{ wb_chunk_bounds_kernel(sx,sy,sz,n,bounds.data(),nChunks); });
+      for (int l=1;l<nLevels;l++)
+        coll+=launch((levelCnt[l]*32+255)/256,256,[&]{ wb_node_bounds_kernel(bounds.data()+levelOff[l-1],levelCnt[l-1],
+                                                                               bounds.data()+levelOff[l],levelCnt[l]); });
+    }
+    else
+    {
+      for (uint32_t k=0;k<nChunks;k++)
+      {
+        WbBound b={INFINITY,-INFINITY,INFINITY,-INFINITY,INFINITY};
+        for (uint64_t j=(uint64_t)k*32;j<n && j<(uint64_t)k*32+32;j++)
+        {
+          b.xmin=fmin(b.xmin,sx[j]); b.xmax=fmax(b.xmax,sx[j]);
+          b.ymin=fmin(b.ymin,sy[j]); b.ymax=fmax(b.ymax,sy[j]);
+          b.zmin=fmin(b.zmin,sz[j]);
+        }
+        bounds[k]=b;
+      }
+      for (int l=1;l<nLevels;l++)
+        for (uint32_t k=0;k<levelCnt[l];k++)
+        {
+          WbBound b={INFINITY,-INFINITY,INFINITY,-INFINITY,INFINITY};
+          for (uint32_t j=k*32;j<levelCnt[l-1] && j<k*32+32;j++)
+          {
+            const WbBound &ch=bounds[levelOff[l-1]+j];
+            b.xmin=fmin(b.xmin,ch.xmin); b.xmax=fmax(b.xmax,ch.xmax);
+            b.ymin=fmin(b.ymin,ch.ymin); b.ymax=fmax(b.ymax,ch.ymax);
+            b.zmin=fmin(b.zmin,ch.zmin);
+          }
+          bounds[levelOff[l]+k]=b;
+        }
+    }
+    boundsOf=sx;
+    boundsN=n;
   }
-  memset(labelSorted,254,n);
+  // one "tile" per point: winner = own index (or none), tHyp = its hyperboloidSize
+  static std::vector<uint32_t> winner,perm,wedge;
+  static std::vector<uint8_t> clsIn,pending;
+  static const double *hypOf=nullptr;
+  if (g_reset || hypOf!=hyp || winner.size()!=n)
+  {
+    winner.resize(n); perm.resize(n); wedge.assign(n,0xffffffffu); clsIn.assign(n,0); pending.assign(nChunks,0);
+    for (uint64_t i=0;i<n;i++)
+    {
+      winner[i]=std::isnan(hyp[i])?0xffffffffu:(uint32_t)i;
+      perm[i]=(uint32_t)i;
+    }
+    hypOf=hyp;
+  }
+  g_reset=false;
+  if (firstChunk==0 && endChunk>=nChunks)
+    memset(labelSorted,254,n);
   if (endChunk>nChunks)
     endChunk=nChunks;
   // the kernels index chunks by blockIdx.x: run the requested range only (every other point still takes part

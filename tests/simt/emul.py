@@ -33,19 +33,34 @@ def lib(variant="", out="libwb_simt.so"):
     return _LIBS[key]
 
 
+_COLUMNS = {}
+
+
+def _columns(points_sorted, hyp):
+    """Contiguous x, y, z, hyp columns, kept while the same arrays are passed again (the emulator library keeps
+    its hierarchy per column pointer: sampling warps of a large cloud must not rebuild it per call)."""
+    key = (id(points_sorted), id(hyp))
+    if key not in _COLUMNS:
+        _COLUMNS.clear()
+        for L in _LIBS.values():
+            L.simt_reset()
+        _COLUMNS[key] = (points_sorted, hyp,
+                         np.ascontiguousarray(points_sorted[:, 0]), np.ascontiguousarray(points_sorted[:, 1]),
+                         np.ascontiguousarray(points_sorted[:, 2]), np.ascontiguousarray(hyp, dtype=np.float64))
+    return _COLUMNS[key][2:]
+
+
 def classify(points_sorted, hyp, max_slope=1.0, thickness=0.0, chunks=None, variant="", out="libwb_simt.so"):
-    """Labels (canonical order) for the queries of chunks [chunks[0], chunks[1]) — all by default; 254 elsewhere,
-    0 for points in no tile.  Also returns the kernel's work counters and the number of warp-wide intrinsics."""
+    """Labels (canonical order) for the queries of chunks [chunks[0], chunks[1]) — all by default; 0 for points in
+    no tile and (partial runs) for chunks not asked for.  Also returns the kernel's work counters and the number
+    of warp-wide intrinsics executed."""
     L = lib(variant, out)
     n = len(points_sorted)
-    sx = np.ascontiguousarray(points_sorted[:, 0])
-    sy = np.ascontiguousarray(points_sorted[:, 1])
-    sz = np.ascontiguousarray(points_sorted[:, 2])
-    hyp = np.ascontiguousarray(hyp, dtype=np.float64)
+    sx, sy, sz, hyp = _columns(points_sorted, hyp)
+    c0, c1 = chunks if chunks else (0, 0xffffffff)
     lab = np.zeros(n, dtype=np.uint8)
     counters = np.zeros(24, dtype=np.uint64)
     coll = C.c_ulonglong()
-    c0, c1 = chunks if chunks else (0, 0xffffffff)
     L.simt_classify(sx.ctypes.data, sy.ctypes.data, sz.ctypes.data, n, hyp.ctypes.data, max_slope, thickness,
                     c0, c1, lab.ctypes.data, counters.ctypes.data, C.byref(coll))
     work = {"margin": int(counters[0]), "untiled": int(counters[1]), "second_walk_points": int(counters[6]),

@@ -1,0 +1,86 @@
+"""Work model of the classify kernel on the real bench workload, without a GPU: the oracle builds the canonical
+order and the tile table of the C2 scene at full size, then the SIMT emulator (tests/simt) runs the kernel source
+on a sample of warps and reports the per-warp work counters.  Usage:
+    python tools/model_bench_scene.py POINTS WARPS [VARIANT_FLAGS...]      e.g. 100000000 300 "-DWB_CL_REFILTER=1"
+The prepared scene is cached in /tmp (npz) so that variants can be compared on identical inputs."""
+import ctypes as C
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests", "simt"))
+from oracle import wb_oracle as O  # noqa: E402
+from wolkenbase_b200 import synth  # noqa: E402
+import emul  # noqa: E402
+
+
+def prepare(scene, n_points, seed):
+    cache = "/tmp/wb_model_scene%d_%d.npz" % (scene, n_points)
+    if os.path.exists(cache):
+        z = np.load(cache)
+        return z["pts"], z["hyp"]
+    L = O.lib()
+    t = time.time()
+    cloud = synth.generate(scene, n_points, seed=seed)
+    n = cloud.n
+    xyz = np.ascontiguousarray(cloud.ints())
+    pts = np.empty((n, 3), dtype=np.float64)
+    L.wbo_coords(xyz.ctypes.data, n, O._d3(cloud.scale), O._d3(cloud.offset), 1.0, pts.ctypes.data)
+    del xyz
+    corners = np.ascontiguousarray(np.array([cloud.min_corner, cloud.max_corner], dtype=np.float64))
+    center, side, cube = (C.c_double * 3)(), C.c_double(), (C.c_double * 4)()
+    L.wbo_size_fit(corners.ctypes.data, 2, center, C.byref(side))
+    L.wbo_bbox_cube(corners.ctypes.data, 2, cube)
+    keys = np.empty(n, dtype=np.uint64)
+    order = np.empty(n, dtype=np.uint32)
+    L.wbo_sort(pts.ctypes.data, n, center, side.value, keys.ctypes.data, order.ctypes.data)
+    del keys
+    pts = np.ascontiguousarray(pts[order])
+    del order
+    print("sorted %d points in %.0f s" % (n, time.time() - t), flush=True)
+    cap = n // 4 + 1024
+    tiles = np.zeros(cap, dtype=O.TILE_DTYPE)
+    nt = L.wbo_scan(pts.ctypes.data, n, cube, 1.0, 0.1, tiles.ctypes.data, cap)
+    assert 0 <= nt <= cap, nt
+    tiles = tiles[:nt].copy()
+    spacing, lo, hi = C.c_double(), C.c_int(), C.c_int()
+    L.wbo_snake_set_size(cube[3], 1.0, C.byref(spacing), C.byref(lo), C.byref(hi))
+    L.wbo_postscan(tiles.ctypes.data, nt, spacing.value)
+    print("%d tiles, spacing %.3f, %.0f s" % (nt, spacing.value, time.time() - t), flush=True)
+    hyp = np.empty(n, dtype=np.float64)
+    L.wbo_point_hyperboloid_sizes(pts.ctypes.data, n, cube, 1.0, tiles.ctypes.data, nt, hyp.ctypes.data)
+    print("hyperboloid sizes: median %.2f max %.1f, %.0f s" % (np.nanmedian(hyp), np.nanmax(hyp), time.time() - t), flush=True)
+    np.savez(cache, pts=pts, hyp=hyp)
+    return pts, hyp
+
+
+def main():
+    n_points = int(sys.argv[1]) if len(sys.argv) > 1 else 3_000_000
+    n_warps = int(sys.argv[2]) if len(sys.argv) > 2 else 200
+    variants = sys.argv[3:] or [""]
+    scene = int(os.environ.get("WB_MODEL_SCENE", "2"))
+    pts, hyp = prepare(scene, n_points, scene)
+    n = len(pts)
+    n_chunks = (n + 31) // 32
+    rng = np.random.default_rng(1)
+    sample = np.sort(rng.choice(n_chunks, size=min(n_warps, n_chunks), replace=False))
+    for i, v in enumerate(variants):
+        tot = {}
+        t = time.time()
+        for c in sample:
+            _, w = emul.classify(pts, hyp, chunks=(int(c), int(c) + 1), variant=v, out="libwb_simt_m%d.so" % i)
+            for k, x in w.items():
+                tot[k] = tot.get(k, 0) + x
+        m = len(sample)
+        print("variant %r: per warp over %d warps: nodes %.1f chunks %.1f pairs %.1f | pass 2: nodes %.1f chunks %.1f "
+              "pairs %.1f | intrinsics %.0f  (%.0f s)" %
+              (v, m, tot["nodes"] / m, tot["chunks"] / m, tot["pairs"] / m, tot["nodes2"] / m, tot["chunks2"] / m,
+               tot["pairs2"] / m, tot["collectives"] / m, time.time() - t), flush=True)
+
+
+if __name__ == "__main__":
+    main()
