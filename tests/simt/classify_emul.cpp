@@ -19,6 +19,20 @@ extern "C" int simt_set_tables(const double *tanTable,const double *cosTable,con
   return 0;
 }
 
+extern "C" void simt_site_counts(unsigned long long *out /* 4096, indexed by source line of wb_kernels.cuh mod 4096 */,int clear)
+{
+  memcpy(out,simt::site_counts(),4096*sizeof(unsigned long long));
+  if (clear)
+    memset(simt::site_counts(),0,4096*sizeof(unsigned long long));
+}
+
+extern "C" void simt_emu_counts(unsigned long long *out /* 16 */,int clear)
+{
+  memcpy(out,simt::emu_counts(),16*sizeof(unsigned long long));
+  if (clear)
+    memset(simt::emu_counts(),0,16*sizeof(unsigned long long));
+}
+
 static bool g_reset=true;
 extern "C" void simt_reset() { g_reset=true; }   // the caller's arrays changed: forget the cached hierarchy
 

@@ -68,3 +68,20 @@ def classify(points_sorted, hyp, max_slope=1.0, thickness=0.0, chunks=None, vari
             "nodes2": int(counters[11]), "chunks2": int(counters[12]), "pairs2": int(counters[13]),
             "collectives": coll.value}
     return lab, work
+
+
+def site_counts(variant="", out="libwb_simt.so", clear=True):
+    """{source line of wb_kernels.cuh: times a warp reached the warp-wide intrinsic on it} since the last clear."""
+    L = lib(variant, out)
+    c = np.zeros(4096, dtype=np.uint64)
+    L.simt_site_counts(c.ctypes.data, 1 if clear else 0)
+    return {int(i): int(c[i]) for i in np.nonzero(c)[0]}
+
+
+def emu_counts(variant="", out="libwb_simt.so", clear=True):
+    """Loop-trip counters (WB_EMU_COUNT slots): 0 = (chunk, query) reach tests at expansion, 1 = the same for
+    internal nodes (WB_CL_XWANTS)."""
+    L = lib(variant, out)
+    c = np.zeros(16, dtype=np.uint64)
+    L.simt_emu_counts(c.ctypes.data, 1 if clear else 0)
+    return [int(x) for x in c]

@@ -38,6 +38,8 @@ struct simt_dim3 { unsigned x=1,y=1,z=1; };
 #define blockDim (simt::cur()->bdim)
 #define gridDim (simt::cur()->gdim)
 
+#define WB_EMU_COUNT(slot) do { if ((simt::cur()->tid.x&31)==0) simt::emu_counts()[(slot)&15]++; } while (0)
+
 // ---- arithmetic --------------------------------------------------------------------------------------
 inline double __dmul_rn(double a,double b) { return a*b; }
 inline double __dadd_rn(double a,double b) { return a+b; }

@@ -102,6 +102,10 @@ struct Warp
 };
 
 inline Warp *&warp_ptr() { static thread_local Warp *w=nullptr; return w; }
+// how often each call site (source line) of a warp-wide intrinsic was reached: a poor man's profile of the kernel
+// loop-trip counters the kernels bump through WB_EMU_COUNT(slot), once per warp and trip (lane 0 counts)
+inline unsigned long long *emu_counts() { static thread_local unsigned long long c[16]; return c; }
+inline unsigned long long *site_counts() { static thread_local unsigned long long c[4096]; return c; }
 inline Lane *cur() { Warp *w=warp_ptr(); return &w->lane[w->current]; }
 
 inline unsigned long long collective(int op,int site,unsigned long long val,unsigned aux,unsigned mask)
@@ -142,6 +146,7 @@ inline void resolve(Warp *w)
   if (first<0)
     return;
   w->collectives++;
+  site_counts()[site&4095]++;
   unsigned ballot=0;
   unsigned long long acc_or=0,acc_min=~0ull,acc_max=0;
   for (int i=0;i<32;i++)

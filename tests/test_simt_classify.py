@@ -19,7 +19,9 @@ CASES = [(2, 8000, 3, {}), (1, 8000, 1, {}), (5, 8000, 5, {}), (4, 8000, 4, {}),
          (2, 6000, 9, {"max_slope": 0.5, "thickness": 0.05, "tile_size": 2.0})]
 VARIANTS = [("", "libwb_simt.so"),
             ("-DWB_CL_FSECTOR=0 -DWB_CL_FREACH=0 -DWB_CL_FSPAN=0", "libwb_simt_double.so"),
-            ("-DWB_CL_REFILTER=1", "libwb_simt_refilter.so")]
+            ("-DWB_CL_REFILTER=1", "libwb_simt_refilter.so"),
+            ("-DWB_CL_XWANTS=1", "libwb_simt_xwants.so"),
+            ("-DWB_CL_XWANTS=1 -DWB_CL_REFILTER=1", "libwb_simt_xr.so")]
 
 
 @pytest.fixture(scope="module")
@@ -50,3 +52,13 @@ def test_refilter_only_removes_rejected_pops(scenes):
     _, ref = emul.classify(res.points_sorted, hyp, variant=VARIANTS[2][0], out=VARIANTS[2][1])
     assert ref["nodes"] < base["nodes"]
     assert (ref["chunks"], ref["pairs"]) == (base["chunks"], base["pairs"])
+
+
+def test_xwants_prunes_pops_not_work(scenes):
+    """Per-query reach + open-sector test at expansion for every level: fewer nodes popped, the same chunks
+    opened and pairs tested."""
+    res, hyp, p = scenes[0]
+    _, base = emul.classify(res.points_sorted, hyp, variant=VARIANTS[0][0], out=VARIANTS[0][1])
+    _, x = emul.classify(res.points_sorted, hyp, variant=VARIANTS[3][0], out=VARIANTS[3][1])
+    assert x["nodes"] < base["nodes"] and x["nodes2"] <= base["nodes2"]
+    assert (x["chunks"], x["pairs"]) == (base["chunks"], base["pairs"])

@@ -76,10 +76,17 @@ def main():
             for k, x in w.items():
                 tot[k] = tot.get(k, 0) + x
         m = len(sample)
+        sites = emul.site_counts(variant=v, out="libwb_simt_m%d.so" % i)
+        trips = emul.emu_counts(variant=v, out="libwb_simt_m%d.so" % i)
+        print("  reach tests at expansion per warp: chunks %.1f, internal nodes %.1f" % (trips[0] / m, trips[1] / m))
         print("variant %r: per warp over %d warps: nodes %.1f chunks %.1f pairs %.1f | pass 2: nodes %.1f chunks %.1f "
               "pairs %.1f | intrinsics %.0f  (%.0f s)" %
               (v, m, tot["nodes"] / m, tot["chunks"] / m, tot["pairs"] / m, tot["nodes2"] / m, tot["chunks2"] / m,
                tot["pairs2"] / m, tot["collectives"] / m, time.time() - t), flush=True)
+        src = open(os.path.join(ROOT, "wolkenbase_b200", "csrc", "wb_kernels.cuh")).read().split("\n")
+        print("  warp-wide intrinsics per warp by source line (both passes):")
+        for line, cnt in sorted(sites.items(), key=lambda kv: -kv[1])[:int(os.environ.get("WB_MODEL_SITES", "16"))]:
+            print("    %7.1f  %4d: %s" % (cnt / m, line, src[line - 1].strip()[:100]))
 
 
 if __name__ == "__main__":

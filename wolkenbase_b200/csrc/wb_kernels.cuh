@@ -900,11 +900,24 @@ wb_postscan_kernel(const int *__restrict__ tNPoints,const uint8_t *__restrict__ 
 #ifndef WB_CL_REFILTER
 #define WB_CL_REFILTER 0
 #endif
+// Round-2 candidate (same status): the per-query reach test at expansion for the children of EVERY level, not only
+// for chunks, and with each query's still-open sectors taken into account — so that a child no single query can
+// use is never pushed (the emulator counts 300 internal-node pops per warp on the bench scene, 235 of them rejected).
+#ifndef WB_CL_XWANTS
+#define WB_CL_XWANTS 0
+#endif
+
+#ifndef WB_EMU_COUNT
+#define WB_EMU_COUNT(slot)              // loop-trip counters of the SIMT emulator (tests/simt); nothing on the GPU
+#endif
 
 struct WbClassifyWarp
 {
   double qx[32],qy[32],qcz[32],qpor2[32];
 #if WB_CL_FREACH
+#if WB_CL_XWANTS
+  unsigned long long openq[32];         // each query's sectors that can still matter (0 once it is decided)
+#endif
   float fx[32],fy[32],fh[32],f2p[32];   // the same queries relative to the warp's origin: xy, vertex height, 2*por
   double org[3];                        // that origin (the warp's first query)
   float fgh,fzq;                        // bounds of |fx|,|fy| and of |fh| over the warp's queries
@@ -1229,6 +1242,10 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
     };
     envelope();
     needed();
+#if WB_CL_XWANTS
+    w.openq[lane]=live?(pass==1?open:wedgeMask):0ull;
+    __syncwarp();
+#endif
     // lanes = children of a node: can any live query reach it, and does any still need its sectors?
     auto childTest=[&](const WbBound &cb,uint32_t &key,unsigned long long &cm)->bool
     {
@@ -1258,7 +1275,7 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
       }
       if (!__any_sync(WB_FULL,ok))
         return;
-      if (childLevel==0)
+      if (childLevel==0 || WB_CL_XWANTS)
       {
         uint32_t lm=askers;
 #if WB_CL_FREACH
@@ -1277,11 +1294,16 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
         {
           const int q=__ffs(lm)-1;
           lm&=lm-1;
+          WB_EMU_COUNT(childLevel==0?0:1);
           const float qx=w.fx[q],qy=w.fy[q],qh=w.fh[q],q2p=w.f2p[q];
           const float dx=fmaxf(0.0f,fmaxf(x0-qx,qx-x1)-ed);
           const float dy=fmaxf(0.0f,fmaxf(y0-qy,qy-y1)-ed);
           const float a=(qh-z0)+ez;
+#if WB_CL_XWANTS
+          if (ok && a>=0.0f && a*(a+q2p)*1.000002f>=(dx*dx+dy*dy)*fs2 && (cm&w.openq[q])!=0)
+#else
           if (ok && a>=0.0f && a*(a+q2p)*1.000002f>=(dx*dx+dy*dy)*fs2)
+#endif
             wants|=1u<<q;
         }
 #else
@@ -1297,9 +1319,12 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
         ok=ok && wants!=0;
         if (!__any_sync(WB_FULL,ok))
           return;
-        w.wants[lane]=wants;
-        w.cm[lane]=cm;
-        w.cb[lane]=cb;
+        if (childLevel==0)
+        {
+          w.wants[lane]=wants;
+          w.cm[lane]=cm;
+          w.cb[lane]=cb;
+        }
       }
       w.keys[sp][lane]=ok?key:0xffffffffu;
       if (lane==0)
@@ -1460,7 +1485,13 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
             done=true;
             live=false;
           }
+#if WB_CL_XWANTS
+          w.openq[lane]=open;
+#endif
         }
+#if WB_CL_XWANTS
+        __syncwarp();
+#endif
         liveMask=__ballot_sync(WB_FULL,live);
         if (!liveMask)
           break;
