@@ -35,111 +35,6 @@ extern "C" void simt_emu_counts(unsigned long long *out /* 16 */,int clear)
     memset(simt::emu_counts(),0,16*sizeof(unsigned long long));
 }
 
-#if WB_CL_PLANES
-static std::vector<WbPlane> g_planes;
-// Prototype of the plane builder (plain loops; the CUDA build kernels are round-2 work): per chunk a trimmed
-// least-squares slope with the intercept lowered until every point is on or above the plane, per node the mean of
-// the children's slopes lowered under every child plane over that child's box; the flat plane z = zmin stays
-// whenever it is the higher one at the box centre.
-static void fitSlopes(const std::vector<double> &u,const std::vector<double> &v,const std::vector<double> &z,
-                      const std::vector<char> &use,double &b,double &c)
-{
-  double n=0,su=0,sv=0,sz=0;
-  for (size_t i=0;i<u.size();i++) if (use[i]) { n++; su+=u[i]; sv+=v[i]; sz+=z[i]; }
-  b=c=0;
-  if (n<3) return;
-  su/=n; sv/=n; sz/=n;
-  double uu=0,uv=0,vv=0,uz=0,vz=0;
-  for (size_t i=0;i<u.size();i++) if (use[i])
-  {
-    double du=u[i]-su,dv=v[i]-sv,dz=z[i]-sz;
-    uu+=du*du; uv+=du*dv; vv+=dv*dv; uz+=du*dz; vz+=dv*dz;
-  }
-  double det=uu*vv-uv*uv;
-  if (!(det>1e-9*(uu*vv+1e-30))) return;
-  b=(uz*vv-vz*uv)/det;
-  c=(vz*uu-uz*uv)/det;
-  if (!(fabs(b)<4 && fabs(c)<4)) b=c=0;          // walls: no useful slope
-}
-
-static void buildPlanes(const double *sx,const double *sy,const double *sz,uint64_t n,const std::vector<WbBound> &bounds,
-                        const std::vector<uint32_t> &levelOff,const std::vector<uint32_t> &levelCnt,int nLevels,
-                        std::vector<WbPlane> &planes)
-{
-  planes.assign(bounds.size(),WbPlane{0,0,0});
-  const uint32_t nChunks=levelCnt[0];
-  std::vector<double> u,v,z,r;
-  std::vector<char> use;
-  for (uint32_t k=0;k<nChunks;k++)
-  {
-    const WbBound &bd=bounds[k];
-    const double xc=0.5*(bd.xmin+bd.xmax),yc=0.5*(bd.ymin+bd.ymax);
-    u.clear(); v.clear(); z.clear();
-    for (uint64_t j=(uint64_t)k*32;j<n && j<(uint64_t)k*32+32;j++) { u.push_back(sx[j]-xc); v.push_back(sy[j]-yc); z.push_back(sz[j]); }
-    use.assign(u.size(),1);
-    double b=0,c=0;
-    for (int it=0;it<3;it++)
-    {
-      fitSlopes(u,v,z,use,b,c);
-      r.resize(u.size());
-      for (size_t i=0;i<u.size();i++) r[i]=z[i]-b*u[i]-c*v[i];
-      std::vector<double> sr(r);
-      std::nth_element(sr.begin(),sr.begin()+sr.size()/2,sr.end());
-      const double med=sr[sr.size()/2];
-      for (size_t i=0;i<u.size();i++) use[i]=r[i]<=med;          // the lower half: ground, not what grows on it
-    }
-    double a=INFINITY;
-    for (size_t i=0;i<u.size();i++) a=fmin(a,z[i]-b*u[i]-c*v[i]);
-    a-=1e-9;
-    if (a>bd.zmin) planes[k]=WbPlane{a,(float)b,(float)c};
-    else planes[k]=WbPlane{bd.zmin,0,0};
-    // the stored slopes are floats: lower a until the plane with the ROUNDED slopes is under every point
-    if (planes[k].b!=0 || planes[k].c!=0)
-    {
-      double aa=INFINITY;
-      for (size_t i=0;i<u.size();i++) aa=fmin(aa,z[i]-(double)planes[k].b*u[i]-(double)planes[k].c*v[i]);
-      planes[k].a=aa-1e-9;
-    }
-  }
-  for (int l=1;l<nLevels;l++)
-    for (uint32_t k=0;k<levelCnt[l];k++)
-    {
-      const WbBound &bd=bounds[levelOff[l]+k];
-      const double xc=0.5*(bd.xmin+bd.xmax),yc=0.5*(bd.ymin+bd.ymax);
-      double sb=0,sc=0,cnt=0;
-      for (uint32_t j=k*32;j<levelCnt[l-1] && j<k*32+32;j++) { sb+=planes[levelOff[l-1]+j].b; sc+=planes[levelOff[l-1]+j].c; cnt++; }
-      const float b=(float)(sb/cnt),c=(float)(sc/cnt);
-      double a=INFINITY;
-      for (uint32_t j=k*32;j<levelCnt[l-1] && j<k*32+32;j++)
-      {
-        const WbBound &cb=bounds[levelOff[l-1]+j];
-        const WbPlane &cp=planes[levelOff[l-1]+j];
-        const double cxc=0.5*(cb.xmin+cb.xmax),cyc=0.5*(cb.ymin+cb.ymax);
-        for (int corner=0;corner<4;corner++)
-        {
-          const double x=(corner&1)?cb.xmax:cb.xmin,y=(corner&2)?cb.ymax:cb.ymin;
-          const double child=cp.a+(double)cp.b*(x-cxc)+(double)cp.c*(y-cyc);
-          a=fmin(a,child-(double)b*(x-xc)-(double)c*(y-yc));
-        }
-      }
-      a-=1e-9;
-      planes[levelOff[l]+k]=(a>bd.zmin)?WbPlane{a,b,c}:WbPlane{bd.zmin,0,0};
-    }
-  // self-check: every point on or above the plane of its chunk and of every ancestor
-  for (uint64_t j=0;j<n;j++)
-  {
-    uint32_t node=(uint32_t)(j/32);
-    for (int l=0;l<nLevels;l++)
-    {
-      const WbBound &bd=bounds[levelOff[l]+node];
-      const WbPlane &pl=planes[levelOff[l]+node];
-      const double low=pl.a+(double)pl.b*(sx[j]-0.5*(bd.xmin+bd.xmax))+(double)pl.c*(sy[j]-0.5*(bd.ymin+bd.ymax));
-      if (sz[j]<low-1e-7) { fprintf(stderr,"plane above point %llu at level %d by %g\n",(unsigned long long)j,l,low-sz[j]); abort(); }
-      node/=32;
-    }
-  }
-}
-#endif
 
 static bool g_reset=true;
 extern "C" void simt_reset() { g_reset=true; }   // the caller's arrays changed: forget the cached hierarchy
@@ -224,9 +119,6 @@ extern "C" int simt_classify(const double *sx,const double *sy,const double *sz,
     }
     boundsOf=sx;
     boundsN=n;
-#if WB_CL_PLANES
-    buildPlanes(sx,sy,sz,n,bounds,levelOff,levelCnt,nLevels,g_planes);
-#endif
   }
   // one "tile" per point: winner = own index (or none), tHyp = its hyperboloidSize
   static std::vector<uint32_t> winner,perm,wedge;
@@ -259,17 +151,11 @@ extern "C" int simt_classify(const double *sx,const double *sy,const double *sz,
           wb_classify_kernel<1>(sx,sy,sz,n,nChunks,bounds.data(),levelOff.data(),levelCnt.data(),nLevels,winner.data(),hyp,
                                 maxSlope,thickness,clsIn.data(),perm.data(),0u,0xffffffffu,labelSorted,counters,
                                 wedge.data(),pending.data()
-#if WB_CL_PLANES
-                                ,g_planes.data()
-#endif
                                 );
         else
           wb_classify_kernel<2>(sx,sy,sz,n,nChunks,bounds.data(),levelOff.data(),levelCnt.data(),nLevels,winner.data(),hyp,
                                 maxSlope,thickness,clsIn.data(),perm.data(),0u,0xffffffffu,labelSorted,counters,
                                 wedge.data(),pending.data()
-#if WB_CL_PLANES
-                                ,g_planes.data()
-#endif
                                 );
       };
       coll+=simt::run_warp(body,0,b,WB_CL_WARPS*32,nChunks);

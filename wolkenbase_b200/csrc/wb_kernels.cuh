@@ -906,16 +906,9 @@ wb_postscan_kernel(const int *__restrict__ tNPoints,const uint8_t *__restrict__ 
 #ifndef WB_CL_XWANTS
 #define WB_CL_XWANTS 0
 #endif
-
-// Round-2 candidate (emulator prototype only: the build kernels for the planes do not exist yet): a lower-bounding
-// PLANE per chunk / node next to the flat zmin, tested per (child, query) at expansion against the tangent plane
-// of the query's hyperboloid at the child's centre.  On sloping ground zmin sits at the downhill corner of a box
-// while the nearest point to the query is elsewhere; a tilted bound removes most of the (query, chunk) pairs in
-// which no point turns out to be inside.  Needs WB_CL_XWANTS and WB_CL_FREACH.
-#ifndef WB_CL_PLANES
-#define WB_CL_PLANES 0
+#if WB_CL_XWANTS && !WB_CL_FREACH
+#error "WB_CL_XWANTS builds on the single-precision reach test (WB_CL_FREACH)"
 #endif
-struct WbPlane { double a; float b,c; };  // every point of the subtree: z >= a + b (x - xc) + c (y - yc), (xc,yc) = centre of its WbBound
 
 #ifndef WB_EMU_COUNT
 #define WB_EMU_COUNT(slot)              // loop-trip counters of the SIMT emulator (tests/simt); nothing on the GPU
@@ -930,9 +923,6 @@ struct WbClassifyWarp
 #endif
   float fx[32],fy[32],fh[32],f2p[32];   // the same queries relative to the warp's origin: xy, vertex height, 2*por
   double org[3];                        // that origin (the warp's first query)
-#if WB_CL_PLANES
-  float ghq,g2p;                        // highest vertex and largest 2*por among the live queries (group plane test)
-#endif
   float fgh,fzq;                        // bounds of |fx|,|fy| and of |fh| over the warp's queries
 #endif
   uint32_t keys[8][32];       // per stack entry: (squared distance | child) of the children still to visit
@@ -1139,11 +1129,7 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
                    const uint8_t *__restrict__ clsIn,const uint32_t *__restrict__ perm,
                    uint32_t ownFirst,uint32_t ownEnd,
                    uint8_t *__restrict__ labelSorted,unsigned long long *__restrict__ counters,
-                   uint32_t *__restrict__ wedgeBuf,uint8_t *__restrict__ chunkPending
-#if WB_CL_PLANES
-                   ,const WbPlane *__restrict__ planes
-#endif
-                   )
+                   uint32_t *__restrict__ wedgeBuf,uint8_t *__restrict__ chunkPending)
 // PASS 1: sector walk, decides every query whose longest empty run is not 24 or 25 sectors and
 //         leaves the bounding sectors of the others in wedgeBuf (chunkPending marks their chunks).
 // PASS 2: exact walk for the pending queries only.
@@ -1250,20 +1236,6 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
       }
       gmx=0.5*(gx0+gx1); gmy=0.5*(gy0+gy1);
       envMask=liveMask;
-#if WB_CL_PLANES
-      {
-        // vertex heights are relative to the origin and may be negative: bias them to sort as unsigned
-        const float hq=live?w.fh[lane]:-1e30f,p2=live?w.f2p[lane]:0.0f;
-        const uint32_t hb=__float_as_uint(hq),hkey=(hb&0x80000000u)?~hb:(hb|0x80000000u);
-        const uint32_t mh=__reduce_max_sync(WB_FULL,hkey),mp=__reduce_max_sync(WB_FULL,__float_as_uint(p2));
-        if (lane==0)
-        {
-          w.ghq=__uint_as_float((mh&0x80000000u)?(mh&0x7fffffffu):~mh);
-          w.g2p=__uint_as_float(mp);
-        }
-        __syncwarp();
-      }
-#endif
     };
     auto needed=[&]()
     {
@@ -1304,29 +1276,6 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
         cb=bounds[levelOff[childLevel]+c];
         ok=childTest(cb,key,cm);
       }
-#if WB_CL_PLANES
-      if ((WB_CL_PLANES&2) && ok)
-      {
-        // the same tangent-plane test once per child for the whole group: the highest vertex and the largest por
-        // over the live queries, the distance taken from the group's box (a concave upper bound of every query's
-        // hyperboloid)
-        const WbPlane gp=planes[levelOff[childLevel]+c];
-        const double ox=w.org[0],oy=w.org[1],oz=w.org[2];
-        const float bx0=(float)(cb.xmin-ox),bx1=(float)(cb.xmax-ox),by0=(float)(cb.ymin-oy),by1=(float)(cb.ymax-oy);
-        const float e=9.5367431640625e-7f*(fmaxf(fmaxf(fabsf(bx0),fabsf(bx1)),fmaxf(fabsf(by0),fabsf(by1)))+w.fgh);
-        const float qx0=(float)(gx0-ox)-e,qx1=(float)(gx1-ox)+e,qy0=(float)(gy0-oy)-e,qy1=(float)(gy1-oy)+e;
-        const float bcx=0.5f*(bx0+bx1),bcy=0.5f*(by0+by1),bhx=0.5f*(bx1-bx0)+e,bhy=0.5f*(by1-by0)+e;
-        const float d0x=bcx-fminf(fmaxf(bcx,qx0),qx1),d0y=bcy-fminf(fmaxf(bcy,qy0),qy1);
-        const float dd=d0x*d0x+d0y*d0y,por=0.5f*w.g2p,fs=(float)s2;
-        const float r0=sqrtf(por*por+fs*dd),drop=fs*dd/(por+r0),ir=1.0f/r0;
-        const float ggx=-fs*d0x*ir,ggy=-fs*d0y*ir;
-        const float pa=(float)(gp.a-oz);
-        const float sl=fabsf(ggx-gp.b)*bhx+fabsf(ggy-gp.c)*bhy;
-        const float ub=(w.ghq-drop-pa)+sl;
-        if (ub<-(2e-3f+4e-6f*(fabsf(w.ghq)+fabsf(pa)+sl+drop)))
-          ok=false;
-      }
-#endif
       if (!__any_sync(WB_FULL,ok))
         return;
       if (childLevel==0 || WB_CL_XWANTS)
@@ -1344,14 +1293,6 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
         const float ed=9.5367431640625e-7f*(fmaxf(fmaxf(fabsf(x0),fabsf(x1)),fmaxf(fabsf(y0),fabsf(y1)))+w.fgh);
         const float ez=9.5367431640625e-7f*(fabsf(z0)+w.fzq)+1e-6f;
         const float fs2=(float)s2*0.999998f;
-#if WB_CL_PLANES
-        // the child's lower-bounding plane, heights relative to the warp's origin; box centre and half widths
-        WbPlane pl={0,0,0};
-        if (c<cc)
-          pl=planes[levelOff[childLevel]+c];
-        const float pa=(float)(pl.a-oz),pcx=0.5f*(x0+x1),pcy=0.5f*(y0+y1),phx=0.5f*(x1-x0)+ed,phy=0.5f*(y1-y0)+ed;
-        const float ps2=(float)s2;
-#endif
         while (lm)
         {
           const int q=__ffs(lm)-1;
@@ -1361,22 +1302,7 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
           const float dx=fmaxf(0.0f,fmaxf(x0-qx,qx-x1)-ed);
           const float dy=fmaxf(0.0f,fmaxf(y0-qy,qy-y1)-ed);
           const float a=(qh-z0)+ez;
-#if WB_CL_PLANES
-          // H(x,y) = vertex + por - sqrt(por^2 + s^2 d^2) is concave: below its tangent plane at the box centre.
-          // If that tangent plane stays under the child's lower-bounding plane over the whole box, nothing in the
-          // child can be inside.  ub bounds max(H - plane) from above; the slack covers the float roundings.
-          bool under=false;
-          if (WB_CL_PLANES&1)
-          {
-            const float d0x=pcx-qx,d0y=pcy-qy,dd=d0x*d0x+d0y*d0y,por=0.5f*q2p;
-            const float r0=sqrtf(por*por+ps2*dd),h0=qh-ps2*dd/(por+r0),ir=1.0f/r0;
-            const float gx=-ps2*d0x*ir,gy=-ps2*d0y*ir;
-            const float sl=fabsf(gx-pl.b)*phx+fabsf(gy-pl.c)*phy;
-            const float ub=(h0-pa)+sl;
-            under=ub<-(2e-3f+4e-6f*(fabsf(qh)+fabsf(pa)+sl+ps2*dd/(por+r0)));
-          }
-          if (ok && !under && a>=0.0f && a*(a+q2p)*1.000002f>=(dx*dx+dy*dy)*fs2 && (cm&w.openq[q])!=0)
-#elif WB_CL_XWANTS
+#if WB_CL_XWANTS
           if (ok && a>=0.0f && a*(a+q2p)*1.000002f>=(dx*dx+dy*dy)*fs2 && (cm&w.openq[q])!=0)
 #else
           if (ok && a>=0.0f && a*(a+q2p)*1.000002f>=(dx*dx+dy*dy)*fs2)
