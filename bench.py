@@ -123,10 +123,7 @@ def run_ours(args):
 
     scene, d, per_gpu, wname = workload(args, 1)
     t0 = time.time()
-    if d.scene == 4:
-        cloud = synth.generate(scene, per_gpu, seed=scene)
-    else:
-        cloud = synth.generate(scene, per_gpu, seed=scene)
+    cloud = synth.generate(scene, per_gpu, seed=scene)
     n, rec_len = cloud.n, cloud.rec_len
     gen_s = time.time() - t0
     # pinned host copy of the file body (what a reader would hand over)
