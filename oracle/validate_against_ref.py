@@ -39,6 +39,93 @@ CASES = [  # name, scene, n, seed, params
 ]
 
 
+# Several input files at once (wolkencanvas.cpp:502-527 reads a list): each part is
+#   {"scene", "n", "seed", "region": None | "left" | "right", "shift": [dx_ticks, dy_ticks], "gps_after": index of the
+#    part whose point count its gpsTime continues from}
+# "shift" re-expresses the same points with another header offset (las.cpp:808 uses each file's own).
+MULTI_CASES = [
+    ("multi_halves_shifted", [
+        {"scene": 2, "n": 40000, "seed": 29, "region": "left", "shift": [0, 0]},
+        {"scene": 2, "n": 40000, "seed": 29, "region": "right", "shift": [20000, -7000], "gps_after": 0}], {}),
+    ("multi_fmt1_fmt6", [
+        {"scene": 2, "n": 20000, "seed": 31, "region": None, "shift": [0, 0]},
+        {"scene": 3, "n": 15000, "seed": 32, "region": None, "shift": [-3000, 5000], "gps_after": 0}], {}),
+]
+
+
+def clouds_from_parts(parts):
+    """The synthetic files a MULTI_CASES entry names (shared with tests/test_oracle_golden.py)."""
+    import ctypes as C
+    clouds = []
+    for part in parts:
+        d = synth.describe(part["scene"], part["n"])
+        region = None
+        if part.get("region") == "left":
+            region = (0, 0, d.grid_nx // 2, d.grid_ny)
+        elif part.get("region") == "right":
+            region = (d.grid_nx // 2, 0, d.grid_nx - d.grid_nx // 2, d.grid_ny)
+        base = clouds[part["gps_after"]].n if "gps_after" in part else 0
+        c = synth.generate(part["scene"], part["n"], seed=part["seed"], region=region, gps_base=base)
+        dx, dy = part.get("shift", [0, 0])
+        if dx or dy:
+            recs = c.records.copy()
+            ints = np.ascontiguousarray(recs[:, :12]).view(np.int32).reshape(-1, 3).copy()
+            ints[:, 0] -= dx
+            ints[:, 1] -= dy
+            recs[:, :12] = ints.view(np.uint8).reshape(-1, 12)
+            nd = synth.SynthDesc()
+            for f, _ in synth.SynthDesc._fields_:
+                setattr(nd, f, getattr(c.desc, f))
+            nd.offset[0] = c.desc.offset[0] + c.desc.scale * dx
+            nd.offset[1] = c.desc.offset[1] + c.desc.scale * dy
+            bbox = c.bbox.copy()
+            bbox[0] -= dx
+            bbox[3] -= dx
+            bbox[1] -= dy
+            bbox[4] -= dy
+            hdr = np.zeros(375, dtype=np.uint8)
+            size = synth.lib().wb_synth_header(C.byref(nd), c.n, bbox.ctypes.data, hdr.ctypes.data)
+            c = synth.Cloud(nd, hdr[:size].copy(), recs, bbox)
+        clouds.append(c)
+    return clouds
+
+
+def compare_multi(name, parts, p, golden_dir=None):
+    clouds = clouds_from_parts(parts)
+    with tempfile.TemporaryDirectory() as td:
+        paths = []
+        for i, c in enumerate(clouds):
+            paths.append(os.path.join(td, "%s_%d.las" % (name, i)))
+            c.write(paths[-1])
+        info, rdump, rlabels, rtiles = run_ref(paths, os.path.join(td, "ref"), p)
+    res = wb_oracle.run([wb_oracle.file_from_cloud(c) for c in clouds], **p)
+    ot = res.tiles
+    rep = {"case": name, "points": int(sum(c.n for c in clouds)),
+           "root": list(res.root_center) == info["root_center"] and res.root_side == info["root_side"],
+           "snake": res.snake_index == info["snake_index"] and res.spacing == info["spacing"],
+           "dump_equal": res.dump == rdump, "tiles": [len(ot), len(rtiles)]}
+    ok = rep["root"] and rep["snake"] and rep["dump_equal"] and len(ot) == len(rtiles)
+    if ok:
+        for fld in ("n", "ex", "ey", "nPoints", "treeFlags"):
+            ok = ok and bool((ot[fld] == rtiles[fld]).all())
+        for fld in ("density", "hyperboloidSize", "height"):
+            ok = ok and bool((ot[fld].view(np.uint64) == rtiles[fld].view(np.uint64)).all())
+    stored = rlabels != 255
+    rep["duplicates"] = [int(res.n_duplicates), int(info["duplicates"]), int((~stored).sum())]
+    ok = ok and len(set(rep["duplicates"])) == 1
+    rep["label_mismatch"] = int((res.labels[stored] != rlabels[stored]).sum()) if len(rlabels) == len(res.labels) else -1
+    ok = ok and rep["label_mismatch"] == 0
+    rep["labels_hist"] = np.bincount(rlabels, minlength=3)[:3].tolist()
+    rep["ok"] = bool(ok)
+    if golden_dir and ok:
+        np.savez_compressed(os.path.join(golden_dir, name + ".npz"), parts=json.dumps(parts), params=json.dumps(p),
+                            ref_dump=np.frombuffer(rdump.encode("utf-8"), dtype=np.uint8),
+                            ref_labels=rlabels, ref_tiles=rtiles,
+                            ref_root=np.array(info["root_center"] + [info["root_side"]]),
+                            ref_spacing=info["spacing"], ref_snake_index=info["snake_index"])
+    return rep
+
+
 def run_ref(las_paths, out_prefix, p):
     cmd = [REF, "-t", "1", "-c", "-o", out_prefix,
            "-T", repr(p.get("tile_size", 1.0)), "-S", repr(p.get("max_slope", 1.0)),
@@ -111,6 +198,12 @@ if __name__ == "__main__":
     allok = True
     for c in CASES:
         r = compare(*c, golden_dir=golden)
+        print(json.dumps(r))
+        allok = allok and r["ok"]
+    if golden:
+        os.makedirs(os.path.join(golden, "multi"), exist_ok=True)
+    for name, parts, p in MULTI_CASES:
+        r = compare_multi(name, parts, p, golden_dir=os.path.join(golden, "multi") if golden else None)
         print(json.dumps(r))
         allok = allok and r["ok"]
     sys.exit(0 if allok else 1)
