@@ -62,3 +62,19 @@ def test_xwants_prunes_pops_not_work(scenes):
     _, x = emul.classify(res.points_sorted, hyp, variant=VARIANTS[3][0], out=VARIANTS[3][1])
     assert x["nodes"] < base["nodes"] and x["nodes2"] <= base["nodes2"]
     assert (x["chunks"], x["pairs"]) == (base["chunks"], base["pairs"])
+
+
+@pytest.mark.parametrize("case", ["urban_40k_slope2", "street_30k_tile3"])
+def test_emulated_kernel_matches_compiled_reference_labels(case, golden_dir):
+    """Straight against the class bytes the UNMODIFIED reference produced (non-default maxSlope / tileSize)."""
+    import json
+    g = np.load(os.path.join(golden_dir, case + ".npz"))
+    p = json.loads(str(g["params"]))
+    cloud = synth.generate(int(g["scene"]), int(g["n"]), seed=int(g["seed"]))
+    res = O.run([O.file_from_cloud(cloud)], **p)
+    assert res.n_duplicates == 0
+    hyp = O.point_hyperboloid_sizes(res, p.get("tile_size", 1.0))
+    lab, _ = emul.classify(res.points_sorted, hyp, p.get("max_slope", 1.0), p.get("thickness", 0.0))
+    in_input_order = np.zeros(len(lab), dtype=np.uint8)
+    in_input_order[res.order] = lab
+    assert (in_input_order == g["ref_labels"]).all()
