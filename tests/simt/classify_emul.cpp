@@ -10,6 +10,7 @@
 #include <cstdio>
 #include "cuda_runtime.h"
 #include "../../wolkenbase_b200/csrc/wb_kernels.cuh"
+#include "../../wolkenbase_b200/csrc/wb_host.h"
 
 extern "C" int simt_set_tables(const double *tanTable,const double *cosTable,const double *sinTable)
 // angle.cpp:305-320 tables, as the library uploads them in wb_create (511/512/512 entries)
@@ -166,5 +167,124 @@ extern "C" int simt_classify(const double *sx,const double *sy,const double *sz,
   run(2);
   if (collectives)
     *collectives=coll;
+  return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------------------------
+// The tile phases from the kernel sources: membership (wb_member_count_kernel, wb_member_fill_kernel), the sort by
+// tile (a host stable sort stands in for the radix sort), wb_segment_kernel, wb_scan_kernel, then
+// wb_tile_extent_kernel / wb_tile_grid_kernel / wb_postscan_kernel — launched in the order and with the grids of
+// wb_scan and wb_postscan (wolken_b200.cu) — and finally the classify kernels with the membership's `winner` and
+// the dense tile table, exactly the arrays the GPU path hands them.
+struct SimtTile { int32_t n,nPoints,treeFlags,pad; double density,hyperboloidSize,height; };
+
+extern "C" int simt_scan_classify(const double *sx,const double *sy,const double *sz,uint64_t n,
+                                  const double cube[4],double tileSize,double minHyp,double maxSlope,double thickness,
+                                  int doPostscan,
+                                  SimtTile *tilesOut,uint64_t tilesCap,uint64_t *nTilesOut,   // non-empty tiles, ascending n
+                                  uint8_t *labelSorted /* n bytes or NULL: skip classify */)
+{
+  {
+    double t[512],co[512],si[512];
+    wbhost::fillTanTables(t,co,si);
+    memcpy(g_tanTable,t,sizeof(t)); memcpy(g_cosTable,co,sizeof(co)); memcpy(g_sinTable,si,sizeof(si));
+    memset(g_fwdTable,0,sizeof(g_fwdTable));
+    for (int i=0;i<6;i++)
+      for (int j=0;j<7;j++)
+        g_fwdTable[i*8+j]=wbhost::kFwdTable[i][j];
+  }
+  WbSnake snake;
+  int lo,hi;
+  double spacing;
+  wbhost::snakeSetSize(cube[3],tileSize,&spacing,&lo,&hi);
+  snake.spacing=spacing; snake.ccx=cube[0]; snake.ccy=cube[1]; snake.radius=spacing*41/71; snake.lo=lo; snake.hi=hi;
+  const uint32_t T=(uint32_t)((long long)hi-lo+1);
+  auto grid=[](uint64_t items,unsigned block) { return (unsigned)((items+block-1)/block); };
+  // membership
+  std::vector<uint32_t> cnt(n+1,0),off(n+1,0),winner(n);
+  std::vector<uint4> tilesOf(n);
+  launch(grid(n,128),128,[&]{ wb_member_count_kernel(sx,sy,n,snake,cnt.data(),tilesOf.data(),winner.data()); });
+  for (uint64_t i=0;i<n;i++)
+    off[i+1]=off[i]+cnt[i];
+  const uint32_t m=off[n];
+  std::vector<unsigned long long> pairKey(m+1);
+  std::vector<uint32_t> pairVal(m+1);
+  launch(grid(n,256),256,[&]{ wb_member_fill_kernel(cnt.data(),off.data(),tilesOf.data(),n,pairKey.data(),pairVal.data()); });
+  {
+    std::vector<uint32_t> idx(m);
+    for (uint32_t i=0;i<m;i++) idx[i]=i;
+    std::stable_sort(idx.begin(),idx.end(),[&](uint32_t a,uint32_t b){ return pairKey[a]<pairKey[b]; });
+    std::vector<unsigned long long> k2(m+1);
+    std::vector<uint32_t> v2(m+1);
+    for (uint32_t i=0;i<m;i++) { k2[i]=pairKey[idx[i]]; v2[i]=pairVal[idx[i]]; }
+    pairKey.swap(k2); pairVal.swap(v2);
+  }
+  std::vector<uint32_t> tStart(T,0),tCount(T,0),tileList(std::min<uint64_t>(T,m)+1);
+  std::vector<int> tNPoints(T,0);
+  std::vector<uint8_t> tTree(T,0);
+  std::vector<double> tDensity(T,0),tHyp(T,0),tHeight(T,0);
+  unsigned long long nList=0;
+  if (m)
+    launch(grid(m,256),256,[&]{ wb_segment_kernel(pairKey.data(),m,tStart.data(),tCount.data(),tileList.data(),&nList); });
+  if (nList)
+    launch(grid(nList,WB_SCAN_WARPS),WB_SCAN_WARPS*32,[&]{ wb_scan_kernel(tileList.data(),(uint32_t)nList,tStart.data(),tCount.data(),
+                                                          pairVal.data(),sx,sy,sz,snake,minHyp,tNPoints.data(),tTree.data(),
+                                                          tDensity.data(),tHyp.data(),tHeight.data()); });
+  if (doPostscan)
+  {
+    int ext[4]={INT_MAX,INT_MAX,INT_MIN,INT_MIN};
+    launch(grid(T,256),256,[&]{ wb_tile_extent_kernel(tNPoints.data(),T,snake,ext); });
+    uint64_t cells=1;
+    if (ext[0]<=ext[2])
+      cells=(uint64_t)((long long)ext[2]-ext[0]+1)*(uint64_t)((long long)ext[3]-ext[1]+1);
+    std::vector<uint8_t> tileGrid(cells,0);
+    launch(grid(T,256),256,[&]{ wb_tile_grid_kernel(tNPoints.data(),tTree.data(),T,snake,ext,tileGrid.data()); });
+    launch(grid(T,128),128,[&]{ wb_postscan_kernel(tNPoints.data(),tTree.data(),T,snake,ext,tileGrid.data(),tHyp.data()); });
+  }
+  uint64_t nt=0;
+  for (uint32_t t=0;t<T;t++)
+    if (tNPoints[t])
+    {
+      if (nt<tilesCap)
+        tilesOut[nt]=SimtTile{(int32_t)((long long)t+lo),tNPoints[t],tTree[t],0,tDensity[t],tHyp[t],tHeight[t]};
+      nt++;
+    }
+  *nTilesOut=nt;
+  if (!labelSorted)
+    return 0;
+  // classify with the membership's winner and the dense table, as wb_classify does
+  const uint32_t nChunks=(uint32_t)((n+31)/32);
+  std::vector<uint32_t> levelOff,levelCnt;
+  uint64_t total=0;
+  uint32_t c=nChunks;
+  while (true)
+  {
+    levelOff.push_back((uint32_t)total); levelCnt.push_back(c); total+=c;
+    if (c<=32) break;
+    c=(c+31)/32;
+  }
+  const int nLevels=(int)levelCnt.size();
+  std::vector<WbBound> bounds(total);
+  levelOff.resize(16); levelCnt.resize(16);
+  launch(grid((uint64_t)nChunks*32,256),256,[&]{ wb_chunk_bounds_kernel(sx,sy,sz,n,bounds.data(),nChunks); });
+  for (int l=1;l<nLevels;l++)
+    launch(grid((uint64_t)levelCnt[l]*32,256),256,[&]{ wb_node_bounds_kernel(bounds.data()+levelOff[l-1],levelCnt[l-1],
+                                                                           bounds.data()+levelOff[l],levelCnt[l]); });
+  std::vector<uint32_t> perm(n),wedge(n,0xffffffffu);
+  std::vector<uint8_t> clsIn(n,0),pending(nChunks,0);
+  for (uint64_t i=0;i<n;i++) perm[i]=(uint32_t)i;
+  unsigned long long counters[24]={0};
+  for (int pass=1;pass<=2;pass++)
+    for (uint32_t b=0;b<nChunks;b++)
+      simt::run_warp([&]
+      {
+        if (pass==1)
+          wb_classify_kernel<1>(sx,sy,sz,n,nChunks,bounds.data(),levelOff.data(),levelCnt.data(),nLevels,winner.data(),tHyp.data(),
+                                maxSlope,thickness,clsIn.data(),perm.data(),0u,0xffffffffu,labelSorted,counters,wedge.data(),pending.data());
+        else
+          wb_classify_kernel<2>(sx,sy,sz,n,nChunks,bounds.data(),levelOff.data(),levelCnt.data(),nLevels,winner.data(),tHyp.data(),
+                                maxSlope,thickness,clsIn.data(),perm.data(),0u,0xffffffffu,labelSorted,counters,wedge.data(),pending.data());
+      },0,b,WB_CL_WARPS*32,nChunks);
   return 0;
 }

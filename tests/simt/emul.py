@@ -85,3 +85,30 @@ def emu_counts(variant="", out="libwb_simt.so", clear=True):
     c = np.zeros(16, dtype=np.uint64)
     L.simt_emu_counts(c.ctypes.data, 1 if clear else 0)
     return [int(x) for x in c]
+
+
+SIMT_TILE = np.dtype([("n", "<i4"), ("nPoints", "<i4"), ("treeFlags", "<i4"), ("_pad", "<i4"),
+                      ("density", "<f8"), ("hyperboloidSize", "<f8"), ("height", "<f8")])
+
+
+def scan_classify(points_sorted, cube, tile_size=1.0, min_hyperboloid_size=0.1, max_slope=1.0, thickness=0.0,
+                  postscan=True, classify=True, variant="", out="libwb_simt.so"):
+    """Membership, tile scan, postscan and classify from the kernel sources, starting from the canonical order.
+    Returns (non-empty tiles ascending n, labels in canonical order or None)."""
+    L = lib(variant, out)
+    n = len(points_sorted)
+    sx = np.ascontiguousarray(points_sorted[:, 0])
+    sy = np.ascontiguousarray(points_sorted[:, 1])
+    sz = np.ascontiguousarray(points_sorted[:, 2])
+    cap = 3 * n + 16
+    tiles = np.zeros(cap, dtype=SIMT_TILE)
+    nt = C.c_uint64()
+    lab = np.zeros(n, dtype=np.uint8) if classify else None
+    cube4 = (C.c_double * 4)(*cube)
+    L.simt_scan_classify.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_double, C.c_double,
+                                     C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    L.simt_scan_classify(sx.ctypes.data, sy.ctypes.data, sz.ctypes.data, n, cube4, tile_size, min_hyperboloid_size,
+                         max_slope, thickness, 1 if postscan else 0, tiles.ctypes.data, cap, C.byref(nt),
+                         lab.ctypes.data if classify else None)
+    assert nt.value <= cap
+    return tiles[:nt.value].copy(), lab

@@ -78,3 +78,40 @@ def test_emulated_kernel_matches_compiled_reference_labels(case, golden_dir):
     in_input_order = np.zeros(len(lab), dtype=np.uint8)
     in_input_order[res.order] = lab
     assert (in_input_order == g["ref_labels"]).all()
+
+
+SCAN_CASES = [(2, 8000, 3, {}), (5, 8000, 5, {}), (1, 8000, 1, {"tile_size": 3.0}),
+              (4, 8000, 4, {"tile_size": 2.0, "min_hyperboloid_size": 0.5, "max_slope": 0.7, "thickness": 0.05})]
+
+
+@pytest.mark.parametrize("scene,n,seed,p", SCAN_CASES)
+def test_emulated_tile_phases_and_classify_match_oracle(scene, n, seed, p):
+    """Membership, tile scan (one warp per tile, shuffle-tree pairwise sums), postscan and classify, all from the
+    kernel sources and launched as wb_scan / wb_postscan / wb_classify launch them: tile table bit-identical to the
+    oracle's, labels identical."""
+    cloud = synth.generate(scene, n, seed=seed)
+    res = O.run([O.file_from_cloud(cloud)], **p)
+    tiles, lab = emul.scan_classify(res.points_sorted, res.cube, p.get("tile_size", 1.0),
+                                    p.get("min_hyperboloid_size", 0.1), p.get("max_slope", 1.0), p.get("thickness", 0.0))
+    ot = res.tiles
+    assert len(tiles) == len(ot)
+    for f in ("n", "nPoints", "treeFlags"):
+        assert (tiles[f] == ot[f]).all(), f
+    for f in ("density", "hyperboloidSize", "height"):
+        assert np.abs(tiles[f].view(np.int64) - ot[f].view(np.int64)).max() <= 4, f
+    assert (lab == res.labels_sorted).all()
+
+
+def test_emulated_tile_phases_match_compiled_reference(golden_dir):
+    """The tile table the UNMODIFIED reference produced (format 6 fixture), from the kernel sources."""
+    import json
+    g = np.load(os.path.join(golden_dir, "multitile_fmt6_40k.npz"))
+    cloud = synth.generate(int(g["scene"]), int(g["n"]), seed=int(g["seed"]))
+    res = O.run([O.file_from_cloud(cloud)], classify=False)
+    tiles, _ = emul.scan_classify(res.points_sorted, res.cube, classify=False)
+    rt = g["ref_tiles"]
+    assert len(tiles) == len(rt)
+    for f in ("n", "nPoints", "treeFlags"):
+        assert (tiles[f] == rt[f]).all(), f
+    for f in ("density", "hyperboloidSize", "height"):
+        assert np.abs(tiles[f].view(np.int64) - rt[f].view(np.int64)).max() <= 4, f
