@@ -10,6 +10,8 @@
 #include <cstdio>
 #include "cuda_runtime.h"
 #include "../../wolkenbase_b200/csrc/wb_kernels.cuh"
+#define WB_NO_HOST_LAUNCH
+#include "../../wolkenbase_b200/csrc/wb_sort.cuh"
 #include "../../wolkenbase_b200/csrc/wb_host.h"
 
 extern "C" int simt_set_tables(const double *tanTable,const double *cosTable,const double *sinTable)
@@ -286,5 +288,70 @@ extern "C" int simt_scan_classify(const double *sx,const double *sy,const double
           wb_classify_kernel<2>(sx,sy,sz,n,nChunks,bounds.data(),levelOff.data(),levelCnt.data(),nLevels,winner.data(),tHyp.data(),
                                 maxSlope,thickness,clsIn.data(),perm.data(),0u,0xffffffffu,labelSorted,counters,wedge.data(),pending.data());
       },0,b,WB_CL_WARPS*32,nChunks);
+  return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------------------------
+// The radix sort (wb_sort.cuh) with whole blocks emulated (its kernels meet at __syncthreads): the launch sequence of
+// wb_exclusive_scan and wb_radix_sort, replayed.
+template <typename F> static void launchBlocks(unsigned nBlocks,unsigned blockThreads,F body)
+{
+  for (unsigned b=0;b<nBlocks;b++)
+    simt::run_block(body,blockThreads,0,b,blockThreads,nBlocks);
+}
+
+static void emuExclusiveScan(const uint32_t *in,uint32_t *out,uint64_t n,std::vector<uint32_t> &blockSums)
+{
+  if (!n)
+    return;
+  const uint64_t nb=(n+WB_SCAN_TILE-1)/WB_SCAN_TILE;
+  blockSums.assign(nb+1024,0);
+  launchBlocks((unsigned)nb,WB_SCAN_THREADS,[&]{ wb_scan_reduce_kernel(in,n,blockSums.data()); });
+  launchBlocks(1,1024,[&]{ wb_scan_single_kernel(blockSums.data(),(uint32_t)nb,nullptr); });
+  launchBlocks((unsigned)nb,WB_SCAN_THREADS,[&]{ wb_scan_apply_kernel(in,out,n,blockSums.data()); });
+}
+
+extern "C" int simt_radix_sort(uint64_t *keys,uint32_t *vals,uint64_t n,int beginBit,int endBit)
+// stable sort of (key,val) by key bits [beginBit,endBit), in place (the result is copied back if it ends in the
+// second buffer)
+{
+  if (!n)
+    return 0;
+  std::vector<uint64_t> kb(n);
+  std::vector<uint32_t> vb(n),table,blockSums;
+  const uint64_t nb=(n+WB_SORT_TILE-1)/WB_SORT_TILE;
+  table.assign(nb*256+256,0);
+  uint64_t *ki=keys,*ko=kb.data();
+  uint32_t *vi=vals,*vo=vb.data();
+  for (int shift=beginBit;shift<endBit;shift+=8)
+  {
+    launchBlocks((unsigned)nb,WB_SORT_THREADS,[&]{ wb_sort_upsweep_kernel(ki,n,shift,table.data(),(uint32_t)nb); });
+    emuExclusiveScan(table.data(),table.data(),nb*256,blockSums);
+    launchBlocks((unsigned)nb,WB_SORT_THREADS,[&]{ wb_sort_downsweep_kernel(ki,vi,ko,vo,n,shift,table.data(),(uint32_t)nb); });
+    std::swap(ki,ko);
+    std::swap(vi,vo);
+  }
+  if (ki!=keys)
+  {
+    memcpy(keys,ki,n*sizeof(uint64_t));
+    memcpy(vals,vi,n*sizeof(uint32_t));
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// LAS decode (wb_decode_kernel: a CTA stages its byte span in shared memory and meets at __syncthreads).
+extern "C" int simt_decode(const uint8_t *recs,uint64_t n,int fmt,int recLen,int dropZeros,int misalign,
+                           int32_t *xi,int32_t *yi,int32_t *zi,uint8_t *cls,uint8_t *ret,unsigned long long *nDropped)
+// misalign (0..15): where the first record starts relative to a 16-byte boundary (the kernel loads aligned vectors
+// that may begin before its span)
+{
+  std::vector<uint8_t> buf(n*recLen+64);
+  uint8_t *base=(uint8_t *)(((uintptr_t)buf.data()+31)&~(uintptr_t)15)+(misalign&15);
+  memcpy(base,recs,n*recLen);
+  *nDropped=0;
+  launchBlocks((unsigned)((n+WB_DEC_THREADS-1)/WB_DEC_THREADS),WB_DEC_THREADS,
+               [&]{ wb_decode_kernel(base,n,fmt,recLen,dropZeros,xi,yi,zi,cls,ret,nDropped); });
   return 0;
 }

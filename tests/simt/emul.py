@@ -112,3 +112,27 @@ def scan_classify(points_sorted, cube, tile_size=1.0, min_hyperboloid_size=0.1, 
                          lab.ctypes.data if classify else None)
     assert nt.value <= cap
     return tiles[:nt.value].copy(), lab
+
+
+def radix_sort(keys, vals, begin_bit=0, end_bit=64, variant="", out="libwb_simt.so"):
+    """wb_radix_sort (wb_sort.cuh) under the emulator: returns the sorted (keys, vals) copies."""
+    L = lib(variant, out)
+    k = np.ascontiguousarray(keys, dtype=np.uint64).copy()
+    v = np.ascontiguousarray(vals, dtype=np.uint32).copy()
+    L.simt_radix_sort.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int]
+    L.simt_radix_sort(k.ctypes.data, v.ctypes.data, len(k), begin_bit, end_bit)
+    return k, v
+
+
+def decode(records, fmt, drop_zeros=False, misalign=0, variant="", out="libwb_simt.so"):
+    """wb_decode_kernel under the emulator: (x, y, z int32, class u8, return number u8, dropped count)."""
+    L = lib(variant, out)
+    recs = np.ascontiguousarray(records)
+    n, rec_len = recs.shape
+    x, y, z = (np.zeros(n, dtype=np.int32) for _ in range(3))
+    cls, ret = np.zeros(n, dtype=np.uint8), np.zeros(n, dtype=np.uint8)
+    dropped = C.c_ulonglong()
+    L.simt_decode.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 6
+    L.simt_decode(recs.ctypes.data, n, fmt, rec_len, 1 if drop_zeros else 0, misalign, x.ctypes.data, y.ctypes.data,
+                  z.ctypes.data, cls.ctypes.data, ret.ctypes.data, C.byref(dropped))
+    return x, y, z, cls, ret, dropped.value

@@ -70,7 +70,7 @@ template <typename T,typename U> inline T atomicMin(T *p,U v) { T o=*p; if ((T)v
 // ---- warp-wide intrinsics -----------------------------------------------------------------------------
 #define SIMT_SITE (__builtin_LINE())
 inline void __syncwarp(unsigned mask=0xffffffffu,int site=SIMT_SITE) { simt::collective(simt::OP_SYNC,site,0,0,mask); }
-inline void __syncthreads(int site=SIMT_SITE) { simt::collective(simt::OP_SYNC,site,0,0,0xffffffffu); }   // one warp per block only
+inline void __syncthreads(int site=SIMT_SITE) { simt::collective(simt::OP_BARRIER,site,0,0,0xffffffffu); }
 inline unsigned __ballot_sync(unsigned mask,int pred,int site=SIMT_SITE)
 { return (unsigned)simt::collective(simt::OP_BALLOT,site,pred?1:0,0,mask); }
 inline int __any_sync(unsigned mask,int pred,int site=SIMT_SITE)

@@ -78,62 +78,68 @@ inline void make_fiber(ucontext_t *c,char *stack,size_t bytes,void (*entry)())
 #endif
 
 struct dim3_ { unsigned x=1,y=1,z=1; };
-enum Op { OP_NONE=0,OP_SYNC,OP_BALLOT,OP_OR,OP_MINU,OP_MAXU,OP_SHFL,OP_MATCH };
+enum Op { OP_NONE=0,OP_SYNC,OP_BALLOT,OP_OR,OP_MINU,OP_MAXU,OP_SHFL,OP_MATCH,OP_BARRIER };
 
 struct Lane
 {
   dim3_ tid,bid,bdim,gdim;
   ucontext_t ctx;
   char *stack=nullptr;
-  bool finished=true;
+  int state=2;                       // 0 runnable, 1 parked at a collective, 2 finished
   // pending collective
   int op=OP_NONE,site=0;
   unsigned long long val=0,result=0;
   unsigned aux=0,mask=0;
 };
 
-struct Warp
+struct Block
 {
-  Lane lane[32];
+  Lane lane[1024];
+  int nLanes=0;
   ucontext_t sched;
   int current=-1;
   std::function<void()> body;
   unsigned long long collectives=0;
 };
+typedef Block Warp;
 
-inline Warp *&warp_ptr() { static thread_local Warp *w=nullptr; return w; }
-// how often each call site (source line) of a warp-wide intrinsic was reached: a poor man's profile of the kernel
+inline Block *&warp_ptr() { static thread_local Block *w=nullptr; return w; }
 // loop-trip counters the kernels bump through WB_EMU_COUNT(slot), once per warp and trip (lane 0 counts)
 inline unsigned long long *emu_counts() { static thread_local unsigned long long c[16]; return c; }
+// how often each call site (source line) of a warp-wide intrinsic was reached: a poor man's profile of the kernel
 inline unsigned long long *site_counts() { static thread_local unsigned long long c[4096]; return c; }
-inline Lane *cur() { Warp *w=warp_ptr(); return &w->lane[w->current]; }
+inline Lane *cur() { Block *w=warp_ptr(); return &w->lane[w->current]; }
 
 inline unsigned long long collective(int op,int site,unsigned long long val,unsigned aux,unsigned mask)
-// Called by a lane: park until every live lane of the warp has arrived at the same call site, then return this
-// lane's result.
+// Called by a lane: park until every live lane of its warp (OP_BARRIER: of its block) has arrived, then return
+// this lane's result.
 {
-  Warp *w=warp_ptr();
+  Block *w=warp_ptr();
   Lane *l=&w->lane[w->current];
   l->op=op; l->site=site; l->val=val; l->aux=aux; l->mask=mask;
+  l->state=1;
   swapcontext(&l->ctx,&w->sched);
   return l->result;
 }
 
 inline void lane_entry()
 {
-  Warp *w=warp_ptr();
+  Block *w=warp_ptr();
   w->body();
-  w->lane[w->current].finished=true;
-  w->lane[w->current].op=OP_NONE;
-  swapcontext(&w->lane[w->current].ctx,&w->sched);
+  Lane &l=w->lane[w->current];
+  l.state=2;
+  l.op=OP_NONE;
+  swapcontext(&l.ctx,&w->sched);
 }
 
-inline void resolve(Warp *w)
-// all live lanes are parked: check uniformity, compute the results
+inline bool resolve_warp(Block *w,int base)
+// lanes base..base+31: if every live lane is parked at a warp-wide intrinsic, compute the results and make them
+// runnable.  Returns false when the warp has nothing to resolve (all finished, or waiting at the block barrier).
 {
   int op=OP_NONE,site=0,first=-1;
-  for (int i=0;i<32;i++)
-    if (!w->lane[i].finished)
+  const int end=base+32<w->nLanes?base+32:w->nLanes;
+  for (int i=base;i<end;i++)
+    if (w->lane[i].state==1)
     {
       if (first<0) { first=i; op=w->lane[i].op; site=w->lane[i].site; }
       else if (w->lane[i].op!=op || w->lane[i].site!=site)
@@ -143,24 +149,26 @@ inline void resolve(Warp *w)
         abort();
       }
     }
-  if (first<0)
-    return;
+    else if (w->lane[i].state==0)
+      return false;                                   // somebody still has to run
+  if (first<0 || op==OP_BARRIER)
+    return false;
   w->collectives++;
   site_counts()[site&4095]++;
   unsigned ballot=0;
   unsigned long long acc_or=0,acc_min=~0ull,acc_max=0;
-  for (int i=0;i<32;i++)
-    if (!w->lane[i].finished)
+  for (int i=base;i<end;i++)
+    if (w->lane[i].state==1)
     {
-      if (w->lane[i].val) ballot|=1u<<i;
+      if (w->lane[i].val) ballot|=1u<<(i-base);
       acc_or|=w->lane[i].val;
       if (w->lane[i].val<acc_min) acc_min=w->lane[i].val;
       if (w->lane[i].val>acc_max) acc_max=w->lane[i].val;
     }
-  for (int i=0;i<32;i++)
+  for (int i=base;i<end;i++)
   {
     Lane &l=w->lane[i];
-    if (l.finished)
+    if (l.state!=1)
       continue;
     switch (op)
     {
@@ -171,60 +179,99 @@ inline void resolve(Warp *w)
       case OP_MAXU: l.result=acc_max; break;
       case OP_SHFL:
       {
-        const Lane &s=w->lane[l.aux&31];
-        l.result=s.finished?l.val:s.val;      // reading an exited lane is undefined on the GPU; keep own value
+        const int src=base+(int)(l.aux&31);
+        const bool there=src<end && w->lane[src].state==1;
+        l.result=there?w->lane[src].val:l.val;        // reading an exited lane is undefined on the GPU; keep own value
         break;
       }
       case OP_MATCH:
       {
         unsigned m=0;
-        for (int j=0;j<32;j++)
-          if (!w->lane[j].finished && w->lane[j].val==l.val)
-            m|=1u<<j;
-        l.result=m;
+        for (int j=base;j<end;j++)
+          if (w->lane[j].state==1 && w->lane[j].val==l.val)
+            m|=1u<<(j-base);
+        l.result=m&l.mask;
         break;
       }
       default: l.result=0;
     }
   }
+  for (int i=base;i<end;i++)
+    if (w->lane[i].state==1)
+      w->lane[i].state=0;
+  return true;
 }
 
-// Run `body` once per lane of one warp.  The lanes see threadIdx.x = firstThread..firstThread+31.
-inline unsigned long long run_warp(const std::function<void()> &body,unsigned firstThread,unsigned block,unsigned blockDim,
-                                   unsigned gridDim,size_t stackBytes=256*1024)
+// Run `body` once per thread of one block of nThreads threads (threadIdx.x = firstThread .. firstThread+nThreads-1;
+// firstThread > 0 runs one warp of a larger block on its own, for kernels whose warps do not interact).
+inline unsigned long long run_block(const std::function<void()> &body,unsigned nThreads,unsigned firstThread,unsigned block,
+                                    unsigned blockDim,unsigned gridDim,size_t stackBytes=128*1024)
 {
-  static thread_local Warp *w=nullptr;
+  static thread_local Block *w=nullptr;
   if (!w)
-  {
-    w=new Warp;
-    for (int i=0;i<32;i++)
-      w->lane[i].stack=(char *)malloc(stackBytes);
-  }
+    w=new Block;
+  if (nThreads>1024) { fprintf(stderr,"simt: block of %u threads\n",nThreads); abort(); }
   warp_ptr()=w;
   w->body=body;
   w->collectives=0;
-  for (int i=0;i<32;i++)
+  w->nLanes=(int)nThreads;
+  for (unsigned i=0;i<nThreads;i++)
   {
     Lane &l=w->lane[i];
+    if (!l.stack)
+      l.stack=(char *)malloc(stackBytes);
     l.tid.x=firstThread+i; l.bid.x=block; l.bdim.x=blockDim; l.gdim.x=gridDim;
-    l.finished=false;
+    l.state=0;
     l.op=OP_NONE;
     make_fiber(&l.ctx,l.stack,stackBytes,lane_entry);
   }
   while (true)
   {
-    bool any=false;
-    for (int i=0;i<32;i++)
-      if (!w->lane[i].finished)
+    bool live=false,progressed=false;
+    for (unsigned i=0;i<nThreads;i++)
+      if (w->lane[i].state==0)
       {
-        any=true;
-        w->current=i;
+        w->current=(int)i;
         swapcontext(&w->sched,&w->lane[i].ctx);     // runs until the lane parks at a collective or finishes
+        progressed=true;
       }
-    if (!any)
+    for (unsigned base=0;base<nThreads;base+=32)
+      if (resolve_warp(w,(int)base))
+        progressed=true;
+    // block barrier: released when every live lane waits at one
+    bool allAtBarrier=true;
+    for (unsigned i=0;i<nThreads;i++)
+      if (w->lane[i].state!=2)
+      {
+        live=true;
+        if (!(w->lane[i].state==1 && w->lane[i].op==OP_BARRIER))
+          allAtBarrier=false;
+      }
+    if (!live)
       break;
-    resolve(w);
+    if (allAtBarrier)
+    {
+      for (unsigned i=0;i<nThreads;i++)
+        if (w->lane[i].state==1)
+        {
+          w->lane[i].result=0;
+          w->lane[i].state=0;
+        }
+      w->collectives++;
+      progressed=true;
+    }
+    if (!progressed)
+    {
+      fprintf(stderr,"simt: deadlock in block %u (a warp split between __syncthreads and a warp-wide intrinsic?)\n",block);
+      abort();
+    }
   }
   return w->collectives;
+}
+
+inline unsigned long long run_warp(const std::function<void()> &body,unsigned firstThread,unsigned block,unsigned blockDim,
+                                   unsigned gridDim)
+{
+  return run_block(body,32,firstThread,block,blockDim,gridDim);
 }
 } // namespace simt

@@ -254,6 +254,7 @@ struct WbScratch
 
 static inline uint64_t wb_div_up(uint64_t a,uint64_t b) { return (a+b-1)/b; }
 
+#ifndef WB_NO_HOST_LAUNCH    // the SIMT emulator (tests/simt) compiles the kernels only and replays these launches itself
 // exclusive scan of n u32 (n < 2^32 * tile), out may alias in.  Launch count returned via *launches.
 static cudaError_t wb_exclusive_scan(const uint32_t *in,uint32_t *out,uint64_t n,uint32_t *blockSums,
                                      uint64_t blockSumsCap,cudaStream_t st,uint64_t *launches)
@@ -303,3 +304,4 @@ static cudaError_t wb_radix_sort(uint64_t *keysA,uint32_t *valsA,uint64_t *keysB
   }
   return cudaGetLastError();
 }
+#endif
