@@ -56,3 +56,19 @@ def test_emulated_decode_matches_oracle(scene, n, misalign):
     assert (ret == np.where(orr == 0, 1, orr)).all() and dropped == 0
     x, y, z, cls, ret, dropped = emul.decode(recs, cloud.fmt, drop_zeros=True, misalign=misalign)
     assert (x == xyz[:, 0]).all() and (cls == oc).all() and (ret == orr).all() and dropped == int((orr == 0).sum())
+
+
+def test_emulated_kernels_are_clean_under_address_sanitizer():
+    """The same kernels, compiled with -fsanitize=address, on ragged and tiny inputs: no out-of-bounds access to a
+    global or shared array (what compute-sanitizer's memcheck looks for on the GPU, here without one)."""
+    import subprocess
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "simt")
+    asan = subprocess.run(["gcc", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    if not os.path.isabs(asan) or not os.path.exists(asan):
+        pytest.skip("libasan not installed")
+    subprocess.check_call([sys.executable, os.path.join(here, "asan_check.py"), "build"])
+    env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0:detect_stack_use_after_return=0")
+    out = subprocess.run([sys.executable, os.path.join(here, "asan_check.py")], capture_output=True, text=True, env=env,
+                         timeout=600)
+    assert "ASAN-CHECK-OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+    assert "AddressSanitizer" not in out.stderr, out.stderr[-4000:]
