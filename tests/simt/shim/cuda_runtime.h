@@ -107,3 +107,54 @@ template <typename T> inline T __shfl_down_sync(unsigned mask,T v,unsigned delta
   int lane=(int)(simt::cur()->tid.x&31);
   return __shfl_sync(mask,v,lane+(int)delta<32?lane+(int)delta:lane,width,site);
 }
+
+// ---- just enough of the CUDA runtime API for wolken_b200.cu to compile and run as host code ----------------------
+// "Device" memory is the heap, streams are immediate (every call completes before it returns), events are wall-clock
+// stamps.  Used by the emulated build of the whole library (tests/simt/gen, libwolken_b200_emulated.so).
+#include <chrono>
+#include <cstdlib>
+#include <vector>
+typedef int cudaError_t;
+enum { cudaSuccess=0,cudaErrorInvalidValue=1,cudaErrorMemoryAllocation=2 };
+enum cudaMemcpyKind { cudaMemcpyHostToHost=0,cudaMemcpyHostToDevice=1,cudaMemcpyDeviceToHost=2,cudaMemcpyDeviceToDevice=3,cudaMemcpyDefault=4 };
+struct simt_stream_t { int id; };
+struct simt_event_t { double t; };
+typedef simt_stream_t *cudaStream_t;
+typedef simt_event_t *cudaEvent_t;
+enum { cudaStreamNonBlocking=1,cudaEventDisableTiming=2,cudaHostAllocDefault=0 };
+inline const char *cudaGetErrorString(cudaError_t e) { return e==cudaSuccess?"no error":(e==cudaErrorMemoryAllocation?"out of memory":"invalid value"); }
+inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+inline cudaError_t cudaGetDeviceCount(int *n) { *n=1; return cudaSuccess; }
+inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+template <typename T> inline cudaError_t cudaMalloc(T **p,size_t n) { *p=(T *)malloc(n?n:1); return *p?cudaSuccess:cudaErrorMemoryAllocation; }
+inline cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
+template <typename T> inline cudaError_t cudaHostAlloc(T **p,size_t n,unsigned) { *p=(T *)malloc(n?n:1); return *p?cudaSuccess:cudaErrorMemoryAllocation; }
+inline cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
+inline cudaError_t cudaMemcpy(void *d,const void *s,size_t n,cudaMemcpyKind) { memmove(d,s,n); return cudaSuccess; }
+inline cudaError_t cudaMemcpyAsync(void *d,const void *s,size_t n,cudaMemcpyKind,cudaStream_t=nullptr) { memmove(d,s,n); return cudaSuccess; }
+inline cudaError_t cudaMemset(void *d,int v,size_t n) { memset(d,v,n); return cudaSuccess; }
+inline cudaError_t cudaMemsetAsync(void *d,int v,size_t n,cudaStream_t=nullptr) { memset(d,v,n); return cudaSuccess; }
+template <typename T> inline cudaError_t cudaMemcpyToSymbol(T &sym,const void *s,size_t n) { memcpy(&sym,s,n); return cudaSuccess; }
+inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s,unsigned) { *s=new simt_stream_t{0}; return cudaSuccess; }
+inline cudaError_t cudaStreamDestroy(cudaStream_t s) { delete s; return cudaSuccess; }
+inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t,cudaEvent_t,unsigned) { return cudaSuccess; }
+inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e=new simt_event_t{0}; return cudaSuccess; }
+inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e,unsigned) { *e=new simt_event_t{0}; return cudaSuccess; }
+inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
+inline cudaError_t cudaEventRecord(cudaEvent_t e,cudaStream_t=nullptr)
+{ e->t=std::chrono::duration<double,std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); return cudaSuccess; }
+inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+inline cudaError_t cudaEventElapsedTime(float *ms,cudaEvent_t a,cudaEvent_t b) { *ms=(float)(b->t-a->t); return cudaSuccess; }
+
+// kernel<<<grid,block,smem,...>>>(args) after tests/simt/gen_host_build.py: the blocks one after another, each with
+// one fiber per thread; `extern __shared__` arrays point into a per-launch buffer of `smem` bytes
+inline std::vector<unsigned long long> &simt_dynamic_buffer() { static thread_local std::vector<unsigned long long> b; return b; }
+inline void *simt_dynamic_smem() { return simt_dynamic_buffer().data(); }
+template <typename F> inline void simt_launch(unsigned long long grid,unsigned block,size_t smem,F body)
+{
+  simt_dynamic_buffer().assign(smem/8+2,0);
+  for (unsigned long long b=0;b<grid;b++)
+    simt::run_block(body,block,0,(unsigned)b,block,(unsigned)grid);
+}

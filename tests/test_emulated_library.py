@@ -1,0 +1,30 @@
+"""The whole library on a CPU, as a test: tests/simt builds wolken_b200.cu itself — C ABI, host orchestration, every
+kernel — for the host (launches rewritten to run block by block under the SIMT emulator, a heap-backed stand-in for
+the CUDA runtime) and a subset of the GPU parity tests is run against it through WB_LIB, unchanged.
+
+This is NOT a CPU path of the product: nothing under wolkenbase_b200/ builds, ships or selects it, and without a
+CUDA device the product library still refuses to create a context (tests/test_abi.py).  It exists so that the
+kernels' logic and the ABI's host code are exercised on every CPU-only run — and so that a kernel change can be
+checked for parity before a GPU is at hand.  The `-m gpu` run on a B200 remains the proof for the nvcc build."""
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SIMT = os.path.join(ROOT, "tests", "simt")
+EMULATED = os.path.join(SIMT, "libwolken_b200_emulated.so")
+
+SUBSET = ("pipeline_matches_oracle and 5000 or ragged_and_tiny or return_number_zero or patch_records or "
+          "error_behaviour or device_math or street_30k_tile3 or identical_locations or encode_same_layout or "
+          "injected_tile")
+
+
+def test_gpu_parity_subset_passes_on_the_emulated_library():
+    subprocess.check_call(["make", "-s", "-C", SIMT, "libwolken_b200_emulated.so"])
+    env = dict(os.environ, WB_LIB=EMULATED)
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-m", "gpu",
+                          "-q", "-x", "-k", SUBSET, "-p", "no:cacheprovider"], capture_output=True, text=True, env=env,
+                         cwd=ROOT, timeout=900)
+    tail = out.stdout[-3000:] + out.stderr[-2000:]
+    assert out.returncode == 0, tail
+    assert " passed" in out.stdout and "failed" not in out.stdout, tail
