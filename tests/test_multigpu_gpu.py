@@ -1,6 +1,8 @@
 """The sharded path (halo exchange, tile-table merge, two-stage build) reproduces the labels of the
 single-GPU run exactly.  Ranks are simulated inside one process on one GPU (multigpu.run_local);
 the same Rank code runs under torch.distributed in bench.py --gpus N."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -38,7 +40,8 @@ def test_sharded_equals_single(world, scene, n, dups):
         clouds.append(c)
     params = dict(tile_size=1.0, max_slope=1.0, thickness=0.0, min_hyperboloid_size=0.1)
     want, tiles = _single(clouds, params)
-    dev = torch.device("cuda", 0)
+    # under the emulated library (tests/test_emulated_library.py) "device" memory is host memory
+    dev = torch.device("cpu") if os.environ.get("WB_EMULATED") else torch.device("cuda", 0)
     ranks = [multigpu.Rank(k, world, api.Context(0), api.Context(0), params, dev) for k in range(world)]
     got = multigpu.run_local(ranks, clouds)
     # the merged, post-scanned tile table equals the single-GPU one
