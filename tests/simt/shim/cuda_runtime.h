@@ -155,6 +155,25 @@ inline void *simt_dynamic_smem() { return simt_dynamic_buffer().data(); }
 template <typename F> inline void simt_launch(unsigned long long grid,unsigned block,size_t smem,F body)
 {
   simt_dynamic_buffer().assign(smem/8+2,0);
-  for (unsigned long long b=0;b<grid;b++)
-    simt::run_block(body,block,0,(unsigned)b,block,(unsigned)grid);
+  // SIMT_BLOCK_ORDER=reverse|shuffle: the GPU runs blocks in no particular order; results must not depend on it
+  static const char *order=getenv("SIMT_BLOCK_ORDER");
+  if (order && order[0]=='r')
+    for (unsigned long long b=grid;b-->0;)
+      simt::run_block(body,block,0,(unsigned)b,block,(unsigned)grid);
+  else if (order && order[0]=='s')
+  {
+    // a fixed odd stride visits every block once (grid and stride coprime when the stride is a large prime)
+    const unsigned long long stride=2654435761ull%(grid?grid:1)|1ull;
+    unsigned long long g=grid,a=stride,t;
+    while (a) { t=g%a; g=a; a=t; }                     // gcd
+    if (g!=1)
+      for (unsigned long long b=grid;b-->0;)
+        simt::run_block(body,block,0,(unsigned)b,block,(unsigned)grid);
+    else
+      for (unsigned long long k=0,b=grid/2;k<grid;k++,b=(b+stride)%grid)
+        simt::run_block(body,block,0,(unsigned)b,block,(unsigned)grid);
+  }
+  else
+    for (unsigned long long b=0;b<grid;b++)
+      simt::run_block(body,block,0,(unsigned)b,block,(unsigned)grid);
 }

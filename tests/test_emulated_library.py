@@ -54,3 +54,15 @@ def test_host_cli_passes_on_the_emulated_library():
     tail = out.stdout[-3000:] + out.stderr[-2000:]
     assert out.returncode == 0, tail
     assert " passed" in out.stdout and "failed" not in out.stdout, tail
+
+
+def test_results_do_not_depend_on_block_order():
+    """The GPU schedules blocks in no particular order; the emulator normally runs them 0..N-1.  Reversed and
+    strided orders must give the same dump, tile table and labels (atomically built lists, duplicate handling)."""
+    subprocess.check_call(["make", "-s", "-C", SIMT, "libwolken_b200_emulated.so"])
+    for order in ("reverse", "shuffle"):
+        env = dict(os.environ, WB_LIB=EMULATED, SIMT_BLOCK_ORDER=order)
+        out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-m",
+                              "gpu", "-q", "-x", "-k", "pipeline_matches_oracle and 5000 or ragged_and_tiny or aerial_20k_dups",
+                              "-p", "no:cacheprovider"], capture_output=True, text=True, env=env, cwd=ROOT, timeout=900)
+        assert out.returncode == 0, order + "\n" + out.stdout[-3000:] + out.stderr[-2000:]
