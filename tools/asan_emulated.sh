@@ -2,6 +2,8 @@
 # The whole library (wolken_b200.cu: ABI, host orchestration, every kernel) built for the host over the SIMT emulator
 # with -fsanitize=address, and the GPU parity tests run against it: a memcheck of host and device code without a GPU.
 # Takes about four minutes.  Usage: tools/asan_emulated.sh [pytest -k expression]
+# (For UBSan: the same g++ line with -fsanitize=undefined -fno-sanitize=vptr, LD_PRELOAD=$(gcc -print-file-name=libubsan.so),
+#  and pytest -s so that the reports are not captured.)
 set -e
 cd "$(dirname "$0")/.."
 make -s -C tests/simt libwolken_b200_emulated.so        # (re)generates tests/simt/gen
