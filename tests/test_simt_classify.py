@@ -15,8 +15,8 @@ from wolkenbase_b200 import synth
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "simt"))
 import emul  # noqa: E402
 
-CASES = [(2, 8000, 3, {}), (1, 8000, 1, {}), (5, 8000, 5, {}), (4, 8000, 4, {}), (3, 6000, 7, {}),
-         (2, 6000, 9, {"max_slope": 0.5, "thickness": 0.05, "tile_size": 2.0})]
+CASES = [(2, 5000, 3, {}), (1, 5000, 1, {}), (5, 5000, 5, {}), (4, 5000, 4, {}), (3, 4000, 7, {}),
+         (2, 4000, 9, {"max_slope": 0.5, "thickness": 0.05, "tile_size": 2.0})]
 VARIANTS = [("", "libwb_simt.so"),
             ("-DWB_CL_FSECTOR=0 -DWB_CL_FREACH=0 -DWB_CL_FSPAN=0", "libwb_simt_double.so"),
             ("-DWB_CL_REFILTER=1", "libwb_simt_refilter.so"),
@@ -80,8 +80,8 @@ def test_emulated_kernel_matches_compiled_reference_labels(case, golden_dir):
     assert (in_input_order == g["ref_labels"]).all()
 
 
-SCAN_CASES = [(2, 8000, 3, {}), (5, 8000, 5, {}), (1, 8000, 1, {"tile_size": 3.0}),
-              (4, 8000, 4, {"tile_size": 2.0, "min_hyperboloid_size": 0.5, "max_slope": 0.7, "thickness": 0.05})]
+SCAN_CASES = [(2, 5000, 3, {}), (5, 5000, 5, {}), (1, 5000, 1, {"tile_size": 3.0}),
+              (4, 5000, 4, {"tile_size": 2.0, "min_hyperboloid_size": 0.5, "max_slope": 0.7, "thickness": 0.05})]
 
 
 @pytest.mark.parametrize("scene,n,seed,p", SCAN_CASES)
