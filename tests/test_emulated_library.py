@@ -66,3 +66,21 @@ def test_results_do_not_depend_on_block_order():
                               "gpu", "-q", "-x", "-k", "pipeline_matches_oracle and 5000 or ragged_and_tiny or aerial_20k_dups",
                               "-p", "no:cacheprovider"], capture_output=True, text=True, env=env, cwd=ROOT, timeout=900)
         assert out.returncode == 0, order + "\n" + out.stdout[-3000:] + out.stderr[-2000:]
+
+
+def test_round2_candidates_pass_on_the_emulated_library():
+    """The classify candidates that are off in the shipped library (WB_CL_XWANTS, WB_CL_REFILTER, WB_CL_COMPACT2),
+    all switched on in an emulated build: same dumps, tile tables and labels."""
+    subprocess.check_call(["make", "-s", "-C", SIMT, "libwolken_b200_emulated.so"])        # (re)generates gen/
+    lib = os.path.join(SIMT, "libwolken_b200_emulated_candidates.so")
+    subprocess.check_call(["g++", "-std=gnu++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-Ishim", "-I.",
+                           "-Igen", "-DWB_CL_XWANTS=1", "-DWB_CL_REFILTER=1", "-DWB_CL_COMPACT2=1", "-Wno-unused-function",
+                           "-o", lib, "gen/wolken_b200.cu.cpp"], cwd=SIMT)
+    env = dict(os.environ, WB_LIB=lib)
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-m", "gpu",
+                          "-q", "-x", "-k", "pipeline_matches_oracle and (5000 or 20000) or ragged_and_tiny or aerial_20k_dups "
+                          "or street_30k_tile3", "-p", "no:cacheprovider"], capture_output=True, text=True, env=env,
+                         cwd=ROOT, timeout=900)
+    tail = out.stdout[-3000:] + out.stderr[-2000:]
+    assert out.returncode == 0, tail
+    assert " passed" in out.stdout and "failed" not in out.stdout, tail

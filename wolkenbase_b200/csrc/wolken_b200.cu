@@ -111,6 +111,9 @@ struct wb_ctx
   DevBuf<double> tDensity,tHyp,tHeight;
   DevBuf<int> tileExt;
   DevBuf<uint32_t> wedgeBuf;
+#if WB_CL_COMPACT2
+  DevBuf<uint32_t> pendingList;
+#endif
   DevBuf<uint8_t> chunkPending;
   DevBuf<uint8_t> tileGrid;
   // results of build
@@ -349,6 +352,10 @@ extern "C" void wb_destroy(wb_ctx *ctx)
   ctx->levelOff.release(); ctx->levelCnt.release();
   ctx->tStart.release(); ctx->tCount.release(); ctx->tileList.release(); ctx->tNPoints.release(); ctx->tTree.release();
   ctx->tDensity.release(); ctx->tHyp.release(); ctx->tHeight.release(); ctx->tileExt.release(); ctx->tileGrid.release(); ctx->wedgeBuf.release(); ctx->chunkPending.release();
+#if WB_CL_COMPACT2
+  ctx->pendingList.release();
+#endif
+ 
   ctx->dupIn.release(); ctx->dupRep.release();
   freeKeptRecords(ctx);
   for (int i=0;i<WB_READ_THREADS;i++)
@@ -1357,11 +1364,38 @@ extern "C" int wb_classify(wb_ctx *ctx)
   wb_classify_kernel<1><<<gridFor(ctx->nChunks,WB_CL_WARPS),WB_CL_WARPS*32,0,st>>>(
       ctx->sx.p,ctx->sy.p,ctx->sz.p,nv,ctx->nChunks,ctx->bounds.p,ctx->levelOff.p,ctx->levelCnt.p,ctx->nLevels,
       ctx->winner.p,ctx->tHyp.p,ctx->prm.maxSlope,ctx->prm.thickness,ctx->cls.p,ctx->perm,
-      ctx->ownFirst,ctx->ownEnd,ctx->labelSorted.p,ctx->counters.p,ctx->wedgeBuf.p,ctx->chunkPending.p);
+      ctx->ownFirst,ctx->ownEnd,ctx->labelSorted.p,ctx->counters.p,ctx->wedgeBuf.p,ctx->chunkPending.p
+#if WB_CL_COMPACT2
+      ,nullptr,0u
+#endif
+      );
+#if WB_CL_COMPACT2
+  {
+    // the queries that need the exact walk, gathered in canonical order into full warps
+    wb_pending_flag_kernel<<<gridFor(nv,256),256,0,st>>>(ctx->wedgeBuf.p,nv,ctx->scr0.p);
+    CK(cudaMemsetAsync(ctx->scr0.p+nv,0,sizeof(uint32_t),st));
+    CK(wb_exclusive_scan(ctx->scr0.p,ctx->scr1.p,nv+1,ctx->blockSums.p,ctx->blockSums.cap,st,&ctx->stats.kernel_launches));
+    uint32_t nPending=0;
+    CK(cudaMemcpyAsync(&nPending,ctx->scr1.p+nv,sizeof(uint32_t),cudaMemcpyDeviceToHost,st));
+    CK(cudaStreamSynchronize(st));
+    CK(ctx->pendingList.ensure((uint64_t)nPending+1));
+    if (nPending)
+    {
+      wb_pending_scatter_kernel<<<gridFor(nv,256),256,0,st>>>(ctx->scr0.p,ctx->scr1.p,nv,ctx->pendingList.p);
+      wb_classify_kernel<2><<<gridFor(wb_div_up(nPending,32),WB_CL_WARPS),WB_CL_WARPS*32,0,st>>>(
+          ctx->sx.p,ctx->sy.p,ctx->sz.p,nv,ctx->nChunks,ctx->bounds.p,ctx->levelOff.p,ctx->levelCnt.p,ctx->nLevels,
+          ctx->winner.p,ctx->tHyp.p,ctx->prm.maxSlope,ctx->prm.thickness,ctx->cls.p,ctx->perm,
+          ctx->ownFirst,ctx->ownEnd,ctx->labelSorted.p,ctx->counters.p,ctx->wedgeBuf.p,ctx->chunkPending.p,
+          ctx->pendingList.p,nPending);
+    }
+    ctx->stats.kernel_launches+=2;
+  }
+#else
   wb_classify_kernel<2><<<gridFor(ctx->nChunks,WB_CL_WARPS),WB_CL_WARPS*32,0,st>>>(
       ctx->sx.p,ctx->sy.p,ctx->sz.p,nv,ctx->nChunks,ctx->bounds.p,ctx->levelOff.p,ctx->levelCnt.p,ctx->nLevels,
       ctx->winner.p,ctx->tHyp.p,ctx->prm.maxSlope,ctx->prm.thickness,ctx->cls.p,ctx->perm,
       ctx->ownFirst,ctx->ownEnd,ctx->labelSorted.p,ctx->counters.p,ctx->wedgeBuf.p,ctx->chunkPending.p);
+#endif
   CK(cudaEventRecord(ctx->evD,st));
   wb_scatter_labels_kernel<<<gridFor(nv,256),256,0,st>>>(ctx->labelSorted.p,ctx->perm,nv,ctx->labelIn.p);
   ctx->stats.kernel_launches+=4;
