@@ -1,7 +1,9 @@
-// classify_emul.cpp — runs the classify kernels of wolkenbase_b200/csrc/wb_kernels.cuh (the very source nvcc
-// compiles for sm_100a) on the CPU, one emulated warp at a time.  TEST INFRASTRUCTURE ONLY: it lets the CPU
-// test suite check the kernel's traversal logic (and variants of it behind WB_CL_* macros) against the oracle's
-// labels before a GPU is at hand.  The GPU tests remain the parity proof for the compiled kernel.
+// classify_emul.cpp — kernel-level harnesses over the SIMT emulator: the classify kernels of
+// wolkenbase_b200/csrc/wb_kernels.cuh (the very source nvcc compiles for sm_100a) on their own, the tile phases + classify
+// launched as wb_scan/wb_postscan/wb_classify launch them, the radix sort, the LAS decode.  TEST INFRASTRUCTURE ONLY: the
+// CPU suite checks the kernels' logic (and variants behind WB_CL_* macros) against the oracle before a GPU is at
+// hand, and tools/model_bench_scene.py counts their work on the real bench scene.  (The whole library, host code
+// included, is the other target of the Makefile.)  The GPU tests remain the parity proof for the compiled kernels.
 #include <cmath>
 #include <cstdint>
 #include <cstring>

@@ -2,9 +2,10 @@
 // under the SIMT emulator of tests/simt/simt.h.  TEST INFRASTRUCTURE ONLY (never on the product path: the
 // product is the nvcc build of the same sources).
 //
-// What is emulated: one warp = 32 fibers (ucontext) run in lock step between warp-wide intrinsics; every
-// *_sync intrinsic is a rendezvous of the warp's live lanes (the emulator checks that all lanes arrive at the
-// same call site, i.e. that the code is warp-uniform where CUDA requires it).  Arithmetic intrinsics map to
+// What is emulated: one block = one fiber per thread, run in lock step between collectives; every *_sync
+// intrinsic is a rendezvous of the warp's live lanes (the emulator checks that all lanes arrive at the same call
+// site, i.e. that the code is warp-uniform where CUDA requires it), __syncthreads one of the block; __shared__ is
+// a per-block static; atomics are plain (blocks and lanes never run concurrently).  Arithmetic intrinsics map to
 // the IEEE operation they name (compile with -ffp-contract=off); __fdividef is an exact float division, so
 // masks built from approximate angles may differ from the GPU's by a rounding — never results.
 #pragma once

@@ -1,5 +1,7 @@
-// simt.h — a warp of 32 fibers in lock step: just enough of the SIMT execution model to run the warp-synchronous
-// kernels of wolkenbase_b200/csrc on a CPU, for tests.  TEST INFRASTRUCTURE ONLY.
+// simt.h — one CUDA block as a set of fibers (one per thread) in lock step: just enough of the SIMT execution model
+// to run the kernels of wolkenbase_b200/csrc on a CPU, for tests.  A warp-wide *_sync intrinsic parks its lane until the
+// warp's live lanes have all arrived (at the same source line, or the emulator aborts), __syncthreads until the
+// block's have; blocks run one after another.  TEST INFRASTRUCTURE ONLY.
 #pragma once
 #include <cstdint>
 #include <cstdio>
