@@ -148,6 +148,32 @@ extern "C" int simt_classify(const double *sx,const double *sy,const double *sz,
   // as a candidate)
   auto run=[&](int pass)
   {
+#if WB_CL_COMPACT2
+    // pass 2 over the pending queries of the chunk range, gathered into full warps (wb_classify does the same with
+    // wb_pending_flag_kernel, a scan and wb_pending_scatter_kernel)
+    std::vector<uint32_t> pendingList;
+    if (pass==2)
+      for (uint64_t i=(uint64_t)firstChunk*32;i<n && i<(uint64_t)endChunk*32;i++)
+        if (wedge[i]!=0xffffffffu)
+          pendingList.push_back((uint32_t)i);
+    const uint32_t nPend=(uint32_t)pendingList.size();
+    const uint32_t b0=pass==1?firstChunk:0,b1=pass==1?endChunk:(nPend+31)/32;
+    for (uint32_t b=b0;b<b1;b++)
+    {
+      auto body=[&]
+      {
+        if (pass==1)
+          wb_classify_kernel<1>(sx,sy,sz,n,nChunks,bounds.data(),levelOff.data(),levelCnt.data(),nLevels,winner.data(),hyp,
+                                maxSlope,thickness,clsIn.data(),perm.data(),0u,0xffffffffu,labelSorted,counters,
+                                wedge.data(),pending.data(),nullptr,0u);
+        else
+          wb_classify_kernel<2>(sx,sy,sz,n,nChunks,bounds.data(),levelOff.data(),levelCnt.data(),nLevels,winner.data(),hyp,
+                                maxSlope,thickness,clsIn.data(),perm.data(),0u,0xffffffffu,labelSorted,counters,
+                                wedge.data(),pending.data(),pendingList.data(),nPend);
+      };
+      coll+=simt::run_warp(body,0,b,WB_CL_WARPS*32,nChunks);
+    }
+#else
     for (uint32_t b=firstChunk;b<endChunk;b++)
     {
       auto body=[&]
@@ -155,16 +181,15 @@ extern "C" int simt_classify(const double *sx,const double *sy,const double *sz,
         if (pass==1)
           wb_classify_kernel<1>(sx,sy,sz,n,nChunks,bounds.data(),levelOff.data(),levelCnt.data(),nLevels,winner.data(),hyp,
                                 maxSlope,thickness,clsIn.data(),perm.data(),0u,0xffffffffu,labelSorted,counters,
-                                wedge.data(),pending.data()
-                                );
+                                wedge.data(),pending.data());
         else
           wb_classify_kernel<2>(sx,sy,sz,n,nChunks,bounds.data(),levelOff.data(),levelCnt.data(),nLevels,winner.data(),hyp,
                                 maxSlope,thickness,clsIn.data(),perm.data(),0u,0xffffffffu,labelSorted,counters,
-                                wedge.data(),pending.data()
-                                );
+                                wedge.data(),pending.data());
       };
       coll+=simt::run_warp(body,0,b,WB_CL_WARPS*32,nChunks);
     }
+#endif
   };
   static_assert(WB_CL_WARPS==1,"the emulator launches one warp per block");
   run(1);
@@ -285,10 +310,18 @@ extern "C" int simt_scan_classify(const double *sx,const double *sy,const double
       {
         if (pass==1)
           wb_classify_kernel<1>(sx,sy,sz,n,nChunks,bounds.data(),levelOff.data(),levelCnt.data(),nLevels,winner.data(),tHyp.data(),
-                                maxSlope,thickness,clsIn.data(),perm.data(),0u,0xffffffffu,labelSorted,counters,wedge.data(),pending.data());
+                                maxSlope,thickness,clsIn.data(),perm.data(),0u,0xffffffffu,labelSorted,counters,wedge.data(),pending.data()
+#if WB_CL_COMPACT2
+                                ,nullptr,0u
+#endif
+                                );
         else
           wb_classify_kernel<2>(sx,sy,sz,n,nChunks,bounds.data(),levelOff.data(),levelCnt.data(),nLevels,winner.data(),tHyp.data(),
-                                maxSlope,thickness,clsIn.data(),perm.data(),0u,0xffffffffu,labelSorted,counters,wedge.data(),pending.data());
+                                maxSlope,thickness,clsIn.data(),perm.data(),0u,0xffffffffu,labelSorted,counters,wedge.data(),pending.data()
+#if WB_CL_COMPACT2
+                                ,nullptr,0u
+#endif
+                                );
       },0,b,WB_CL_WARPS*32,nChunks);
   return 0;
 }

@@ -2,7 +2,9 @@
 order and the tile table of the C2 scene at full size, then the SIMT emulator (tests/simt) runs the kernel source
 on a sample of warps and reports the per-warp work counters.  Usage:
     python tools/model_bench_scene.py POINTS WARPS [VARIANT_FLAGS...]      e.g. 100000000 300 "-DWB_CL_REFILTER=1"
-The prepared scene is cached in /tmp (npz) so that variants can be compared on identical inputs."""
+The prepared scene is cached in /tmp (npz) so that variants can be compared on identical inputs.
+WB_MODEL_RUN=64 samples contiguous runs of 64 chunks instead of single ones (needed to model WB_CL_COMPACT2, which
+gathers the pending queries of neighbouring chunks); WB_MODEL_SITES=N prints the N busiest intrinsic call sites."""
 import ctypes as C
 import os
 import sys
@@ -67,15 +69,16 @@ def main():
     n = len(pts)
     n_chunks = (n + 31) // 32
     rng = np.random.default_rng(1)
-    sample = np.sort(rng.choice(n_chunks, size=min(n_warps, n_chunks), replace=False))
+    run = int(os.environ.get("WB_MODEL_RUN", "1"))          # warps per sample: >1 takes contiguous runs of chunks
+    sample = np.sort(rng.choice(max(1, n_chunks - run), size=min(max(1, n_warps // run), n_chunks), replace=False))
     for i, v in enumerate(variants):
         tot = {}
         t = time.time()
         for c in sample:
-            _, w = emul.classify(pts, hyp, chunks=(int(c), int(c) + 1), variant=v, out="libwb_simt_m%d.so" % i)
+            _, w = emul.classify(pts, hyp, chunks=(int(c), int(c) + run), variant=v, out="libwb_simt_m%d.so" % i)
             for k, x in w.items():
                 tot[k] = tot.get(k, 0) + x
-        m = len(sample)
+        m = len(sample) * run
         sites = emul.site_counts(variant=v, out="libwb_simt_m%d.so" % i)
         trips = emul.emu_counts(variant=v, out="libwb_simt_m%d.so" % i)
         print("  reach tests at expansion per warp: chunks %.1f, internal nodes %.1f" % (trips[0] / m, trips[1] / m))
