@@ -10,7 +10,15 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def build(variant="", out="libwb_simt.so"):
-    subprocess.check_call(["make", "-s", "-C", _HERE, "OUT=" + out, "VARIANT=" + variant])
+    """make the library; a change of the -D flags behind the same file name forces a rebuild (make only sees files)."""
+    stamp = os.path.join(_HERE, out + ".flags")
+    old = open(stamp).read() if os.path.exists(stamp) else None
+    cmd = ["make", "-s", "-C", _HERE, "OUT=" + out, "VARIANT=" + variant]
+    if old != variant:
+        cmd.insert(1, "-B")
+    subprocess.check_call(cmd + [out])
+    with open(stamp, "w") as f:
+        f.write(variant)
     return os.path.join(_HERE, out)
 
 
