@@ -259,18 +259,20 @@ def run_ours(args):
     print(json.dumps(line))
 
 
-def scaling_base(ctx, args):
+def scaling_base(ctx, args, world=8, rank=0, steps=2):
     """The N>1 runs shard BASELINE configs[2] (C3, 125 M points per GPU, LAS format 6) while the N=1 line is
     configs[1] (C2), whose tile spacing and hyperboloid sizes make a point several times dearer.  So that
     N-GPU values can be set against a like-for-like single-GPU figure, the N=1 line also carries one GPU's
     throughput on ONE GPU'S SHARE of the 8-GPU scene: rank 0's x-strip of the 1 B-point cloud, with the whole
     scene's geometry (same root cube, same tile lattice), no halo and no exchange.  Records resident in HBM,
-    CUDA events on the library's stream, 1 warm-up + 2 timed passes."""
+    CUDA events on the library's stream, 1 warm-up + `steps` timed passes.  (`--strip W:R` runs the same thing for
+    rank R's strip of the W-GPU scene and prints it alone: the tool that showed where the 4-GPU run of round 1 went.)"""
     import torch
     from wolkenbase_b200 import synth
-    per_gpu, world = 125_000_000, 8
+    per_gpu = args.points or 125_000_000
     d = synth.describe(3, per_gpu * world)
-    cloud = synth.generate(3, per_gpu * world, seed=3, region=(0, 0, d.grid_nx // world, d.grid_ny))
+    c0, c1 = d.grid_nx * rank // world, d.grid_nx * (rank + 1) // world
+    cloud = synth.generate(3, per_gpu * world, seed=3, region=(c0, 0, c1 - c0, d.grid_ny), gps_base=d.grid_ny * c0)
     n = cloud.n
     lo = (d.offset[0], d.offset[1], cloud.min_corner[2])
     hi = (d.offset[0] + d.scale * d.extent_ticks, d.offset[1] + d.scale * d.extent_ticks, cloud.max_corner[2])
@@ -280,25 +282,33 @@ def scaling_base(ctx, args):
     def step():
         ctx.clear()
         ctx.add_extent(cloud.min_corner, cloud.max_corner)
-        ctx.add_extent(lo, hi)                     # the other seven strips' corners: the scene's full xy extent
+        ctx.add_extent(lo, hi)                     # the other strips' corners: the scene's full xy extent
         ctx.add_las_device(dev.data_ptr(), n, cloud.fmt, cloud.rec_len, cloud.scale, cloud.offset)
         ctx.run()
 
     step()
-    steps = 2
+    phase = {}
     ctx.mark(4)
     for _ in range(steps):
         step()
+        for k, v in ctx.stats().items():
+            if k.startswith("ms_"):
+                phase[k[3:]] = round(phase.get(k[3:], 0.0) + v / steps, 3)
     ctx.mark(5)
     ms = ctx.mark_elapsed(4, 5) / steps
     st = ctx.stats()
     g = ctx.geometry()
+    hist = ctx.count_classes()
     del dev
-    return {"workload": "C3 multi-tile aerial scene, rank 0's strip of the 8-GPU run: %d points, LAS format %d "
-                        "(%d B records), the 1 B-point scene's geometry (tile spacing %.3f m), no halo"
-                        % (n, cloud.fmt, cloud.rec_len, g.spacing),
+    return {"workload": "C3 multi-tile aerial scene, rank %d's strip of the %d-GPU run: %d points, LAS format %d "
+                        "(%d B records), the whole scene's geometry (tile spacing %.3f m), no halo"
+                        % (rank, world, n, cloud.fmt, cloud.rec_len, g.spacing),
             "value": n / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps, "warmup": 1,
-            "classify_kernel_ms": st["ms_classify_kernel"]}
+            "classify_kernel_ms": st["ms_classify_kernel"], "phases_ms": phase,
+            "max_hyperboloid_size": ctx.max_hyperboloid_size(),
+            "labels": {"ground": int(hist[2]), "nonground": int(hist[1])},
+            "classify_work": {"nodes": st["cl_nodes"] * 32.0 / n, "chunks": st["cl_chunks"] * 32.0 / n,
+                              "pairs": st["cl_pairs"] * 32.0 / n}}
 
 
 def cpu_baseline(scene, sample_points, bounded=True, threads=None):
@@ -379,7 +389,16 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-scaling-base", action="store_true",
                     help="skip the single-GPU run of the multi-GPU workload (weak_scaling_base)")
+    ap.add_argument("--strip", default="", help="W:R — only time rank R's strip of the W-GPU C3 scene on one GPU")
     args = ap.parse_args()
+    if args.strip:
+        from wolkenbase_b200 import api
+        w, r = (int(v) for v in args.strip.split(":"))
+        ctx = api.Context(0)
+        ctx.set_params(**PARAMS)
+        print(json.dumps(scaling_base(ctx, args, w, r, steps=max(1, args.steps))))
+        ctx.close()
+        return
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -305,7 +305,21 @@ extern "C" int simt_scan_classify(const double *sx,const double *sy,const double
   for (uint64_t i=0;i<n;i++) perm[i]=(uint32_t)i;
   unsigned long long counters[24]={0};
   for (int pass=1;pass<=2;pass++)
-    for (uint32_t b=0;b<nChunks;b++)
+  {
+    uint32_t nBlocks=nChunks;
+#if WB_CL_COMPACT2
+    // pass 2 walks the pending queries gathered into full warps, as wb_classify does (flag, scan, scatter)
+    std::vector<uint32_t> pendingList;
+    if (pass==2)
+    {
+      for (uint64_t i=0;i<n;i++)
+        if (wedge[i]!=0xffffffffu)
+          pendingList.push_back((uint32_t)i);
+      nBlocks=(uint32_t)((pendingList.size()+31)/32);
+    }
+    const uint32_t nPend=(uint32_t)pendingList.size();
+#endif
+    for (uint32_t b=0;b<nBlocks;b++)
       simt::run_warp([&]
       {
         if (pass==1)
@@ -319,10 +333,11 @@ extern "C" int simt_scan_classify(const double *sx,const double *sy,const double
           wb_classify_kernel<2>(sx,sy,sz,n,nChunks,bounds.data(),levelOff.data(),levelCnt.data(),nLevels,winner.data(),tHyp.data(),
                                 maxSlope,thickness,clsIn.data(),perm.data(),0u,0xffffffffu,labelSorted,counters,wedge.data(),pending.data()
 #if WB_CL_COMPACT2
-                                ,nullptr,0u
+                                ,pendingList.data(),nPend
 #endif
                                 );
-      },0,b,WB_CL_WARPS*32,nChunks);
+      },0,b,WB_CL_WARPS*32,nBlocks);
+  }
   return 0;
 }
 

@@ -1,8 +1,8 @@
 """The classify kernels' own source (wolkenbase_b200/csrc/wb_kernels.cuh), compiled as host C++ and run warp by
 warp under the SIMT emulator of tests/simt, against the oracle's labels.  This checks the traversal logic —
 pruning, sector occupancy, the exact second walk, the single-precision shortcuts — on the CPU; the GPU tests remain
-the parity proof of the nvcc build.  Variants behind WB_CL_* macros (round-2 candidates that are off in the
-shipped library) are held to the same standard here before they ever reach a GPU."""
+the parity proof of the nvcc build.  Variants behind WB_CL_* macros (the round-1 kernel, each round-2 change
+alone, the shipped combination) are all held to the same standard here."""
 import os
 import sys
 
@@ -17,11 +17,12 @@ import emul  # noqa: E402
 
 CASES = [(2, 5000, 3, {}), (1, 5000, 1, {}), (5, 5000, 5, {}), (4, 5000, 4, {}), (3, 4000, 7, {}),
          (2, 4000, 9, {"max_slope": 0.5, "thickness": 0.05, "tile_size": 2.0})]
-VARIANTS = [("", "libwb_simt.so"),
-            ("-DWB_CL_FSECTOR=0 -DWB_CL_FREACH=0 -DWB_CL_FSPAN=0", "libwb_simt_double.so"),
-            ("-DWB_CL_REFILTER=1", "libwb_simt_refilter.so"),
-            ("-DWB_CL_XWANTS=1", "libwb_simt_xwants.so"),
-            ("-DWB_CL_XWANTS=1 -DWB_CL_REFILTER=1", "libwb_simt_xr.so")]
+OFF = "-DWB_CL_XWANTS=0 -DWB_CL_REFILTER=0 -DWB_CL_COMPACT2=0"     # the round-1 kernel (all three are on since round 2)
+VARIANTS = [(OFF, "libwb_simt_r1.so"),
+            (OFF + " -DWB_CL_FSECTOR=0 -DWB_CL_FREACH=0 -DWB_CL_FSPAN=0", "libwb_simt_double.so"),
+            ("-DWB_CL_XWANTS=0 -DWB_CL_REFILTER=1 -DWB_CL_COMPACT2=0", "libwb_simt_refilter.so"),
+            ("-DWB_CL_XWANTS=1 -DWB_CL_REFILTER=0 -DWB_CL_COMPACT2=0", "libwb_simt_xwants.so"),
+            ("", "libwb_simt.so")]                                   # the shipped configuration
 
 
 @pytest.fixture(scope="module")

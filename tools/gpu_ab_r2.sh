@@ -4,7 +4,7 @@
 # the emulator-validated classify candidates on the bench workload, then the whole GPU suite on the combination.
 mkdir -p gpurun_out
 for v in base xwants refilter compact2 xr all; do
-  WB_LIB=$PWD/build/variants/lib_$v.so timeout 60 python bench.py --steps 2 --warmup 1 --no-cpu --no-scaling-base \
+  WB_LIB=$PWD/build/variants/lib_$v.so timeout 240 python bench.py --steps 2 --warmup 1 --no-cpu --no-scaling-base \
       > gpurun_out/r2_ab_$v.json 2> gpurun_out/r2_ab_$v.err
   python - "$v" <<'PY'
 import json, sys

@@ -895,26 +895,26 @@ wb_postscan_kernel(const int *__restrict__ tNPoints,const uint8_t *__restrict__ 
 #ifndef WB_CL_FSPAN
 #define WB_CL_FSPAN 1
 #endif
-// Round-2 candidate, written without a GPU at hand and therefore off until it has been through the parity suite
-// and an A/B on the bench workload ("next"): bulk re-filter of a chunk entry's waiting children.
+// Bulk re-filter of a chunk entry's waiting children after an occupancy change (B200, 100 M-point tile: 843 -> 832 ms
+// alone; profiles/r2_classify_ab.md).
 #ifndef WB_CL_REFILTER
-#define WB_CL_REFILTER 0
+#define WB_CL_REFILTER 1
 #endif
-// Round-2 candidate (same status): the per-query reach test at expansion for the children of EVERY level, not only
-// for chunks, and with each query's still-open sectors taken into account — so that a child no single query can
-// use is never pushed (the emulator counts 300 internal-node pops per warp on the bench scene, 235 of them rejected).
+// The per-query reach test at expansion for the children of EVERY level, not only for chunks, and with each query's
+// still-open sectors taken into account — so that a child no single query can use is never pushed (node pops per
+// warp 555 -> 273 on the bench scene, 843 -> 804 ms alone).
 #ifndef WB_CL_XWANTS
-#define WB_CL_XWANTS 0
+#define WB_CL_XWANTS 1
 #endif
 #if WB_CL_XWANTS && !WB_CL_FREACH
 #error "WB_CL_XWANTS builds on the single-precision reach test (WB_CL_FREACH)"
 #endif
 
-// Round-2 candidate (same status): pass 2 over COMPACTED pending queries.  On the bench scene 9.6 % of the queries
-// need the exact walk but they sit in 65 % of the warps, a handful each; gathered (in canonical order, so still
-// neighbours) into full warps the same walks are shared by 32 queries instead of ~5.
+// Pass 2 over COMPACTED pending queries.  On the bench scene 9.6 % of the queries need the exact walk but they sit
+// in 65 % of the warps, a handful each; gathered (in canonical order, so still neighbours) into full warps the same
+// walks are shared by 32 queries instead of ~5 (843 -> 793 ms alone; all three together 750 ms, same labels).
 #ifndef WB_CL_COMPACT2
-#define WB_CL_COMPACT2 0
+#define WB_CL_COMPACT2 1
 #endif
 
 #ifndef WB_EMU_COUNT
