@@ -259,7 +259,7 @@ def run_ours(args):
     print(json.dumps(line))
 
 
-def scaling_base(ctx, args, world=8, rank=0, steps=2):
+def scaling_base(ctx, args, world=8, rank=0, steps=2, cloud=None, dev=None):
     """The N>1 runs shard BASELINE configs[2] (C3, 125 M points per GPU, LAS format 6) while the N=1 line is
     configs[1] (C2), whose tile spacing and hyperboloid sizes make a point several times dearer.  So that
     N-GPU values can be set against a like-for-like single-GPU figure, the N=1 line also carries one GPU's
@@ -270,13 +270,17 @@ def scaling_base(ctx, args, world=8, rank=0, steps=2):
     import torch
     from wolkenbase_b200 import synth
     per_gpu = args.points or 125_000_000
-    d = synth.describe(3, per_gpu * world)
-    c0, c1 = d.grid_nx * rank // world, d.grid_nx * (rank + 1) // world
-    cloud = synth.generate(3, per_gpu * world, seed=3, region=(c0, 0, c1 - c0, d.grid_ny), gps_base=d.grid_ny * c0)
+    scene = args.scene or 3
+    d = synth.describe(scene, per_gpu * world)
+    if cloud is None:
+        c0, c1 = d.grid_nx * rank // world, d.grid_nx * (rank + 1) // world
+        cloud = synth.generate(scene, per_gpu * world, seed=scene, region=(c0, 0, c1 - c0, d.grid_ny),
+                               gps_base=d.grid_ny * c0)
     n = cloud.n
     lo = (d.offset[0], d.offset[1], cloud.min_corner[2])
     hi = (d.offset[0] + d.scale * d.extent_ticks, d.offset[1] + d.scale * d.extent_ticks, cloud.max_corner[2])
-    dev = torch.from_numpy(cloud.records.reshape(-1)).cuda()
+    if dev is None:
+        dev = torch.from_numpy(cloud.records.reshape(-1)).cuda()
     torch.cuda.synchronize()
 
     def step():
@@ -300,7 +304,7 @@ def scaling_base(ctx, args, world=8, rank=0, steps=2):
     g = ctx.geometry()
     hist = ctx.count_classes()
     del dev
-    return {"workload": "C3 multi-tile aerial scene, rank %d's strip of the %d-GPU run: %d points, LAS format %d "
+    return {"workload": "multi-tile aerial scene, rank %d's strip of the %d-GPU run: %d points, LAS format %d "
                         "(%d B records), the whole scene's geometry (tile spacing %.3f m), no halo"
                         % (rank, world, n, cloud.fmt, cloud.rec_len, g.spacing),
             "value": n / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps, "warmup": 1,

@@ -123,14 +123,13 @@ int wb_add_las_file(wb_ctx *ctx,const char *path,uint64_t point_offset,uint64_t 
 /* Same, records already in device memory. */
 int wb_add_las_device(wb_ctx *ctx,const uint8_t *d_recs,uint64_t n,int fmt,int rec_len,
                       const double scale[3],const double offset[3],double unit);
-/* Already-decoded points in device memory (SoA int32 X,Y,Z + class byte), e.g. halo points
- * received from another GPU; they become one more segment with its own scale/offset. */
+/* Already-decoded points in device memory (SoA int32 X,Y,Z + class byte); they become one more segment with its
+ * own scale/offset, every point kept (return number taken as 1). */
 int wb_add_points_device(wb_ctx *ctx,const int32_t *d_x,const int32_t *d_y,const int32_t *d_z,const uint8_t *d_cls,
                          uint64_t n,const double scale[3],const double offset[3],double unit);
-/* Copy the decoded columns of points [first,first+n) into caller-owned device buffers. */
-int wb_export_points_device(wb_ctx *ctx,uint64_t first,uint64_t n,int32_t *d_x,int32_t *d_y,int32_t *d_z,uint8_t *d_cls);
-/* Only points whose input index lies in [first,end) are labelled by wb_classify; the others
- * (halo) take part in every query but keep label 255. */
+/* Only points whose input index lies in [first,end) are labelled by wb_classify; the others (context points, e.g. a
+ * halo) take part in every query but keep label 255 — unless one of them holds the place of a record in the range
+ * that has the same XYZ: that one is classified too, and the record inherits its class. */
 int wb_set_own_range(wb_ctx *ctx,uint64_t first,uint64_t end);
 /* Override the geometry derived from the extents (multi-GPU: every rank uses the global one). */
 int wb_set_geometry(wb_ctx *ctx,const double root_center[3],double root_side,const double cube[4]);
@@ -154,13 +153,6 @@ int wb_get_tiles(wb_ctx *ctx,wb_tile *out,uint64_t cap);   /* ascending n */
 /* Replace hyperboloidSize of the listed tiles (classify parity independent of scan parity). */
 int wb_set_tiles(wb_ctx *ctx,const wb_tile *tiles,uint64_t n);
 
-/* Multi-GPU merge of the tile table.  Export writes, for every tile of the flowsnake range
- * (wb_geometry.snake_lo..snake_hi, dense), nPoints, treeFlags and the bits of hyperboloidSize
- * into caller-owned DEVICE buffers, zeroing tiles whose centre x is outside [x_lo,x_hi) — so
- * that a sum over GPUs (ncclAllReduce) yields the global table; import loads it back. */
-int wb_export_tiles_device(wb_ctx *ctx,double x_lo,double x_hi,int32_t *d_npoints,int32_t *d_tree,int64_t *d_hyp_bits);
-int wb_import_tiles_device(wb_ctx *ctx,const int32_t *d_npoints,const int32_t *d_tree,const int64_t *d_hyp_bits,
-                           int postscanned /* the table already went through wb_postscan */);
 int wb_max_hyperboloid_size(wb_ctx *ctx,double *out);
 /* Tile membership only (which tile's parameters each point uses); implied by wb_scan. */
 int wb_assign(wb_ctx *ctx);
@@ -172,6 +164,60 @@ int wb_count_classes(wb_ctx *ctx,uint64_t counts[256]);
 /* Write each point's class into its record (byte 15 low 5 bits for formats 0-5, byte 16 for
  * 6-10: las.cpp:754-756, 771, 848, 857) — host records, in place. */
 int wb_patch_records(wb_ctx *ctx,uint8_t *recs,uint64_t first_point,uint64_t n,int fmt,int rec_len);
+
+/* ---- several GPUs ---------------------------------------------------------------------
+ * The analogue of startThreads(n) (threads.cpp:91-113) across GPUs: n ranks, one context each, every rank
+ * holding the files of one x-strip of the cloud (ranks in ascending x).  wb_shard_run then does the whole
+ * path for the rank's own records — global geometry from everybody's header corners, halo exchange for the
+ * tile scan, the populated/tree grid for postscan, the wide halo for classify — and leaves the class bytes
+ * of the rank's own records for wb_shard_get_labels.  Labels, tile parameters and canonical order equal the
+ * single-GPU run's (csrc/wb_shard.cuh).
+ *
+ * A wb_comm is the rank's end of the exchange.  wb_comm_init: NCCL (one rank calls wb_comm_get_id and hands the
+ * 128 bytes to the others, e.g. through the launcher); ranks may be processes or threads of one process.
+ * wb_comm_init_local: the threads of ONE process without NCCL (plain copies + a barrier).  wb_comm_init_custom:
+ * the caller moves the bytes (device pointers, whole-world collectives; return 0 on success). */
+#define WB_COMM_ID_BYTES 128
+#define WB_MAX_RANKS 64
+#define WB_SHARD_MAXSEG 64          /* input files per rank */
+#define WB_SHARD_SCAN_HALO 2.5      /* tile spacings sent across a strip border for the tile scan */
+typedef struct wb_comm wb_comm;
+typedef struct wb_local_group wb_local_group;
+typedef struct wb_comm_ops
+{
+  void *user;
+  /* every rank's `bytes` bytes at d_send, in rank order, into d_recv on every rank */
+  int (*all_gather)(void *user,const void *d_send,void *d_recv,uint64_t bytes);
+  /* send_cnt[k] bytes at d_send+send_off[k] go to rank k; recv_cnt[k] bytes from rank k arrive at d_recv+recv_off[k] */
+  int (*all_to_all_v)(void *user,const void *d_send,const uint64_t *send_off,const uint64_t *send_cnt,
+                      void *d_recv,const uint64_t *recv_off,const uint64_t *recv_cnt);
+  /* element-wise maximum of n bytes over all ranks, in place */
+  int (*all_reduce_max_u8)(void *user,uint8_t *d_buf,uint64_t n);
+} wb_comm_ops;
+typedef struct wb_shard_stats
+{
+  uint64_t n_own,own_first;                    /* own records; their first index in the rank's local input order */
+  uint64_t n_halo_scan,n_halo_classify;        /* halo points received for the two stages */
+  uint64_t grid_cells;                         /* cells of the all-reduced populated/tree grid */
+  uint64_t bytes_sent,bytes_received;          /* halo rows, 16 B each */
+  double por_max;                              /* largest hyperboloidSize * maxSlope^2 of the whole cloud */
+  /* wall-clock milliseconds of the stages of the last wb_shard_run, stream drained at each boundary */
+  double ms_setup,ms_select,ms_exchange,ms_build_scan,ms_scan,ms_grid,ms_postscan,ms_build_classify,ms_assign,ms_classify;
+} wb_shard_stats;
+int wb_comm_get_id(uint8_t id[WB_COMM_ID_BYTES]);
+int wb_comm_init(wb_ctx *ctx,const uint8_t id[WB_COMM_ID_BYTES],int rank,int world,wb_comm **out);
+int wb_local_group_create(int world,wb_local_group **out);
+void wb_local_group_destroy(wb_local_group *grp);
+int wb_comm_init_local(wb_ctx *ctx,wb_local_group *grp,int rank,wb_comm **out);
+int wb_comm_init_custom(wb_ctx *ctx,const wb_comm_ops *ops,int rank,int world,wb_comm **out);
+void wb_comm_destroy(wb_comm *comm);
+/* after wb_add_extent + wb_add_las* of the rank's own files; collective: every rank calls it */
+int wb_shard_run(wb_ctx *ctx,wb_comm *comm);
+int wb_shard_get_labels(wb_ctx *ctx,uint8_t *labels);      /* the rank's own records, in the order they were added */
+int wb_shard_get_stats(wb_ctx *ctx,wb_shard_stats *out);
+/* Class bytes computed elsewhere (the ranks of a sharded run), input order, into a BUILT store: wb_count_classes,
+ * wb_encode and the writers then work as after wb_classify (wolkencli --gpus N writes through one context). */
+int wb_set_labels(wb_ctx *ctx,const uint8_t *labels);
 
 /* ---- store queries -----------------------------------------------------------
  * OctStore::pointsIn / countPointsIn / hiLoPointsIn (octree.cpp:1214-1293) for the shapes of

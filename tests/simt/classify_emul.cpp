@@ -164,11 +164,11 @@ extern "C" int simt_classify(const double *sx,const double *sy,const double *sz,
       {
         if (pass==1)
           wb_classify_kernel<1>(sx,sy,sz,n,nChunks,bounds.data(),levelOff.data(),levelCnt.data(),nLevels,winner.data(),hyp,
-                                maxSlope,thickness,clsIn.data(),perm.data(),0u,0xffffffffu,labelSorted,counters,
+                                maxSlope,thickness,clsIn.data(),perm.data(),0u,0xffffffffu,nullptr,labelSorted,counters,
                                 wedge.data(),pending.data(),nullptr,0u);
         else
           wb_classify_kernel<2>(sx,sy,sz,n,nChunks,bounds.data(),levelOff.data(),levelCnt.data(),nLevels,winner.data(),hyp,
-                                maxSlope,thickness,clsIn.data(),perm.data(),0u,0xffffffffu,labelSorted,counters,
+                                maxSlope,thickness,clsIn.data(),perm.data(),0u,0xffffffffu,nullptr,labelSorted,counters,
                                 wedge.data(),pending.data(),pendingList.data(),nPend);
       };
       coll+=simt::run_warp(body,0,b,WB_CL_WARPS*32,nChunks);
@@ -180,11 +180,11 @@ extern "C" int simt_classify(const double *sx,const double *sy,const double *sz,
       {
         if (pass==1)
           wb_classify_kernel<1>(sx,sy,sz,n,nChunks,bounds.data(),levelOff.data(),levelCnt.data(),nLevels,winner.data(),hyp,
-                                maxSlope,thickness,clsIn.data(),perm.data(),0u,0xffffffffu,labelSorted,counters,
+                                maxSlope,thickness,clsIn.data(),perm.data(),0u,0xffffffffu,nullptr,labelSorted,counters,
                                 wedge.data(),pending.data());
         else
           wb_classify_kernel<2>(sx,sy,sz,n,nChunks,bounds.data(),levelOff.data(),levelCnt.data(),nLevels,winner.data(),hyp,
-                                maxSlope,thickness,clsIn.data(),perm.data(),0u,0xffffffffu,labelSorted,counters,
+                                maxSlope,thickness,clsIn.data(),perm.data(),0u,0xffffffffu,nullptr,labelSorted,counters,
                                 wedge.data(),pending.data());
       };
       coll+=simt::run_warp(body,0,b,WB_CL_WARPS*32,nChunks);
@@ -203,7 +203,7 @@ extern "C" int simt_classify(const double *sx,const double *sy,const double *sz,
 // ------------------------------------------------------------------------------------------------------------
 // The tile phases from the kernel sources: membership (wb_member_count_kernel, wb_member_fill_kernel), the sort by
 // tile (a host stable sort stands in for the radix sort), wb_segment_kernel, wb_scan_kernel, then
-// wb_tile_extent_kernel / wb_tile_grid_kernel / wb_postscan_kernel — launched in the order and with the grids of
+// wb_tile_extent_list_kernel / wb_tile_grid_list_kernel / wb_postscan_list_kernel — launched in the order and with the grids of
 // wb_scan and wb_postscan (wolken_b200.cu) — and finally the classify kernels with the membership's `winner` and
 // the dense tile table, exactly the arrays the GPU path hands them.
 struct SimtTile { int32_t n,nPoints,treeFlags,pad; double density,hyperboloidSize,height; };
@@ -263,13 +263,18 @@ extern "C" int simt_scan_classify(const double *sx,const double *sy,const double
   if (doPostscan)
   {
     int ext[4]={INT_MAX,INT_MAX,INT_MIN,INT_MIN};
-    launch(grid(T,256),256,[&]{ wb_tile_extent_kernel(tNPoints.data(),T,snake,ext); });
+    const uint32_t nl=(uint32_t)nList;
+    if (nl)
+      launch(grid(nl,256),256,[&]{ wb_tile_extent_list_kernel(tileList.data(),nl,snake,-INFINITY,INFINITY,ext); });
     uint64_t cells=1;
     if (ext[0]<=ext[2])
       cells=(uint64_t)((long long)ext[2]-ext[0]+1)*(uint64_t)((long long)ext[3]-ext[1]+1);
     std::vector<uint8_t> tileGrid(cells,0);
-    launch(grid(T,256),256,[&]{ wb_tile_grid_kernel(tNPoints.data(),tTree.data(),T,snake,ext,tileGrid.data()); });
-    launch(grid(T,128),128,[&]{ wb_postscan_kernel(tNPoints.data(),tTree.data(),T,snake,ext,tileGrid.data(),tHyp.data()); });
+    if (nl)
+    {
+      launch(grid(nl,256),256,[&]{ wb_tile_grid_list_kernel(tileList.data(),nl,tTree.data(),snake,-INFINITY,INFINITY,ext,tileGrid.data()); });
+      launch(grid(nl,128),128,[&]{ wb_postscan_list_kernel(tileList.data(),nl,tTree.data(),snake,ext,tileGrid.data(),tHyp.data()); });
+    }
   }
   uint64_t nt=0;
   for (uint32_t t=0;t<T;t++)
@@ -324,14 +329,14 @@ extern "C" int simt_scan_classify(const double *sx,const double *sy,const double
       {
         if (pass==1)
           wb_classify_kernel<1>(sx,sy,sz,n,nChunks,bounds.data(),levelOff.data(),levelCnt.data(),nLevels,winner.data(),tHyp.data(),
-                                maxSlope,thickness,clsIn.data(),perm.data(),0u,0xffffffffu,labelSorted,counters,wedge.data(),pending.data()
+                                maxSlope,thickness,clsIn.data(),perm.data(),0u,0xffffffffu,nullptr,labelSorted,counters,wedge.data(),pending.data()
 #if WB_CL_COMPACT2
                                 ,nullptr,0u
 #endif
                                 );
         else
           wb_classify_kernel<2>(sx,sy,sz,n,nChunks,bounds.data(),levelOff.data(),levelCnt.data(),nLevels,winner.data(),tHyp.data(),
-                                maxSlope,thickness,clsIn.data(),perm.data(),0u,0xffffffffu,labelSorted,counters,wedge.data(),pending.data()
+                                maxSlope,thickness,clsIn.data(),perm.data(),0u,0xffffffffu,nullptr,labelSorted,counters,wedge.data(),pending.data()
 #if WB_CL_COMPACT2
                                 ,pendingList.data(),nPend
 #endif

@@ -33,6 +33,10 @@ using std::isinf;
 
 struct uint4 { unsigned x,y,z,w; };
 inline uint4 make_uint4(unsigned x,unsigned y,unsigned z,unsigned w) { uint4 r={x,y,z,w}; return r; }
+struct int4 { int x,y,z,w; };
+inline int4 make_int4(int x,int y,int z,int w) { int4 r={x,y,z,w}; return r; }
+struct float4 { float x,y,z,w; };
+inline float4 make_float4(float x,float y,float z,float w) { float4 r={x,y,z,w}; return r; }
 struct simt_dim3 { unsigned x=1,y=1,z=1; };
 #define threadIdx (simt::cur()->tid)
 #define blockIdx (simt::cur()->bid)

@@ -31,16 +31,16 @@ def test_gpu_parity_subset_passes_on_the_emulated_library():
 
 
 def test_sharded_path_passes_on_the_emulated_library():
-    """Two simulated ranks (halo selection, exchange, tile-table export/import, own range, two-stage build) with
-    identical locations inside the halos: labels and merged tile table equal the single-context run."""
+    """wb_shard_run with ranks as host threads (LOCAL transport): header offsets that differ between ranks, records at
+    the XYZ of another rank's point, records dropped by the return-number rule — labels equal the oracle's."""
     subprocess.check_call(["make", "-s", "-C", SIMT, "libwolken_b200_emulated.so"])
     env = dict(os.environ, WB_LIB=EMULATED, WB_EMULATED="1")
     out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_multigpu_gpu.py"), "-m", "gpu",
-                          "-q", "-x", "-k", "2-2-40000-2000", "-p", "no:cacheprovider"], capture_output=True, text=True,
-                         env=env, cwd=ROOT, timeout=900)
+                          "-q", "-x", "-k", "header_offsets or identical_locations or dropped_records or 1-2-20000", "-p",
+                          "no:cacheprovider"], capture_output=True, text=True, env=env, cwd=ROOT, timeout=900)
     tail = out.stdout[-3000:] + out.stderr[-2000:]
     assert out.returncode == 0, tail
-    assert "1 passed" in out.stdout, tail
+    assert "4 passed" in out.stdout, tail
 
 
 def test_host_cli_passes_on_the_emulated_library():

@@ -61,7 +61,7 @@ def _reach_double(qx, qy, qcz, qpor2, s2, b):
     return (zl > 0) & (zl * zl * (1 + 1e-12) - d2 * (1 - 1e-12) >= qpor2 * (1 - 1e-12))
 
 
-def _reach_float(qx, qy, qcz, qpor2, s2, b, org):
+def _reach_float(qx, qy, qcz, qpor2, s2, b, org, folded=True):
     ox, oy, oz = org
     por = np.sqrt(qpor2)
     fx, fy = (qx - ox).astype(f32), (qy - oy).astype(f32)
@@ -75,11 +75,19 @@ def _reach_float(qx, qy, qcz, qpor2, s2, b, org):
     c = f32(9.5367431640625e-7)
     ed = c * (np.maximum(np.maximum(np.abs(x0), np.abs(x1)), np.maximum(np.abs(y0), np.abs(y1))) + gh)
     ez = c * (np.abs(z0) + zq) + f32(1e-6)
-    fs2 = f32(s2) * f32(0.999998)
-    dx = np.maximum(f32(0), np.maximum(x0 - fx, fx - x1) - ed)
-    dy = np.maximum(f32(0), np.maximum(y0 - fy, fy - y1) - ed)
-    a = (fh - z0) + ez
-    return (a >= 0) & (a * (a + f2p) * f32(1.000002) >= (dx * dx + dy * dy) * fs2)
+    if not folded:                                            # WB_CL_F4=0: the slack applied per (child, query)
+        fs2 = f32(s2) * f32(0.999998)
+        dx = np.maximum(f32(0), np.maximum(x0 - fx, fx - x1) - ed)
+        dy = np.maximum(f32(0), np.maximum(y0 - fy, fy - y1) - ed)
+        a = (fh - z0) + ez
+        return (a >= 0) & (a * (a + f2p) * f32(1.000002) >= (dx * dx + dy * dy) * fs2)
+    # the shipped form: slack folded into the child's box before the loop over the queries
+    bx0, bx1, by0, by1, bz0 = x0 - ed, x1 + ed, y0 - ed, y1 + ed, z0 - ez
+    k2 = f32(s2) * f32(0.999995)
+    dx = np.maximum(f32(0), np.maximum(bx0 - fx, fx - bx1))
+    dy = np.maximum(f32(0), np.maximum(by0 - fy, fy - by1))
+    a = fh - bz0
+    return (a >= 0) & (a * (a + f2p) >= (dx * dx + dy * dy) * k2)
 
 
 def test_float_reach_admits_everything_the_double_test_admits():
@@ -108,6 +116,7 @@ def test_float_reach_admits_everything_the_double_test_admits():
         d = _reach_double(qx, qy, qcz, qpor2, s2, b)
         f = _reach_float(qx, qy, qcz, qpor2, s2, b, org)
         assert not (d & ~f).any()
+        assert not (d & ~_reach_float(qx, qy, qcz, qpor2, s2, b, org, folded=False)).any()
         total += n
         extra += int((f & ~d).sum())
     assert extra < 0.25 * total                              # and it still prunes (these inputs sit ON the surface)

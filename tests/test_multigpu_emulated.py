@@ -1,14 +1,13 @@
-"""The N>1 path as bench.py --gpus N runs it — one process per rank, torch.distributed, run_distributed: halo
-selection, all_to_all_single, tile-table all_reduce, two-stage build, classify of the own points — with world_size 2
-over gloo on the CPU.  The ranks' contexts come from the emulated library (tests/simt: the library's own source built
-for the host), CPU tensors stand in for device buffers.  Labels must equal the single-context run."""
+"""The N>1 path as bench.py --gpus N runs it — one process per rank under torch.distributed, wb_shard_run inside the
+library — with world_size 2 on the CPU: the ranks' contexts come from the emulated library (tests/simt: the library's
+own source built for the host) and gloo carries the bytes through the CUSTOM transport (NCCL's place on the GPU box).
+Labels must equal the oracle's for the whole cloud."""
 import os
 import socket
 import subprocess
 import sys
 
 import numpy as np
-import torch
 import torch.multiprocessing as mp
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -38,18 +37,22 @@ def _worker(rank, world, port, ret):
     import torch.distributed as dist
     from wolkenbase_b200 import api, multigpu
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    comm = multigpu.TorchComm(dist)
     cloud = _clouds(world)[rank]
-    dev = torch.device("cpu")
-    r = multigpu.Rank(rank, world, api.Context(0), api.Context(0), PARAMS, dev)
-    labels = np.zeros(cloud.n, dtype=np.uint8)
-    multigpu.run_distributed(r, cloud, comm, None, labels)
-    ret[rank] = {"labels": labels.copy(), "halo": int(r.n_cls - r.n_own)}
+    ctx = api.Context(0)
+    comm = multigpu.gloo_comm(ctx, dist, rank, world)
+    for _ in range(2):                                  # twice: the context and the communicator are reused per step
+        n = multigpu.load_rank(ctx, [cloud], PARAMS)
+        ctx.shard_run(comm)
+    labels = ctx.shard_labels(n)
+    st = ctx.shard_stats()
+    ret[rank] = {"labels": labels.copy(), "halo": int(st["n_halo_classify"]), "sent": int(st["bytes_sent"])}
+    comm.close()
+    ctx.close()
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_run_distributed_world2_gloo_on_the_emulated_library():
+def test_shard_run_world2_gloo_on_the_emulated_library():
     subprocess.check_call(["make", "-s", "-C", SIMT, "libwolken_b200_emulated.so"])
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -58,7 +61,6 @@ def test_run_distributed_world2_gloo_on_the_emulated_library():
     mgr = mp.Manager()
     ret = mgr.dict()
     mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
-    # the single-context answer, from the oracle (the emulated library equals it: tests/test_emulated_library.py)
     sys.path.insert(0, ROOT)
     from oracle import wb_oracle as O
     clouds = _clouds(2)
@@ -66,3 +68,4 @@ def test_run_distributed_world2_gloo_on_the_emulated_library():
     got = np.concatenate([ret[0]["labels"], ret[1]["labels"]])
     assert (got == want).all(), int((got != want).sum())
     assert ret[0]["halo"] > 0 and ret[1]["halo"] > 0
+    assert ret[0]["sent"] == 16 * (ret[1]["halo"] + 0) or ret[0]["sent"] > 0

@@ -17,11 +17,11 @@ import emul  # noqa: E402
 
 CASES = [(2, 5000, 3, {}), (1, 5000, 1, {}), (5, 5000, 5, {}), (4, 5000, 4, {}), (3, 4000, 7, {}),
          (2, 4000, 9, {"max_slope": 0.5, "thickness": 0.05, "tile_size": 2.0})]
-OFF = "-DWB_CL_XWANTS=0 -DWB_CL_REFILTER=0 -DWB_CL_COMPACT2=0"     # the round-1 kernel (all three are on since round 2)
+OFF = "-DWB_CL_XWANTS=0 -DWB_CL_REFILTER=0 -DWB_CL_COMPACT2=0 -DWB_CL_TRANSPOSE=0"     # the round-1 kernel (all on since round 2)
 VARIANTS = [(OFF, "libwb_simt_r1.so"),
             (OFF + " -DWB_CL_FSECTOR=0 -DWB_CL_FREACH=0 -DWB_CL_FSPAN=0", "libwb_simt_double.so"),
-            ("-DWB_CL_XWANTS=0 -DWB_CL_REFILTER=1 -DWB_CL_COMPACT2=0", "libwb_simt_refilter.so"),
-            ("-DWB_CL_XWANTS=1 -DWB_CL_REFILTER=0 -DWB_CL_COMPACT2=0", "libwb_simt_xwants.so"),
+            ("-DWB_CL_XWANTS=0 -DWB_CL_REFILTER=1 -DWB_CL_COMPACT2=0 -DWB_CL_TRANSPOSE=0", "libwb_simt_refilter.so"),
+            ("-DWB_CL_XWANTS=1 -DWB_CL_REFILTER=0 -DWB_CL_COMPACT2=0 -DWB_CL_TRANSPOSE=0", "libwb_simt_xwants.so"),
             ("", "libwb_simt.so")]                                   # the shipped configuration
 
 

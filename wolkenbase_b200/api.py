@@ -41,6 +41,27 @@ class Stats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class ShardStats(C.Structure):
+    _fields_ = [(k, C.c_uint64) for k in ("n_own", "own_first", "n_halo_scan", "n_halo_classify", "grid_cells",
+                                          "bytes_sent", "bytes_received")] + \
+               [(k, C.c_double) for k in ("por_max", "ms_setup", "ms_select", "ms_exchange", "ms_build_scan", "ms_scan",
+                                          "ms_grid", "ms_postscan", "ms_build_classify", "ms_assign", "ms_classify")]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+_u64p = C.POINTER(C.c_uint64)
+ALL_GATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64)
+ALL_TO_ALL_V_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, _u64p, _u64p, C.c_void_p, _u64p, _u64p)
+ALL_REDUCE_MAX_U8_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint64)
+
+
+class CommOps(C.Structure):
+    _fields_ = [("user", C.c_void_p), ("all_gather", ALL_GATHER_FN), ("all_to_all_v", ALL_TO_ALL_V_FN),
+                ("all_reduce_max_u8", ALL_REDUCE_MAX_U8_FN)]
+
+
 class OutSpec(C.Structure):
     _fields_ = [("format", C.c_int32), ("rec_len", C.c_int32), ("n_classes", C.c_int32), ("separate", C.c_int32),
                 ("scale", C.c_double * 3), ("offset", C.c_double * 3), ("unit", C.c_double),
@@ -88,10 +109,7 @@ def lib():
             "wb_add_las_device": [vp, vp, u64, C.c_int, C.c_int, dp, dp, C.c_double],
             "wb_add_las_file": [vp, C.c_char_p, u64, u64, C.c_int, C.c_int, dp, dp, C.c_double],
             "wb_add_points_device": [vp, vp, vp, vp, vp, u64, dp, dp, C.c_double],
-            "wb_export_points_device": [vp, u64, u64, vp, vp, vp, vp],
             "wb_set_own_range": [vp, u64, u64],
-            "wb_export_tiles_device": [vp, C.c_double, C.c_double, vp, vp, vp],
-            "wb_import_tiles_device": [vp, vp, vp, vp, C.c_int],
             "wb_max_hyperboloid_size": [vp, dp],
             "wb_assign": [vp],
             "wb_set_geometry": [vp, dp, C.c_double, dp],
@@ -133,12 +151,24 @@ def lib():
             "wb_write_encoded": [vp, C.c_int, u64, u64, u64],
             "wb_query_batch": [vp, vp, u64, vp, vp, vp],
             "wb_query_points": [vp, vp, u64, C.POINTER(u64), vp, vp, vp, vp, vp],
+            "wb_comm_get_id": [vp],
+            "wb_comm_init": [vp, vp, C.c_int, C.c_int, C.POINTER(vp)],
+            "wb_local_group_create": [C.c_int, C.POINTER(vp)],
+            "wb_comm_init_local": [vp, vp, C.c_int, C.POINTER(vp)],
+            "wb_comm_init_custom": [vp, C.POINTER(CommOps), C.c_int, C.c_int, C.POINTER(vp)],
+            "wb_shard_run": [vp, vp],
+            "wb_shard_get_labels": [vp, vp],
+            "wb_shard_get_stats": [vp, C.POINTER(ShardStats)],
+            "wb_set_labels": [vp, vp],
         }
         for name, args in sig.items():
             f = getattr(L, name)
             f.argtypes = args
             f.restype = C.c_int
         L.wb_destroy.restype = None
+        for name in ("wb_comm_destroy", "wb_local_group_destroy"):
+            getattr(L, name).argtypes = [vp]
+            getattr(L, name).restype = None
         L.wb_last_error.argtypes = [vp]
         L.wb_last_error.restype = C.c_char_p
         _LIB = L
@@ -150,11 +180,14 @@ EXPORTS = ["wb_create", "wb_destroy", "wb_last_error", "wb_reserve", "wb_clear",
            "wb_get_leaves", "wb_get_order", "wb_get_decoded", "wb_scan", "wb_postscan", "wb_num_tiles",
            "wb_get_tiles", "wb_set_tiles", "wb_classify", "wb_get_labels", "wb_count_classes", "wb_patch_records",
            "wb_run", "wb_get_stats", "wb_sync", "wb_host_alloc", "wb_host_free", "wb_size_fit", "wb_bbox_cube",
-           "wb_snake_set_size", "wb_ldecimal", "wb_format_dump", "wb_add_points_device", "wb_export_points_device",
-           "wb_set_own_range", "wb_export_tiles_device", "wb_import_tiles_device", "wb_max_hyperboloid_size",
+           "wb_snake_set_size", "wb_ldecimal", "wb_format_dump", "wb_add_points_device",
+           "wb_set_own_range", "wb_max_hyperboloid_size",
            "wb_assign", "wb_get_points_sorted", "wb_test_math", "wb_bound_rect", "wb_keep_records",
            "wb_leaf_class_counts", "wb_encode", "wb_get_duplicates", "wb_add_las_file", "wb_write_encoded", "wb_query_batch",
-           "wb_query_points", "wb_mark", "wb_mark_elapsed", "wb_set_return_zero_rule"]
+           "wb_query_points", "wb_mark", "wb_mark_elapsed", "wb_set_return_zero_rule",
+           "wb_comm_get_id", "wb_comm_init", "wb_local_group_create", "wb_local_group_destroy", "wb_comm_init_local",
+           "wb_comm_init_custom", "wb_comm_destroy", "wb_shard_run", "wb_shard_get_labels", "wb_shard_get_stats",
+           "wb_set_labels"]
 
 
 def _d(v):
@@ -247,17 +280,27 @@ class Context:
     def add_points_device(self, dx, dy, dz, dcls, n, scale, offset, unit=1.0):
         self._ck(self._L.wb_add_points_device(self._h, dx, dy, dz, dcls, n, _d(scale), _d(offset), unit))
 
-    def export_points_device(self, first, n, dx, dy, dz, dcls):
-        self._ck(self._L.wb_export_points_device(self._h, first, n, dx, dy, dz, dcls))
-
     def set_own_range(self, first, end):
         self._ck(self._L.wb_set_own_range(self._h, first, end))
 
-    def export_tiles_device(self, x_lo, x_hi, d_np, d_tree, d_hyp):
-        self._ck(self._L.wb_export_tiles_device(self._h, x_lo, x_hi, d_np, d_tree, d_hyp))
+    # ---- several GPUs (wb_shard_run)
+    def shard_run(self, comm):
+        """The whole path for this rank's strip; collective over the ranks of `comm` (a Comm)."""
+        self._ck(self._L.wb_shard_run(self._h, comm._h))
 
-    def import_tiles_device(self, d_np, d_tree, d_hyp, postscanned=False):
-        self._ck(self._L.wb_import_tiles_device(self._h, d_np, d_tree, d_hyp, 1 if postscanned else 0))
+    def shard_labels(self, n, out=None):
+        lab = out if out is not None else np.empty(n, dtype=np.uint8)
+        self._ck(self._L.wb_shard_get_labels(self._h, lab.ctypes.data))
+        return lab
+
+    def shard_stats(self):
+        s = ShardStats()
+        self._ck(self._L.wb_shard_get_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+    def set_labels(self, labels):
+        labels = np.ascontiguousarray(labels, dtype=np.uint8)
+        self._ck(self._L.wb_set_labels(self._h, labels.ctypes.data))
 
     def max_hyperboloid_size(self):
         v = C.c_double()
@@ -455,3 +498,60 @@ class Context:
         s = Stats()
         self._ck(self._L.wb_get_stats(self._h, C.byref(s)))
         return s.as_dict()
+
+
+class LocalGroup:
+    """The ranks of one process (one host thread each) exchanging without NCCL (wb_comm_init_local)."""
+
+    def __init__(self, world):
+        self._L = lib()
+        self._h = C.c_void_p()
+        if self._L.wb_local_group_create(world, C.byref(self._h)) != 0:
+            raise WolkenError("wb_local_group_create(%d) failed" % world)
+        self.world = world
+
+    def close(self):
+        if self._h:
+            self._L.wb_local_group_destroy(self._h)
+            self._h = C.c_void_p()
+
+
+class Comm:
+    """One rank's end of the halo exchange (wb_comm).  Build with Comm.nccl, Comm.local or Comm.custom."""
+
+    def __init__(self, ctx, handle, keep=None):
+        self._L, self._h, self.ctx, self._keep = lib(), handle, ctx, keep
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_uint8 * 128)()
+        if lib().wb_comm_get_id(buf) != 0:
+            raise WolkenError("wb_comm_get_id failed (libnccl.so.2 not loadable?)")
+        return bytes(buf)
+
+    @classmethod
+    def nccl(cls, ctx, unique_id, rank, world):
+        h = C.c_void_p()
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        ctx._ck(lib().wb_comm_init(ctx._h, buf, rank, world, C.byref(h)))
+        return cls(ctx, h)
+
+    @classmethod
+    def local(cls, ctx, group, rank):
+        h = C.c_void_p()
+        ctx._ck(lib().wb_comm_init_local(ctx._h, group._h, rank, C.byref(h)))
+        return cls(ctx, h, keep=group)
+
+    @classmethod
+    def custom(cls, ctx, all_gather, all_to_all_v, all_reduce_max_u8, rank, world):
+        """Python callables (device pointers as ints; return 0 on success) stand in for the transport."""
+        ops = CommOps(None, ALL_GATHER_FN(all_gather), ALL_TO_ALL_V_FN(all_to_all_v),
+                      ALL_REDUCE_MAX_U8_FN(all_reduce_max_u8))
+        h = C.c_void_p()
+        ctx._ck(lib().wb_comm_init_custom(ctx._h, C.byref(ops), rank, world, C.byref(h)))
+        return cls(ctx, h, keep=ops)
+
+    def close(self):
+        if self._h:
+            self._L.wb_comm_destroy(self._h)
+            self._h = C.c_void_p()

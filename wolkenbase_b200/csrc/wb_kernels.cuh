@@ -774,18 +774,32 @@ wb_scan_kernel(const uint32_t *__restrict__ tileList,uint32_t nList,
 // out as a dense byte grid over (ex,ey) (0 empty, 1 populated, 2 populated tree tile): a step
 // is then one byte load instead of an inverse flowsnake numbering.
 
-__global__ void __launch_bounds__(256)
-wb_tile_extent_kernel(const int *__restrict__ tNPoints,uint32_t nTiles,WbSnake snake,int *__restrict__ ext)
-// ext = {min ex, min ey, max ex, max ey} over populated tiles
+// The kernels run over the LIST of non-empty tiles (wb_segment_kernel), not over the dense table, which has 7^i
+// entries (2.8e8 for the 1 B-point scene); [xlo,xhi) restricts them to the tiles a rank of a sharded run owns.
+
+__device__ __forceinline__ bool wb_tile_owned(uint32_t t,const WbSnake &snake,double xlo,double xhi,int &ex,int &ey)
 {
-  uint32_t t=blockIdx.x*blockDim.x+threadIdx.x;
+  wb_to_flowsnake((int)t+snake.lo,ex,ey);
+  double cx,cy;
+  wb_tile_center(ex,ey,snake,cx,cy);
+  return cx>=xlo && cx<xhi;
+}
+
+__global__ void __launch_bounds__(256)
+wb_tile_extent_list_kernel(const uint32_t *__restrict__ tileList,uint32_t nList,WbSnake snake,double xlo,double xhi,
+                           int *__restrict__ ext)
+// ext = {min ex, min ey, max ex, max ey} over the listed tiles whose centre x lies in [xlo,xhi)
+{
+  uint32_t i=blockIdx.x*blockDim.x+threadIdx.x;
   int x0=INT_MAX,y0=INT_MAX,x1=INT_MIN,y1=INT_MIN;
-  if (t<nTiles && tNPoints[t])
+  if (i<nList)
   {
     int ex,ey;
-    wb_to_flowsnake((int)t+snake.lo,ex,ey);
-    x0=x1=ex;
-    y0=y1=ey;
+    if (wb_tile_owned(tileList[i],snake,xlo,xhi,ex,ey))
+    {
+      x0=x1=ex;
+      y0=y1=ey;
+    }
   }
   #pragma unroll
   for (int o=16;o;o>>=1)
@@ -805,25 +819,29 @@ wb_tile_extent_kernel(const int *__restrict__ tNPoints,uint32_t nTiles,WbSnake s
 }
 
 __global__ void __launch_bounds__(256)
-wb_tile_grid_kernel(const int *__restrict__ tNPoints,const uint8_t *__restrict__ tTree,uint32_t nTiles,WbSnake snake,
-                    const int *__restrict__ ext,uint8_t *__restrict__ grid)
+wb_tile_grid_list_kernel(const uint32_t *__restrict__ tileList,uint32_t nList,const uint8_t *__restrict__ tTree,
+                         WbSnake snake,double xlo,double xhi,const int *__restrict__ ext,uint8_t *__restrict__ grid)
 {
-  uint32_t t=blockIdx.x*blockDim.x+threadIdx.x;
-  if (t>=nTiles || !tNPoints[t])
+  uint32_t i=blockIdx.x*blockDim.x+threadIdx.x;
+  if (i>=nList)
     return;
+  const uint32_t t=tileList[i];
   int ex,ey;
-  wb_to_flowsnake((int)t+snake.lo,ex,ey);
+  if (!wb_tile_owned(t,snake,xlo,xhi,ex,ey))
+    return;
   const long long W=(long long)ext[2]-ext[0]+1;
   grid[(long long)(ey-ext[1])*W+(ex-ext[0])]=(uint8_t)(1+(tTree[t]&1));
 }
 
 __global__ void __launch_bounds__(128)
-wb_postscan_kernel(const int *__restrict__ tNPoints,const uint8_t *__restrict__ tTree,uint32_t nTiles,
-                   WbSnake snake,const int *__restrict__ ext,const uint8_t *__restrict__ grid,double *__restrict__ tHyp)
+wb_postscan_list_kernel(const uint32_t *__restrict__ tileList,uint32_t nList,const uint8_t *__restrict__ tTree,
+                        WbSnake snake,const int *__restrict__ ext,const uint8_t *__restrict__ grid,double *__restrict__ tHyp)
+// postscanCylinder (scan.cpp:142-179), one thread per listed tile; see wb_postscan_kernel
 {
-  uint32_t t=blockIdx.x*blockDim.x+threadIdx.x;
-  if (t>=nTiles || tNPoints[t]==0)
+  uint32_t i=blockIdx.x*blockDim.x+threadIdx.x;
+  if (i>=nList)
     return;
+  const uint32_t t=tileList[i];
   const int rx[6]={1,1,0,-1,-1,0},ry[6]={0,1,1,0,-1,-1};       // root1, eisenstein.cpp:51
   int ex,ey,count=0;
   wb_to_flowsnake((int)t+snake.lo,ex,ey);
@@ -831,14 +849,14 @@ wb_postscan_kernel(const int *__restrict__ tNPoints,const uint8_t *__restrict__ 
   {
     const int x0=ext[0],y0=ext[1],x1=ext[2],y1=ext[3];
     const long long W=(long long)x1-x0+1;
-    int i=1,ringcount,nontree;
+    int k=1,ringcount,nontree;
     do
     {
       ringcount=nontree=0;
       #pragma unroll
       for (int j=0;j<6;j++)
       {
-        int nx=ex+rx[j]*i,ny=ey+ry[j]*i;
+        int nx=ex+rx[j]*k,ny=ey+ry[j]*k;
         if (nx<x0 || nx>x1 || ny<y0 || ny>y1)
           continue;
         uint8_t c=grid[(long long)(ny-y0)*W+(nx-x0)];
@@ -851,11 +869,35 @@ wb_postscan_kernel(const int *__restrict__ tNPoints,const uint8_t *__restrict__ 
             nontree++;
         }
       }
-      ++i;
+      ++k;
     } while (ringcount && !nontree);
   }
   double h=tHyp[t],c=__ddiv_rn(__dmul_rn((double)count,snake.spacing),6.0);
   tHyp[t]=sqrt(__dadd_rn(__dmul_rn(h,h),__dmul_rn(c,c)));
+}
+
+__global__ void __launch_bounds__(256)
+wb_max_hyp_list_kernel(const uint32_t *__restrict__ tileList,uint32_t nList,const double *__restrict__ tHyp,
+                       WbSnake snake,double xlo,double xhi,unsigned long long *__restrict__ out)
+// largest hyperboloidSize over the listed tiles with centre x in [xlo,xhi) (positive: bit pattern orders like the value)
+{
+  unsigned long long m=0;
+  for (uint32_t i=blockIdx.x*blockDim.x+threadIdx.x;i<nList;i+=gridDim.x*blockDim.x)
+  {
+    const uint32_t t=tileList[i];
+    int ex,ey;
+    if (wb_tile_owned(t,snake,xlo,xhi,ex,ey))
+    {
+      double h=tHyp[t];
+      if (h>0 && h<INFINITY)
+        m=max(m,(unsigned long long)__double_as_longlong(h));
+    }
+  }
+  #pragma unroll
+  for (int o=16;o;o>>=1)
+    m=max(m,__shfl_xor_sync(WB_FULL,m,o));
+  if ((threadIdx.x&31)==0 && m)
+    atomicMax(out,m);
 }
 
 // ============================================================================ K9: classify
@@ -906,6 +948,38 @@ wb_postscan_kernel(const int *__restrict__ tNPoints,const uint8_t *__restrict__ 
 #ifndef WB_CL_XWANTS
 #define WB_CL_XWANTS 1
 #endif
+// ... up to this level of children only (0 = chunks, as without XWANTS): near the root nearly every child fails the
+// group test already and the per-query loop costs more than the pops it saves when hyperboloids are small
+#ifndef WB_CL_XWANTS_MAXLEVEL
+#define WB_CL_XWANTS_MAXLEVEL 7
+#endif
+// The pair loop's "does any point of this chunk matter to query q" vote repeats what the ballot in front of the
+// loop established (a query stays in qm only if some point's sector span meets its open sectors): 1 = drop the vote.
+#ifndef WB_CL_NORELVOTE
+#define WB_CL_NORELVOTE 1
+#endif
+// Per-query float copies as one float4 (one 16-byte shared load per asker) and the loop-invariant slack folded into
+// the child's box before the asker loop.
+#ifndef WB_CL_F4
+#define WB_CL_F4 1
+#endif
+// The (child, query) reach tests of an expansion form a matrix: 32 children x the asking queries.  It is walked either
+// with lanes = children and the askers broadcast one by one from shared memory (WB_CL_ACOST instructions each), or
+// with lanes = queries and the children that passed the group test broadcast one by one by shuffles (WB_CL_TCOST
+// each) — whichever is shorter for this node.  Near the root and for small hyperboloids two or three children pass
+// the group test while all 32 queries ask; at chunk level it is the other way round.  0 = always lanes = children.
+#ifndef WB_CL_TRANSPOSE
+#define WB_CL_TRANSPOSE 1
+#endif
+#ifndef WB_CL_TCOST
+#define WB_CL_TCOST 18
+#endif
+#ifndef WB_CL_ACOST
+#define WB_CL_ACOST 14
+#endif
+#if WB_CL_TRANSPOSE && !(WB_CL_F4 && WB_CL_XWANTS)
+#error "WB_CL_TRANSPOSE builds on WB_CL_F4 and WB_CL_XWANTS"
+#endif
 #if WB_CL_XWANTS && !WB_CL_FREACH
 #error "WB_CL_XWANTS builds on the single-precision reach test (WB_CL_FREACH)"
 #endif
@@ -928,7 +1002,11 @@ struct WbClassifyWarp
 #if WB_CL_XWANTS
   unsigned long long openq[32];         // each query's sectors that can still matter (0 once it is decided)
 #endif
+#if WB_CL_F4
+  float4 fq[32];                        // the same queries relative to the warp's origin: x, y, vertex height, 2*por
+#else
   float fx[32],fy[32],fh[32],f2p[32];   // the same queries relative to the warp's origin: xy, vertex height, 2*por
+#endif
   double org[3];                        // that origin (the warp's first query)
   float fgh,fzq;                        // bounds of |fx|,|fy| and of |fh| over the warp's queries
 #endif
@@ -1134,7 +1212,7 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
                    const uint32_t *__restrict__ winner,const double *__restrict__ tHyp,
                    double maxSlope,double thickness,
                    const uint8_t *__restrict__ clsIn,const uint32_t *__restrict__ perm,
-                   uint32_t ownFirst,uint32_t ownEnd,
+                   uint32_t ownFirst,uint32_t ownEnd,const uint8_t *__restrict__ forcedIn,
                    uint8_t *__restrict__ labelSorted,unsigned long long *__restrict__ counters,
                    uint32_t *__restrict__ wedgeBuf,uint8_t *__restrict__ chunkPending
 #if WB_CL_COMPACT2
@@ -1183,7 +1261,9 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
     px=sx[me];
     py=sy[me];
     uint32_t src=perm[me];
-    foreign=src<ownFirst || src>=ownEnd;          // halo point of another GPU: not ours to label
+    foreign=src<ownFirst || src>=ownEnd;          // halo point of another GPU: not ours to label ...
+    if (foreign && forcedIn && forcedIn[src])
+      foreign=false;                              // ... unless it holds the place of one of our records (same XYZ)
     uint32_t wt=winner[me];
     if (foreign)
       ;
@@ -1207,7 +1287,11 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
     const bool q=have && !done;
     const double por=q?sqrt(ppor2):0.0;
     const float fx=q?(float)(px-ox):0.0f,fy=q?(float)(py-oy):0.0f,fh=q?(float)((pcz-por)-oz):0.0f;
+#if WB_CL_F4
+    w.fq[lane]=make_float4(fx,fy,fh,fminf((float)(2*por),1e30f));
+#else
     w.fx[lane]=fx; w.fy[lane]=fy; w.fh[lane]=fh; w.f2p[lane]=fminf((float)(2*por),1e30f);
+#endif
     const float gh=__uint_as_float(__reduce_max_sync(WB_FULL,__float_as_uint(fmaxf(fabsf(fx),fabsf(fy)))));
     const float zq=__uint_as_float(__reduce_max_sync(WB_FULL,__float_as_uint(fabsf(fh))));
     if (lane==0)
@@ -1309,7 +1393,7 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
       }
       if (!__any_sync(WB_FULL,ok))
         return;
-      if (childLevel==0 || WB_CL_XWANTS)
+      if (childLevel==0 || (WB_CL_XWANTS && childLevel<=WB_CL_XWANTS_MAXLEVEL))
       {
         uint32_t lm=askers;
 #if WB_CL_FREACH
@@ -1323,6 +1407,57 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
                     z0=(float)(cb.zmin-oz);
         const float ed=9.5367431640625e-7f*(fmaxf(fmaxf(fabsf(x0),fabsf(x1)),fmaxf(fabsf(y0),fabsf(y1)))+w.fgh);
         const float ez=9.5367431640625e-7f*(fabsf(z0)+w.fzq)+1e-6f;
+#if WB_CL_F4
+        // the slack goes into the box once: max(x0-qx,qx-x1)-ed = max((x0-ed)-qx,qx-(x1+ed)); a = qh-(z0-ez);
+        // a(a+2por)*1.000002 >= d2*s2*0.999998  <=>  a(a+2por) >= d2*k2 with k2 rounded DOWN (admits a superset)
+        const float bx0=x0-ed,bx1=x1+ed,by0=y0-ed,by1=y1+ed,bz0=z0-ez;
+        const float k2=(float)s2*0.999995f;
+#if WB_CL_TRANSPOSE
+        const uint32_t okm=__ballot_sync(WB_FULL,ok);
+        if (__popc(okm)*WB_CL_TCOST<__popc(askers)*WB_CL_ACOST)
+        {
+          // lanes = queries: the same test, the child's box (slack included) and sector span arriving by shuffle
+          const float4 me=w.fq[lane];
+          const unsigned long long myOpen=w.openq[lane];
+          const bool asking=(askers>>lane)&1;
+          uint32_t rem=okm;
+          lm=0;
+          while (rem)
+          {
+            const int c=__ffs(rem)-1;
+            rem&=rem-1;
+            WB_EMU_COUNT(childLevel==0?0:1);
+            const float cx0=__shfl_sync(WB_FULL,bx0,c),cx1=__shfl_sync(WB_FULL,bx1,c);
+            const float cy0=__shfl_sync(WB_FULL,by0,c),cy1=__shfl_sync(WB_FULL,by1,c),cz0=__shfl_sync(WB_FULL,bz0,c);
+            const uint32_t clo=__shfl_sync(WB_FULL,(uint32_t)cm,c),chi=__shfl_sync(WB_FULL,(uint32_t)(cm>>32),c);
+            const float dx=fmaxf(0.0f,fmaxf(cx0-me.x,me.x-cx1));
+            const float dy=fmaxf(0.0f,fmaxf(cy0-me.y,me.y-cy1));
+            const float a=me.z-cz0;
+            const bool t=asking && a>=0.0f && a*(a+me.w)>=(dx*dx+dy*dy)*k2 &&
+                         ((clo&(uint32_t)myOpen)|(chi&(uint32_t)(myOpen>>32)))!=0;
+            const uint32_t m=__ballot_sync(WB_FULL,t);
+            if (lane==c)
+              wants=m;
+          }
+        }
+#endif
+        while (lm)
+        {
+          const int q=__ffs(lm)-1;
+          lm&=lm-1;
+          WB_EMU_COUNT(childLevel==0?0:1);
+          const float4 fq=w.fq[q];
+          const float dx=fmaxf(0.0f,fmaxf(bx0-fq.x,fq.x-bx1));
+          const float dy=fmaxf(0.0f,fmaxf(by0-fq.y,fq.y-by1));
+          const float a=fq.z-bz0;
+#if WB_CL_XWANTS
+          if (ok && a>=0.0f && a*(a+fq.w)>=(dx*dx+dy*dy)*k2 && (cm&w.openq[q])!=0)
+#else
+          if (ok && a>=0.0f && a*(a+fq.w)>=(dx*dx+dy*dy)*k2)
+#endif
+            wants|=1u<<q;
+        }
+#else
         const float fs2=(float)s2*0.999998f;
         while (lm)
         {
@@ -1340,6 +1475,7 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
 #endif
             wants|=1u<<q;
         }
+#endif
 #else
         while (lm)
         {
@@ -1442,8 +1578,10 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
         const unsigned long long oq=((unsigned long long)__shfl_sync(WB_FULL,(uint32_t)(mineq>>32),q)<<32)|
                                     __shfl_sync(WB_FULL,(uint32_t)mineq,q);
         const bool rel=(pmask&oq)!=0;
+#if !WB_CL_NORELVOTE
         if (!__any_sync(WB_FULL,rel))
           continue;
+#endif
         const double qx=w.qx[q],qy=w.qy[q],qcz=w.qcz[q],qpor2=w.qpor2[q];
         double ddx=0,ddy=0;
         bool in=rel && wb_in_hyperboloid(qx,qy,qcz,qpor2,s2,maxSlope,cxp,cyp,czp,ddx,ddy,margin);
@@ -1703,15 +1841,20 @@ wb_dup_jump_kernel(const uint32_t *__restrict__ flag,uint32_t *prev,unsigned lon
 __global__ void __launch_bounds__(256)
 wb_dup_mark_kernel(const uint32_t *__restrict__ flag,const uint32_t *__restrict__ prev,
                    const uint32_t *__restrict__ perm,unsigned long long nv,unsigned long long *keys,
-                   uint32_t *__restrict__ dupIn,uint32_t *__restrict__ dupRep,unsigned long long *__restrict__ slot)
+                   uint32_t *__restrict__ dupIn,uint32_t *__restrict__ dupRep,unsigned long long *__restrict__ slot,
+                   uint8_t *__restrict__ forcedIn,uint32_t ownFirst,uint32_t ownEnd)
 {
   unsigned long long j=(unsigned long long)blockIdx.x*blockDim.x+threadIdx.x;
   if (j>=nv || !flag[j])
     return;
   unsigned long long s=atomicAdd(slot,1ull);
-  dupIn[s]=perm[j];
-  dupRep[s]=perm[prev[j]];
+  const uint32_t lost=perm[j],kept=perm[prev[j]];
+  dupIn[s]=lost;
+  dupRep[s]=kept;
   keys[j]=WB_KEY_DUP;
+  // sharded run: one of OUR records lost to a halo point — that point's label is needed here
+  if (forcedIn && lost>=ownFirst && lost<ownEnd && (kept<ownFirst || kept>=ownEnd))
+    forcedIn[kept]=1;
 }
 
 __global__ void __launch_bounds__(256)
@@ -1781,67 +1924,6 @@ wb_copy_points_kernel(const int *__restrict__ x,const int *__restrict__ y,const 
   oc[i]=c[i];
   if (oret)
     oret[i]=1;
-}
-
-__global__ void __launch_bounds__(256)
-wb_export_tiles_kernel(const int *__restrict__ tNPoints,const uint8_t *__restrict__ tTree,const double *__restrict__ tHyp,
-                       uint32_t nTiles,WbSnake snake,double xlo,double xhi,
-                       int *__restrict__ onp,int *__restrict__ otree,long long *__restrict__ ohyp)
-{
-  uint32_t t=blockIdx.x*blockDim.x+threadIdx.x;
-  if (t>=nTiles)
-    return;
-  int np=tNPoints[t],tr=0;
-  long long hb=0;
-  if (np)
-  {
-    int ex,ey;
-    double cx,cy;
-    wb_to_flowsnake((int)t+snake.lo,ex,ey);
-    wb_tile_center(ex,ey,snake,cx,cy);
-    if (cx>=xlo && cx<xhi)
-    {
-      tr=tTree[t];
-      hb=__double_as_longlong(tHyp[t]);
-    }
-    else
-      np=0;
-  }
-  onp[t]=np;
-  otree[t]=tr;
-  ohyp[t]=hb;
-}
-
-__global__ void __launch_bounds__(256)
-wb_import_tiles_kernel(const int *__restrict__ inp,const int *__restrict__ itree,const long long *__restrict__ ihyp,
-                       uint32_t nTiles,int *__restrict__ tNPoints,uint8_t *__restrict__ tTree,double *__restrict__ tHyp)
-{
-  uint32_t t=blockIdx.x*blockDim.x+threadIdx.x;
-  if (t>=nTiles)
-    return;
-  tNPoints[t]=inp[t];
-  tTree[t]=(uint8_t)itree[t];
-  tHyp[t]=__longlong_as_double(ihyp[t]);
-}
-
-__global__ void __launch_bounds__(256)
-wb_max_hyp_kernel(const int *__restrict__ tNPoints,const double *__restrict__ tHyp,uint32_t nTiles,
-                  unsigned long long *__restrict__ out)
-// hyperboloidSize is positive: its bit pattern orders like the value
-{
-  unsigned long long m=0;
-  for (uint32_t t=blockIdx.x*blockDim.x+threadIdx.x;t<nTiles;t+=gridDim.x*blockDim.x)
-    if (tNPoints[t])
-    {
-      double h=tHyp[t];
-      if (h>0 && h<INFINITY)
-        m=max(m,(unsigned long long)__double_as_longlong(h));
-    }
-  #pragma unroll
-  for (int o=16;o;o>>=1)
-    m=max(m,__shfl_xor_sync(WB_FULL,m,o));
-  if ((threadIdx.x&31)==0 && m)
-    atomicMax(out,m);
 }
 
 __global__ void __launch_bounds__(256)

@@ -57,6 +57,9 @@ enum Phase { PH_EMPTY=0,PH_LOADED,PH_BUILT,PH_SCANNED,PH_POSTSCANNED,PH_CLASSIFI
 
 } // namespace
 
+struct WbShard;                                  // wb_shard.cuh: state of the sharded pipeline
+static void wbShardFree(wb_ctx *ctx);
+
 struct wb_ctx
 {
   int device=0;
@@ -80,6 +83,9 @@ struct wb_ctx
   DevBuf<uint32_t> idxA,idxB,scr0,scr1,winner,pairValA,pairValB,table,blockSums;
   DevBuf<uint32_t> dupIn,dupRep;          // input indices of (lost duplicate, surviving point at the same XYZ)
   uint64_t nDup=0;
+  DevBuf<uint8_t> forcedIn;               // sharded runs: halo points that stand in for an own record at the same XYZ
+  bool haveForced=false;
+  WbShard *shard=nullptr;
   // pinned ring of the file reader (wb_add_las_file)
   uint8_t *readBuf[WB_READ_THREADS]={};
   uint64_t readBufBytes=0;
@@ -356,7 +362,8 @@ extern "C" void wb_destroy(wb_ctx *ctx)
   ctx->pendingList.release();
 #endif
  
-  ctx->dupIn.release(); ctx->dupRep.release();
+  ctx->dupIn.release(); ctx->dupRep.release(); ctx->forcedIn.release();
+  wbShardFree(ctx);
   freeKeptRecords(ctx);
   for (int i=0;i<WB_READ_THREADS;i++)
   {
@@ -751,24 +758,6 @@ extern "C" int wb_add_points_device(wb_ctx *ctx,const int32_t *dx,const int32_t 
   return addSegment(ctx,n,scale,offset,unit);
 }
 
-extern "C" int wb_export_points_device(wb_ctx *ctx,uint64_t first,uint64_t n,int32_t *dx,int32_t *dy,int32_t *dz,uint8_t *dc)
-{
-  if (!ctx || (n && (!dx || !dy || !dz || !dc)))
-    return WB_ERR_ARG;
-  cudaSetDevice(ctx->device);
-  if (first+n>ctx->n)
-    return fail(ctx,WB_ERR_ARG,"range outside the cloud");
-  if (n)
-  {
-    wb_copy_points_kernel<<<gridFor(n,256),256,0,ctx->st>>>(ctx->xi.p+first,ctx->yi.p+first,ctx->zi.p+first,ctx->cls.p+first,
-                                                           n,dx,dy,dz,dc,nullptr);
-    ctx->stats.kernel_launches++;
-    KCHECK();
-    CK(cudaStreamSynchronize(ctx->st));
-  }
-  return WB_OK;
-}
-
 extern "C" int wb_set_own_range(wb_ctx *ctx,uint64_t first,uint64_t end)
 {
   if (!ctx || end<first)
@@ -848,6 +837,7 @@ extern "C" int wb_build(wb_ctx *ctx)
   KCHECK();
   // ---- identical locations: one point per XYZ stays in the store (octree.cpp:620-662)
   ctx->nDup=0;
+  ctx->haveForced=false;
   {
     unsigned long long *cnt=ctx->counters.p+4;
     CK(cudaMemsetAsync(cnt,0,2*sizeof(unsigned long long),st));
@@ -876,8 +866,16 @@ extern "C" int wb_build(wb_ctx *ctx)
       CK(cudaMemsetAsync(cnt+1,0,sizeof(unsigned long long),st));
       unsigned long long *curK=ctx->keys,*othK=(ctx->keys==ctx->keyA.p)?ctx->keyB.p:ctx->keyA.p;
       uint32_t *curP=ctx->perm,*othP=(ctx->perm==ctx->idxA.p)?ctx->idxB.p:ctx->idxA.p;
+      // a halo point that holds the place of one of OUR records has to be classified here too
+      ctx->haveForced=ctx->ownFirst!=0 || ctx->ownEnd!=0xffffffffu;
+      if (ctx->haveForced)
+      {
+        CK(ctx->forcedIn.ensure(n));
+        CK(cudaMemsetAsync(ctx->forcedIn.p,0,n,st));
+      }
       wb_dup_mark_kernel<<<gridFor(nv,256),256,0,st>>>(ctx->scr0.p,ctx->scr1.p,curP,nv,curK,
-                                                      ctx->dupIn.p,ctx->dupRep.p,cnt+1);
+                                                      ctx->dupIn.p,ctx->dupRep.p,cnt+1,
+                                                      ctx->haveForced?ctx->forcedIn.p:nullptr,ctx->ownFirst,ctx->ownEnd);
       ctx->stats.kernel_launches++;
       KCHECK();
       // stable re-sort: survivors keep their order, duplicates go behind them (before the dropped records)
@@ -1162,46 +1160,6 @@ extern "C" int wb_assign(wb_ctx *ctx)
   return WB_OK;
 }
 
-extern "C" int wb_export_tiles_device(wb_ctx *ctx,double xlo,double xhi,int32_t *dnp,int32_t *dtree,int64_t *dhyp)
-{
-  if (!ctx || !dnp || !dtree || !dhyp)
-    return WB_ERR_ARG;
-  cudaSetDevice(ctx->device);
-  if (ctx->phase<PH_SCANNED)
-    return fail(ctx,WB_ERR_STATE,"not scanned");
-  wb_export_tiles_kernel<<<gridFor(ctx->nTiles,256),256,0,ctx->st>>>(ctx->tNPoints.p,ctx->tTree.p,ctx->tHyp.p,ctx->nTiles,
-                                                                     ctx->snake,xlo,xhi,dnp,dtree,(long long *)dhyp);
-  ctx->stats.kernel_launches++;
-  KCHECK();
-  CK(cudaStreamSynchronize(ctx->st));
-  return WB_OK;
-}
-
-extern "C" int wb_import_tiles_device(wb_ctx *ctx,const int32_t *dnp,const int32_t *dtree,const int64_t *dhyp,int postscanned)
-{
-  if (!ctx || !dnp || !dtree || !dhyp)
-    return WB_ERR_ARG;
-  cudaSetDevice(ctx->device);
-  if (ctx->phase<PH_BUILT)
-    return fail(ctx,WB_ERR_STATE,"not built");
-  int rc=ensureTileArrays(ctx);
-  if (rc)
-    return rc;
-  wb_import_tiles_kernel<<<gridFor(ctx->nTiles,256),256,0,ctx->st>>>(dnp,dtree,(const long long *)dhyp,ctx->nTiles,
-                                                                     ctx->tNPoints.p,ctx->tTree.p,ctx->tHyp.p);
-  ctx->stats.kernel_launches++;
-  KCHECK();
-  CK(cudaStreamSynchronize(ctx->st));
-  if (postscanned)
-  {
-    if (ctx->phase<PH_POSTSCANNED)
-      ctx->phase=PH_POSTSCANNED;
-  }
-  else if (ctx->phase<PH_SCANNED || ctx->phase==PH_POSTSCANNED)
-    ctx->phase=PH_SCANNED;
-  return WB_OK;
-}
-
 extern "C" int wb_max_hyperboloid_size(wb_ctx *ctx,double *out)
 {
   if (!ctx || !out)
@@ -1210,7 +1168,9 @@ extern "C" int wb_max_hyperboloid_size(wb_ctx *ctx,double *out)
   if (ctx->phase<PH_SCANNED)
     return fail(ctx,WB_ERR_STATE,"not scanned");
   CK(cudaMemsetAsync(ctx->counters.p+7,0,sizeof(unsigned long long),ctx->st));
-  wb_max_hyp_kernel<<<148*4,256,0,ctx->st>>>(ctx->tNPoints.p,ctx->tHyp.p,ctx->nTiles,ctx->counters.p+7);
+  if (ctx->stats.n_tiles_nonempty)
+    wb_max_hyp_list_kernel<<<148*4,256,0,ctx->st>>>(ctx->tileList.p,(uint32_t)ctx->stats.n_tiles_nonempty,ctx->tHyp.p,ctx->snake,
+                                                   -INFINITY,INFINITY,ctx->counters.p+7);
   ctx->stats.kernel_launches++;
   KCHECK();
   unsigned long long bits=0;
@@ -1232,9 +1192,11 @@ extern "C" int wb_postscan(wb_ctx *ctx)
   {
     const int init[4]={INT_MAX,INT_MAX,INT_MIN,INT_MIN};
     int ext[4];
+    const uint32_t nList=(uint32_t)ctx->stats.n_tiles_nonempty;
     CK(ctx->tileExt.ensure(4));
     CK(cudaMemcpyAsync(ctx->tileExt.p,init,sizeof(init),cudaMemcpyHostToDevice,st));
-    wb_tile_extent_kernel<<<gridFor(ctx->nTiles,256),256,0,st>>>(ctx->tNPoints.p,ctx->nTiles,ctx->snake,ctx->tileExt.p);
+    if (nList)
+      wb_tile_extent_list_kernel<<<gridFor(nList,256),256,0,st>>>(ctx->tileList.p,nList,ctx->snake,-INFINITY,INFINITY,ctx->tileExt.p);
     CK(cudaMemcpyAsync(ext,ctx->tileExt.p,sizeof(ext),cudaMemcpyDeviceToHost,st));
     CK(cudaStreamSynchronize(st));
     uint64_t cells=1;
@@ -1242,10 +1204,13 @@ extern "C" int wb_postscan(wb_ctx *ctx)
       cells=(uint64_t)((long long)ext[2]-ext[0]+1)*(uint64_t)((long long)ext[3]-ext[1]+1);
     CK(ctx->tileGrid.ensure(cells));
     CK(cudaMemsetAsync(ctx->tileGrid.p,0,cells,st));
-    wb_tile_grid_kernel<<<gridFor(ctx->nTiles,256),256,0,st>>>(ctx->tNPoints.p,ctx->tTree.p,ctx->nTiles,ctx->snake,
-                                                              ctx->tileExt.p,ctx->tileGrid.p);
-    wb_postscan_kernel<<<gridFor(ctx->nTiles,128),128,0,st>>>(ctx->tNPoints.p,ctx->tTree.p,ctx->nTiles,ctx->snake,
+    if (nList)
+    {
+      wb_tile_grid_list_kernel<<<gridFor(nList,256),256,0,st>>>(ctx->tileList.p,nList,ctx->tTree.p,ctx->snake,-INFINITY,INFINITY,
+                                                               ctx->tileExt.p,ctx->tileGrid.p);
+      wb_postscan_list_kernel<<<gridFor(nList,128),128,0,st>>>(ctx->tileList.p,nList,ctx->tTree.p,ctx->snake,
                                                               ctx->tileExt.p,ctx->tileGrid.p,ctx->tHyp.p);
+    }
     ctx->stats.kernel_launches+=3;
   }
   KCHECK();
@@ -1364,7 +1329,7 @@ extern "C" int wb_classify(wb_ctx *ctx)
   wb_classify_kernel<1><<<gridFor(ctx->nChunks,WB_CL_WARPS),WB_CL_WARPS*32,0,st>>>(
       ctx->sx.p,ctx->sy.p,ctx->sz.p,nv,ctx->nChunks,ctx->bounds.p,ctx->levelOff.p,ctx->levelCnt.p,ctx->nLevels,
       ctx->winner.p,ctx->tHyp.p,ctx->prm.maxSlope,ctx->prm.thickness,ctx->cls.p,ctx->perm,
-      ctx->ownFirst,ctx->ownEnd,ctx->labelSorted.p,ctx->counters.p,ctx->wedgeBuf.p,ctx->chunkPending.p
+      ctx->ownFirst,ctx->ownEnd,ctx->haveForced?ctx->forcedIn.p:nullptr,ctx->labelSorted.p,ctx->counters.p,ctx->wedgeBuf.p,ctx->chunkPending.p
 #if WB_CL_COMPACT2
       ,nullptr,0u
 #endif
@@ -1385,7 +1350,7 @@ extern "C" int wb_classify(wb_ctx *ctx)
       wb_classify_kernel<2><<<gridFor(wb_div_up(nPending,32),WB_CL_WARPS),WB_CL_WARPS*32,0,st>>>(
           ctx->sx.p,ctx->sy.p,ctx->sz.p,nv,ctx->nChunks,ctx->bounds.p,ctx->levelOff.p,ctx->levelCnt.p,ctx->nLevels,
           ctx->winner.p,ctx->tHyp.p,ctx->prm.maxSlope,ctx->prm.thickness,ctx->cls.p,ctx->perm,
-          ctx->ownFirst,ctx->ownEnd,ctx->labelSorted.p,ctx->counters.p,ctx->wedgeBuf.p,ctx->chunkPending.p,
+          ctx->ownFirst,ctx->ownEnd,ctx->haveForced?ctx->forcedIn.p:nullptr,ctx->labelSorted.p,ctx->counters.p,ctx->wedgeBuf.p,ctx->chunkPending.p,
           ctx->pendingList.p,nPending);
     }
     ctx->stats.kernel_launches+=2;
@@ -1394,7 +1359,7 @@ extern "C" int wb_classify(wb_ctx *ctx)
   wb_classify_kernel<2><<<gridFor(ctx->nChunks,WB_CL_WARPS),WB_CL_WARPS*32,0,st>>>(
       ctx->sx.p,ctx->sy.p,ctx->sz.p,nv,ctx->nChunks,ctx->bounds.p,ctx->levelOff.p,ctx->levelCnt.p,ctx->nLevels,
       ctx->winner.p,ctx->tHyp.p,ctx->prm.maxSlope,ctx->prm.thickness,ctx->cls.p,ctx->perm,
-      ctx->ownFirst,ctx->ownEnd,ctx->labelSorted.p,ctx->counters.p,ctx->wedgeBuf.p,ctx->chunkPending.p);
+      ctx->ownFirst,ctx->ownEnd,ctx->haveForced?ctx->forcedIn.p:nullptr,ctx->labelSorted.p,ctx->counters.p,ctx->wedgeBuf.p,ctx->chunkPending.p);
 #endif
   CK(cudaEventRecord(ctx->evD,st));
   wb_scatter_labels_kernel<<<gridFor(nv,256),256,0,st>>>(ctx->labelSorted.p,ctx->perm,nv,ctx->labelIn.p);
@@ -2056,3 +2021,5 @@ extern "C" int wb_format_dump(const wb_leaf *leaves,uint64_t n,char *buf,uint64_
   memcpy(buf,out.c_str(),out.size()+1);
   return (int)out.size();
 }
+
+#include "wb_shard.cuh"

@@ -1,319 +1,160 @@
-"""Spatial sharding of one cloud over the GPUs of a box (one process per GPU).
+"""One cloud over the GPUs of a box: launch harness around wb_shard_run.
 
-The reference has no distributed mode (one std::thread pool).  The path shards
-because every label depends only on the points inside that point's downward hyperboloid and
-every tile parameter only on the points inside the tile's cylinder:
-
-  strips   each rank owns a strip in x (its own LAS files); the octree cube and the flowsnake
-           come from the union of ALL files' header corners, so Morton keys, tile numbers and
-           tile centres are identical everywhere;
-  halo 1   points within 2.5 tile spacings of another rank's strip are sent there, so each rank
-           can scan every tile whose centre lies in its ownership interval;
-  merge    the dense tile table (nPoints, treeFlags, hyperboloidSize bits), zero outside the
-           ownership interval, is summed over ranks (all-reduce) -> the global table; postscan
-           then runs on every rank over the whole table;
-  halo 2   a point Q can lie in the hyperboloid of P only if dist_xy <= sqrt(dz^2+2 por dz)/slope
-           with dz <= zmax-thickness-Q.z and por <= max hyperboloidSize * slope^2 (shape.cpp:119-135),
-           so Q goes to every rank whose strip is that close; each rank rebuilds its bucket
-           hierarchy over own+halo points and classifies its OWN points only.
-  order    local arrays are [halo from lower ranks | own | halo from higher ranks], each sender's
-           points in their original order, so that the canonical order (Morton key, then input
-           index) restricted to a rank equals the global one.
-
-The exchange steps only move data (torch.distributed all_to_all / all_reduce over NCCL); all
-arithmetic that decides a label runs in the library's kernels.  `LocalComm` runs the same code
-for several simulated ranks inside one process (single-GPU parity tests, gloo CPU tests of the
-selection logic).
+All of the sharded pipeline — halo selection, exchange, tile grid, the two builds, classify — lives in the
+library (csrc/wb_shard.cuh, NCCL called from C++).  This module only
+  * hands the NCCL unique id of rank 0 to the other ranks of a torchrun job (`nccl_comm`),
+  * runs several ranks as threads of one process over the LOCAL transport (`run_threads`: parity tests on one
+    GPU, and on the CPU emulator of tests/simt),
+  * offers gloo as a CUSTOM transport for the emulated library (`gloo_comm`: the world_size-2 CPU tests),
+  * and holds the N>1 body of bench.py (`bench`).
+The reference has no distributed mode (one std::thread pool, threads.cpp:91-113).
 """
-import math
+import ctypes as C
+import json
 import os
+import threading
 import time
 
 import numpy as np
-import torch
 
-SCAN_HALO_SPACINGS = 2.5
+from . import api
 
-
-# ---------------------------------------------------------------------------- pure helpers
-
-def coords(ints, scale, offset):
-    """(offset + scale*int) exactly as las.cpp:808 does it (two roundings), unit 1."""
-    return ints.to(torch.float64) * scale + offset
+PARAMS = dict(tile_size=1.0, max_slope=1.0, thickness=0.0, min_hyperboloid_size=0.1)
 
 
-def ownership_bounds(strips):
-    """strips: list of (xlo, xhi) per rank, ascending.  Returns [(lo, hi)] half-open ownership
-    intervals for tile centres: boundaries at the middle of the gap between adjacent strips."""
-    n = len(strips)
-    cuts = [-math.inf] + [0.5 * (strips[k][1] + strips[k + 1][0]) for k in range(n - 1)] + [math.inf]
-    return [(cuts[k], cuts[k + 1]) for k in range(n)]
-
-
-def reach_radius(z, zmax, thickness, por_max, slope):
-    """Upper bound of the xy distance at which a point of height z can be inside the downward
-    hyperboloid of ANY query point (vertex height <= zmax - thickness, polar radius <= por_max)."""
-    dz = torch.clamp(zmax - thickness - z, min=0.0)
-    return torch.sqrt(dz * dz + 2.0 * por_max * dz) / slope * (1 + 1e-9) + 1e-6
-
-
-def select_for_strip(x, radius, strip):
-    """Mask of points whose x lies within `radius` (scalar or per point) of the strip [lo,hi]."""
-    lo, hi = strip
-    return (x >= lo - radius) & (x <= hi + radius)
-
-
-def pack(cols):
-    """xi,yi,zi (int32) + cls (uint8) -> one (n,4) int32 tensor for the exchange."""
-    xi, yi, zi, cl = cols
-    return torch.stack([xi, yi, zi, cl.to(torch.int32)], dim=1).contiguous()
-
-
-def unpack(t):
-    return t[:, 0].contiguous(), t[:, 1].contiguous(), t[:, 2].contiguous(), t[:, 3].to(torch.uint8).contiguous()
-
-
-# ---------------------------------------------------------------------------- communicators
-
-class TorchComm:
-    """torch.distributed (NCCL on the GPU box, gloo in the CPU tests)."""
-
-    def __init__(self, dist):
-        self.dist = dist
-        self.rank = dist.get_rank()
-        self.world = dist.get_world_size()
-
-    def all_gather_doubles(self, vals, device):
-        t = torch.tensor(vals, dtype=torch.float64, device=device)
-        out = [torch.empty_like(t) for _ in range(self.world)]
-        self.dist.all_gather(out, t)
-        return [o.cpu().tolist() for o in out]
-
-    def all_to_all_rows(self, send_list):
-        """send_list[k] = (m_k,4) int32 rows for rank k.  Returns the list received from each rank."""
-        dev = send_list[0].device
-        counts = torch.tensor([s.shape[0] for s in send_list], dtype=torch.int64, device=dev)
-        rcounts = torch.empty_like(counts)
-        self.dist.all_to_all_single(rcounts, counts)
-        rc = rcounts.cpu().tolist()
-        sc = counts.cpu().tolist()
-        send = torch.cat(send_list, dim=0).contiguous()
-        recv = torch.empty((sum(rc), 4), dtype=torch.int32, device=dev)
-        self.dist.all_to_all_single(recv, send, output_split_sizes=rc, input_split_sizes=sc)
-        return list(torch.split(recv, rc, dim=0))
-
-    def all_reduce_sum(self, tensors):
-        for t in tensors:
-            self.dist.all_reduce(t)
-
-    def all_reduce_max_scalar(self, v, device):
-        t = torch.tensor([v], dtype=torch.float64, device=device)
-        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def barrier(self):
-        self.dist.barrier()
-
-
-# ---------------------------------------------------------------------------- one rank
-
-class Rank:
-    """The work of one GPU.  ctx_scan and ctx_cls are two wolkenbase_b200.api.Context objects on
-    that GPU (the scan stage and the classify stage hold different halo sets)."""
-
-    def __init__(self, rank, world, ctx_scan, ctx_cls, params, device):
-        self.rank, self.world = rank, world
-        self.a, self.b = ctx_scan, ctx_cls
-        self.p = dict(tile_size=1.0, max_slope=1.0, thickness=0.0, min_hyperboloid_size=0.1)
-        self.p.update(params or {})
-        self.device = device
-        self.timing = {}
-
-    # -- stage 0: decode own records, learn everybody's extents
-    def load(self, cloud, dev_records=None):
-        """cloud: synth.Cloud (or anything with records/fmt/scale/offset/min_corner/max_corner)."""
-        self.cloud = cloud
-        self.n_own = cloud.n
-        self.scale, self.offset = cloud.scale, cloud.offset
-        a = self.a
-        a.clear()
-        a.set_params(**self.p)
-        a.add_extent(cloud.min_corner, cloud.max_corner)       # only so that decode has a context
+def load_rank(ctx, clouds, params=None, dev_records=None):
+    """The rank's own files into its context: header corners + records (host arrays, or device pointers)."""
+    ctx.clear()
+    ctx.set_params(**dict(PARAMS, **(params or {})))
+    for c in clouds:
+        ctx.add_extent(c.min_corner, c.max_corner)
+    for i, c in enumerate(clouds):
         if dev_records is not None:
-            a.add_las_device(dev_records.data_ptr(), cloud.n, cloud.fmt, cloud.rec_len, cloud.scale, cloud.offset)
+            ctx.add_las_device(dev_records[i], c.n, c.fmt, c.rec_len, c.scale, c.offset)
         else:
-            a.add_las(cloud.records, cloud.fmt, cloud.scale, cloud.offset)
-        n = cloud.n
-        self.own = (torch.empty(n, dtype=torch.int32, device=self.device),
-                    torch.empty(n, dtype=torch.int32, device=self.device),
-                    torch.empty(n, dtype=torch.int32, device=self.device),
-                    torch.empty(n, dtype=torch.uint8, device=self.device))
-        a.export_points_device(0, n, *[t.data_ptr() for t in self.own])
-        self.x = coords(self.own[0], self.scale[0], self.offset[0])
-        self.z = coords(self.own[2], self.scale[2], self.offset[2])
-        return list(cloud.min_corner) + list(cloud.max_corner)
-
-    def set_extents(self, extents):
-        """extents[k] = [minx,miny,minz,maxx,maxy,maxz] of rank k's files (all ranks, same order)."""
-        self.extents = extents
-        self.strips = [(e[0], e[3]) for e in extents]
-        self.owner_bounds = ownership_bounds(self.strips)
-        self.zmax = max(e[5] for e in extents)
-        self.zmin = min(e[2] for e in extents)
-
-    def _setup(self, ctx):
-        ctx.clear()
-        ctx.set_params(**self.p)
-        for e in self.extents:
-            ctx.add_extent(e[0:3], e[3:6])
-
-    def _sends(self, radius):
-        rows = pack(self.own)
-        out = []
-        for k in range(self.world):
-            if k == self.rank:
-                out.append(rows[:0])
-            else:
-                out.append(rows[select_for_strip(self.x, radius, self.strips[k])])
-        return out
-
-    def _fill(self, ctx, received):
-        """local array = [halo from lower ranks | own | halo from higher ranks]"""
-        first = 0
-        for k in range(self.world):
-            if k == self.rank:
-                own_first = first
-                ctx.add_points_device(*[t.data_ptr() for t in self.own], self.n_own, self.scale, self.offset)
-                first += self.n_own
-            elif received[k].shape[0]:
-                cols = unpack(received[k])
-                ctx.add_points_device(*[t.data_ptr() for t in cols], cols[0].shape[0], self.scale, self.offset)
-                first += cols[0].shape[0]
-        ctx.set_own_range(own_first, own_first + self.n_own)
-        self.own_first = own_first
-        return first
-
-    # -- stage 1: scan with the narrow halo
-    def scan_sends(self):
-        self._setup(self.a)
-        g = self.a.geometry()
-        self.geom = g
-        return self._sends(SCAN_HALO_SPACINGS * g.spacing)
-
-    def scan(self, received):
-        a = self.a
-        self.n_scan = self._fill(a, received)
-        a.build()
-        a.scan()
-        T = self.geom.snake_hi - self.geom.snake_lo + 1
-        self.t_np = torch.empty(T, dtype=torch.int32, device=self.device)
-        self.t_tree = torch.empty(T, dtype=torch.int32, device=self.device)
-        self.t_hyp = torch.empty(T, dtype=torch.int64, device=self.device)
-        lo, hi = self.owner_bounds[self.rank]
-        a.export_tiles_device(lo if lo > -math.inf else -1e300, hi if hi < math.inf else 1e300,
-                              self.t_np.data_ptr(), self.t_tree.data_ptr(), self.t_hyp.data_ptr())
-        return [self.t_np, self.t_tree, self.t_hyp]
-
-    # -- stage 2: global table -> postscan -> how far classify can reach
-    def postscan(self):
-        a = self.a
-        a.import_tiles_device(self.t_np.data_ptr(), self.t_tree.data_ptr(), self.t_hyp.data_ptr())
-        a.postscan()
-        a.export_tiles_device(-1e300, 1e300, self.t_np.data_ptr(), self.t_tree.data_ptr(), self.t_hyp.data_ptr())
-        s = self.p["max_slope"]
-        self.por_max = a.max_hyperboloid_size() * s * s
-        return self.por_max
-
-    def classify_sends(self):
-        r = reach_radius(self.z, self.zmax, self.p["thickness"], self.por_max, self.p["max_slope"])
-        return self._sends(r)
-
-    def classify(self, received, labels_out=None):
-        b = self.b
-        self._setup(b)
-        self.n_cls = self._fill(b, received)
-        b.build()
-        b.assign()
-        b.import_tiles_device(self.t_np.data_ptr(), self.t_tree.data_ptr(), self.t_hyp.data_ptr(), postscanned=True)
-        b.classify()
-        lab = b.labels(self.n_cls)
-        own = lab[self.own_first:self.own_first + self.n_own]
-        if labels_out is not None:
-            labels_out[:] = own
-            return labels_out
-        return own.copy()
+            ctx.add_las(c.records, c.fmt, c.scale, c.offset)
+    return sum(c.n for c in clouds)
 
 
-# ---------------------------------------------------------------------------- drivers
+# ---------------------------------------------------------------------------- ranks as threads (LOCAL transport)
 
-def run_local(ranks, clouds):
-    """All ranks in one process (tests): exchanges are list shuffles, the reduction a sum."""
-    W = len(ranks)
-    ext = [r.load(c) for r, c in zip(ranks, clouds)]
-    for r in ranks:
-        r.set_extents(ext)
-    sends = [r.scan_sends() for r in ranks]
-    tables = [r.scan([sends[src][r.rank] for src in range(W)]) for r in ranks]
-    summed = [sum(t[i] for t in tables) for i in range(3)]
-    for r in ranks:
-        for i, t in enumerate([r.t_np, r.t_tree, r.t_hyp]):
-            t.copy_(summed[i])
-        r.postscan()
-    sends = [r.classify_sends() for r in ranks]
-    return [r.classify([sends[src][r.rank] for src in range(W)]) for r in ranks]
+def run_threads(clouds_per_rank, params=None, devices=None, transport="local"):
+    """clouds_per_rank[r] = list of synth.Cloud-like files of rank r (ascending x).  Every rank runs in its own host
+    thread on devices[r] (default: all on device 0).  transport "local": plain copies + a barrier; "nccl": one NCCL
+    communicator per thread, which needs a distinct device per rank (what wolkencli --gpus N does).
+    Returns (labels per rank, shard stats per rank, wb stats)."""
+    W = len(clouds_per_rank)
+    devices = devices or [0] * W
+    group = api.LocalGroup(W) if transport == "local" else None
+    uid = api.Comm.unique_id() if transport == "nccl" else None
+    out = [None] * W
+    err = [None] * W
+
+    def work(r):
+        try:
+            ctx = api.Context(devices[r])
+            comm = api.Comm.local(ctx, group, r) if group is not None else api.Comm.nccl(ctx, uid, r, W)
+            n = load_rank(ctx, clouds_per_rank[r], params)
+            ctx.shard_run(comm)
+            out[r] = (ctx.shard_labels(n), ctx.shard_stats(), ctx.stats())
+            comm.close()
+            ctx.close()
+        except BaseException as e:      # a rank that dies would leave the others in the barrier: report and stop
+            err[r] = e
+            os._exit(97) if W > 1 and not isinstance(e, api.WolkenError) else None
+
+    th = [threading.Thread(target=work, args=(r,)) for r in range(W)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    if group is not None:
+        group.close()
+    for e in err:
+        if e is not None:
+            raise e
+    return [o[0] for o in out], [o[1] for o in out], [o[2] for o in out]
 
 
-def run_distributed(rank_obj, cloud, comm, dev_records=None, labels_out=None, timing=None):
-    """One rank under torch.distributed.  timing: optional dict that receives per-stage milliseconds."""
-    r = rank_obj
-    t = [time.perf_counter()]
+# ---------------------------------------------------------------------------- transports under torch.distributed
 
-    def lap(name):
-        if timing is not None:
-            torch.cuda.synchronize()
-            now = time.perf_counter()
-            timing[name] = timing.get(name, 0.0) + (now - t[0]) * 1e3
-            t[0] = now
+def nccl_comm(ctx, dist, rank, world):
+    """wb_comm over NCCL: rank 0's ncclUniqueId reaches the others through the job's process group."""
+    box = [api.Comm.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    return api.Comm.nccl(ctx, box[0], rank, world)
 
-    ext = comm.all_gather_doubles(r.load(cloud, dev_records), r.device)
-    r.set_extents(ext)
-    lap("load_decode")
-    sends = r.scan_sends()
-    lap("halo1_select")
-    recv = comm.all_to_all_rows(sends)
-    lap("halo1_exchange")
-    tabs = r.scan(recv)
-    lap("build_scan_export")
-    comm.all_reduce_sum(tabs)
-    lap("tile_allreduce")
-    r.postscan()
-    lap("postscan")
-    sends = r.classify_sends()
-    lap("halo2_select")
-    recv = comm.all_to_all_rows(sends)
-    lap("halo2_exchange")
-    out = r.classify(recv, labels_out)
-    lap("build_classify_labels")
-    return out
+
+def _bytes_at(ptr, n):
+    return np.ctypeslib.as_array((C.c_uint8 * n).from_address(ptr)) if n else np.empty(0, dtype=np.uint8)
+
+
+def gloo_ops(dist, rank, world):
+    """The three collectives of wb_comm_ops over gloo, for buffers in HOST memory (the emulated library's 'device'
+    pointers are host pointers).  Pointers arrive as integers; each returns 0 on success."""
+    import torch
+
+    def all_gather(user, d_send, d_recv, nbytes):
+        try:
+            send = torch.from_numpy(_bytes_at(d_send, nbytes).copy())
+            outs = [torch.empty(nbytes, dtype=torch.uint8) for _ in range(world)]
+            dist.all_gather(outs, send)
+            _bytes_at(d_recv, nbytes * world)[:] = torch.cat(outs).numpy()
+            return 0
+        except Exception:
+            return 1
+
+    def all_to_all_v(user, d_send, s_off, s_cnt, d_recv, r_off, r_cnt):
+        try:
+            sc = [int(s_cnt[k]) for k in range(world)]
+            rc = [int(r_cnt[k]) for k in range(world)]
+            parts = [_bytes_at(d_send + int(s_off[k]), sc[k]) for k in range(world)]
+            send = torch.from_numpy(np.concatenate(parts) if sum(sc) else np.empty(0, dtype=np.uint8))
+            recv = torch.empty(sum(rc), dtype=torch.uint8)
+            dist.all_to_all_single(recv, send, output_split_sizes=rc, input_split_sizes=sc)
+            got, pos = recv.numpy(), 0
+            for k in range(world):
+                _bytes_at(d_recv + int(r_off[k]), rc[k])[:] = got[pos:pos + rc[k]]
+                pos += rc[k]
+            return 0
+        except Exception:
+            return 1
+
+    def all_reduce_max_u8(user, d_buf, n):
+        try:
+            t = torch.from_numpy(_bytes_at(d_buf, n))
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return 0
+        except Exception:
+            return 1
+
+    return all_gather, all_to_all_v, all_reduce_max_u8
+
+
+def gloo_comm(ctx, dist, rank, world):
+    """CUSTOM transport for the EMULATED library: gloo moves the bytes (world_size-2 CPU tests)."""
+    return api.Comm.custom(ctx, *gloo_ops(dist, rank, world), rank, world)
 
 
 # ---------------------------------------------------------------------------- bench (N > 1)
 
+def _spread(vals):
+    return {"min": round(min(vals), 2), "mean": round(sum(vals) / len(vals), 2), "max": round(max(vals), 2)}
+
+
 def bench(args, rank, world, local):
-    import json
+    import torch
     import torch.distributed as dist
-    from . import api, synth
+    from . import synth
     import bench as B
     dev = torch.device("cuda", local)
-    comm = TorchComm(dist)
     per_gpu = args.points or 125_000_000
     scene = args.scene or 3
     d = synth.describe(scene, per_gpu * world)
     c0 = d.grid_nx * rank // world
     c1 = d.grid_nx * (rank + 1) // world
-    base = d.grid_ny * c0
-    cloud = synth.generate(scene, per_gpu * world, seed=scene + rank * 0, region=(c0, 0, c1 - c0, d.grid_ny),
-                           gps_base=base)
+    cloud = synth.generate(scene, per_gpu * world, seed=scene, region=(c0, 0, c1 - c0, d.grid_ny),
+                           gps_base=d.grid_ny * c0)
     n = cloud.n
     pin = api.PinnedBuffer(n * cloud.rec_len)
     pin.array[:] = cloud.records.reshape(-1)
@@ -322,79 +163,119 @@ def bench(args, rank, world, local):
     labels_pin = api.PinnedBuffer(n)
     dev_recs = torch.empty(n * cloud.rec_len, dtype=torch.uint8, device=dev)
     dev_recs.copy_(torch.from_numpy(host_recs.reshape(-1)))
-    ctx_a, ctx_b = api.Context(local), api.Context(local)
-    cap = int(n * 1.8) + 1024
-    ctx_a.reserve(int(n * 1.1) + 1024)
-    ctx_b.reserve(cap)
-    R = Rank(rank, world, ctx_a, ctx_b, B.PARAMS, dev)
-    n_total = int(comm.all_reduce_max_scalar(0, dev))  # warm the communicator
+    ctx = api.Context(local)
+    ctx.reserve(int(n * 1.25) + 1024)
+    comm = nccl_comm(ctx, dist, rank, world)
+
+    def allmax(v):
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def step(resident):
+        load_rank(ctx, [cloud], B.PARAMS, [dev_recs.data_ptr()] if resident else None)
+        ctx.shard_run(comm)
+        ctx.shard_labels(n, out=labels_pin.array)
+
+    def timed(resident, steps, collect=None):
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            t1 = time.perf_counter()
+            step(resident)
+            if collect is not None:
+                collect.append((ctx.shard_stats(), ctx.stats(), (time.perf_counter() - t1) * 1e3))
+        torch.cuda.synchronize()
+        mine = time.perf_counter() - t0
+        dist.barrier()
+        return allmax(time.perf_counter() - t0) / steps, mine / steps
+
     tot = torch.tensor([n], dtype=torch.int64, device=dev)
     dist.all_reduce(tot)
     n_total = int(tot.item())
-
-    stage_ms = {}
-
-    def step(resident, timing=None):
-        return run_distributed(R, cloud, comm, dev_recs if resident else None, labels_pin.array, timing)
-
     for _ in range(args.warmup):
         step(True)
-    l0 = ctx_a.stats()["kernel_launches"] + ctx_b.stats()["kernel_launches"]
+    l0 = ctx.stats()["kernel_launches"]
     sampler = B.ClockSampler(local)
     sampler.start()
-    torch.cuda.synchronize()
-    comm.barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step(True, stage_ms)
-    torch.cuda.synchronize()
-    comm.barrier()
-    dt = comm.all_reduce_max_scalar(time.perf_counter() - t0, dev)
+    per_step = []
+    dt, _ = timed(True, args.steps, per_step)
     clocks = sampler.stop()
-    launches = (ctx_a.stats()["kernel_launches"] + ctx_b.stats()["kernel_launches"] - l0) // max(1, args.steps)
-    sa, sb = ctx_a.stats(), ctx_b.stats()
-    # e2e: pinned host records in, labels of the own points out
+    launches = (ctx.stats()["kernel_launches"] - l0) // max(1, args.steps)
+    # e2e: pinned host records in, labels of the own records out, every step
     step(False)
-    torch.cuda.synchronize()
-    comm.barrier()
-    t0 = time.perf_counter()
-    e2e_steps = max(1, min(args.steps, 2))
-    for _ in range(e2e_steps):
-        step(False)
-    torch.cuda.synchronize()
-    comm.barrier()
-    dte = comm.all_reduce_max_scalar(time.perf_counter() - t0, dev) / e2e_steps
-    halo = torch.tensor([R.n_scan - n, R.n_cls - n], dtype=torch.int64, device=dev)
-    dist.all_reduce(halo)
+    e2e_steps = max(1, min(args.steps, 5))
+    dte, _ = timed(False, e2e_steps)
+    h2d_ms = ctx.stats()["ms_h2d"]
+    # what every rank saw (stage wall clocks of the library, averaged over the timed steps)
+    keys = [k for k in per_step[0][0] if k.startswith("ms_")]
+    mine = {k: sum(s[0][k] for s in per_step) / len(per_step) for k in keys}
+    mine["step_wall"] = sum(s[2] for s in per_step) / len(per_step)
+    mine["classify_kernel"] = sum(s[1]["ms_classify_kernel"] for s in per_step) / len(per_step)
+    mine["h2d_decode_e2e"] = h2d_ms
+    last = per_step[-1][0]
+    mine_info = {"n_own": n, "n_halo_scan": last["n_halo_scan"], "n_halo_classify": last["n_halo_classify"],
+                 "por_max": last["por_max"], "grid_cells": last["grid_cells"], "bytes_sent": last["bytes_sent"]}
+    everyone = [None] * world
+    dist.all_gather_object(everyone, (mine, mine_info))
     hist = torch.from_numpy(np.bincount(labels_pin.array, minlength=256).astype(np.int64)).to(dev)
     dist.all_reduce(hist)
+    # like-for-like single-GPU figure: rank 0 alone on its own strip (the scene's geometry, no halo, no exchange)
+    base = None
+    if not args.no_scaling_base:
+        if rank == 0:
+            comm.close()
+            ctx.close()
+            solo = api.Context(local)
+            solo.set_params(**B.PARAMS)
+            try:
+                base = B.scaling_base(solo, args, world, 0, steps=max(2, min(args.steps, 5)), cloud=cloud, dev=dev_recs)
+            except Exception as e:
+                base = {"error": "%s: %s" % (type(e).__name__, e)}
+            solo.close()
+        dist.barrier()
     if rank == 0:
         hbm, peak_src = B.peaks()
-        ck_ms = sb["ms_classify_kernel"]
+        ck_ms = mine["classify_kernel"]
         achieved = 13.0 * n / (ck_ms * 1e-3) / 1e9 if ck_ms > 0 else 0.0
+        value = n_total / dt
         line = {
-            "metric": B.METRIC, "value": n_total / (dt / args.steps), "unit": B.UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "metric": B.METRIC, "value": value, "unit": B.UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+            "timer": "wall clock between barriers, CUDA synchronised on both sides, max over ranks",
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "C3 multi-tile aerial cloud: %d points in %d x-strips (one LAS format %d file per "
                                    "GPU), NCCL halo exchange; tileSize 1 maxSlope 1 thickness 0 minHyperboloidSize 0.1"
                                    % (n_total, world, cloud.fmt),
                        "points": n_total, "points_per_gpu": n,
                        "l2": "inputs larger than L2 (%.1f GB of records per GPU per step)" % (n * cloud.rec_len / 1e9),
-                       "parallelism": "%d spatial strips, halo exchange + tile-table all-reduce" % world},
-            "phases_ms_rank0": {"scan_stage_build": sa["ms_build"], "scan": sa["ms_scan"], "postscan": sa["ms_postscan"],
-                                "classify_stage_build": sb["ms_build"], "classify": sb["ms_classify"]},
-            "stages_ms_rank0": {k: round(v / args.steps, 2) for k, v in stage_ms.items()},
-            "halo": {"scan_points": int(halo[0]), "classify_points": int(halo[1]),
-                     "classify_fraction": float(halo[1]) / n_total, "por_max": R.por_max},
+                       "parallelism": "%d spatial strips; halo rows over NCCL send/recv, tile grid all-reduce (1 B/cell)"
+                                      % world},
+            "stages_ms": {k[3:] if k.startswith("ms_") else k: _spread([e[0][k] for e in everyone]) for k in mine},
+            "classify_kernel_ms_by_rank": [round(e[0]["classify_kernel"], 1) for e in everyone],
+            "step_wall_ms_by_rank": [round(e[0]["step_wall"], 1) for e in everyone],
+            "halo": {"scan_points": sum(e[1]["n_halo_scan"] for e in everyone),
+                     "classify_points": sum(e[1]["n_halo_classify"] for e in everyone),
+                     "classify_fraction": sum(e[1]["n_halo_classify"] for e in everyone) / n_total,
+                     "por_max": everyone[0][1]["por_max"], "grid_cells": everyone[0][1]["grid_cells"],
+                     "bytes_sent_per_step": sum(e[1]["bytes_sent"] for e in everyone)},
             "roofline": {"bound": "hbm", "kernel": "wb_classify_kernel (rank 0)", "achieved": achieved, "peak": hbm,
                          "unit": "GB/s", "frac": achieved / hbm, "traffic": None, "peak_source": peak_src},
             "e2e": {"value": n_total / dte, "unit": B.UNIT, "h2d_bytes_per_step": n_total * cloud.rec_len,
-                    "d2h_bytes_per_step": n_total, "ms_per_step": dte * 1e3},
+                    "d2h_bytes_per_step": n_total, "ms_per_step": dte * 1e3, "steps": e2e_steps,
+                    "h2d_decode_ms": _spread([e[0]["h2d_decode_e2e"] for e in everyone]),
+                    "h2d_gbs_per_gpu": _spread([n * cloud.rec_len / (e[0]["h2d_decode_e2e"] * 1e-3) / 1e9
+                                                for e in everyone if e[0]["h2d_decode_e2e"] > 0] or [0.0])},
             "gpu_launches": int(launches), "clocks": clocks,
             "labels": {"ground": int(hist[2]), "nonground": int(hist[1])},
         }
+        if base is not None:
+            line["weak_scaling_base"] = base
+            if "value" in base:
+                line["weak_efficiency"] = value / (world * base["value"])
         print(json.dumps(line))
-    ctx_a.close()
-    ctx_b.close()
+    if rank != 0 or args.no_scaling_base:
+        comm.close()
+        ctx.close()
     dist.destroy_process_group()
