@@ -92,9 +92,11 @@ typedef struct wb_stats
   double ms_h2d,ms_decode,ms_build,ms_scan,ms_postscan,ms_classify,ms_d2h;  /* last run, CUDA events */
   double ms_sort,ms_leaves,ms_hier,ms_pairs,ms_classify_kernel;
   double ms_encode,ms_encode_d2h;   /* wb_encode: kernel, copy of the records to the host */
+  double ms_classify_order;         /* wb_classify: Hilbert re-sort of the store + hierarchy over it (part of ms_classify) */
 } wb_stats;
 
 /* ---- life cycle ---------------------------------------------------------- */
+int wb_device_count(int *out);                      /* CUDA devices this process can use */
 int wb_create(int device,wb_ctx **out);
 void wb_destroy(wb_ctx *ctx);
 const char *wb_last_error(wb_ctx *ctx);
@@ -272,6 +274,17 @@ int wb_encode(wb_ctx *ctx,const wb_out_spec *spec,const uint64_t *dest,const uin
  * [arena_off, arena_off+bytes) of them into the open file descriptor at file_pos (D2H through a pinned
  * ring, pwrite on worker threads). */
 int wb_write_encoded(wb_ctx *ctx,int fd,uint64_t file_pos,uint64_t arena_off,uint64_t bytes);
+/* censusPoints() (testpattern.cpp:56-123, run after every write, threads.cpp:613): test data carries the point number
+ * as GPS time; every point of the store sets one bit.  status -1: some GPS time is not a non-negative integer (not
+ * test data; nothing else is reported), 1: a number occurs twice ("Duplicate point"), 0: neither.  max_point = one
+ * past the highest number, n_missing = numbers below it that no stored point carries; up to `cap` of them,
+ * ascending, go to `missing` (may be NULL).  Needs the records on the device (wb_keep_records) and a built store. */
+typedef struct wb_census_result
+{
+  int32_t status,pad_;
+  uint64_t n_stored,max_point,n_missing,n_duplicate;
+} wb_census_result;
+int wb_census(wb_ctx *ctx,wb_census_result *out,uint64_t *missing,uint64_t cap);
 /* Records lost to an identical XYZ (octree.cpp:620-662): input index of each and of the point that
  * holds its place in the store; wb_stats.n_duplicates entries. */
 int wb_get_duplicates(wb_ctx *ctx,uint32_t *dup,uint32_t *rep,uint64_t cap);

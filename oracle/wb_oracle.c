@@ -1129,9 +1129,9 @@ int wbo_point_hyperboloid_sizes(const double *pts,uint64_t n,const double cube[4
   return 0;
 }
 
-int wbo_classify(const double *pts,uint64_t n,const double cube[4],double tile_size,
+static int classify_impl(const double *pts,uint64_t n,const double cube[4],double tile_size,
                  double max_slope,double thickness,const wbo_tile *tiles,int64_t n_tiles,
-                 uint8_t *labels,uint64_t *margin_count)
+                 const uint64_t *sel,uint64_t n_sel,uint8_t *labels,uint64_t *margin_count)
 /* classifyCylinder: classify.cpp:96-173, as a pure per-point function:
  *   tile  = the LAST tile in flowsnake order whose cylinder contains P (1-thread reference:
  *           a later tile re-classifies and overwrites, classify.cpp:158-165);
@@ -1147,7 +1147,8 @@ int wbo_classify(const double *pts,uint64_t n,const double cube[4],double tile_s
   int64_t gx,gy,*cellStart,ncell;
   uint32_t *cellPts;
   double *cellMinZ;
-  uint64_t i,margins=0;
+  uint64_t i,margins=0,si;
+  const uint64_t n_query=sel?n_sel:n;   /* sel: classify only these points (each still against the WHOLE cloud) */
   snake_init(&s,cube,tile_size);
   if (!tablesFilled)
     wbo_fill_tan_tables();
@@ -1195,8 +1196,9 @@ int wbo_classify(const double *pts,uint64_t n,const double cube[4],double tile_s
     int32_t *dirs=NULL;
     int dcap=0;
     #pragma omp for schedule(dynamic,256)
-    for (i=0;i<n;i++)
+    for (si=0;si<n_query;si++)
     {
+      const uint64_t i=sel?sel[si]:si;
       const double *P=pts+3*i;
       int64_t ns[19],best=LLONG_MIN;
       int exs[19],eys[19],c=covering_tiles(&s,P[0],P[1],ns,exs,eys),j,nd=0,marg=0;
@@ -1214,7 +1216,7 @@ int wbo_classify(const double *pts,uint64_t n,const double cube[4],double tile_s
       }
       if (!t)
       {
-        labels[i]=0;      /* in no tile: the reference never classifies it */
+        labels[si]=0;     /* in no tile: the reference never classifies it */
         continue;
       }
       r=t->hyperboloidSize;
@@ -1280,7 +1282,7 @@ int wbo_classify(const double *pts,uint64_t n,const double cube[4],double tile_s
             break;
         }
       }
-      labels[i]=wbo_surround(dirs,nd)?1:2;
+      labels[si]=wbo_surround(dirs,nd)?1:2;
       margins+=marg;
     }
     free(dirs);
@@ -1292,4 +1294,20 @@ int wbo_classify(const double *pts,uint64_t n,const double cube[4],double tile_s
   free(cellMinZ);
   free(cellPts);
   return 0;
+}
+
+int wbo_classify(const double *pts,uint64_t n,const double cube[4],double tile_size,
+                 double max_slope,double thickness,const wbo_tile *tiles,int64_t n_tiles,
+                 uint8_t *labels,uint64_t *margin_count)
+{
+  return classify_impl(pts,n,cube,tile_size,max_slope,thickness,tiles,n_tiles,NULL,0,labels,margin_count);
+}
+
+int wbo_classify_sel(const double *pts,uint64_t n,const double cube[4],double tile_size,
+                     double max_slope,double thickness,const wbo_tile *tiles,int64_t n_tiles,
+                     const uint64_t *sel,uint64_t n_sel,uint8_t *labels,uint64_t *margin_count)
+/* the same test for the points sel[0..n_sel) only (positions in pts), labels[k] for sel[k]: the whole cloud is
+ * still searched for every one of them, so a sample of a cloud too large to classify in full can be checked */
+{
+  return classify_impl(pts,n,cube,tile_size,max_slope,thickness,tiles,n_tiles,sel,n_sel,labels,margin_count);
 }

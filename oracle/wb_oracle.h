@@ -77,6 +77,11 @@ int wbo_classify(const double *pts_sorted,uint64_t n,const double cube[4],double
                  double max_slope,double thickness,const wbo_tile *tiles,int64_t n_tiles,
                  uint8_t *labels,uint64_t *margin_count);
 
+/* the same for the points at positions sel[0..n_sel) only, labels[k] for sel[k] (a sample of a very large cloud) */
+int wbo_classify_sel(const double *pts_sorted,uint64_t n,const double cube[4],double tile_size,
+                     double max_slope,double thickness,const wbo_tile *tiles,int64_t n_tiles,
+                     const uint64_t *sel,uint64_t n_sel,uint8_t *labels,uint64_t *margin_count);
+
 /* hyperboloidSize of the tile that classifies each point (NaN: in no tile); same arguments as wbo_classify */
 int wbo_point_hyperboloid_sizes(const double *pts_sorted,uint64_t n,const double cube[4],double tile_size,
                                 const wbo_tile *tiles,int64_t n_tiles,double *out);

@@ -76,6 +76,8 @@ def lib():
                                                   C.c_void_p]
         L.wbo_classify.argtypes = [C.c_void_p, C.c_uint64, dp, C.c_double, C.c_double, C.c_double,
                                    C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_uint64)]
+        L.wbo_classify_sel.argtypes = [C.c_void_p, C.c_uint64, dp, C.c_double, C.c_double, C.c_double,
+                                       C.c_void_p, C.c_int64, C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64)]
         L.wbo_shape_in.argtypes = [C.c_int, dp, dp]
         L.wbo_shape_intersects_cube.argtypes = [C.c_int, dp, dp, C.c_double]
         L.wbo_shape_filter.argtypes = [C.c_int, dp, C.c_void_p, C.c_uint64, C.c_void_p]

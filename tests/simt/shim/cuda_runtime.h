@@ -60,6 +60,7 @@ inline double __longlong_as_double(long long l) { double d; memcpy(&d,&l,8); ret
 inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 inline int __ffsll(long long v) { return __builtin_ffsll(v); }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
 inline unsigned __funnelshift_r(unsigned lo,unsigned hi,unsigned s)
 {
   unsigned long long v=((unsigned long long)hi<<32)|lo;
@@ -70,6 +71,7 @@ template <typename T> inline T __ldg(const T *p) { return *p; }
 // ---- memory (one warp runs at a time on this OS thread: plain operations) -------------------------------
 template <typename T,typename U> inline T atomicAdd(T *p,U v) { T o=*p; *p=(T)(o+(T)v); return o; }
 template <typename T,typename U> inline T atomicMax(T *p,U v) { T o=*p; if ((T)v>o) *p=(T)v; return o; }
+template <typename T,typename U> inline T atomicOr(T *p,U v) { T o=*p; *p=(T)(o|(T)v); return o; }
 template <typename T,typename U> inline T atomicMin(T *p,U v) { T o=*p; if ((T)v<o) *p=(T)v; return o; }
 
 // ---- warp-wide intrinsics -----------------------------------------------------------------------------

@@ -1,5 +1,9 @@
 """Full parity at a few million points (the oracle needs ~15 s per scene on the GPU box's cores):
-byte-identical dump, bit-identical hyperboloidSize, identical labels.  WB_LARGE=1 adds a 10 M run."""
+byte-identical dump, bit-identical hyperboloidSize, identical labels.  WB_LARGE=1 adds a 10 M run.
+And parity at CONFIG scale — BASELINE configs[0] (10 M street scene) and configs[1] (the 100 M aerial tile the bench
+times) — against vectors the oracle produced for exactly those clouds (tests/golden/make_config_scale.py): digests
+of canonical order, octree dump and tile table, and the class bytes of a 300-400 k point sample."""
+import hashlib
 import os
 
 import numpy as np
@@ -36,5 +40,42 @@ def test_full_parity_millions(scene, n):
           "label mismatches %d, margin points gpu %d / oracle %d"
           % (scene, cloud.n, st["n_leaves"], len(tiles), tiles["nPoints"].max(), int((ulp > 0).sum()), int(ulp.max()),
              mism, st["n_margin"], res.margin_count))
-    assert ulp.max() <= 4
+    assert ulp.max() == 0          # bit-identical on every scene so far; a tolerance here would hide a regression
     assert mism <= st["n_margin"] + res.margin_count
+
+
+def _tiles_digest(tiles):
+    h = hashlib.sha256()
+    for f, dt in (("n", np.int32), ("nPoints", np.int32), ("treeFlags", np.int32)):
+        h.update(np.ascontiguousarray(tiles[f].astype(dt)).tobytes())
+    h.update(np.ascontiguousarray(tiles["hyperboloidSize"].astype(np.float64)).view(np.uint64).tobytes())
+    return h.hexdigest()
+
+
+@pytest.mark.parametrize("name", ["config_scale_s1_10000000.npz", "config_scale_s2_100000000.npz"])
+def test_config_scale_against_oracle_vectors(name, golden_dir):
+    g = np.load(os.path.join(golden_dir, name))
+    scene, n_points = int(g["scene"]), int(g["n_points"])
+    cloud = synth.generate(scene, n_points, seed=scene)
+    assert cloud.n == int(g["n"])
+    ctx = api.Context(0)
+    ctx.set_params()
+    ctx.add_cloud(cloud)
+    ctx.run()
+    lab = ctx.labels(cloud.n)
+    st = ctx.stats()
+    order, _ = ctx.order(int(st["n_points"]))
+    dump = ctx.dump()
+    tiles = ctx.tiles()
+    ctx.close()
+    assert int(st["n_duplicates"]) == int(g["n_duplicates"]) == 0
+    assert hashlib.sha256(order.tobytes()).hexdigest() == str(g["order_sha256"]), "canonical order"
+    assert int(st["n_leaves"]) == int(g["n_leaves"])
+    assert hashlib.sha256(dump.encode("utf-8")).hexdigest() == str(g["dump_sha256"]), "octree dump"
+    assert len(tiles) == int(g["n_tiles"])
+    assert float(tiles["hyperboloidSize"].max()) == float(g["hyp_max"])
+    assert _tiles_digest(tiles) == str(g["tiles_sha256"]), "tile table"
+    mism = int((lab[g["sample"]] != g["labels"]).sum())
+    print("%s: %d points, %d leaves, %d tiles, %d sampled labels, %d mismatches, margin gpu %d / oracle sample %d"
+          % (name, cloud.n, st["n_leaves"], len(tiles), len(g["sample"]), mism, st["n_margin"], int(g["margin"])))
+    assert mism <= int(st["n_margin"]) + int(g["margin"])

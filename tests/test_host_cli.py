@@ -291,3 +291,45 @@ def test_device_writer_equals_host_writer(tmp_path, case):
     if case.startswith("mixed"):
         info, recs = _las14(str(tmp_path / "device" / sorted(out["device"])[0]))
         assert info["fmt"] == (6 if case == "mixed_1_6" else 7)
+
+
+def _strip_files(tmp_path, scene, n, strips, seed=61):
+    d = synth.describe(scene, n)
+    cuts = [d.grid_nx * k // strips for k in range(strips + 1)]
+    clouds, names, base = [], [], 0
+    for k in range(strips):
+        c = synth.generate(scene, n, seed=seed, region=(cuts[k], 0, cuts[k + 1] - cuts[k], d.grid_ny), gps_base=base)
+        base += c.n
+        name = str(tmp_path / ("strip%d.las" % k))
+        c.write(name)
+        clouds.append(c)
+        names.append(name)
+    return clouds, names
+
+
+@pytest.mark.parametrize("gpus,strips", [(2, 3), (4, 4)])
+def test_cli_gpus_equals_oracle_and_one_gpu(tmp_path, gpus, strips):
+    """wolkencli --gpus N (startThreads(N): one worker per GPU, x-strips, wb_shard_run) against the oracle's labels
+    for the whole cloud and against the same command line on one GPU.  The files are given in shuffled order: the
+    CLI puts them in ascending x.  On a one-GPU box the workers share the device over the LOCAL transport
+    (WOLKEN_TRANSPORT=local); with one GPU per worker the transport is NCCL (tests/test_multigpu_nccl.py)."""
+    import torch
+    clouds, names = _strip_files(tmp_path, 2, 60000, strips)
+    env = dict(os.environ)
+    if os.environ.get("WB_EMULATED") or torch.cuda.device_count() < gpus:
+        env["WOLKEN_TRANSPORT"] = "local"
+    shuffled = names[1:] + names[:1]
+    outs = {}
+    for g in (gpus, 1):
+        o = subprocess.run([CLI, "--gpus", str(g), "-o", str(tmp_path / ("o%d" % g)), "--lossless", "--separate-classes",
+                            "0", "--dump", str(tmp_path / ("d%d" % g))] + (shuffled if g > 1 else names), capture_output=True,
+                           text=True, env=env)
+        assert o.returncode == 0, o.stdout[-2000:] + o.stderr[-2000:]
+        outs[g] = o.stdout
+    assert "%d GPUs" % min(gpus, strips) in outs[gpus] and "GPUs" not in outs[1]
+    res = O.run([O.file_from_cloud(c) for c in clouds])
+    _, recs, _ = _read_las(str(tmp_path / ("o%d.las" % gpus)))
+    assert recs.shape[0] == sum(c.n for c in clouds)
+    assert ((recs[:, 15] & 31) == res.labels).all()
+    assert open(tmp_path / ("o%d.las" % gpus), "rb").read() == open(tmp_path / "o1.las", "rb").read()
+    assert open(tmp_path / ("d%d" % gpus), encoding="utf-8").read() == res.dump

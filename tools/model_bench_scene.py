@@ -60,12 +60,56 @@ def prepare(scene, n_points, seed):
     return pts, hyp
 
 
+def _spread(v):
+    v = v & np.uint64(0xfffff)
+    for sh, mask in ((16, 0x0000ffff0000ffff), (8, 0x00ff00ff00ff00ff), (4, 0x0f0f0f0f0f0f0f0f),
+                     (2, 0x3333333333333333), (1, 0x5555555555555555)):
+        v = (v | (v << np.uint64(sh))) & np.uint64(mask)
+    return v
+
+
+def _hilbert(ix, iy, bits):
+    """Hilbert index of integer cells (vectorised x,y -> d)."""
+    x, y = ix.astype(np.int64), iy.astype(np.int64)
+    d = np.zeros(len(x), dtype=np.int64)
+    s = 1 << (bits - 1)
+    while s > 0:
+        rx = ((x & s) > 0).astype(np.int64)
+        ry = ((y & s) > 0).astype(np.int64)
+        d += s * s * ((3 * rx) ^ ry)
+        flip = (ry == 0) & (rx == 1)
+        x = np.where(flip, s - 1 - x, x)
+        y = np.where(flip, s - 1 - y, y)
+        swap = ry == 0
+        x, y = np.where(swap, y, x), np.where(swap, x, y)
+        x &= s - 1
+        y &= s - 1
+        s >>= 1
+    return d
+
+
+def reorder(pts, hyp, how):
+    """WB_MODEL_ORDER=xy|hilbert: the same points chunked along a 2-D curve over xy instead of the canonical
+    (3-D Morton) order — what a classify-only re-sort would give."""
+    if not how:
+        return pts, hyp
+    x, y = pts[:, 0], pts[:, 1]
+    bits = 20
+    side = max(x.max() - x.min(), y.max() - y.min()) + 1e-9
+    ix = ((x - x.min()) / side * (1 << bits)).astype(np.uint64)
+    iy = ((y - y.min()) / side * (1 << bits)).astype(np.uint64)
+    key = _hilbert(ix, iy, bits) if how == "hilbert" else (_spread(ix) | (_spread(iy) << np.uint64(1)))
+    o = np.argsort(key, kind="stable")
+    return np.ascontiguousarray(pts[o]), np.ascontiguousarray(hyp[o])
+
+
 def main():
     n_points = int(sys.argv[1]) if len(sys.argv) > 1 else 3_000_000
     n_warps = int(sys.argv[2]) if len(sys.argv) > 2 else 200
     variants = sys.argv[3:] or [""]
     scene = int(os.environ.get("WB_MODEL_SCENE", "2"))
     pts, hyp = prepare(scene, n_points, scene)
+    pts, hyp = reorder(pts, hyp, os.environ.get("WB_MODEL_ORDER", ""))
     n = len(pts)
     n_chunks = (n + 31) // 32
     rng = np.random.default_rng(1)

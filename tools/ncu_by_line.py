@@ -14,7 +14,7 @@ for r in rows:
         kern = r[1]; continue
     if r and r[0] == 'Line No':
         hdr = r; continue
-    if hdr is None or len(r) < len(hdr) or r[0] == '' or want not in (kern or ""):
+    if hdr is None or len(r) < 9 or r[0] == '' or want not in (kern or ""):
         continue
     try:
         inst, samp, tinst = int(r[7]), int(r[6]), int(r[8])

@@ -35,7 +35,8 @@ class Stats(C.Structure):
                                           "cl_pairs2", "cl_warps2", "kernel_launches")] + \
                [(k, C.c_double) for k in ("ms_h2d", "ms_decode", "ms_build", "ms_scan", "ms_postscan",
                                           "ms_classify", "ms_d2h", "ms_sort", "ms_leaves", "ms_hier",
-                                          "ms_pairs", "ms_classify_kernel", "ms_encode", "ms_encode_d2h")]
+                                          "ms_pairs", "ms_classify_kernel", "ms_encode", "ms_encode_d2h",
+                                          "ms_classify_order")]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -55,6 +56,11 @@ _u64p = C.POINTER(C.c_uint64)
 ALL_GATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64)
 ALL_TO_ALL_V_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, _u64p, _u64p, C.c_void_p, _u64p, _u64p)
 ALL_REDUCE_MAX_U8_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_uint64)
+
+
+class CensusResult(C.Structure):
+    _fields_ = [("status", C.c_int32), ("pad_", C.c_int32), ("n_stored", C.c_uint64), ("max_point", C.c_uint64),
+                ("n_missing", C.c_uint64), ("n_duplicate", C.c_uint64)]
 
 
 class CommOps(C.Structure):
@@ -145,6 +151,8 @@ def lib():
             "wb_ldecimal": [C.c_double, C.c_char_p, C.c_int],
             "wb_format_dump": [vp, u64, C.c_char_p, u64],
             "wb_keep_records": [vp, C.c_int],
+            "wb_census": [vp, C.POINTER(CensusResult), vp, C.c_uint64],
+            "wb_device_count": [C.POINTER(C.c_int)],
             "wb_leaf_class_counts": [vp, vp, C.c_int, C.c_int, vp],
             "wb_encode": [vp, C.POINTER(OutSpec), vp, vp, C.c_uint32, vp, u64, vp],
             "wb_get_duplicates": [vp, vp, vp, u64],
@@ -187,7 +195,7 @@ EXPORTS = ["wb_create", "wb_destroy", "wb_last_error", "wb_reserve", "wb_clear",
            "wb_query_points", "wb_mark", "wb_mark_elapsed", "wb_set_return_zero_rule",
            "wb_comm_get_id", "wb_comm_init", "wb_local_group_create", "wb_local_group_destroy", "wb_comm_init_local",
            "wb_comm_init_custom", "wb_comm_destroy", "wb_shard_run", "wb_shard_get_labels", "wb_shard_get_stats",
-           "wb_set_labels"]
+           "wb_set_labels", "wb_device_count", "wb_census"]
 
 
 def _d(v):
@@ -475,6 +483,16 @@ class Context:
         lab = out if out is not None else np.empty(n, dtype=np.uint8)
         self._ck(self._L.wb_get_labels(self._h, lab.ctypes.data))
         return lab
+
+    def census(self, cap=64):
+        """censusPoints() (testpattern.cpp:84-123) over the store: dict with status, max_point, n_missing, n_duplicate
+        and up to `cap` missing point numbers.  Needs keep_records() before the records were added."""
+        r = CensusResult()
+        miss = np.zeros(max(1, cap), dtype=np.uint64)
+        self._ck(self._L.wb_census(self._h, C.byref(r), miss.ctypes.data if cap else None, cap))
+        return {"status": int(r.status), "n_stored": int(r.n_stored), "max_point": int(r.max_point),
+                "n_missing": int(r.n_missing), "n_duplicate": int(r.n_duplicate),
+                "missing": miss[:min(cap, int(r.n_missing))].tolist()}
 
     def count_classes(self):
         c = np.zeros(256, dtype=np.uint64)

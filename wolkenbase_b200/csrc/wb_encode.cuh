@@ -284,3 +284,79 @@ wb_encode_kernel(const WbLeafDev *__restrict__ leaves,uint32_t nLeaves,
     }
   }
 }
+
+// ============================================================================ census (testpattern.cpp:56-123)
+// censusPoints(): test data carries its point number as GPS time; after a write the reference walks every block of
+// the store, sets one bit per number and reports numbers seen twice and numbers missing below the highest one.
+// One thread per stored point, two passes: the highest number (which sizes the bit set), then the bits.
+struct WbCensus { unsigned long long notInteger,duplicate,maxPlusOne; };
+
+__global__ void __launch_bounds__(256)
+wb_census_mark_kernel(const uint32_t *__restrict__ src,unsigned long long nv,const WbSegments *__restrict__ segs,
+                      const WbRecSegs *__restrict__ rsegs,unsigned long long *__restrict__ bits /* NULL: first pass */,
+                      WbCensus *__restrict__ out)
+{
+  unsigned long long j=(unsigned long long)blockIdx.x*blockDim.x+threadIdx.x;
+  if (j>=nv)
+    return;
+  const uint32_t i=src[j];
+  int lo=0,hi=segs->n-1;
+  while (lo<hi)
+  {
+    int mid=(lo+hi+1)>>1;
+    if (segs->s[mid].first<=i)
+      lo=mid;
+    else
+      hi=mid-1;
+  }
+  const int fi=rsegs->s[lo].fmt;
+  const uint8_t *r=rsegs->s[lo].recs+(unsigned long long)(i-segs->s[lo].first)*rsegs->s[lo].recLen;
+  double t=0;                                       // formats without GPS time read as 0 (LasPoint ctor, las.cpp:128)
+  if ((1<<fi)&0x7fa)                                // MASK_GPSTIME: 10-5, 4, 3, 1 (las.cpp:776)
+  {
+    unsigned long long u=0;
+    const uint8_t *g=r+(fi<6?20:22);
+    #pragma unroll
+    for (int k=7;k>=0;k--)
+      u=(u<<8)|g[k];
+    t=__longlong_as_double((long long)u);
+  }
+  // n=lrint(t); n!=t || n<0 -> not test data (testpattern.cpp:68-70; n is an int there: numbers stay below 2^31)
+  if (!(t>=0) || t>=2147483648.0 || t!=rint(t))
+  {
+    if (!bits)
+      atomicAdd(&out->notInteger,1ull);
+    return;
+  }
+  const unsigned long long nn=(unsigned long long)t;
+  if (!bits)
+  {
+    atomicMax(&out->maxPlusOne,nn+1);
+    return;
+  }
+  const unsigned long long m=1ull<<(nn&63);
+  if (atomicOr(&bits[nn>>6],m)&m)
+    atomicAdd(&out->duplicate,1ull);
+}
+
+__global__ void __launch_bounds__(256)
+wb_census_missing_kernel(const unsigned long long *__restrict__ bits,unsigned long long top,
+                         unsigned long long *__restrict__ nMissing,unsigned long long *__restrict__ list,unsigned long long cap)
+// numbers below top = maxPoint that no stored point carries; `cap` of them (any) go into list
+{
+  unsigned long long w=(unsigned long long)blockIdx.x*blockDim.x+threadIdx.x;
+  if (w*64>=top)
+    return;
+  unsigned long long miss=~bits[w];
+  if ((w+1)*64>top)
+    miss&=(1ull<<(top-w*64))-1;
+  if (!miss)
+    return;
+  unsigned long long at=atomicAdd(nMissing,(unsigned long long)__popcll(miss));
+  while (miss && at<cap)
+  {
+    int b=__ffsll((long long)miss)-1;
+    miss&=miss-1;
+    list[at++]=w*64+b;
+  }
+}

@@ -52,6 +52,10 @@ template <typename T> struct DevBuf
     cap=0;
   }
 };
+template <typename T> struct TmpBuf:DevBuf<T>      // a scratch buffer of one call
+{
+  ~TmpBuf() { this->release(); }
+};
 
 enum Phase { PH_EMPTY=0,PH_LOADED,PH_BUILT,PH_SCANNED,PH_POSTSCANNED,PH_CLASSIFIED };
 
@@ -122,6 +126,12 @@ struct wb_ctx
 #endif
   DevBuf<uint8_t> chunkPending;
   DevBuf<uint8_t> tileGrid;
+  // classify order (Hilbert over xy): sort scratch, the store's columns in that order, the hierarchy over them
+  DevBuf<unsigned long long> hKeyA,hKeyB;
+  DevBuf<uint32_t> hIdxA,hIdxB,hWinner,hPerm;
+  DevBuf<double> hx,hy,hz;
+  DevBuf<uint8_t> hLabel;
+  DevBuf<WbBound> hBounds;
   // results of build
   unsigned long long *keys=nullptr;   // sorted keys (keyA or keyB)
   uint32_t *perm=nullptr;             // sorted -> input
@@ -303,6 +313,17 @@ int checkFormat(wb_ctx *ctx,int fmt,int recLen)
 
 // ============================================================================ life cycle
 
+extern "C" int wb_device_count(int *out)
+{
+  if (!out)
+    return WB_ERR_ARG;
+  int ndev=0;
+  if (cudaGetDeviceCount(&ndev)!=cudaSuccess)
+    ndev=0;
+  *out=ndev;
+  return ndev>0?WB_OK:WB_ERR_CUDA;
+}
+
 extern "C" int wb_create(int device,wb_ctx **out)
 {
   if (!out)
@@ -356,6 +377,8 @@ extern "C" void wb_destroy(wb_ctx *ctx)
   ctx->staging[0].release(); ctx->staging[1].release(); ctx->dsegs.release();
   ctx->nodesA.release(); ctx->nodesB.release(); ctx->leaves.release(); ctx->bounds.release();
   ctx->levelOff.release(); ctx->levelCnt.release();
+  ctx->hKeyA.release(); ctx->hKeyB.release(); ctx->hIdxA.release(); ctx->hIdxB.release(); ctx->hWinner.release(); ctx->hPerm.release();
+  ctx->hx.release(); ctx->hy.release(); ctx->hz.release(); ctx->hLabel.release(); ctx->hBounds.release();
   ctx->tStart.release(); ctx->tCount.release(); ctx->tileList.release(); ctx->tNPoints.release(); ctx->tTree.release();
   ctx->tDensity.release(); ctx->tHyp.release(); ctx->tHeight.release(); ctx->tileExt.release(); ctx->tileGrid.release(); ctx->wedgeBuf.release(); ctx->chunkPending.release();
 #if WB_CL_COMPACT2
@@ -1322,14 +1345,53 @@ extern "C" int wb_classify(wb_ctx *ctx)
   CK(cudaMemsetAsync(ctx->counters.p,0,2*sizeof(unsigned long long),st));
   CK(cudaMemsetAsync(ctx->counters.p+6,0,18*sizeof(unsigned long long),st));
   wb_init_labels_kernel<<<gridFor(ctx->n,256),256,0,st>>>(ctx->cls.p,ctx->n,ctx->labelIn.p);
+  const double *qx=ctx->sx.p,*qy=ctx->sy.p,*qz=ctx->sz.p;
+  const uint32_t *qwinner=ctx->winner.p,*qperm=ctx->perm,*hord=nullptr;
+  const WbBound *qbounds=ctx->bounds.p;
+  uint8_t *qlabel=ctx->labelSorted.p;
+#if WB_CL_HILBERT
+  if (nv)
+  {
+    // the store along a Hilbert curve over xy (see wb_kernels.cuh, "classify order")
+    CK(ctx->hKeyA.ensure(nv)); CK(ctx->hKeyB.ensure(nv)); CK(ctx->hIdxA.ensure(nv)); CK(ctx->hIdxB.ensure(nv));
+    CK(ctx->hx.ensure(nv)); CK(ctx->hy.ensure(nv)); CK(ctx->hz.ensure(nv)); CK(ctx->hWinner.ensure(nv)); CK(ctx->hPerm.ensure(nv));
+    CK(ctx->hLabel.ensure(nv));
+    CK(ctx->hBounds.ensure(ctx->hLevelOff.back()+ctx->hLevelCnt.back()));
+    const wb_geometry &g=ctx->geom;
+    const double x0=g.root_center[0]-g.root_side,y0=g.root_center[1]-g.root_side;
+    const double cells=(double)(1u<<WB_HILBERT_BITS)/(2*g.root_side);
+    wb_hilbert_key_kernel<<<gridFor(nv,256),256,0,st>>>(ctx->sx.p,ctx->sy.p,nv,x0,y0,cells,ctx->hKeyA.p,ctx->hIdxA.p);
+    ctx->stats.kernel_launches++;
+    bool inA=true;
+    CK(wb_radix_sort((uint64_t *)ctx->hKeyA.p,ctx->hIdxA.p,(uint64_t *)ctx->hKeyB.p,ctx->hIdxB.p,nv,0,2*WB_HILBERT_BITS,
+                     ctx->table.p,ctx->table.cap,ctx->blockSums.p,ctx->blockSums.cap,st,&inA,&ctx->stats.kernel_launches));
+    hord=inA?ctx->hIdxA.p:ctx->hIdxB.p;
+    wb_classify_gather_kernel<<<gridFor(nv,256),256,0,st>>>(hord,nv,ctx->sx.p,ctx->sy.p,ctx->sz.p,ctx->winner.p,ctx->perm,
+                                                           ctx->hx.p,ctx->hy.p,ctx->hz.p,ctx->hWinner.p,ctx->hPerm.p);
+    wb_chunk_bounds_kernel<<<gridFor((uint64_t)ctx->nChunks*32,256),256,0,st>>>(ctx->hx.p,ctx->hy.p,ctx->hz.p,nv,
+                                                                              ctx->hBounds.p,ctx->nChunks);
+    ctx->stats.kernel_launches+=2;
+    for (int l=1;l<ctx->nLevels;l++)
+    {
+      wb_node_bounds_kernel<<<gridFor((uint64_t)ctx->hLevelCnt[l]*32,256),256,0,st>>>(
+          ctx->hBounds.p+ctx->hLevelOff[l-1],ctx->hLevelCnt[l-1],ctx->hBounds.p+ctx->hLevelOff[l],ctx->hLevelCnt[l]);
+      ctx->stats.kernel_launches++;
+    }
+    KCHECK();
+    qx=ctx->hx.p; qy=ctx->hy.p; qz=ctx->hz.p;
+    qwinner=ctx->hWinner.p; qperm=ctx->hPerm.p;
+    qbounds=ctx->hBounds.p;
+    qlabel=ctx->hLabel.p;
+  }
+#endif
   CK(cudaEventRecord(ctx->evC,st));
   CK(ctx->wedgeBuf.ensure(nv));
   CK(ctx->chunkPending.ensure(ctx->nChunks));
   CK(cudaMemsetAsync(ctx->chunkPending.p,0,ctx->nChunks,st));
   wb_classify_kernel<1><<<gridFor(ctx->nChunks,WB_CL_WARPS),WB_CL_WARPS*32,0,st>>>(
-      ctx->sx.p,ctx->sy.p,ctx->sz.p,nv,ctx->nChunks,ctx->bounds.p,ctx->levelOff.p,ctx->levelCnt.p,ctx->nLevels,
-      ctx->winner.p,ctx->tHyp.p,ctx->prm.maxSlope,ctx->prm.thickness,ctx->cls.p,ctx->perm,
-      ctx->ownFirst,ctx->ownEnd,ctx->haveForced?ctx->forcedIn.p:nullptr,ctx->labelSorted.p,ctx->counters.p,ctx->wedgeBuf.p,ctx->chunkPending.p
+      qx,qy,qz,nv,ctx->nChunks,qbounds,ctx->levelOff.p,ctx->levelCnt.p,ctx->nLevels,
+      qwinner,ctx->tHyp.p,ctx->prm.maxSlope,ctx->prm.thickness,ctx->cls.p,qperm,
+      ctx->ownFirst,ctx->ownEnd,ctx->haveForced?ctx->forcedIn.p:nullptr,qlabel,ctx->counters.p,ctx->wedgeBuf.p,ctx->chunkPending.p
 #if WB_CL_COMPACT2
       ,nullptr,0u
 #endif
@@ -1348,20 +1410,25 @@ extern "C" int wb_classify(wb_ctx *ctx)
     {
       wb_pending_scatter_kernel<<<gridFor(nv,256),256,0,st>>>(ctx->scr0.p,ctx->scr1.p,nv,ctx->pendingList.p);
       wb_classify_kernel<2><<<gridFor(wb_div_up(nPending,32),WB_CL_WARPS),WB_CL_WARPS*32,0,st>>>(
-          ctx->sx.p,ctx->sy.p,ctx->sz.p,nv,ctx->nChunks,ctx->bounds.p,ctx->levelOff.p,ctx->levelCnt.p,ctx->nLevels,
-          ctx->winner.p,ctx->tHyp.p,ctx->prm.maxSlope,ctx->prm.thickness,ctx->cls.p,ctx->perm,
-          ctx->ownFirst,ctx->ownEnd,ctx->haveForced?ctx->forcedIn.p:nullptr,ctx->labelSorted.p,ctx->counters.p,ctx->wedgeBuf.p,ctx->chunkPending.p,
+          qx,qy,qz,nv,ctx->nChunks,qbounds,ctx->levelOff.p,ctx->levelCnt.p,ctx->nLevels,
+          qwinner,ctx->tHyp.p,ctx->prm.maxSlope,ctx->prm.thickness,ctx->cls.p,qperm,
+          ctx->ownFirst,ctx->ownEnd,ctx->haveForced?ctx->forcedIn.p:nullptr,qlabel,ctx->counters.p,ctx->wedgeBuf.p,ctx->chunkPending.p,
           ctx->pendingList.p,nPending);
     }
     ctx->stats.kernel_launches+=2;
   }
 #else
   wb_classify_kernel<2><<<gridFor(ctx->nChunks,WB_CL_WARPS),WB_CL_WARPS*32,0,st>>>(
-      ctx->sx.p,ctx->sy.p,ctx->sz.p,nv,ctx->nChunks,ctx->bounds.p,ctx->levelOff.p,ctx->levelCnt.p,ctx->nLevels,
-      ctx->winner.p,ctx->tHyp.p,ctx->prm.maxSlope,ctx->prm.thickness,ctx->cls.p,ctx->perm,
-      ctx->ownFirst,ctx->ownEnd,ctx->haveForced?ctx->forcedIn.p:nullptr,ctx->labelSorted.p,ctx->counters.p,ctx->wedgeBuf.p,ctx->chunkPending.p);
+      qx,qy,qz,nv,ctx->nChunks,qbounds,ctx->levelOff.p,ctx->levelCnt.p,ctx->nLevels,
+      qwinner,ctx->tHyp.p,ctx->prm.maxSlope,ctx->prm.thickness,ctx->cls.p,qperm,
+      ctx->ownFirst,ctx->ownEnd,ctx->haveForced?ctx->forcedIn.p:nullptr,qlabel,ctx->counters.p,ctx->wedgeBuf.p,ctx->chunkPending.p);
 #endif
   CK(cudaEventRecord(ctx->evD,st));
+  if (hord)
+  {
+    wb_classify_scatter_kernel<<<gridFor(nv,256),256,0,st>>>(hord,ctx->hLabel.p,nv,ctx->labelSorted.p);
+    ctx->stats.kernel_launches++;
+  }
   wb_scatter_labels_kernel<<<gridFor(nv,256),256,0,st>>>(ctx->labelSorted.p,ctx->perm,nv,ctx->labelIn.p);
   ctx->stats.kernel_launches+=4;
   if (ctx->nDup)
@@ -1384,6 +1451,7 @@ extern "C" int wb_classify(wb_ctx *ctx)
   ctx->stats.cl_warps2=c[14];
   ctx->stats.ms_classify=elapsed(ctx->evA,ctx->evB);
   ctx->stats.ms_classify_kernel=elapsed(ctx->evC,ctx->evD);
+  ctx->stats.ms_classify_order=elapsed(ctx->evA,ctx->evC);
   ctx->stats.n_margin=c[0];
   ctx->stats.n_untiled=c[1];
   ctx->phase=PH_CLASSIFIED;
@@ -1690,6 +1758,88 @@ extern "C" int wb_encode(wb_ctx *ctx,const wb_out_spec *spec,const uint64_t *des
   }
   ctx->stats.ms_encode=elapsed(ctx->evA,ctx->evB);
   ctx->stats.ms_encode_d2h=elapsed(ctx->evB,ctx->evC);
+  return WB_OK;
+}
+
+extern "C" int wb_census(wb_ctx *ctx,wb_census_result *out,uint64_t *missing,uint64_t cap)
+{
+  if (!ctx || !out || (cap && !missing))
+    return WB_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  memset(out,0,sizeof(*out));
+  if (ctx->phase<PH_BUILT)
+    return fail(ctx,WB_ERR_STATE,"not built");
+  if (ctx->recSegs.size()!=ctx->segs.size())
+    return fail(ctx,WB_ERR_STATE,"internal: record segments");
+  for (size_t i=0;i<ctx->segs.size();i++)
+    if (ctx->segs[i].count && !ctx->recSegs[i].recs)
+      return fail(ctx,WB_ERR_STATE,"the records were not kept: call wb_keep_records(ctx,1) before wb_add_las");
+  cudaStream_t st=ctx->st;
+  const uint64_t nv=ctx->nValid;
+  out->n_stored=nv;
+  {
+    WbRecSegs hr;
+    memset(&hr,0,sizeof(hr));
+    for (size_t i=0;i<ctx->recSegs.size();i++)
+      hr.s[i]=ctx->recSegs[i];
+    CK(ctx->drsegs.ensure(1));
+    CK(cudaMemcpyAsync(ctx->drsegs.p,&hr,sizeof(hr),cudaMemcpyHostToDevice,st));
+    CK(cudaStreamSynchronize(st));
+  }
+  const uint32_t *src=ctx->perm;
+  if (ctx->nDup)
+  {
+    // the store holds the LAST record put at a location (octree.cpp:620-662)
+    CK(ctx->invPerm.ensure(ctx->n)); CK(ctx->attrSrc.ensure(nv));
+    wb_attr_source_kernel<<<gridFor(nv,256),256,0,st>>>(ctx->perm,nv,ctx->invPerm.p,ctx->attrSrc.p);
+    wb_attr_last_kernel<<<gridFor(ctx->nDup,256),256,0,st>>>(ctx->dupIn.p,ctx->dupRep.p,ctx->nDup,ctx->invPerm.p,ctx->attrSrc.p);
+    ctx->stats.kernel_launches+=2;
+    src=ctx->attrSrc.p;
+  }
+  TmpBuf<unsigned long long> bits,list;
+  TmpBuf<WbCensus> cen;
+  CK(cen.ensure(1)); CK(list.ensure(cap+1));
+  CK(cudaMemsetAsync(cen.p,0,sizeof(WbCensus),st));
+  CK(cudaMemsetAsync(ctx->counters.p+15,0,sizeof(unsigned long long),st));
+  WbCensus h;
+  memset(&h,0,sizeof(h));
+  if (nv)
+  {
+    wb_census_mark_kernel<<<gridFor(nv,256),256,0,st>>>(src,nv,ctx->dsegs.p,ctx->drsegs.p,nullptr,cen.p);
+    ctx->stats.kernel_launches++;
+    KCHECK();
+    CK(cudaMemcpyAsync(&h,cen.p,sizeof(h),cudaMemcpyDeviceToHost,st));
+    CK(cudaStreamSynchronize(st));
+  }
+  if (h.notInteger)
+  {
+    out->status=-1;
+    return WB_OK;
+  }
+  unsigned long long nMissing=0;
+  if (h.maxPlusOne)
+  {
+    const uint64_t nWords=wb_div_up(h.maxPlusOne,64);
+    CK(bits.ensure(nWords));
+    CK(cudaMemsetAsync(bits.p,0,nWords*sizeof(unsigned long long),st));
+    wb_census_mark_kernel<<<gridFor(nv,256),256,0,st>>>(src,nv,ctx->dsegs.p,ctx->drsegs.p,bits.p,cen.p);
+    wb_census_missing_kernel<<<gridFor(nWords,256),256,0,st>>>(bits.p,h.maxPlusOne,ctx->counters.p+15,list.p,cap);
+    ctx->stats.kernel_launches+=2;
+    KCHECK();
+    CK(cudaMemcpyAsync(&h,cen.p,sizeof(h),cudaMemcpyDeviceToHost,st));
+    CK(cudaMemcpyAsync(&nMissing,ctx->counters.p+15,sizeof(nMissing),cudaMemcpyDeviceToHost,st));
+    CK(cudaStreamSynchronize(st));
+  }
+  out->status=h.duplicate?1:0;
+  out->max_point=h.maxPlusOne;
+  out->n_duplicate=h.duplicate;
+  out->n_missing=nMissing;
+  const uint64_t k=std::min<uint64_t>(cap,nMissing);
+  if (k)
+  {
+    CK(cudaMemcpy(missing,list.p,k*sizeof(uint64_t),cudaMemcpyDeviceToHost));
+    std::sort(missing,missing+k);
+  }
   return WB_OK;
 }
 

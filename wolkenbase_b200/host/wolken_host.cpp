@@ -10,6 +10,9 @@
 #include <sys/stat.h>
 #include <unistd.h>
 #include <chrono>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include "wolken_host.h"
 
 using namespace std;
@@ -24,10 +27,12 @@ double minHyperboloidSize=0.1,maxSlope=1,thickness=0,tileSize=1;
 bool keepRecordsOnDevice=false;
 bool hostQueries=false;
 double hostTimes[4]={0,0,0,0};        // seconds in wb_create, wb_add_las_file, wb_build, wb_encode+write
+ShardReport shardReport;
 
 namespace
 {
 wb_ctx *g_ctx=nullptr;
+int g_nGpus=1;
 int g_command=TH_WAIT;
 struct InputSeg { LasHeader *h; size_t firstRec,count; };   // a run of records of one open file
 vector<InputSeg> g_files;              // in read order: input index = concatenation of these runs
@@ -948,15 +953,145 @@ void OctStore::clear()
   g_labels.clear();
 }
 
+// ---------------------------------------------------------------- cloud.cpp
+vector<xyz> cloud;
+
+int64_t getNumCloudBlocks()
+{
+  return (int64_t)((cloud.size()+RECORDS-1)/RECORDS);
+}
+
+vector<LasPoint> getCloudBlock(int64_t n)
+{
+  vector<LasPoint> ret;
+  if (n<0)
+    return ret;
+  LasPoint pnt;
+  for (size_t i=(size_t)n*RECORDS;i<(size_t)(n+1)*RECORDS && i<cloud.size();i++)
+  {
+    pnt.location=cloud[i];
+    ret.push_back(pnt);
+  }
+  return ret;
+}
+
+// ---------------------------------------------------------------- testpattern.cpp: the census
+namespace
+{
+vector<uint64_t> g_pointCensus;
+}
+
+int censusPoints(vector<LasPoint> points)
+// 1: a number was already counted; -1: a GPS time is no point number; 0: all new
+{
+  int ret=0;
+  for (size_t i=0;i<points.size() && ret>=0;i++)
+  {
+    const double t=points[i].gpsTime;
+    if (!(t>=0) || t>=2147483648.0 || t!=rint(t))
+      ret=-1;
+    else
+    {
+      const uint64_t n=(uint64_t)t;
+      if (g_pointCensus.size()<n/64+1)
+        g_pointCensus.resize(n/64+1);
+      const uint64_t mask=(uint64_t)1<<(n%64);
+      if (g_pointCensus[n/64]&mask)
+        ret=1;
+      g_pointCensus[n/64]|=mask;
+    }
+  }
+  return ret;
+}
+
+long long censusPoints(ostream *report)
+{
+  ostream &os=report?*report:cout;
+  ensureBuilt();
+  int err=0;
+  uint64_t maxPoint=0,nMissing=0;
+  vector<uint64_t> missing;
+  if (keepRecordsOnDevice)
+  {
+    wb_census_result r;
+    missing.resize(4096);
+    if (wb_census(g_ctx,&r,missing.data(),missing.size())!=WB_OK)
+    {
+      die("census");
+      return -1;
+    }
+    err=r.status;
+    maxPoint=r.max_point;
+    nMissing=r.n_missing;
+    missing.resize(min<uint64_t>(missing.size(),nMissing));
+  }
+  else
+  {
+    g_pointCensus.clear();
+    bool dup=false;
+    for (size_t i=0;i<octStore.getNumBlocks() && err>=0;i++)
+    {
+      err=censusPoints(octStore.getAll((int64_t)i));
+      dup=dup || err>0;
+    }
+    if (err>=0)
+    {
+      err=dup?1:0;
+      int b=0;
+      while (b<64 && !g_pointCensus.empty() && (g_pointCensus.back()>>b))
+        b++;
+      maxPoint=g_pointCensus.empty()?0:(g_pointCensus.size()-1)*64+b;
+      for (uint64_t i=0;i<maxPoint;i++)
+      {
+        if (g_pointCensus[i/64]==~(uint64_t)0)
+        {
+          i+=63-(i&63);
+          continue;
+        }
+        if (!(g_pointCensus[i/64]&((uint64_t)1<<(i&63))))   // the reference shifts an int here (testpattern.cpp:108)
+        {
+          nMissing++;
+          if (missing.size()<4096)
+            missing.push_back(i);
+        }
+      }
+    }
+  }
+  if (err<0)
+    return -1;
+  if (err>0 && maxPoint>64)                          // all GPS times 0: the format may simply have none
+    os<<"Duplicate point\n";
+  os<<"Max point "<<maxPoint<<endl;
+  if (nMissing)
+  {
+    os<<"Missing points: ";
+    for (size_t i=0;i<missing.size();i++)
+      os<<(i?",":"")<<missing[i];
+    if (nMissing>missing.size())
+      os<<",... ("<<nMissing<<" in all)";
+    os<<endl;
+  }
+  return (long long)nMissing;
+}
+
 // ---------------------------------------------------------------- the phase protocol (threads.h)
-void startThreads(int)
+void startThreads(int n)
+// threads.cpp:91-113 starts n worker threads; here n is the number of GPUs the tile phases are spread over (one
+// worker = one GPU with its own context and its x-strip of the cloud, csrc/wb_shard.cuh).  The store that answers
+// queries and feeds the writer stays on the first device.
 {
   ensureContext();
+  int ndev=1;
+  wb_device_count(&ndev);
+  const char *share=getenv("WOLKEN_TRANSPORT");
+  g_nGpus=max(1,n);
+  if (!(share && !strcmp(share,"local")))          // NCCL wants one device per rank; the LOCAL transport can share one
+    g_nGpus=min(g_nGpus,max(1,ndev));
   g_command=TH_WAIT;
 }
 
 void joinThreads() {}
-int nThreads() { return 1; }
+int nThreads() { return g_nGpus; }
 double busyFraction() { return 0; }
 bool actionQueueEmpty() { return true; }
 bool resultQueueEmpty() { return g_results.empty(); }
@@ -1113,9 +1248,188 @@ void waitForQueueEmpty()
     ensureBuilt();
 }
 
+namespace
+{
+struct RankBarrier
+// the ranks meet here before the first collective: one that failed on its own (no device, unreadable file) makes
+// everybody turn back instead of leaving the others inside NCCL
+{
+  mutex m;
+  condition_variable cv;
+  int world,arrived=0,failed=0;
+  unsigned gen=0;
+  explicit RankBarrier(int w):world(w) {}
+  bool meet(bool ok)
+  {
+    unique_lock<mutex> lk(m);
+    if (!ok)
+      failed++;
+    unsigned g=gen;
+    if (++arrived==world)
+    {
+      arrived=0;
+      gen++;
+      cv.notify_all();
+    }
+    else
+      cv.wait(lk,[&]{ return gen!=g; });
+    return failed==0;
+  }
+};
+
+bool shardable()
+// every run is a whole file and there are at least two of them, in ascending x (wb_shard_run checks the order)
+{
+  if (g_nGpus<2 || g_files.size()<2)
+    return false;
+  for (auto &f:g_files)
+    if (f.firstRec!=0 || f.count!=f.h->numberPoints())
+      return false;
+  return true;
+}
+
+bool classifySharded()
+// One worker per GPU: each reads the files of its strip, takes part in wb_shard_run and hands back the class bytes
+// of its own records; they go into the (built) store of the first device with wb_set_labels, so that counting,
+// queries and the writers work as after a single-GPU classify.
+{
+  const int W=(int)min<size_t>(g_nGpus,g_files.size());
+  const auto t0=chrono::steady_clock::now();
+  size_t total=0;
+  for (auto &f:g_files)
+    total+=f.count;
+  // contiguous groups of files, about total/W records each, none empty
+  vector<size_t> firstFile(W+1,g_files.size());
+  {
+    size_t cum=0,i=0;
+    for (int r=0;r<W;r++)
+    {
+      firstFile[r]=i;
+      const size_t target=(size_t)((double)total*(r+1)/W);
+      do
+        cum+=g_files[i++].count;
+      while (i<g_files.size()-(W-1-r) && cum+g_files[i].count/2<=target);
+    }
+    firstFile[W]=g_files.size();
+  }
+  const char *tr=getenv("WOLKEN_TRANSPORT");
+  const bool local=tr && !strcmp(tr,"local");
+  const char *d0=getenv("WOLKEN_DEVICE");
+  const int base=d0?atoi(d0):0;
+  int ndev=1;
+  wb_device_count(&ndev);
+  uint8_t id[WB_COMM_ID_BYTES];
+  wb_local_group *grp=nullptr;
+  if (local)
+  {
+    if (wb_local_group_create(W,&grp)!=WB_OK)
+      return false;
+  }
+  else if (wb_comm_get_id(id)!=WB_OK)
+  {
+    cerr<<"NCCL is not available (libnccl.so.2; set WB_NCCL_LIB)\n";
+    return false;
+  }
+  vector<uint8_t> labels(total);
+  vector<string> errors(W);
+  shardReport=ShardReport();
+  shardReport.ranks.assign(W,wb_shard_stats());
+  shardReport.files.assign(W,0);
+  shardReport.device.assign(W,0);
+  RankBarrier gate(W);
+  auto work=[&](int r)
+  {
+    wb_ctx *c=nullptr;
+    wb_comm *cm=nullptr;
+    const int dev=local?(base+r)%max(1,ndev):base+r;
+    bool ok=wb_create(dev,&c)==WB_OK;
+    if (!ok)
+      errors[r]="no CUDA device "+to_string(dev);
+    size_t firstRecord=0;
+    for (size_t i=0;i<firstFile[r];i++)
+      firstRecord+=g_files[i].count;
+    if (ok)
+    {
+      wb_set_params(c,g_snakeTile,maxSlope,thickness,minHyperboloidSize);
+      for (size_t i=firstFile[r];ok && i<firstFile[r+1];i++)
+      {
+        LasHeader *h=g_files[i].h;
+        xyz a=h->minCorner(),b=h->maxCorner();
+        double mn[3]={a.getx(),a.gety(),a.getz()},mx[3]={b.getx(),b.gety(),b.getz()};
+        ok=wb_add_extent(c,mn,mx)==WB_OK;
+      }
+      for (size_t i=firstFile[r];ok && i<firstFile[r+1];i++)
+      {
+        LasHeader *h=g_files[i].h;
+        double sc[3]={h->rawScale(0),h->rawScale(1),h->rawScale(2)},of[3]={h->rawOffset(0),h->rawOffset(1),h->rawOffset(2)};
+        ok=wb_add_las_file(c,h->getFileName().c_str(),h->getPointOffset(),h->numberPoints(),h->getPointFormat(),
+                           h->getPointLength(),sc,of,h->getUnit())==WB_OK;
+      }
+      if (!ok)
+        errors[r]=wb_last_error(c);
+    }
+    if (gate.meet(ok))
+    {
+      // from here on every call is collective: a failure cannot be survived by the others
+      int rc=local?wb_comm_init_local(c,grp,r,&cm):wb_comm_init(c,id,r,W,&cm);
+      if (rc==WB_OK)
+        rc=wb_shard_run(c,cm);
+      if (rc==WB_OK)
+        rc=wb_shard_get_labels(c,labels.data()+firstRecord);
+      if (rc!=WB_OK)
+      {
+        cerr<<"GPU "<<dev<<": "<<wb_last_error(c)<<endl;
+        exit(4);
+      }
+      wb_shard_get_stats(c,&shardReport.ranks[r]);
+      shardReport.files[r]=firstFile[r+1]-firstFile[r];
+      shardReport.device[r]=dev;
+    }
+    if (cm)
+      wb_comm_destroy(cm);
+    if (c)
+      wb_destroy(c);
+  };
+  vector<thread> th;
+  for (int r=0;r<W;r++)
+    th.emplace_back(work,r);
+  for (auto &t:th)
+    t.join();
+  if (grp)
+    wb_local_group_destroy(grp);
+  for (int r=0;r<W;r++)
+    if (!errors[r].empty())
+    {
+      cerr<<"GPU worker "<<r<<": "<<errors[r]<<endl;
+      return false;
+    }
+  if (wb_set_labels(g_ctx,labels.data())!=WB_OK)
+  {
+    die("labels");
+    return false;
+  }
+  shardReport.world=W;
+  shardReport.seconds=chrono::duration<double>(chrono::steady_clock::now()-t0).count();
+  return true;
+}
+} // namespace
+
 void waitForThreads(int newStatus)
 {
   g_command=newStatus;
+  if (shardable() && (newStatus==TH_SCAN || newStatus==TH_POSTSCAN || newStatus==TH_SPLIT))
+  {
+    // several GPUs: the three tile phases are one collective run (scan and postscan results stay on the workers)
+    ensureBuilt();
+    if (newStatus==TH_SPLIT && !g_classified)
+    {
+      if (!classifySharded())
+        exit(4);
+      g_scanned=g_postscanned=g_classified=true;
+      g_labels.clear();
+    }
+    return;
+  }
   switch (newStatus)
   {
     case TH_SCAN:
@@ -1696,6 +2010,31 @@ void CloudOutput::writeFiles()
   }
 }
 
+void CloudOutput::writeCloudBlocks()
+{
+  int nextBlocks[256];
+  for (int64_t i=0;i<getNumCloudBlocks();i++)
+  {
+    for (auto &k:headers)
+    {
+      long long mn=(long long)grandTotal;
+      for (size_t j=0;j<k.second.size();j++)
+        if ((long long)k.second[j].numberPoints()<mn)
+        {
+          nextBlocks[k.first]=(int)j;
+          mn=(long long)k.second[j].numberPoints();
+        }
+    }
+    for (auto &p:getCloudBlock(i))
+    {
+      int cls=separateClasses?p.classification:0;
+      auto it=headers.find(cls);
+      if (it!=headers.end() && !it->second.empty())
+        it->second[nextBlocks[cls]].writePoint(p);
+    }
+  }
+}
+
 int CloudOutput::writeFilesDevice()
 // writeFiles with the per-point work on the GPU: the sequential part (which file a bucket's points
 // of one class go to, cloudoutput.cpp:197-206) stays here and needs only per-bucket class counts.
@@ -1827,12 +2166,16 @@ int writeReferenceStyle(const deque<LasHeader> &inputs,const OutputOptions &opt,
     for (uint8_t l:g_labels)
       totals[l]++;
   }
+  if (!cloud.empty())
+    totals[0]+=cloud.size();                         // getCloudBlock's points carry the default class
   cloudOutput.openFiles(opt.baseName,totals);
   int rc=0;
   if (keepRecordsOnDevice)
     rc=cloudOutput.writeFilesDevice();
   else
     cloudOutput.writeFiles();
+  if (!rc)
+    cloudOutput.writeCloudBlocks();
   cloudOutput.closeFiles();
   if (rc)
     return rc;

@@ -252,6 +252,7 @@ public:
   void openFiles(std::string name,std::map<int,size_t> classTotals);
   void writeFiles();
   int writeFilesDevice();                           // the same files, records made by wb_encode
+  void writeCloudBlocks();                          // cloudoutput.cpp:213-229: the points of `cloud` after the store's
   void closeFiles();
   std::vector<std::string> written;
 private:
@@ -350,6 +351,21 @@ public:
   void shrink() {}
 };
 
+// ---------------------------------------------------------------- cloud.h
+// Points that came from a non-LAS source (the reference's PLY/XYZ readers, ply.cpp:54, fileio.cpp:81-94) wait here,
+// outside the octree; the writer appends them, unclassified, after the store's blocks (cloudoutput.cpp:213-229).
+extern std::vector<xyz> cloud;
+int64_t getNumCloudBlocks();                        // cloud.cpp:29-32
+std::vector<LasPoint> getCloudBlock(int64_t n);     // cloud.cpp:34-45
+
+// ---------------------------------------------------------------- testpattern.h
+// Test data carries its point number as GPS time.  censusPoints() walks the store and prints, as the reference does
+// after every write (threads.cpp:613), "Duplicate point" if a number occurs twice, "Max point N", and the missing
+// numbers below N; returns the number of missing points (-1: not test data).  With the records on the device
+// (keepRecordsOnDevice) the walk is wb_census; otherwise block by block through getAll.
+int censusPoints(std::vector<LasPoint> points);     // testpattern.cpp:56-82
+long long censusPoints(std::ostream *report=nullptr);   // testpattern.cpp:84-123 (report: default std::cout)
+
 extern Octree octRoot;
 extern OctStore octStore;
 extern Flowsnake snake;
@@ -420,6 +436,17 @@ void classifyCylinder(Eisenstein cylAddress);       // classify.h:24
 void fillTanTables();                               // uploaded by wb_create; kept for source compatibility
 
 // ---------------------------------------------------------------- the CLI's additions
+// startThreads(n) with n > 1 spreads scan, postscan and classify over n GPUs when the inputs are at least two whole
+// files in ascending x (x-strips): what each worker did in the last such run.
+struct ShardReport
+{
+  int world=0;
+  double seconds=0;                                 // wall time of the whole collective run, file reads included
+  std::vector<wb_shard_stats> ranks;
+  std::vector<size_t> files;                        // input files per worker
+  std::vector<int> device;
+};
+extern ShardReport shardReport;
 wb_ctx *wolkenContext();
 const char *wolkenLastError();
 std::vector<uint8_t> wolkenLabels();                // class byte per input record (files in read order)

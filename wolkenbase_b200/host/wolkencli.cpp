@@ -6,7 +6,12 @@
 //     --tile-size T  --max-slope S  --thickness K  --min-hyperboloid-size M   (QSettings keys, mainwindow.cpp:398-411)
 //     --points-per-file N        split outputs every N points (0 = no split)
 //     --separate-classes 0|1     one file per class (default 1, as the GUI)
-//     --threads N                accepted for compatibility, ignored
+//     --gpus N, --threads N      spread scan, postscan and classify over N GPUs (startThreads(N), threads.cpp:91-113):
+//                                the input files are taken in ascending x and dealt out as N x-strips; needs at least
+//                                two files that do not interleave in x, else one GPU does the work
+//     --census                   after writing, count the stored points by their GPS time (test data carries the point
+//                                number there; censusPoints, threads.cpp:613): always done when the records are on
+//                                the GPU (the default writer), on request with --lossless / --host-writer
 //     --dump FILE                where to write the octree dump (default "dumpfile")
 //     --host-writer              make the output records on the CPU (LasHeader::writePoint) instead of on the GPU
 //     --timing                   print the wall time of each phase (seconds) as one JSON line at the end
@@ -14,6 +19,7 @@
 //                                point, wolkencli.cpp:104-108) instead of one ACT_READ per file
 //     --lossless                 keep the inputs' own records (format, scale, offset) and only replace the class
 //                                byte, instead of the reference's LAS 1.4 re-encoding (CloudOutput)
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <deque>
@@ -29,7 +35,8 @@ int main(int argc,char **argv)
   vector<string> inputFiles;
   OutputOptions out;
   string dumpName="dumpfile";
-  bool classify=false,lossless=false,hostWriter=false,timing=false,perPoint=false;
+  bool classify=false,lossless=false,hostWriter=false,timing=false,perPoint=false,census=false;
+  int nGpus=1;
   auto now=[]{ return chrono::duration<double>(chrono::steady_clock::now().time_since_epoch()).count(); };
   double t0=now(),tRead=0,tScan=0,tPost=0,tClass=0,tWrite=0,tDump=0,tOpen=0;
   for (int i=1;i<argc;i++)
@@ -43,18 +50,33 @@ int main(int argc,char **argv)
     else if (a=="--min-hyperboloid-size") minHyperboloidSize=atof(val());
     else if (a=="--points-per-file") out.pointsPerFile=strtoull(val(),nullptr,10);
     else if (a=="--separate-classes") out.separateClasses=atoi(val())!=0;
-    else if (a=="--threads" || a=="--gpus") val();
+    else if (a=="--threads" || a=="--gpus") nGpus=max(1,atoi(val()));
     else if (a=="--dump") dumpName=val();
     else if (a=="--lossless") lossless=true;
     else if (a=="--host-writer") hostWriter=true;
     else if (a=="--timing") timing=true;
     else if (a=="--embuffer") perPoint=true;
+    else if (a=="--census") census=true;
     else if (a.size() && a[0]=='-') { cerr<<"unknown option "<<a<<endl; return 2; }
     else inputFiles.push_back(a);
   }
   if (out.baseName.size()>4 && out.baseName.substr(out.baseName.size()-4)==".las")
     out.baseName.resize(out.baseName.size()-4);
   keepRecordsOnDevice=classify && !lossless && !hostWriter;
+  if (nGpus>1 && inputFiles.size()>1)
+  {
+    // strips in ascending x: the order of the files is the input order of the points, on one GPU as on several
+    vector<pair<double,string>> byX;
+    for (auto &name:inputFiles)
+    {
+      LasHeader h;
+      h.openRead(name);
+      byX.emplace_back(h.isValid()?h.minCorner().getx():INFINITY,name);
+    }
+    stable_sort(byX.begin(),byX.end(),[](const pair<double,string> &a,const pair<double,string> &b){ return a.first<b.first; });
+    for (size_t i=0;i<byX.size();i++)
+      inputFiles[i]=byX[i].second;
+  }
   deque<LasHeader> files(inputFiles.size());
   vector<xyz> limits;
   double mn[3]={INFINITY,INFINITY,INFINITY},mx[3]={-INFINITY,-INFINITY,-INFINITY};
@@ -94,7 +116,7 @@ int main(int argc,char **argv)
   }
   tOpen=now()-t0;
   double t=now();
-  startThreads(1);
+  startThreads(nGpus);
   waitForThreads(TH_READ);
   for (size_t i=0;i<files.size();i++)
   {
@@ -143,6 +165,8 @@ int main(int argc,char **argv)
       return 5;
     for (auto &w:written)
       cout<<"Wrote "<<w<<endl;
+    if (census || keepRecordsOnDevice)
+      censusPoints();
     tWrite=now()-t;
   }
   t=now();
@@ -157,6 +181,16 @@ int main(int argc,char **argv)
   wb_stats gst;
   memset(&gst,0,sizeof(gst));
   wb_get_stats(wolkenContext(),&gst);
+  if (shardReport.world>1)
+  {
+    cout<<shardReport.world<<" GPUs, "<<shardReport.seconds<<" s:\n";
+    for (int r=0;r<shardReport.world;r++)
+    {
+      const wb_shard_stats &q=shardReport.ranks[r];
+      cout<<"  GPU "<<shardReport.device[r]<<": "<<shardReport.files[r]<<" files, "<<q.n_own<<" points, halo "<<q.n_halo_scan
+          <<" + "<<q.n_halo_classify<<", classify "<<q.ms_classify<<" ms\n";
+    }
+  }
   if (timing)
     cout<<"{\"open_s\": "<<tOpen<<", \"read_build_s\": "<<tRead<<", \"scan_s\": "<<tScan<<", \"postscan_s\": "<<tPost
         <<", \"classify_s\": "<<tClass<<", \"count_write_s\": "<<tWrite<<", \"dump_s\": "<<tDump
