@@ -2,7 +2,7 @@
 leaves, tile scan and postscan over the WHOLE synthetic cloud the bench uses, then classifies a SAMPLE of its points —
 each one against the whole cloud (wbo_classify_sel) — because classifying all 1e8 points takes the CPU hours.
     python tests/golden/make_config_scale.py SCENE POINTS [SAMPLE]      e.g. 2 100000000 400000   (about 25 min)
-Writes tests/golden/config_scale_s<SCENE>_<POINTS>.npz:
+Writes tests/golden/config/config_scale_s<SCENE>_<POINTS>.npz:
     sample      input indices of the sampled points (uint32): random singles plus whole runs of 2048 neighbours in
                 canonical order, so that both the typical and the locally worst case are in it
     labels      the oracle's class bytes for them
@@ -92,7 +92,7 @@ def main():
                        tiles.ctypes.data, nt, pos.ctypes.data, len(pos), lab.ctypes.data, C.byref(margins))
     print("classified %d sampled points, %.0f s" % (len(pos), time.time() - t0), flush=True)
     hyp = tiles["hyperboloidSize"]
-    out = os.path.join(ROOT, "tests", "golden", "config_scale_s%d_%d.npz" % (scene, n_points))
+    out = os.path.join(ROOT, "tests", "golden", "config", "config_scale_s%d_%d.npz" % (scene, n_points))
     np.savez_compressed(out, scene=scene, n_points=n_points, n=n, sample=order[pos.astype(np.int64)], labels=lab,
                         margin=int(margins.value), dump_sha256=dump_sha, tiles_sha256=tiles_digest(tiles),
                         order_sha256=order_sha, n_leaves=int(nl), n_tiles=int(nt), n_duplicates=int(n_dup),

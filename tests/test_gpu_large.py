@@ -54,7 +54,7 @@ def _tiles_digest(tiles):
 
 @pytest.mark.parametrize("name", ["config_scale_s1_10000000.npz", "config_scale_s2_100000000.npz"])
 def test_config_scale_against_oracle_vectors(name, golden_dir):
-    g = np.load(os.path.join(golden_dir, name))
+    g = np.load(os.path.join(golden_dir, "config", name))
     scene, n_points = int(g["scene"]), int(g["n_points"])
     cloud = synth.generate(scene, n_points, seed=scene)
     assert cloud.n == int(g["n"])
