@@ -321,7 +321,7 @@ def cpu_baseline(scene, sample_points, bounded=True, threads=None):
     from wolkenbase_b200 import synth
     from oracle import wb_oracle
     cores = os.cpu_count() or 1
-    cloud = synth.generate(scene if scene != 3 else 2, sample_points, seed=scene)
+    cloud = synth.generate(scene, sample_points, seed=scene)
     ref = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
     sample = "%d-point crop of the same scene (same density and surface model)" % cloud.n
     if os.path.exists(ref):

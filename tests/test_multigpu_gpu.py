@@ -114,3 +114,19 @@ def test_dropped_records_stay_dropped():
         files.append([plain(cl, recs)])
     ref, sst, st = check(files)
     assert sum(int(s["n_dropped"]) for s in st) > 5000
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_run_equals_committed_oracle_labels(world, golden_dir):
+    """The fixture bench.py --gpus N checks its own ranks against (multigpu.parity_check), here with the ranks as
+    threads on one GPU: 8 files dealt out to 2, 4 or 8 ranks."""
+    import os
+    g = np.load(os.path.join(golden_dir, "sharded", "c3_8strips_400k.npz"))
+    clouds = multigpu.parity_strips()
+    per = multigpu.PARITY_STRIPS // world
+    labs, sst, st = multigpu.run_threads([clouds[r * per:(r + 1) * per] for r in range(world)], multigpu.PARAMS)
+    got = np.concatenate(labs)
+    assert len(got) == len(g["labels"])
+    mism = int((got != g["labels"]).sum())
+    assert mism <= sum(int(s["n_margin"]) for s in st) + int(g["margin"])
+    assert all(s["por_max"] == float(g["hyp_max"]) for s in sst)

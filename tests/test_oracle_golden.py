@@ -68,3 +68,17 @@ def test_oracle_matches_reference_on_several_files(case, golden_dir):
 
 def test_multi_fixtures_present():
     assert len(MULTI) >= 2
+
+
+def test_sharded_fixture_is_what_the_oracle_says(golden_dir):
+    """tests/golden/sharded/c3_8strips_400k.npz (what bench.py --gpus N checks its ranks against) regenerated."""
+    import os
+    import numpy as np
+    from oracle import wb_oracle as O
+    from wolkenbase_b200 import multigpu
+    g = np.load(os.path.join(golden_dir, "sharded", "c3_8strips_400k.npz"))
+    clouds = multigpu.parity_strips()
+    assert [c.n for c in clouds] == g["counts"].tolist()
+    res = O.run([O.file_from_cloud(c) for c in clouds], **multigpu.PARAMS)
+    assert (res.labels == g["labels"]).all()
+    assert float(res.tiles["hyperboloidSize"].max()) == float(g["hyp_max"])

@@ -534,6 +534,7 @@ __device__ void wb_gausselim(WbMat3 &m)
 }
 
 #define WB_SCAN_WARPS 4
+#define WB_SCAN_BUNDLE 32             // tiles per warp
 
 __global__ void __launch_bounds__(WB_SCAN_WARPS*32)
 wb_scan_kernel(const uint32_t *__restrict__ tileList,uint32_t nList,
@@ -543,227 +544,270 @@ wb_scan_kernel(const uint32_t *__restrict__ tileList,uint32_t nList,
                WbSnake snake,double minHyp,
                int *__restrict__ tNPoints,uint8_t *__restrict__ tTree,double *__restrict__ tDensity,
                double *__restrict__ tHyp,double *__restrict__ tHeight)
-// scanCylinder (scan.cpp:31-140): ONE WARP PER NON-EMPTY TILE.  The tile's points (canonical order)
-// are taken 32 at a time, one per lane.  The eight normal-equation sums keep the reference's
-// association (pairwisesum, manysum.cpp:120-154 = perfect binary trees over aligned power-of-two
-// blocks, merged like a binary counter): inside a batch the tree is a butterfly of warp shuffles
-// (block sums of size 2^s are read off before step s for the tail of the last batch); across
-// batches lane j (j<8) carries quantity j's counter in shared memory.
+// scanCylinder (scan.cpp:31-140): ONE WARP PER BUNDLE OF 32 NON-EMPTY TILES.
+//   sums    tile after tile, the warp takes the tile's points (canonical order) 32 at a time, one per lane.  The eight
+//           normal-equation sums keep the reference's association (pairwisesum, manysum.cpp:120-154 = perfect binary
+//           trees over aligned power-of-two blocks, merged like a binary counter): inside a batch the tree is a
+//           butterfly of warp shuffles (block sums of size 2^s are read off before step s for the tail of the last
+//           batch); across batches lane j (j<8) carries quantity j's counter in shared memory.
+//   plane   the 3x3 normal equations (matrix.cpp's Gauss-Jordan, a long scalar code full of divisions) are solved
+//           with LANE = TILE, 32 tiles at once: one warp per tile solved the same system on all 32 lanes and spent
+//           most of the kernel's issue slots there (aerial tiles hold 10-60 points: one or two batches).
+//   layers  tile after tile again: lowest untilted point, bottom layer, seven-sector histogram.
 {
   __shared__ double lvAll[WB_SCAN_WARPS][8][28];
-  __shared__ double totAll[WB_SCAN_WARPS][8];
+  __shared__ double totAll[WB_SCAN_WARPS][WB_SCAN_BUNDLE][8];
   const int lane=threadIdx.x&31,wi=threadIdx.x>>5;
-  const uint32_t widx=blockIdx.x*WB_SCAN_WARPS+wi;
-  if (widx>=nList)
+  const uint32_t first=(blockIdx.x*WB_SCAN_WARPS+wi)*WB_SCAN_BUNDLE;
+  if (first>=nList)
     return;
+  const int nT=(int)min((uint32_t)WB_SCAN_BUNDLE,nList-first);
   double (*lv)[28]=lvAll[wi];
-  double *tot=totAll[wi];
-  const uint32_t t=tileList[widx];
-  const uint32_t start=tStart[t];
-  uint32_t cnt=tCount[t];
-  if (cnt>=(1u<<27))
-    cnt=(1u<<27)-1;                   // 28 counter levels; unreachable below the 2^32-point limit
-  int ex,ey;
-  wb_to_flowsnake((int)t+snake.lo,ex,ey);
-  double ccx,ccy;
-  wb_tile_center(ex,ey,snake,ccx,ccy);
-  const uint32_t nBatch=(cnt+31)>>5;
-  // ---- phase 1: pairwise sums of x*x, y*x, y*y, x, y, x*z, y*z, z  (1*1 sums to cnt exactly)
-  for (uint32_t b=0;b<nBatch;b++)
+  // ---- lane = tile: where its points are, where its centre is
+  uint32_t myT=0,myStart=0,myCnt=0;
+  double myCx=0,myCy=0;
+  if (lane<nT)
   {
-    const uint32_t i=b*32+lane;
-    const bool valid=i<cnt;
-    double v[8]={0,0,0,0,0,0,0,0};
-    if (valid)
+    myT=tileList[first+lane];
+    myStart=tStart[myT];
+    myCnt=tCount[myT];
+    if (myCnt>=(1u<<27))
+      myCnt=(1u<<27)-1;               // 28 counter levels; unreachable below the 2^32-point limit
+    int ex,ey;
+    wb_to_flowsnake((int)myT+snake.lo,ex,ey);
+    wb_tile_center(ex,ey,snake,myCx,myCy);
+  }
+  // ---- phase 1: pairwise sums of x*x, y*x, y*y, x, y, x*z, y*z, z  (1*1 sums to cnt exactly)
+  for (int ti=0;ti<nT;ti++)
+  {
+    const uint32_t start=__shfl_sync(WB_FULL,myStart,ti),cnt=__shfl_sync(WB_FULL,myCnt,ti);
+    const double ccx=__shfl_sync(WB_FULL,myCx,ti),ccy=__shfl_sync(WB_FULL,myCy,ti);
+    const uint32_t nBatch=(cnt+31)>>5;
+    for (uint32_t b=0;b<nBatch;b++)
     {
-      const uint32_t k=pairVal[start+i];
-      const double x=__dsub_rn(sx[k],ccx),y=__dsub_rn(sy[k],ccy),z=sz[k];
-      v[0]=__dmul_rn(x,x);
-      v[1]=__dmul_rn(y,x);
-      v[2]=__dmul_rn(y,y);
-      v[3]=x;
-      v[4]=y;
-      v[5]=__dmul_rn(x,z);
-      v[6]=__dmul_rn(y,z);
-      v[7]=z;
-    }
-    const uint32_t r=min(32u,cnt-b*32);
-    #pragma unroll
-    for (int s=0;s<5;s++)
-    {
-      if (r<32 && ((r>>s)&1))
+      const uint32_t i=b*32+lane;
+      const bool valid=i<cnt;
+      double v[8]={0,0,0,0,0,0,0,0};
+      if (valid)
       {
-        // the block of size 2^s of the tail starts where the higher bits of r end
-        const int pos=(int)(r&~((2u<<s)-1));
+        const uint32_t k=pairVal[start+i];
+        const double x=__dsub_rn(sx[k],ccx),y=__dsub_rn(sy[k],ccy),z=sz[k];
+        v[0]=__dmul_rn(x,x);
+        v[1]=__dmul_rn(y,x);
+        v[2]=__dmul_rn(y,y);
+        v[3]=x;
+        v[4]=y;
+        v[5]=__dmul_rn(x,z);
+        v[6]=__dmul_rn(y,z);
+        v[7]=z;
+      }
+      const uint32_t r=min(32u,cnt-b*32);
+      #pragma unroll
+      for (int s=0;s<5;s++)
+      {
+        if (r<32 && ((r>>s)&1))
+        {
+          // the block of size 2^s of the tail starts where the higher bits of r end
+          const int pos=(int)(r&~((2u<<s)-1));
+          double mine=0;
+          #pragma unroll
+          for (int j=0;j<8;j++)
+          {
+            double e=__shfl_sync(WB_FULL,v[j],pos);
+            if (lane==j)
+              mine=e;
+          }
+          if (lane<8)
+            lv[lane][s]=mine;
+        }
+        #pragma unroll
+        for (int j=0;j<8;j++)
+          v[j]=__dadd_rn(v[j],__shfl_xor_sync(WB_FULL,v[j],1<<s));
+      }
+      if (r==32)
+      {
         double mine=0;
         #pragma unroll
         for (int j=0;j<8;j++)
-        {
-          double e=__shfl_sync(WB_FULL,v[j],pos);
           if (lane==j)
-            mine=e;
-        }
+            mine=v[j];
         if (lane<8)
-          lv[lane][s]=mine;
-      }
-      #pragma unroll
-      for (int j=0;j<8;j++)
-        v[j]=__dadd_rn(v[j],__shfl_xor_sync(WB_FULL,v[j],1<<s));
-    }
-    if (r==32)
-    {
-      double mine=0;
-      #pragma unroll
-      for (int j=0;j<8;j++)
-        if (lane==j)
-          mine=v[j];
-      if (lane<8)
-      {
-        int l=5;
-        uint32_t m=b;
-        while (m&1)
         {
-          mine=__dadd_rn(lv[lane][l],mine);
-          m>>=1;
-          l++;
+          int l=5;
+          uint32_t m=b;
+          while (m&1)
+          {
+            mine=__dadd_rn(lv[lane][l],mine);
+            m>>=1;
+            l++;
+          }
+          lv[lane][l]=mine;
         }
-        lv[lane][l]=mine;
       }
+      __syncwarp();
+    }
+    if (lane<8)
+    {
+      double sum=0;
+      for (int l=0;l<28;l++)
+        if ((cnt>>l)&1)
+          sum=__dadd_rn(sum,lv[lane][l]);
+      totAll[wi][ti][lane]=sum;
     }
     __syncwarp();
   }
-  if (lane<8)
+  // ---- phase 2: 3x3 normal equations, lane = tile
+  double mySl0=0,mySl1=0;
+  if (lane<nT)
   {
-    double sum=0;
-    for (int l=0;l<28;l++)
-      if ((cnt>>l)&1)
-        sum=__dadd_rn(sum,lv[lane][l]);
-    tot[lane]=sum;
+    const double *tot=totAll[wi][lane];
+    WbMat3 m;
+    m.a[0][0]=tot[0];
+    m.a[1][0]=m.a[0][1]=tot[1];
+    m.a[1][1]=tot[2];
+    m.a[2][0]=m.a[0][2]=tot[3];
+    m.a[2][1]=m.a[1][2]=tot[4];
+    m.a[2][2]=(double)myCnt;
+    m.b[0]=tot[5];
+    m.b[1]=tot[6];
+    m.b[2]=tot[7];
+    wb_gausselim(m);
+    double sl0=m.a[0][0]==0?NAN:m.b[0],sl1=m.a[1][1]==0?NAN:m.b[1];
+    const double len=wb_hypot(sl0,sl1);
+    if (len>1)
+    {
+      sl0=__ddiv_rn(sl0,len);
+      sl1=__ddiv_rn(sl1,len);
+    }
+    if (isnan(sl0) || isnan(sl1))
+      sl0=sl1=0;
+    mySl0=sl0;
+    mySl1=sl1;
   }
   __syncwarp();
-  // ---- phase 2: 3x3 normal equations (every lane, same result)
-  WbMat3 m;
-  m.a[0][0]=tot[0];
-  m.a[1][0]=m.a[0][1]=tot[1];
-  m.a[1][1]=tot[2];
-  m.a[2][0]=m.a[0][2]=tot[3];
-  m.a[2][1]=m.a[1][2]=tot[4];
-  m.a[2][2]=(double)cnt;
-  m.b[0]=tot[5];
-  m.b[1]=tot[6];
-  m.b[2]=tot[7];
-  wb_gausselim(m);
-  double sl0=m.a[0][0]==0?NAN:m.b[0],sl1=m.a[1][1]==0?NAN:m.b[1];
-  const double len=wb_hypot(sl0,sl1);
-  if (len>1)
+  for (int ti=0;ti<nT;ti++)
   {
-    sl0=__ddiv_rn(sl0,len);
-    sl1=__ddiv_rn(sl1,len);
-  }
-  if (isnan(sl0) || isnan(sl1))
-    sl0=sl1=0;
-  // ---- phase 3: bottom = lowest untilted z, f = its first position, top; then
-  //      bottom2 = lowest untilted z BEFORE position f (scan.cpp:78-87: the update only fires on a
-  //      strict new minimum), = bottom if there is none
-  double bestv=INFINITY,top=-INFINITY;
-  uint32_t besti=0xffffffffu;
-  for (uint32_t b=0;b<nBatch;b++)
-  {
-    const uint32_t i=b*32+lane;
-    if (i<cnt)
+    const uint32_t t=__shfl_sync(WB_FULL,myT,ti),start=__shfl_sync(WB_FULL,myStart,ti),cnt=__shfl_sync(WB_FULL,myCnt,ti);
+    const double ccx=__shfl_sync(WB_FULL,myCx,ti),ccy=__shfl_sync(WB_FULL,myCy,ti);
+    const double sl0=__shfl_sync(WB_FULL,mySl0,ti),sl1=__shfl_sync(WB_FULL,mySl1,ti);
+    const uint32_t nBatch=(cnt+31)>>5;
+    // ---- phase 3: bottom = lowest untilted z, f = its first position, top; then
+    //      bottom2 = lowest untilted z BEFORE position f (scan.cpp:78-87: the update only fires on a
+    //      strict new minimum), = bottom if there is none
+    double bestv=INFINITY,top=-INFINITY;
+    uint32_t besti=0xffffffffu;
+    double x0=0,y0=0,zu0=INFINITY;                  // the first batch stays in registers (most tiles have no other)
+    for (uint32_t b=0;b<nBatch;b++)
     {
-      const uint32_t k=pairVal[start+i];
-      const double x=__dsub_rn(sx[k],ccx),y=__dsub_rn(sy[k],ccy);
-      const double zu=__dsub_rn(sz[k],__dadd_rn(__dmul_rn(sl1,y),__dmul_rn(sl0,x)));   // dot(): a.y*b.y+a.x*b.x
-      if (zu<bestv)
+      const uint32_t i=b*32+lane;
+      if (i<cnt)
       {
-        bestv=zu;
-        besti=i;
-      }
-      if (zu>top)
-        top=zu;
-    }
-  }
-  #pragma unroll
-  for (int o=16;o;o>>=1)
-  {
-    const double ov=__shfl_xor_sync(WB_FULL,bestv,o);
-    const uint32_t oi=__shfl_xor_sync(WB_FULL,besti,o);
-    if (ov<bestv || (ov==bestv && oi<besti))
-    {
-      bestv=ov;
-      besti=oi;
-    }
-    top=fmax(top,__shfl_xor_sync(WB_FULL,top,o));
-  }
-  const double bottom=bestv;
-  double bottom2=INFINITY;
-  for (uint32_t b=0;b*32<besti && b<nBatch;b++)
-  {
-    const uint32_t i=b*32+lane;
-    if (i<besti && i<cnt)
-    {
-      const uint32_t k=pairVal[start+i];
-      const double x=__dsub_rn(sx[k],ccx),y=__dsub_rn(sy[k],ccy);
-      const double zu=__dsub_rn(sz[k],__dadd_rn(__dmul_rn(sl1,y),__dmul_rn(sl0,x)));
-      bottom2=fmin(bottom2,zu);
-    }
-  }
-  #pragma unroll
-  for (int o=16;o;o>>=1)
-    bottom2=fmin(bottom2,__shfl_xor_sync(WB_FULL,bottom2,o));
-  if (isinf(bottom2))
-    bottom2=bottom;
-  // ---- phase 4: seven-sector histogram of the bottom layer
-  int histo[7]={0,0,0,0,0,0,0};
-  uint32_t nBottom=0;
-  const double cut=__dadd_rn(bottom2,__dmul_rn(2.0,snake.radius));
-  const double rin=__ddiv_rn(snake.radius,WB_SQRT7);
-  for (uint32_t b=0;b<nBatch;b++)
-  {
-    const uint32_t i=b*32+lane;
-    int sector=-1;
-    if (i<cnt)
-    {
-      const uint32_t k=pairVal[start+i];
-      const double x=__dsub_rn(sx[k],ccx),y=__dsub_rn(sy[k],ccy);
-      const double zu=__dsub_rn(sz[k],__dadd_rn(__dmul_rn(sl1,y),__dmul_rn(sl0,x)));
-      if (zu<cut)
-      {
-        sector=(int)wb_lrint(__ddiv_rn(__dmul_rn(atan2(y,x),3.0),WB_PI));
-        if (sector<0)
-          sector+=6;
-        sector=(sector%6)+1;
-        if (wb_hypot(x,y)<rin)
-          sector=0;
+        const uint32_t k=pairVal[start+i];
+        const double x=__dsub_rn(sx[k],ccx),y=__dsub_rn(sy[k],ccy);
+        const double zu=__dsub_rn(sz[k],__dadd_rn(__dmul_rn(sl1,y),__dmul_rn(sl0,x)));   // dot(): a.y*b.y+a.x*b.x
+        if (b==0)
+        {
+          x0=x;
+          y0=y;
+          zu0=zu;
+        }
+        if (zu<bestv)
+        {
+          bestv=zu;
+          besti=i;
+        }
+        if (zu>top)
+          top=zu;
       }
     }
     #pragma unroll
-    for (int j=0;j<7;j++)
+    for (int o=16;o;o>>=1)
     {
-      const int c=__popc(__ballot_sync(WB_FULL,sector==j));
-      histo[j]+=c;
-      nBottom+=c;
+      const double ov=__shfl_xor_sync(WB_FULL,bestv,o);
+      const uint32_t oi=__shfl_xor_sync(WB_FULL,besti,o);
+      if (ov<bestv || (ov==bestv && oi<besti))
+      {
+        bestv=ov;
+        besti=oi;
+      }
+      top=fmax(top,__shfl_xor_sync(WB_FULL,top,o));
     }
-  }
-  if (lane==0)
-  {
-    double density=0;
-    for (int j=0;j<7;j++)
-      density=__dadd_rn(density,(double)(histo[j]*histo[j]));
-    int tree=0;
-    if (cnt>nBottom && density<7)
-      tree=1;
-    density=__ddiv_rn(__ddiv_rn(__dmul_rn(sqrt(density),WB_SQRT7),__dmul_rn(snake.radius,snake.radius)),WB_PI);
-    if (cnt>nBottom && density<0.5)
-      tree=1;
-    if (__dsub_rn(top,bottom)>1.5)
-      tree=1;
-    tNPoints[t]=(int)cnt;
-    tTree[t]=(uint8_t)tree;
-    tDensity[t]=density;
-    tHyp[t]=sqrt(__dadd_rn(__ddiv_rn(1.0,density),__dmul_rn(minHyp,minHyp)));
-    tHeight[t]=__dsub_rn(top,bottom);
+    const double bottom=bestv;
+    double bottom2=INFINITY;
+    if ((uint32_t)lane<besti && (uint32_t)lane<cnt)
+      bottom2=zu0;
+    for (uint32_t b=1;b*32<besti && b<nBatch;b++)
+    {
+      const uint32_t i=b*32+lane;
+      if (i<besti && i<cnt)
+      {
+        const uint32_t k=pairVal[start+i];
+        const double x=__dsub_rn(sx[k],ccx),y=__dsub_rn(sy[k],ccy);
+        const double zu=__dsub_rn(sz[k],__dadd_rn(__dmul_rn(sl1,y),__dmul_rn(sl0,x)));
+        bottom2=fmin(bottom2,zu);
+      }
+    }
+    #pragma unroll
+    for (int o=16;o;o>>=1)
+      bottom2=fmin(bottom2,__shfl_xor_sync(WB_FULL,bottom2,o));
+    if (isinf(bottom2))
+      bottom2=bottom;
+    // ---- phase 4: seven-sector histogram of the bottom layer
+    int histo[7]={0,0,0,0,0,0,0};
+    uint32_t nBottom=0;
+    const double cut=__dadd_rn(bottom2,__dmul_rn(2.0,snake.radius));
+    const double rin=__ddiv_rn(snake.radius,WB_SQRT7);
+    for (uint32_t b=0;b<nBatch;b++)
+    {
+      const uint32_t i=b*32+lane;
+      int sector=-1;
+      if (i<cnt)
+      {
+        double x=x0,y=y0,zu=zu0;
+        if (b)
+        {
+          const uint32_t k=pairVal[start+i];
+          x=__dsub_rn(sx[k],ccx);
+          y=__dsub_rn(sy[k],ccy);
+          zu=__dsub_rn(sz[k],__dadd_rn(__dmul_rn(sl1,y),__dmul_rn(sl0,x)));
+        }
+        if (zu<cut)
+        {
+          sector=(int)wb_lrint(__ddiv_rn(__dmul_rn(atan2(y,x),3.0),WB_PI));
+          if (sector<0)
+            sector+=6;
+          sector=(sector%6)+1;
+          if (wb_hypot(x,y)<rin)
+            sector=0;
+        }
+      }
+      #pragma unroll
+      for (int j=0;j<7;j++)
+      {
+        const int c=__popc(__ballot_sync(WB_FULL,sector==j));
+        histo[j]+=c;
+        nBottom+=c;
+      }
+    }
+    if (lane==0)
+    {
+      double density=0;
+      for (int j=0;j<7;j++)
+        density=__dadd_rn(density,(double)(histo[j]*histo[j]));
+      int tree=0;
+      if (cnt>nBottom && density<7)
+        tree=1;
+      density=__ddiv_rn(__ddiv_rn(__dmul_rn(sqrt(density),WB_SQRT7),__dmul_rn(snake.radius,snake.radius)),WB_PI);
+      if (cnt>nBottom && density<0.5)
+        tree=1;
+      if (__dsub_rn(top,bottom)>1.5)
+        tree=1;
+      tNPoints[t]=(int)cnt;
+      tTree[t]=(uint8_t)tree;
+      tDensity[t]=density;
+      tHyp[t]=sqrt(__dadd_rn(__ddiv_rn(1.0,density),__dmul_rn(minHyp,minHyp)));
+      tHeight[t]=__dsub_rn(top,bottom);
+    }
   }
 }
 

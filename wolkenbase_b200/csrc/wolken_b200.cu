@@ -1141,7 +1141,7 @@ extern "C" int wb_scan(wb_ctx *ctx)
   CK(cudaMemcpyAsync(&nList,ctx->counters.p+3,sizeof(nList),cudaMemcpyDeviceToHost,st));
   CK(cudaStreamSynchronize(st));
   if (nList)
-    wb_scan_kernel<<<gridFor(nList,WB_SCAN_WARPS),WB_SCAN_WARPS*32,0,st>>>(ctx->tileList.p,(uint32_t)nList,ctx->tStart.p,ctx->tCount.p,
+    wb_scan_kernel<<<gridFor(nList,WB_SCAN_WARPS*WB_SCAN_BUNDLE),WB_SCAN_WARPS*32,0,st>>>(ctx->tileList.p,(uint32_t)nList,ctx->tStart.p,ctx->tCount.p,
                                               ctx->pairVals,ctx->sx.p,ctx->sy.p,ctx->sz.p,
                                               ctx->snake,ctx->prm.minHyp,ctx->tNPoints.p,ctx->tTree.p,ctx->tDensity.p,
                                               ctx->tHyp.p,ctx->tHeight.p);

@@ -136,6 +136,45 @@ def gloo_comm(ctx, dist, rank, world):
     return api.Comm.custom(ctx, *gloo_ops(dist, rank, world), rank, world)
 
 
+# ---------------------------------------------------------------------------- parity on the ranks of a real job
+
+PARITY_SCENE, PARITY_POINTS, PARITY_STRIPS, PARITY_SEED = 3, 400_000, 8, 17
+
+
+def parity_strips():
+    """The 8 files of the committed sharded fixture (tests/golden/make_sharded.py)."""
+    from . import synth
+    d = synth.describe(PARITY_SCENE, PARITY_POINTS)
+    cuts = [d.grid_nx * k // PARITY_STRIPS for k in range(PARITY_STRIPS + 1)]
+    clouds, base = [], 0
+    for k in range(PARITY_STRIPS):
+        c = synth.generate(PARITY_SCENE, PARITY_POINTS, seed=PARITY_SEED,
+                           region=(cuts[k], 0, cuts[k + 1] - cuts[k], d.grid_ny), gps_base=base)
+        base += c.n
+        clouds.append(c)
+    return clouds
+
+
+def parity_check(ctx, comm, rank, world):
+    """One small sharded run on the job's own ranks and transport, compared with the labels the oracle produced for
+    the whole cloud (tests/golden/sharded/c3_8strips_400k.npz, committed; the oracle is not imported here).
+    Returns {"points", "mismatches", "margin"} for this rank's records."""
+    g = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "sharded",
+                             "c3_8strips_400k.npz"))
+    clouds = parity_strips()
+    counts = [int(c) for c in g["counts"]]
+    assert [c.n for c in clouds] == counts, "the generator no longer makes the fixture's cloud"
+    f0, f1 = PARITY_STRIPS * rank // world, PARITY_STRIPS * (rank + 1) // world
+    mine = clouds[f0:f1]
+    n = load_rank(ctx, mine, PARAMS)
+    ctx.shard_run(comm)
+    lab = ctx.shard_labels(n)
+    want = g["labels"][sum(counts[:f0]):sum(counts[:f1])]
+    st = ctx.shard_stats()
+    return {"points": int(n), "mismatches": int((lab != want).sum()),
+            "margin": int(ctx.stats()["n_margin"]) + int(g["margin"]), "por_max_equal": st["por_max"] == float(g["hyp_max"])}
+
+
 # ---------------------------------------------------------------------------- bench (N > 1)
 
 def _spread(vals):
@@ -194,6 +233,16 @@ def bench(args, rank, world, local):
     tot = torch.tensor([n], dtype=torch.int64, device=dev)
     dist.all_reduce(tot)
     n_total = int(tot.item())
+    # labels of THIS job's ranks over THIS transport against the oracle's (a committed fixture), before any timing
+    parity = None
+    if world in (2, 4, 8):
+        try:
+            parity = parity_check(ctx, comm, rank, world)
+        except Exception as e:
+            parity = {"error": "%s: %s" % (type(e).__name__, e)}
+        allp = [None] * world
+        dist.all_gather_object(allp, parity)
+        parity = allp
     for _ in range(args.warmup):
         step(True)
     l0 = ctx.stats()["kernel_launches"]
@@ -270,6 +319,13 @@ def bench(args, rank, world, local):
             "gpu_launches": int(launches), "clocks": clocks,
             "labels": {"ground": int(hist[2]), "nonground": int(hist[1])},
         }
+        if parity is not None:
+            ok = all("error" not in p and p["mismatches"] <= p["margin"] and p["por_max_equal"] for p in parity)
+            line["parity"] = {"check": "C3 scene, 400 k points in 8 files over these %d ranks and NCCL, against the oracle's "
+                                       "labels (tests/golden/sharded/c3_8strips_400k.npz)" % world,
+                              "ok": ok, "points": sum(p.get("points", 0) for p in parity),
+                              "mismatches": sum(p.get("mismatches", 0) for p in parity),
+                              "errors": [p["error"] for p in parity if "error" in p]}
         if base is not None:
             line["weak_scaling_base"] = base
             if "value" in base:
