@@ -181,7 +181,9 @@ def run_ours(args):
     for k in phase:
         phase[k] /= args.steps
 
-    # e2e: pinned host records in, labels out, every step
+    # e2e: pinned host records in, labels out, every step.  Serial first (copy, then compute, then labels), then the
+    # way a job with more than one cloud runs: two contexts, the next step's records are copied and decoded into one
+    # (loader thread) while the other classifies — every step's H2D and D2H still lie inside the timed region.
     step_e2e()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -190,10 +192,42 @@ def run_ours(args):
     for _ in range(e2e_steps):
         step_e2e()
     ctx.mark(3)
-    dte = ctx.mark_elapsed(2, 3) * 1e-3 / e2e_steps
+    dte_serial = ctx.mark_elapsed(2, 3) * 1e-3 / e2e_steps
     torch.cuda.synchronize()
-    dte_wall = (time.perf_counter() - t0) / e2e_steps
+    dte_serial_wall = (time.perf_counter() - t0) / e2e_steps
     ste = ctx.stats()
+    ctx2 = api.Context(local)
+    ctx2.set_params(**PARAMS)
+    ctx2.reserve(n)
+    pair = [ctx, ctx2]
+
+    def load_e2e(i):
+        c = pair[i % 2]
+        c.clear()
+        c.add_extent(cloud.min_corner, cloud.max_corner)
+        c.add_las(host_recs, cloud.fmt, cloud.scale, cloud.offset)
+
+    def run_pipelined(steps):
+        load_e2e(0)
+        for i in range(steps):
+            th = None
+            if i + 1 < steps:
+                th = threading.Thread(target=load_e2e, args=(i + 1,))
+                th.start()
+            pair[i % 2].run()
+            pair[i % 2].labels(n, out=labels_pin.array)
+            if th is not None:
+                th.join()
+
+    run_pipelined(2)                                   # warm-up of the second context
+    pipe_steps = max(2, min(args.steps, 5))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    run_pipelined(pipe_steps)
+    torch.cuda.synchronize()
+    dte = (time.perf_counter() - t0) / pipe_steps
+    dte_wall = dte
+    ctx2.close()
     hist = ctx.count_classes()
 
     hbm, peak_src = peaks()
@@ -234,7 +268,12 @@ def run_ours(args):
                             if phase.get("ms_decode", 0.0) > 0 else 0.0,
                             "note": "L+14 B/point: record read, 3 x int32 + class + return number written"},
         "e2e": {"value": n / dte, "unit": UNIT, "h2d_bytes_per_step": n * rec_len, "d2h_bytes_per_step": n,
-                "ms_per_step": dte * 1e3, "ms_per_step_wall": dte_wall * 1e3, "ms_h2d_decode": ste["ms_h2d"], "ms_d2h": ste["ms_d2h"]},
+                "ms_per_step": dte * 1e3, "ms_per_step_wall": dte_wall * 1e3, "steps": pipe_steps,
+                "timer": "wall clock around the K steps, device synchronised on both sides",
+                "pipelined": "two contexts: step i+1's H2D + decode overlap step i's build/scan/classify and label D2H",
+                "serial": {"value": n / dte_serial, "ms_per_step": dte_serial * 1e3, "ms_per_step_wall": dte_serial_wall * 1e3,
+                           "steps": e2e_steps},
+                "ms_h2d_decode": ste["ms_h2d"], "ms_d2h": ste["ms_d2h"]},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "labels": {"ground": int(hist[2]), "nonground": int(hist[1]), "margin_points": int(st["n_margin"]),

@@ -237,31 +237,43 @@ __device__ __forceinline__ void wb_tile_center(int ex,int ey,const WbSnake &s,do
 __device__ __forceinline__ int wb_covering_tiles(const WbSnake &s,double px,double py,int *nrel)
 // All tiles whose cylinder (Cylinder::in, shape.cpp:214-218: hypot <= radius) contains the
 // point; candidates are the 19 lattice addresses within hex distance 2 of the rounded one (a
-// superset of every centre within 41/71 spacing however the rounding falls).  One rolled loop:
-// an unrolled first-ring-only variant measured 2.3x slower (divergent copies of the inverse
-// flowsnake).  Returns the count (<= 3 in practice, capped at 4) and the sequence numbers minus lo.
+// superset of every centre within 41/71 spacing however the rounding falls).  Two stages, so that the
+// lanes of a warp stay together: first the cheap squared-distance test over all 19 (the few survivors
+// are remembered), then libm's hypot and the inverse flowsnake for the survivors only — in one loop
+// the long inverse ran in whichever of the 19 iterations some lane happened to hit (2.0x slower).
+// Returns the count (<= 3 in practice, capped at 4) and the sequence numbers minus lo.
 {
   double u=(px-s.ccx)/s.spacing,v=(py-s.ccy)/s.spacing;
-  int y0=(int)wb_lrint(v/WB_SQRT_3_4),x0=(int)wb_lrint(u+y0*0.5),cnt=0;
+  int y0=(int)wb_lrint(v/WB_SQRT_3_4),x0=(int)wb_lrint(u+y0*0.5),cnt=0,cand=0;
   double r2hi=s.radius*s.radius*(1+1e-9);
+  uint32_t hits=0;                                   // up to 6 survivors, 5 bits each: (dy+2)*5+(dx+2)
   for (int dy=-2;dy<=2;dy++)
     for (int dx=-2;dx<=2;dx++)
     {
       if (dx-dy>2 || dy-dx>2)
         continue;
-      int ex=x0+dx,ey=y0+dy;
       double cx,cy;
-      wb_tile_center(ex,ey,s,cx,cy);
+      wb_tile_center(x0+dx,y0+dy,s,cx,cy);
       double ddx=__dsub_rn(cx,px),ddy=__dsub_rn(cy,py);
-      if (ddx*ddx+ddy*ddy>r2hi)
+      if (ddx*ddx+ddy*ddy>r2hi || cand>=6)
         continue;
-      if (!(wb_hypot(ddx,ddy)<=s.radius))
-        continue;
-      long long n;
-      if (!wb_from_flowsnake(ex,ey,n) || n<s.lo || n>s.hi)
-        continue;
-      if (cnt<4)
-        nrel[cnt++]=(int)(n-s.lo);
+      hits|=(uint32_t)((dy+2)*5+(dx+2))<<(5*cand);
+      cand++;
     }
+  for (int k=0;k<cand;k++)
+  {
+    const int code=(int)((hits>>(5*k))&31),dy=code/5-2,dx=code%5-2;
+    int ex=x0+dx,ey=y0+dy;
+    double cx,cy;
+    wb_tile_center(ex,ey,s,cx,cy);
+    double ddx=__dsub_rn(cx,px),ddy=__dsub_rn(cy,py);
+    if (!(wb_hypot(ddx,ddy)<=s.radius))
+      continue;
+    long long n;
+    if (!wb_from_flowsnake(ex,ey,n) || n<s.lo || n>s.hi)
+      continue;
+    if (cnt<4)
+      nrel[cnt++]=(int)(n-s.lo);
+  }
   return cnt;
 }

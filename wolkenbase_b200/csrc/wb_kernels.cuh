@@ -1035,6 +1035,18 @@ wb_max_hyp_list_kernel(const uint32_t *__restrict__ tileList,uint32_t nList,cons
 #define WB_CL_COMPACT2 1
 #endif
 
+// A popped INTERNAL node asks every live query again whether it reaches the node and still needs its sectors (double
+// reach test + silhouette span, all lanes).  The expansion that pushed the node already knows which queries wanted
+// it (the per-query float test of WB_CL_XWANTS): 1 = keep that set per stack entry and ask only "still live?" at the
+// pop (stale sectors are caught by the next expansion's per-query test); 2 = also drop the queries whose open sectors
+// miss the node's span as seen from the group (one span for the warp instead of one per query).  0 = ask again.
+#ifndef WB_CL_POPWANTS
+#define WB_CL_POPWANTS (WB_CL_XWANTS?1:0)
+#endif
+#if WB_CL_POPWANTS && !WB_CL_XWANTS
+#error "WB_CL_POPWANTS builds on WB_CL_XWANTS"
+#endif
+
 #ifndef WB_EMU_COUNT
 #define WB_EMU_COUNT(slot)              // loop-trip counters of the SIMT emulator (tests/simt); nothing on the GPU
 #endif
@@ -1055,6 +1067,9 @@ struct WbClassifyWarp
   float fgh,fzq;                        // bounds of |fx|,|fy| and of |fh| over the warp's queries
 #endif
   uint32_t keys[8][32];       // per stack entry: (squared distance | child) of the children still to visit
+#if WB_CL_POPWANTS
+  uint32_t wantsLv[8][32];    // ... and the queries that wanted each child when it was pushed
+#endif
   WbBound cb[32];             // bounds of the chunks of the open level-0 entry
   uint32_t wants[32];         // ... live queries that reach each chunk
   unsigned long long cm[32];  // ... and the sectors the chunk can occupy, seen from anywhere in the group
@@ -1541,6 +1556,9 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
         }
       }
       w.keys[sp][lane]=ok?key:0xffffffffu;
+#if WB_CL_POPWANTS
+      w.wantsLv[sp][lane]=(childLevel==0 || (WB_CL_XWANTS && childLevel<=WB_CL_XWANTS_MAXLEVEL))?wants:askers;
+#endif
       if (lane==0)
       {
         w.stLevel[sp]=childLevel;
@@ -1570,6 +1588,17 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
       bool want=false;
       if (level>0)
       {
+#if WB_CL_POPWANTS
+        uint32_t askers=w.wantsLv[sp-1][bit]&liveMask;
+#if WB_CL_POPWANTS==2
+        if (askers)
+        {
+          const WbBound nb=bounds[levelOff[level]+node];
+          const unsigned long long bs=wb_span_mask(nb.xmin-gx1,nb.xmax-gx0,nb.ymin-gy1,nb.ymax-gy0);
+          askers&=__ballot_sync(WB_FULL,(bs&(pass==1?open:wedgeMask))!=0);
+        }
+#endif
+#else
         WbBound nb=bounds[levelOff[level]+node];
         if (live && wb_reach(px,px,py,py,pcz,ppor2,s2,nb))
         {
@@ -1577,6 +1606,7 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
           want=pass==1?(bs&open)!=0:(bs&wedgeMask)!=0;
         }
         const uint32_t askers=__ballot_sync(WB_FULL,want);
+#endif
         if (askers)
           expand(level-1,node*32,askers);
         continue;
@@ -1618,9 +1648,13 @@ wb_classify_kernel(const double *__restrict__ sx,const double *__restrict__ sy,c
       {
         const int q=__ffs(qm)-1;
         qm&=qm-1;
+#if WB_CL_XWANTS
+        const unsigned long long oq=w.openq[q];      // = query q's open (pass 2: wedge) sectors; refreshed after every chunk
+#else
         const unsigned long long mineq=pass==1?open:wedgeMask;
         const unsigned long long oq=((unsigned long long)__shfl_sync(WB_FULL,(uint32_t)(mineq>>32),q)<<32)|
                                     __shfl_sync(WB_FULL,(uint32_t)mineq,q);
+#endif
         const bool rel=(pmask&oq)!=0;
 #if !WB_CL_NORELVOTE
         if (!__any_sync(WB_FULL,rel))
