@@ -518,6 +518,37 @@ class Context:
         return s.as_dict()
 
 
+def bind_to_gpu_numa(device):
+    """Bind this process to the CPUs of the NUMA node the GPU hangs off (sysfs), so that pinned buffers allocated
+    afterwards — the caller's records, the file reader's ring — are local to the GPU's PCIe root.  What `numactl
+    --cpunodebind` does for a one-process-per-GPU job; a no-op where the topology is not exposed.  Returns the node
+    or -1."""
+    import os
+    import subprocess
+    try:
+        bus = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(device)],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if bus.startswith("0000"):
+            bus = bus[4:]
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read().strip())
+        if node < 0:
+            return -1
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return -1
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return -1
+
+
 class LocalGroup:
     """The ranks of one process (one host thread each) exchanging without NCCL (wb_comm_init_local)."""
 

@@ -293,6 +293,7 @@ int commAllGather(wb_comm *cm,const void *dSend,void *dRecv,uint64_t bytes)
   if (cm->kind==0)
   {
     NCK(ncclApi()->AllGather(dSend,dRecv,(size_t)bytes,WB_NCCL_UINT8,cm->nccl,st));
+    CK(cudaStreamSynchronize(st));     // see commAllToAllV
     return WB_OK;
   }
   if (cm->kind==2)
@@ -338,6 +339,11 @@ int commAllToAllV(wb_comm *cm,const void *dSend,const uint64_t *sOff,const uint6
         NCK(N->Recv((uint8_t *)dRecv+rOff[k],(size_t)rCnt[k],WB_NCCL_UINT8,k,cm->nccl,st));
     }
     NCK(N->GroupEnd());
+    // Drain before the caller touches the CUDA runtime again: with the ranks as THREADS of one process a later
+    // cudaMalloc/cudaFree of this thread (device-synchronising, and serialised with the other threads' calls inside
+    // the driver) could otherwise wait for this NCCL kernel while the peer's launch waits for that call — the
+    // well-known NCCL + blocking-CUDA-call deadlock.  The stages are separated by a stream sync anyway.
+    CK(cudaStreamSynchronize(st));
     return WB_OK;
   }
   if (cm->kind==2)
@@ -373,6 +379,7 @@ int commAllReduceMaxU8(wb_comm *cm,uint8_t *dBuf,uint64_t n)
   if (cm->kind==0)
   {
     NCK(ncclApi()->AllReduce(dBuf,dBuf,(size_t)n,WB_NCCL_UINT8,WB_NCCL_MAX,cm->nccl,st));
+    CK(cudaStreamSynchronize(st));     // see commAllToAllV
     return WB_OK;
   }
   if (cm->kind==2)

@@ -187,6 +187,8 @@ def bench(args, rank, world, local):
     from . import synth
     import bench as B
     dev = torch.device("cuda", local)
+    # one process per GPU: run on the CPUs next to it, so that the pinned record buffer is local to its PCIe root
+    numa = api.bind_to_gpu_numa(local) if os.environ.get("WB_NUMA_BIND", "1") != "0" else -1
     per_gpu = args.points or 125_000_000
     scene = args.scene or 3
     d = synth.describe(scene, per_gpu * world)
@@ -307,10 +309,11 @@ def bench(args, rank, world, local):
     dist.all_reduce(hist)
     # like-for-like single-GPU figure: rank 0 alone on its own strip (the scene's geometry, no halo, no exchange)
     base = None
+    # every rank lets go of its communicator at the same point (ncclCommDestroy waits for the peers in NCCL 2.28)
+    comm.close()
+    ctx.close()
     if not args.no_scaling_base:
         if rank == 0:
-            comm.close()
-            ctx.close()
             solo = api.Context(local)
             solo.set_params(**B.PARAMS)
             try:
@@ -350,6 +353,7 @@ def bench(args, rank, world, local):
                     "d2h_bytes_per_step": n_total, "ms_per_step": dte * 1e3, "steps": pipe_steps,
                     "pipelined": "two contexts per rank: step i+1's H2D + decode overlap step i's sharded run and label D2H",
                     "serial": {"value": n_total / dts, "ms_per_step": dts * 1e3, "steps": e2e_steps},
+                    "numa_node_rank0": numa,
                     "h2d_decode_ms": _spread([e[0]["h2d_decode_e2e"] for e in everyone]),
                     "h2d_gbs_per_gpu": _spread([n * cloud.rec_len / (e[0]["h2d_decode_e2e"] * 1e-3) / 1e9
                                                 for e in everyone if e[0]["h2d_decode_e2e"] > 0] or [0.0])},
@@ -368,7 +372,4 @@ def bench(args, rank, world, local):
             if "value" in base:
                 line["weak_efficiency"] = value / (world * base["value"])
         print(json.dumps(line))
-    if rank != 0 or args.no_scaling_base:
-        comm.close()
-        ctx.close()
     dist.destroy_process_group()
