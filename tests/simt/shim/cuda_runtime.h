@@ -24,6 +24,7 @@
 #define __restrict__
 #define __launch_bounds__(...)
 #define __shared__ static thread_local
+#define __align__(n) alignas(n)
 #define __constant__
 
 using std::min;
@@ -144,6 +145,8 @@ inline cudaError_t cudaMemset(void *d,int v,size_t n) { memset(d,v,n); return cu
 inline cudaError_t cudaMemsetAsync(void *d,int v,size_t n,cudaStream_t=nullptr) { memset(d,v,n); return cudaSuccess; }
 template <typename T> inline cudaError_t cudaMemcpyToSymbol(T &sym,const void *s,size_t n) { memcpy(&sym,s,n); return cudaSuccess; }
 inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s,unsigned) { *s=new simt_stream_t{0}; return cudaSuccess; }
+inline cudaError_t cudaStreamCreateWithPriority(cudaStream_t *s,unsigned,int) { *s=new simt_stream_t{0}; return cudaSuccess; }
+inline cudaError_t cudaDeviceGetStreamPriorityRange(int *least,int *greatest) { *least=0; *greatest=-5; return cudaSuccess; }
 inline cudaError_t cudaStreamDestroy(cudaStream_t s) { delete s; return cudaSuccess; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaStreamWaitEvent(cudaStream_t,cudaEvent_t,unsigned) { return cudaSuccess; }

@@ -244,9 +244,9 @@ __device__ __forceinline__ int wb_covering_tiles(const WbSnake &s,double px,doub
 // Returns the count (<= 3 in practice, capped at 4) and the sequence numbers minus lo.
 {
   double u=(px-s.ccx)/s.spacing,v=(py-s.ccy)/s.spacing;
-  int y0=(int)wb_lrint(v/WB_SQRT_3_4),x0=(int)wb_lrint(u+y0*0.5),cnt=0,cand=0;
+  int y0=(int)wb_lrint(v/WB_SQRT_3_4),x0=(int)wb_lrint(u+y0*0.5),cnt=0;
   double r2hi=s.radius*s.radius*(1+1e-9);
-  uint32_t hits=0;                                   // up to 6 survivors, 5 bits each: (dy+2)*5+(dx+2)
+  uint32_t hits=0;                                   // survivors of the first stage: bit (dy+2)*5+(dx+2)
   for (int dy=-2;dy<=2;dy++)
     for (int dx=-2;dx<=2;dx++)
     {
@@ -255,14 +255,14 @@ __device__ __forceinline__ int wb_covering_tiles(const WbSnake &s,double px,doub
       double cx,cy;
       wb_tile_center(x0+dx,y0+dy,s,cx,cy);
       double ddx=__dsub_rn(cx,px),ddy=__dsub_rn(cy,py);
-      if (ddx*ddx+ddy*ddy>r2hi || cand>=6)
+      if (ddx*ddx+ddy*ddy>r2hi)
         continue;
-      hits|=(uint32_t)((dy+2)*5+(dx+2))<<(5*cand);
-      cand++;
+      hits|=1u<<((dy+2)*5+(dx+2));
     }
-  for (int k=0;k<cand;k++)
+  while (hits)                                       // ascending (dy,dx), as the one-loop form visited them
   {
-    const int code=(int)((hits>>(5*k))&31),dy=code/5-2,dx=code%5-2;
+    const int code=__ffs(hits)-1,dy=code/5-2,dx=code%5-2;
+    hits&=hits-1;
     int ex=x0+dx,ey=y0+dy;
     double cx,cy;
     wb_tile_center(ex,ey,s,cx,cy);

@@ -11,8 +11,42 @@
 //   tiles    dense arrays indexed by flowsnake sequence number - lo
 #pragma once
 #include "wb_device.cuh"
+#if defined(__CUDACC__) && !defined(WB_DEC_NO_BULK)
+#include <cuda/barrier>                 // cp.async.bulk (TMA, 1-D) for the decode kernel's staging
+#define WB_DEC_BULK 1
+#else
+#define WB_DEC_BULK 0                   // the host build of tests/simt takes the vector-load path
+#endif
 
 #define WB_FULL 0xffffffffu
+#define WB_HILBERT_BITS 20
+
+__device__ __forceinline__ unsigned long long wb_hilbert_index(double px,double py,double x0,double y0,double cellsPerUnit)
+// index of (px,py) along a Hilbert curve of 2^20 x 2^20 cells whose corner is (x0,y0)
+{
+  const double lim=(double)((1u<<WB_HILBERT_BITS)-1);
+  uint32_t x=(uint32_t)fmin(fmax((px-x0)*cellsPerUnit,0.0),lim);
+  uint32_t y=(uint32_t)fmin(fmax((py-y0)*cellsPerUnit,0.0),lim);
+  unsigned long long d=0;
+  #pragma unroll 4
+  for (uint32_t s=1u<<(WB_HILBERT_BITS-1);s;s>>=1)
+  {
+    const uint32_t rx=(x&s)?1u:0u,ry=(y&s)?1u:0u;
+    d=(d<<2)|((3u*rx)^ry);
+    if (!ry)
+    {
+      if (rx)
+      {
+        x=~x;
+        y=~y;
+      }
+      const uint32_t t=x;
+      x=y;
+      y=t;
+    }
+  }
+  return d;
+}
 
 struct WbBound { double xmin,xmax,ymin,ymax,zmin; };
 
@@ -48,7 +82,7 @@ wb_decode_kernel(const uint8_t *__restrict__ recs,unsigned long long n,int fmt,i
                  int *__restrict__ xi,int *__restrict__ yi,int *__restrict__ zi,
                  uint8_t *__restrict__ cls,uint8_t *__restrict__ ret,unsigned long long *nDropped)
 {
-  __shared__ uint32_t sw[(WB_DEC_THREADS*WB_DEC_MAXLEN+32)/4+2];
+  __align__(16) __shared__ uint32_t sw[(WB_DEC_THREADS*WB_DEC_MAXLEN+32)/4+4];
   const unsigned long long first=(unsigned long long)blockIdx.x*WB_DEC_THREADS;
   const unsigned long long cnt=n-first<WB_DEC_THREADS?n-first:WB_DEC_THREADS;
   const unsigned long long b0=first*recLen,b1=(first+cnt)*recLen;
@@ -58,6 +92,35 @@ wb_decode_kernel(const uint8_t *__restrict__ recs,unsigned long long n,int fmt,i
   const uint32_t total=head+(uint32_t)(b1-b0);
   const uint32_t nvec=(total+15)/16;
   const uintptr_t endAll=(uintptr_t)recs+n*(unsigned long long)recLen;
+#if WB_DEC_BULK
+  // The CTA's span, rounded out to 16-byte boundaries, is ONE bulk copy into shared memory (cp.async.bulk, the 1-D
+  // form of TMA: SASS UBLKCP): a single thread issues it, the bytes arrive by the async proxy and complete an
+  // mbarrier transaction — no thread spends registers or load slots on the 5-10 KB.  Only the first and last CTA of
+  // a buffer (whose rounded span would reach outside it) take the vector-load path below.
+  #pragma nv_diag_suppress static_var_with_dynamic_init
+  __shared__ cuda::barrier<cuda::thread_scope_block> bar;
+  const bool bulk=a0>=(uintptr_t)recs && a0+(uintptr_t)nvec*16<=endAll;       // CTA-uniform
+  if (bulk)
+  {
+    namespace cde=cuda::device::experimental;
+    if (threadIdx.x==0)
+    {
+      init(&bar,WB_DEC_THREADS);
+      cde::fence_proxy_async_shared_cta();
+    }
+    __syncthreads();
+    cuda::barrier<cuda::thread_scope_block>::arrival_token token;
+    if (threadIdx.x==0)
+    {
+      cde::cp_async_bulk_global_to_shared(sw,reinterpret_cast<const void *>(a0),nvec*16,bar);
+      token=cuda::device::barrier_arrive_tx(bar,1,nvec*16);
+    }
+    else
+      token=bar.arrive();
+    bar.wait(std::move(token));
+  }
+  else
+#endif
   for (uint32_t v=threadIdx.x;v<nvec;v+=WB_DEC_THREADS)
   {
     uintptr_t a=a0+(uintptr_t)v*16;
@@ -149,8 +212,10 @@ __device__ __forceinline__ unsigned long long wb_morton(double x,double y,double
 __global__ void __launch_bounds__(256)
 wb_keygen_kernel(const int *__restrict__ xi,const int *__restrict__ yi,const int *__restrict__ zi,
                  const uint8_t *__restrict__ ret,unsigned long long first,unsigned long long cnt,
-                 WbSegment seg,double cx,double cy,double cz,double side,
+                 WbSegment seg,double cx,double cy,double cz,double side,int hilbert,
                  unsigned long long *__restrict__ key,uint32_t *__restrict__ idx)
+// hilbert: the key of a CLASSIFY-ONLY store (wb_hilbert_index over xy, see "classify order" below) instead of the
+// octree's Morton key
 {
   unsigned long long t=(unsigned long long)blockIdx.x*blockDim.x+threadIdx.x;
   if (t>=cnt)
@@ -159,7 +224,8 @@ wb_keygen_kernel(const int *__restrict__ xi,const int *__restrict__ yi,const int
   double x=wb_coord(seg.offset[0],seg.scale[0],xi[i],seg.unit);
   double y=wb_coord(seg.offset[1],seg.scale[1],yi[i],seg.unit);
   double z=wb_coord(seg.offset[2],seg.scale[2],zi[i],seg.unit);
-  unsigned long long k=wb_morton(x,y,z,cx,cy,cz,side);
+  unsigned long long k=hilbert?wb_hilbert_index(x,y,cx-side,cy-side,(double)(1u<<WB_HILBERT_BITS)/(2*side))
+                              :wb_morton(x,y,z,cx,cy,cz,side);
   if (ret[i]==0)
     k=~0ull;                                          // dropped record: sorts behind every real key
   key[i]=k;
@@ -1852,8 +1918,6 @@ finish:
 #ifndef WB_CL_HILBERT
 #define WB_CL_HILBERT 1
 #endif
-#define WB_HILBERT_BITS 20
-
 __global__ void __launch_bounds__(256)
 wb_hilbert_key_kernel(const double *__restrict__ sx,const double *__restrict__ sy,unsigned long long n,
                       double x0,double y0,double cellsPerUnit,unsigned long long *__restrict__ key,uint32_t *__restrict__ idx)
@@ -1861,28 +1925,7 @@ wb_hilbert_key_kernel(const double *__restrict__ sx,const double *__restrict__ s
   unsigned long long j=(unsigned long long)blockIdx.x*blockDim.x+threadIdx.x;
   if (j>=n)
     return;
-  const double lim=(double)((1u<<WB_HILBERT_BITS)-1);
-  uint32_t x=(uint32_t)fmin(fmax((sx[j]-x0)*cellsPerUnit,0.0),lim);
-  uint32_t y=(uint32_t)fmin(fmax((sy[j]-y0)*cellsPerUnit,0.0),lim);
-  unsigned long long d=0;
-  #pragma unroll 4
-  for (uint32_t s=1u<<(WB_HILBERT_BITS-1);s;s>>=1)
-  {
-    const uint32_t rx=(x&s)?1u:0u,ry=(y&s)?1u:0u;
-    d=(d<<2)|((3u*rx)^ry);
-    if (!ry)
-    {
-      if (rx)
-      {
-        x=~x;
-        y=~y;
-      }
-      const uint32_t t=x;
-      x=y;
-      y=t;
-    }
-  }
-  key[j]=d;
+  key[j]=wb_hilbert_index(sx[j],sy[j],x0,y0,cellsPerUnit);
   idx[j]=(uint32_t)j;
 }
 

@@ -953,7 +953,9 @@ extern "C" int wb_shard_run(wb_ctx *ctx,wb_comm *cm)
   S.st.n_halo_classify=nRecv;
   if ((rc=assemble(ctx,cm,S,ownSegs,nOwn,ownDropped,cntFrom,nRecv)))
     return rc;
-  if ((rc=wb_build(ctx)))
+  // classify walks the store along a Hilbert curve over xy whatever order it is kept in, and nothing else is asked
+  // of this second store: it is built in that order straight away (no Morton sort, no octree leaves)
+  if ((rc=buildStore(ctx,true)))
     return rc;
   S.st.ms_build_classify=clk.lap();
   if ((rc=wb_assign(ctx)))

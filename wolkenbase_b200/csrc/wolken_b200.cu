@@ -68,7 +68,7 @@ struct wb_ctx
 {
   int device=0;
   std::string err;
-  cudaStream_t st=nullptr,stCopy=nullptr;
+  cudaStream_t st=nullptr,stCopy=nullptr,stLoad=nullptr;   // stLoad: decode of arriving records, highest priority
   cudaEvent_t evA=nullptr,evB=nullptr,evC=nullptr,evD=nullptr,evCopy[2]={nullptr,nullptr},evDec[2]={nullptr,nullptr};
   cudaEvent_t evMark[WB_MARKS]={},evJoin=nullptr;     // wb_mark: caller-placed timing events on the compute stream
   WbParams prm{1,1,0,0.1};
@@ -144,6 +144,7 @@ struct wb_ctx
   std::vector<uint32_t> hLevelOff,hLevelCnt;
   wb_stats stats{};
   bool tablesUploaded=false;
+  bool storeHilbert=false;            // the store is a classify-only one (buildStore(ctx,true)): Hilbert order, no leaves
 };
 
 static int ensureTileArrays(wb_ctx *ctx);
@@ -341,6 +342,16 @@ extern "C" int wb_create(int device,wb_ctx **out)
   }
   cudaStreamCreateWithFlags(&ctx->st,cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&ctx->stCopy,cudaStreamNonBlocking);
+  {
+    // Records may arrive for one context while ANOTHER context of the same device is deep in classify (a job that
+    // streams clouds through two contexts, bench.py's e2e): the decode kernels are tiny but would queue behind the
+    // millions of blocks classify still has pending, and the H2D pipeline with them.  Highest priority lets their
+    // blocks take the next free slots.
+    int least=0,greatest=0;
+    cudaDeviceGetStreamPriorityRange(&least,&greatest);
+    cudaStreamCreateWithPriority(&ctx->stLoad,cudaStreamNonBlocking,greatest);
+    cudaEventCreateWithFlags(&ctx->evJoin,cudaEventDisableTiming);
+  }
   cudaEventCreate(&ctx->evA); cudaEventCreate(&ctx->evB); cudaEventCreate(&ctx->evC); cudaEventCreate(&ctx->evD);
   for (int i=0;i<2;i++)
   {
@@ -395,7 +406,7 @@ extern "C" void wb_destroy(wb_ctx *ctx)
   }
   ctx->drsegs.release(); ctx->outArena.release(); ctx->encLut.release(); ctx->encDest.release(); ctx->encCount.release();
   ctx->encFile.release(); ctx->encCounts.release(); ctx->attrSrc.release(); ctx->invPerm.release(); ctx->encMinMax.release();
-  cudaStreamDestroy(ctx->st); cudaStreamDestroy(ctx->stCopy);
+  cudaStreamDestroy(ctx->st); cudaStreamDestroy(ctx->stCopy); cudaStreamDestroy(ctx->stLoad);
   cudaEventDestroy(ctx->evA); cudaEventDestroy(ctx->evB); cudaEventDestroy(ctx->evC); cudaEventDestroy(ctx->evD);
   for (int i=0;i<2;i++)
   {
@@ -567,7 +578,10 @@ extern "C" int wb_add_las(wb_ctx *ctx,const uint8_t *recs,uint64_t n,int fmt,int
   else
     for (int b=0;b<2;b++)
       CK(ctx->staging[b].ensure(std::min<uint64_t>(chunkBytes,n*recLen)+64));
-  CK(cudaEventRecord(ctx->evA,ctx->st));
+  cudaStream_t ld=ctx->stLoad;                       // after whatever the context's own stream still has queued
+  CK(cudaEventRecord(ctx->evJoin,ctx->st));
+  CK(cudaStreamWaitEvent(ld,ctx->evJoin,0));
+  CK(cudaEventRecord(ctx->evA,ld));
   uint64_t done=0;
   int b=0,used[2]={0,0};
   while (done<n)
@@ -578,16 +592,16 @@ extern "C" int wb_add_las(wb_ctx *ctx,const uint8_t *recs,uint64_t n,int fmt,int
       CK(cudaStreamWaitEvent(ctx->stCopy,ctx->evDec[b],0));   // staging[b] free again?
     CK(cudaMemcpyAsync(dst,recs+done*recLen,cnt*recLen,cudaMemcpyHostToDevice,ctx->stCopy));
     CK(cudaEventRecord(ctx->evCopy[b],ctx->stCopy));
-    CK(cudaStreamWaitEvent(ctx->st,ctx->evCopy[b],0));
-    if ((rc=decodeDevice(ctx,dst,ctx->n+done,cnt,fmt,recLen,dropZeros,ctx->st)))
+    CK(cudaStreamWaitEvent(ld,ctx->evCopy[b],0));
+    if ((rc=decodeDevice(ctx,dst,ctx->n+done,cnt,fmt,recLen,dropZeros,ld)))
       return rc;
-    CK(cudaEventRecord(ctx->evDec[b],ctx->st));
+    CK(cudaEventRecord(ctx->evDec[b],ld));
     used[b]=1;
     done+=cnt;
     b^=1;
   }
-  CK(cudaEventRecord(ctx->evB,ctx->st));
-  CK(cudaStreamSynchronize(ctx->st));
+  CK(cudaEventRecord(ctx->evB,ld));
+  CK(cudaStreamSynchronize(ld));
   ctx->stats.ms_h2d+=elapsed(ctx->evA,ctx->evB);       // copy and decode overlap: one figure for both
   return addSegment(ctx,n,scale,offset,unit,kept,fmt,recLen);
 }
@@ -707,7 +721,10 @@ extern "C" int wb_add_las_file(wb_ctx *ctx,const char *path,uint64_t pointOffset
     close(fd);
     return code;
   };
-  cudaError_t ce=cudaEventRecord(ctx->evA,ctx->st);
+  cudaStream_t ld=ctx->stLoad;
+  cudaEventRecord(ctx->evJoin,ctx->st);
+  cudaStreamWaitEvent(ld,ctx->evJoin,0);
+  cudaError_t ce=cudaEventRecord(ctx->evA,ld);
   int dropZeros=0,used[2]={0,0};
   for (uint64_t k=0;k<nChunks && ce==cudaSuccess;k++)
   {
@@ -729,12 +746,12 @@ extern "C" int wb_add_las_file(wb_ctx *ctx,const char *path,uint64_t pointOffset
       ce=cudaStreamWaitEvent(ctx->stCopy,ctx->evDec[b],0);
     if (ce==cudaSuccess) ce=cudaMemcpyAsync(dst,src,cnt*recLen,cudaMemcpyHostToDevice,ctx->stCopy);
     if (ce==cudaSuccess) ce=cudaEventRecord(ctx->evRead[t],ctx->stCopy);
-    if (ce==cudaSuccess) ce=cudaStreamWaitEvent(ctx->st,ctx->evRead[t],0);
+    if (ce==cudaSuccess) ce=cudaStreamWaitEvent(ld,ctx->evRead[t],0);
     if (ce!=cudaSuccess)
       break;
-    if ((rc=decodeDevice(ctx,dst,ctx->n+k*chunkRecs,cnt,fmt,recLen,dropZeros,ctx->st)))
+    if ((rc=decodeDevice(ctx,dst,ctx->n+k*chunkRecs,cnt,fmt,recLen,dropZeros,ld)))
       return finish(rc);
-    ce=cudaEventRecord(ctx->evDec[b],ctx->st);
+    ce=cudaEventRecord(ctx->evDec[b],ld);
     used[b]=1;
     if (k>=1 && ce==cudaSuccess)
     { // the previous chunk's copy is done by now or soon: hand its buffer back to its reader
@@ -749,9 +766,9 @@ extern "C" int wb_add_las_file(wb_ctx *ctx,const char *path,uint64_t pointOffset
   }
   if (ce!=cudaSuccess)
     return finish(fail(ctx,WB_ERR_CUDA,"%s",cudaGetErrorString(ce)));
-  ce=cudaEventRecord(ctx->evB,ctx->st);
+  ce=cudaEventRecord(ctx->evB,ld);
   if (ce==cudaSuccess) ce=cudaStreamSynchronize(ctx->stCopy);
-  if (ce==cudaSuccess) ce=cudaStreamSynchronize(ctx->st);
+  if (ce==cudaSuccess) ce=cudaStreamSynchronize(ld);
   if (ce!=cudaSuccess)
     return finish(fail(ctx,WB_ERR_CUDA,"%s",cudaGetErrorString(ce)));
   finish(0);
@@ -792,7 +809,16 @@ extern "C" int wb_set_own_range(wb_ctx *ctx,uint64_t first,uint64_t end)
 
 // ============================================================================ build
 
+static int buildStore(wb_ctx *ctx,bool hilbert);
+
 extern "C" int wb_build(wb_ctx *ctx)
+{
+  return buildStore(ctx,false);
+}
+
+static int buildStore(wb_ctx *ctx,bool hilbert)
+// hilbert = a CLASSIFY-ONLY store (the second stage of wb_shard_run): the points sorted along the Hilbert curve
+// classify walks anyway, no octree leaves; everything that needs the canonical order refuses such a store.
 {
   if (!ctx)
     return WB_ERR_ARG;
@@ -821,15 +847,18 @@ extern "C" int wb_build(wb_ctx *ctx)
     if (!sg.count)
       continue;
     wb_keygen_kernel<<<gridFor(sg.count,256),256,0,st>>>(ctx->xi.p,ctx->yi.p,ctx->zi.p,ctx->ret.p,sg.first,sg.count,sg,
-        ctx->geom.root_center[0],ctx->geom.root_center[1],ctx->geom.root_center[2],ctx->geom.root_side,
+        ctx->geom.root_center[0],ctx->geom.root_center[1],ctx->geom.root_center[2],ctx->geom.root_side,hilbert?1:0,
         ctx->keyA.p,ctx->idxA.p);
     ctx->stats.kernel_launches++;
   }
   KCHECK();
-  // ---- sort (63 key bits -> 8 passes)
+  // ---- sort (63 key bits -> 8 passes; Hilbert keys: 40 bits, the two special keys ~0 and WB_KEY_DUP have every
+  //      higher bit set -> 48 bits order them behind the real ones, 6 passes)
+  const int keyBits=hilbert?48:64;
+  ctx->storeHilbert=hilbert;
   CK(cudaEventRecord(ctx->evC,st));
   bool inA=true;
-  CK(wb_radix_sort((uint64_t *)ctx->keyA.p,ctx->idxA.p,(uint64_t *)ctx->keyB.p,ctx->idxB.p,n,0,64,
+  CK(wb_radix_sort((uint64_t *)ctx->keyA.p,ctx->idxA.p,(uint64_t *)ctx->keyB.p,ctx->idxB.p,n,0,keyBits,
                    ctx->table.p,ctx->table.cap,ctx->blockSums.p,ctx->blockSums.cap,st,&inA,&ctx->stats.kernel_launches));
   ctx->keys=inA?ctx->keyA.p:ctx->keyB.p;
   ctx->perm=inA?ctx->idxA.p:ctx->idxB.p;
@@ -903,7 +932,7 @@ extern "C" int wb_build(wb_ctx *ctx)
       KCHECK();
       // stable re-sort: survivors keep their order, duplicates go behind them (before the dropped records)
       bool inCur=true;
-      CK(wb_radix_sort((uint64_t *)curK,curP,(uint64_t *)othK,othP,n,0,64,ctx->table.p,ctx->table.cap,
+      CK(wb_radix_sort((uint64_t *)curK,curP,(uint64_t *)othK,othP,n,0,keyBits,ctx->table.p,ctx->table.cap,
                        ctx->blockSums.p,ctx->blockSums.cap,st,&inCur,&ctx->stats.kernel_launches));
       ctx->keys=inCur?curK:othK;
       ctx->perm=inCur?curP:othP;
@@ -920,6 +949,8 @@ extern "C" int wb_build(wb_ctx *ctx)
   }
   // ---- leaves: level-synchronous top-down split
   CK(cudaEventRecord(ctx->evC,st));
+  ctx->nLeaves=0;
+  if (!hilbert)
   {
     uint64_t nodeCap=nv/256+64;
     CK(ctx->nodesA.ensure(nodeCap)); CK(ctx->nodesB.ensure(nodeCap));
@@ -1004,6 +1035,8 @@ extern "C" int wb_num_leaves(wb_ctx *ctx,uint64_t *n)
     return WB_ERR_ARG;
   if (ctx->phase<PH_BUILT)
     return fail(ctx,WB_ERR_STATE,"not built");
+  if (ctx->storeHilbert)
+    return fail(ctx,WB_ERR_STATE,"classify-only store (second stage of wb_shard_run): it has no canonical order or leaves");
   *n=ctx->nLeaves;
   return WB_OK;
 }
@@ -1015,6 +1048,8 @@ extern "C" int wb_get_leaves(wb_ctx *ctx,wb_leaf *out,uint64_t cap)
   cudaSetDevice(ctx->device);
   if (ctx->phase<PH_BUILT)
     return fail(ctx,WB_ERR_STATE,"not built");
+  if (ctx->storeHilbert)
+    return fail(ctx,WB_ERR_STATE,"classify-only store (second stage of wb_shard_run): it has no canonical order or leaves");
   if (cap<ctx->nLeaves)
     return fail(ctx,WB_ERR_ARG,"leaf buffer too small");
   std::vector<WbLeafDev> h(ctx->nLeaves);
@@ -1053,6 +1088,8 @@ extern "C" int wb_get_order(wb_ctx *ctx,uint32_t *order,uint64_t *keys)
   cudaSetDevice(ctx->device);
   if (ctx->phase<PH_BUILT)
     return fail(ctx,WB_ERR_STATE,"not built");
+  if (ctx->storeHilbert)
+    return fail(ctx,WB_ERR_STATE,"classify-only store (second stage of wb_shard_run): it has no canonical order or leaves");
   if (order)
     CK(cudaMemcpy(order,ctx->perm,sizeof(uint32_t)*ctx->nValid,cudaMemcpyDeviceToHost));
   if (keys)
@@ -1067,6 +1104,8 @@ extern "C" int wb_get_points_sorted(wb_ctx *ctx,double *x,double *y,double *z)
   cudaSetDevice(ctx->device);
   if (ctx->phase<PH_BUILT)
     return fail(ctx,WB_ERR_STATE,"not built");
+  if (ctx->storeHilbert)
+    return fail(ctx,WB_ERR_STATE,"classify-only store (second stage of wb_shard_run): it has no canonical order or leaves");
   if (x) CK(cudaMemcpy(x,ctx->sx.p,sizeof(double)*ctx->nValid,cudaMemcpyDeviceToHost));
   if (y) CK(cudaMemcpy(y,ctx->sy.p,sizeof(double)*ctx->nValid,cudaMemcpyDeviceToHost));
   if (z) CK(cudaMemcpy(z,ctx->sz.p,sizeof(double)*ctx->nValid,cudaMemcpyDeviceToHost));
@@ -1096,6 +1135,8 @@ extern "C" int wb_scan(wb_ctx *ctx)
   cudaSetDevice(ctx->device);
   if (ctx->phase<PH_BUILT)
     return fail(ctx,WB_ERR_STATE,"not built");
+  if (ctx->storeHilbert)
+    return fail(ctx,WB_ERR_STATE,"classify-only store (second stage of wb_shard_run): it has no canonical order or leaves");
   const uint64_t nv=ctx->nValid;
   const uint32_t T=ctx->nTiles;
   cudaStream_t st=ctx->st;
@@ -1350,7 +1391,7 @@ extern "C" int wb_classify(wb_ctx *ctx)
   const WbBound *qbounds=ctx->bounds.p;
   uint8_t *qlabel=ctx->labelSorted.p;
 #if WB_CL_HILBERT
-  if (nv)
+  if (nv && !ctx->storeHilbert)
   {
     // the store along a Hilbert curve over xy (see wb_kernels.cuh, "classify order")
     CK(ctx->hKeyA.ensure(nv)); CK(ctx->hKeyB.ensure(nv)); CK(ctx->hIdxA.ensure(nv)); CK(ctx->hIdxB.ensure(nv));
@@ -1544,6 +1585,8 @@ extern "C" int wb_query_points(wb_ctx *ctx,const wb_shape *shape,uint64_t cap,ui
   cudaSetDevice(ctx->device);
   if (ctx->phase<PH_BUILT)
     return fail(ctx,WB_ERR_STATE,"not built");
+  if (ctx->storeHilbert)
+    return fail(ctx,WB_ERR_STATE,"classify-only store (second stage of wb_shard_run): it has no canonical order or leaves");
   int rc=checkShapes(ctx,shape,1);
   if (rc)
     return rc;
@@ -1646,6 +1689,8 @@ extern "C" int wb_leaf_class_counts(wb_ctx *ctx,const uint8_t *classes,int nClas
   cudaSetDevice(ctx->device);
   if (ctx->phase<PH_CLASSIFIED)
     return fail(ctx,WB_ERR_STATE,"not classified");
+  if (ctx->storeHilbert)
+    return fail(ctx,WB_ERR_STATE,"classify-only store (second stage of wb_shard_run): it has no canonical order or leaves");
   const int K=separate?nClasses:1;
   int rc=uploadClassLut(ctx,classes,nClasses,separate);
   if (rc)
@@ -1669,6 +1714,8 @@ extern "C" int wb_encode(wb_ctx *ctx,const wb_out_spec *spec,const uint64_t *des
   cudaSetDevice(ctx->device);
   if (ctx->phase<PH_CLASSIFIED)
     return fail(ctx,WB_ERR_STATE,"not classified");
+  if (ctx->storeHilbert)
+    return fail(ctx,WB_ERR_STATE,"classify-only store (second stage of wb_shard_run): it has no canonical order or leaves");
   static const int len[11]={20,28,26,34,57,63,30,36,38,59,67};
   if (spec->format<0 || spec->format>10 || spec->rec_len!=len[spec->format] || spec->rec_len>WB_DEC_MAXLEN)
     return fail(ctx,WB_ERR_FORMAT,"output format %d / record length %d not supported",spec->format,spec->rec_len);
