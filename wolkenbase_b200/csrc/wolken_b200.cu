@@ -655,27 +655,23 @@ extern "C" int wb_add_las_file(wb_ctx *ctx,const char *path,uint64_t pointOffset
   int fd=open(path,O_RDONLY);
   if (fd<0)
     return fail(ctx,WB_ERR_ARG,"cannot open %s",path);
+  struct FdGuard { int fd; ~FdGuard() { if (fd>=0) close(fd); } } fdGuard{fd};    // every early return closes the file
+  // what a failure has to put back: the dropped-record count of the chunks already decoded (wb_build subtracts it)
+  unsigned long long dropped0=0;
+  CK(cudaMemcpyAsync(&dropped0,ctx->counters.p+2,sizeof(dropped0),cudaMemcpyDeviceToHost,ctx->st));
+  CK(cudaStreamSynchronize(ctx->st));
   if ((rc=ensurePointArrays(ctx,ctx->n+n)))
-  {
-    close(fd);
     return rc;
-  }
   const int T=WB_READ_THREADS;
   const uint64_t chunkRecs=(uint64_t)1<<20;          // 1 Mi records (multiple of 16: chunks stay 16-byte aligned)
   const uint64_t chunkBytes=chunkRecs*recLen;
   const uint64_t nChunks=wb_div_up(n,chunkRecs);
   const uint64_t bufBytes=std::min<uint64_t>(chunkBytes,n*recLen)+64;
   if ((rc=ensureRing(ctx,bufBytes)))
-  {
-    close(fd);
     return rc;
-  }
   uint8_t *kept=nullptr;
   if (ctx->keepRecords && n)
-  {
     CK(cudaMalloc((void **)&kept,(size_t)(n*recLen+64)));
-    ctx->recBufs.push_back(kept);
-  }
   else
     for (int b=0;b<2;b++)
       CK(ctx->staging[b].ensure(bufBytes));
@@ -718,7 +714,14 @@ extern "C" int wb_add_las_file(wb_ctx *ctx,const char *path,uint64_t pointOffset
     ring.cv.notify_all();
     for (auto &th:threads)
       th.join();
-    close(fd);
+    if (code)
+    { // leave the context as it was before the call: no half-read segment, no stale counts, no orphaned buffer
+      cudaStreamSynchronize(ctx->stCopy);
+      cudaStreamSynchronize(ctx->stLoad);
+      cudaMemcpy(ctx->counters.p+2,&dropped0,sizeof(dropped0),cudaMemcpyHostToDevice);
+      if (kept)
+        cudaFree(kept);
+    }
     return code;
   };
   cudaStream_t ld=ctx->stLoad;
@@ -773,6 +776,8 @@ extern "C" int wb_add_las_file(wb_ctx *ctx,const char *path,uint64_t pointOffset
     return finish(fail(ctx,WB_ERR_CUDA,"%s",cudaGetErrorString(ce)));
   finish(0);
   ctx->stats.ms_h2d+=elapsed(ctx->evA,ctx->evB);       // file read, copy and decode overlap: one figure
+  if (kept)
+    ctx->recBufs.push_back(kept);
   return addSegment(ctx,n,scale,offset,unit,kept,fmt,recLen);
 }
 

@@ -520,8 +520,14 @@ void LasHeader::openRead(string fileName)
       nPoints[i]=0;
   if (pointLength==0)
     versionMajor=versionMinor=nPoints[0]=0;
-  if ((uint64_t)pointOffset+(uint64_t)nPoints[0]*pointLength>mapLen)
-    nPoints[0]=pointLength?(mapLen-pointOffset)/pointLength:0;   // truncated file: read what is there
+  {
+    // truncated file: read what is there.  The limit is a quotient (a product of header fields could wrap), and a
+    // point offset beyond the file leaves no points at all (advice, round 1: the unsigned difference was huge)
+    const uint64_t room=(uint64_t)pointOffset<mapLen?mapLen-(uint64_t)pointOffset:0;
+    const uint64_t fit=pointLength?room/pointLength:0;
+    if ((uint64_t)nPoints[0]>fit)
+      nPoints[0]=fit;
+  }
   zipFlag=pointOffset>=headerSize+8 && mapLen>=headerSize+8 && !memcmp(map+headerSize+2,"laszip",6);
   if (zipFlag)
     cout<<filename<<" is laszipped\n";
@@ -529,6 +535,9 @@ void LasHeader::openRead(string fileName)
 
 bool LasHeader::isValid() const
 {
+  static const int minLen[11]={20,28,26,34,57,63,30,36,38,59,67};       // las.cpp:38
+  if (pointFormat>=0 && pointFormat<=10 && pointLength<minLen[pointFormat])
+    return false;                                    // readPoint would walk past the record
   return versionMajor>0 && versionMinor>0 && headerSize>0 && pointLength>0 && (headerSize>0xe3 || pointFormat<6);
 }
 
