@@ -231,11 +231,13 @@ def run_ours(args):
     hist = ctx.count_classes()
 
     hbm, peak_src = peaks()
-    traffic = None
+    # DRAM bytes of one launch of the dominant kernel from the latest committed `ncu --set full` capture of THIS kernel
+    # version on THIS workload (profiles/r2_traffic.json names the capture); null when the point count differs
+    traffic, traffic_src = None, None
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["wb_classify_kernel"]
-        if abs(tj["points"] - n) <= 0.01 * n:
-            traffic = tj["dram_bytes_per_launch"]
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))["wb_classify_kernel"]
+        if abs(tj["points"] - n) <= 0.01 * n and scene == tj.get("scene", 2):
+            traffic, traffic_src = tj["dram_bytes_per_launch"], tj.get("source")
     except Exception:
         pass
     ck_ms = phase.get("ms_classify_kernel", 0.0)
@@ -256,7 +258,8 @@ def run_ours(args):
                    "parallelism": "1 GPU"},
         "phases_ms": {k[3:]: round(v, 3) for k, v in sorted(phase.items())},
         "roofline": {"bound": "hbm", "kernel": "wb_classify_kernel", "achieved": achieved, "peak": hbm,
-                     "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic, "peak_source": peak_src,
+                     "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic, "traffic_source": traffic_src,
+                     "peak_source": peak_src,
                      "note": "algorithmic 13 B/point; the kernel is bound by its FP64/shared-memory inner loop "
                              "(SURVEY 8d), DRAM traffic from ncu is in profiles/"},
         "roofline_sort": {"bound": "hbm", "kernel": "radix sort (8 passes)", "achieved": sort_bytes / (sort_ms * 1e-3) / 1e9
