@@ -1,7 +1,10 @@
 """Golden vectors at CONFIG scale (BASELINE.json configs[0], [1]): the oracle runs decode, canonical order, octree
 leaves, tile scan and postscan over the WHOLE synthetic cloud the bench uses, then classifies a SAMPLE of its points —
 each one against the whole cloud (wbo_classify_sel) — because classifying all 1e8 points takes the CPU hours.
-    python tests/golden/make_config_scale.py SCENE POINTS [SAMPLE]      e.g. 2 100000000 400000   (about 25 min)
+    python tests/golden/make_config_scale.py SCENE POINTS [SAMPLE [STRIPS]]      e.g. 2 100000000 400000   (about 25 min)
+STRIPS > 1: the cloud is the concatenation of that many x-strip files, generated exactly as bench.py --gpus STRIPS
+generates them (BASELINE configs[2], the multi-tile scene); the vectors are then for the SHARDED run, input order =
+strip after strip (file name ..._stripsW.npz).
 Writes tests/golden/config/config_scale_s<SCENE>_<POINTS>.npz:
     sample      input indices of the sampled points (uint32): random singles plus whole runs of 2048 neighbours in
                 canonical order, so that both the typical and the locally worst case are in it
@@ -38,11 +41,24 @@ def tiles_digest(tiles):
 def main():
     scene, n_points = int(sys.argv[1]), int(sys.argv[2])
     n_sample = int(sys.argv[3]) if len(sys.argv) > 3 else 400000
+    strips = int(sys.argv[4]) if len(sys.argv) > 4 else 1
     t0 = time.time()
     L = O.lib()
-    cloud = synth.generate(scene, n_points, seed=scene)
-    n = cloud.n
-    xyz = np.ascontiguousarray(cloud.ints())
+    if strips > 1:
+        d = synth.describe(scene, n_points)
+        clouds = []
+        for r in range(strips):
+            c0, c1 = d.grid_nx * r // strips, d.grid_nx * (r + 1) // strips
+            clouds.append(synth.generate(scene, n_points, seed=scene, region=(c0, 0, c1 - c0, d.grid_ny),
+                                         gps_base=d.grid_ny * c0))
+    else:
+        clouds = [synth.generate(scene, n_points, seed=scene)]
+    cloud = clouds[0]
+    assert all(c.scale == cloud.scale and c.offset == cloud.offset for c in clouds)
+    n = sum(c.n for c in clouds)
+    xyz = np.ascontiguousarray(np.concatenate([c.ints() for c in clouds]))
+    for c in clouds:
+        c.records = None
     pts = np.empty((n, 3), dtype=np.float64)
     L.wbo_coords(xyz.ctypes.data, n, O._d3(cloud.scale), O._d3(cloud.offset), 1.0, pts.ctypes.data)
     # identical locations: the first in input order keeps its place (octree.cpp:620-662)
@@ -51,10 +67,10 @@ def main():
     n_dup = n - len(first)
     del key, xyz
     assert n_dup == 0, "scene with identical locations: extend this script with the representative map"
-    corners = np.ascontiguousarray(np.array([cloud.min_corner, cloud.max_corner], dtype=np.float64))
+    corners = np.ascontiguousarray(np.array([k for c in clouds for k in (c.min_corner, c.max_corner)], dtype=np.float64))
     center, side, cube = (C.c_double * 3)(), C.c_double(), (C.c_double * 4)()
-    L.wbo_size_fit(corners.ctypes.data, 2, center, C.byref(side))
-    L.wbo_bbox_cube(corners.ctypes.data, 2, cube)
+    L.wbo_size_fit(corners.ctypes.data, len(corners), center, C.byref(side))
+    L.wbo_bbox_cube(corners.ctypes.data, len(corners), cube)
     keys = np.empty(n, dtype=np.uint64)
     order = np.empty(n, dtype=np.uint32)
     L.wbo_sort(pts.ctypes.data, n, center, side.value, keys.ctypes.data, order.ctypes.data)
@@ -92,8 +108,9 @@ def main():
                        tiles.ctypes.data, nt, pos.ctypes.data, len(pos), lab.ctypes.data, C.byref(margins))
     print("classified %d sampled points, %.0f s" % (len(pos), time.time() - t0), flush=True)
     hyp = tiles["hyperboloidSize"]
-    out = os.path.join(ROOT, "tests", "golden", "config", "config_scale_s%d_%d.npz" % (scene, n_points))
-    np.savez_compressed(out, scene=scene, n_points=n_points, n=n, sample=order[pos.astype(np.int64)], labels=lab,
+    out = os.path.join(ROOT, "tests", "golden", "config", "config_scale_s%d_%d%s.npz"
+                       % (scene, n_points, "_strips%d" % strips if strips > 1 else ""))
+    np.savez_compressed(out, scene=scene, n_points=n_points, n=n, strips=strips, counts=np.array([c.n for c in clouds]), sample=order[pos.astype(np.int64)], labels=lab,
                         margin=int(margins.value), dump_sha256=dump_sha, tiles_sha256=tiles_digest(tiles),
                         order_sha256=order_sha, n_leaves=int(nl), n_tiles=int(nt), n_duplicates=int(n_dup),
                         hyp_median=float(np.median(hyp)), hyp_max=float(hyp.max()), spacing=spacing.value)

@@ -79,3 +79,29 @@ def test_config_scale_against_oracle_vectors(name, golden_dir):
     print("%s: %d points, %d leaves, %d tiles, %d sampled labels, %d mismatches, margin gpu %d / oracle sample %d"
           % (name, cloud.n, st["n_leaves"], len(tiles), len(g["sample"]), mism, st["n_margin"], int(g["margin"])))
     assert mism <= int(st["n_margin"]) + int(g["margin"])
+
+
+def test_sharded_config_scale_against_oracle_vectors(golden_dir):
+    """BASELINE configs[2] at the size bench.py --gpus 2 runs it (250 M points, two x-strip files of LAS format 6):
+    wb_shard_run with the two ranks as threads on this GPU against the oracle's vectors for the concatenated cloud."""
+    from wolkenbase_b200 import multigpu
+    path = os.path.join(golden_dir, "config", "config_scale_s3_250000000_strips2.npz")
+    if not os.path.exists(path):
+        pytest.skip("fixture not generated (tests/golden/make_config_scale.py 3 250000000 400000 2)")
+    g = np.load(path)
+    scene, n_points, strips = int(g["scene"]), int(g["n_points"]), int(g["strips"])
+    d = synth.describe(scene, n_points)
+    clouds = []
+    for r in range(strips):
+        c0, c1 = d.grid_nx * r // strips, d.grid_nx * (r + 1) // strips
+        clouds.append(synth.generate(scene, n_points, seed=scene, region=(c0, 0, c1 - c0, d.grid_ny),
+                                     gps_base=d.grid_ny * c0))
+    assert [c.n for c in clouds] == g["counts"].tolist()
+    labs, sst, st = multigpu.run_threads([[c] for c in clouds], multigpu.PARAMS)
+    got = np.concatenate(labs)
+    mism = int((got[g["sample"]] != g["labels"]).sum())
+    margin = sum(int(s["n_margin"]) for s in st) + int(g["margin"])
+    print("%d points in %d strips, %d sampled labels, %d mismatches, margin %d, por_max %g"
+          % (len(got), strips, len(g["sample"]), mism, margin, sst[0]["por_max"]))
+    assert mism <= margin
+    assert all(s["por_max"] == float(g["hyp_max"]) for s in sst)
