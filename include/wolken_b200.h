@@ -181,7 +181,7 @@ int wb_patch_records(wb_ctx *ctx,uint8_t *recs,uint64_t first_point,uint64_t n,i
  * the caller moves the bytes (device pointers, whole-world collectives; return 0 on success). */
 #define WB_COMM_ID_BYTES 128
 #define WB_MAX_RANKS 64
-#define WB_SHARD_MAXSEG 64          /* input files per rank */
+#define WB_SHARD_MAXSEG 512         /* input files per rank */
 #define WB_SHARD_SCAN_HALO 2.5      /* tile spacings sent across a strip border for the tile scan */
 typedef struct wb_comm wb_comm;
 typedef struct wb_local_group wb_local_group;

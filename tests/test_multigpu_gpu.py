@@ -130,3 +130,11 @@ def test_sharded_run_equals_committed_oracle_labels(world, golden_dir):
     mism = int((got != g["labels"]).sum())
     assert mism <= sum(int(s["n_margin"]) for s in st) + int(g["margin"])
     assert all(s["por_max"] == float(g["hyp_max"]) for s in sst)
+
+
+def test_many_files_per_rank():
+    """70 files per rank (a project of small tiles): every file is its own segment with its own header on both sides of
+    the exchange (WB_SHARD_MAXSEG was 64 until round 2)."""
+    c = strips(2, 60000, 140)
+    ref, sst, st = check([c[:70], c[70:]])
+    assert all(s["n_halo_classify"] > 0 for s in sst)

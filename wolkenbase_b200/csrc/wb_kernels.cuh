@@ -55,7 +55,7 @@ struct WbSegment            // one wb_add_las call
   unsigned long long first,count;
   double scale[3],offset[3],unit;
 };
-#define WB_MAX_SEGMENTS 256
+#define WB_MAX_SEGMENTS 2048
 struct WbSegments
 {
   int n;
