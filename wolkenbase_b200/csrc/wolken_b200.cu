@@ -567,7 +567,7 @@ extern "C" int wb_add_las(wb_ctx *ctx,const uint8_t *recs,uint64_t n,int fmt,int
   if (ctx->keepZeroReturns)
     dropZeros=0;
   // double-buffered pipeline: copy chunk i+1 on the copy stream while chunk i is decoded
-  const uint64_t chunkRecs=(uint64_t)1<<21;          // 2 Mi records (multiple of 16: chunks stay 16-byte aligned)
+  const uint64_t chunkRecs=(uint64_t)1<<19;          // 512 Ki records = 10-20 MB (multiple of 16: chunks stay 16-byte aligned)
   const uint64_t chunkBytes=chunkRecs*recLen;
   uint8_t *kept=nullptr;
   if (ctx->keepRecords && n)
@@ -588,6 +588,12 @@ extern "C" int wb_add_las(wb_ctx *ctx,const uint8_t *recs,uint64_t n,int fmt,int
   {
     uint64_t cnt=std::min(chunkRecs,n-done);
     uint8_t *dst=kept?kept+done*recLen:ctx->staging[b].p;
+    // At most two chunk copies are ever queued: the copy engine takes its work in order, and a context that is
+    // classifying on this device meanwhile (bench.py's pipelined e2e, any job that streams clouds) sends small
+    // host->device copies of its own between its kernels — behind sixty queued 60 MB chunks each of them would
+    // wait for the whole load.
+    if (used[b])
+      CK(cudaEventSynchronize(ctx->evCopy[b]));
     if (used[b] && !kept)
       CK(cudaStreamWaitEvent(ctx->stCopy,ctx->evDec[b],0));   // staging[b] free again?
     CK(cudaMemcpyAsync(dst,recs+done*recLen,cnt*recLen,cudaMemcpyHostToDevice,ctx->stCopy));
