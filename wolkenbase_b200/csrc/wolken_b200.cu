@@ -144,6 +144,7 @@ struct wb_ctx
   std::vector<uint32_t> hLevelOff,hLevelCnt;
   wb_stats stats{};
   bool tablesUploaded=false;
+  bool pacedCopies=true;              // wb_add_las keeps at most two chunk copies queued (WB_H2D_PACED=0: all at once)
   bool storeHilbert=false;            // the store is a classify-only one (buildStore(ctx,true)): Hilbert order, no leaves
 };
 
@@ -351,6 +352,8 @@ extern "C" int wb_create(int device,wb_ctx **out)
     cudaDeviceGetStreamPriorityRange(&least,&greatest);
     cudaStreamCreateWithPriority(&ctx->stLoad,cudaStreamNonBlocking,greatest);
     cudaEventCreateWithFlags(&ctx->evJoin,cudaEventDisableTiming);
+    const char *paced=getenv("WB_H2D_PACED");
+    ctx->pacedCopies=!(paced && paced[0]=='0');
   }
   cudaEventCreate(&ctx->evA); cudaEventCreate(&ctx->evB); cudaEventCreate(&ctx->evC); cudaEventCreate(&ctx->evD);
   for (int i=0;i<2;i++)
@@ -567,7 +570,7 @@ extern "C" int wb_add_las(wb_ctx *ctx,const uint8_t *recs,uint64_t n,int fmt,int
   if (ctx->keepZeroReturns)
     dropZeros=0;
   // double-buffered pipeline: copy chunk i+1 on the copy stream while chunk i is decoded
-  const uint64_t chunkRecs=(uint64_t)1<<19;          // 512 Ki records = 10-20 MB (multiple of 16: chunks stay 16-byte aligned)
+  const uint64_t chunkRecs=(uint64_t)1<<21;          // 2 Mi records (multiple of 16: chunks stay 16-byte aligned)
   const uint64_t chunkBytes=chunkRecs*recLen;
   uint8_t *kept=nullptr;
   if (ctx->keepRecords && n)
@@ -592,7 +595,7 @@ extern "C" int wb_add_las(wb_ctx *ctx,const uint8_t *recs,uint64_t n,int fmt,int
     // classifying on this device meanwhile (bench.py's pipelined e2e, any job that streams clouds) sends small
     // host->device copies of its own between its kernels — behind sixty queued 60 MB chunks each of them would
     // wait for the whole load.
-    if (used[b])
+    if (used[b] && ctx->pacedCopies)
       CK(cudaEventSynchronize(ctx->evCopy[b]));
     if (used[b] && !kept)
       CK(cudaStreamWaitEvent(ctx->stCopy,ctx->evDec[b],0));   // staging[b] free again?
