@@ -55,7 +55,9 @@ struct WbSegment            // one wb_add_las call
   unsigned long long first,count;
   double scale[3],offset[3],unit;
 };
+#ifndef WB_MAX_SEGMENTS
 #define WB_MAX_SEGMENTS 2048
+#endif
 struct WbSegments
 {
   int n;

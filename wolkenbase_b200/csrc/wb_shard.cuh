@@ -542,6 +542,7 @@ struct WbShard
   DevBuf<uint8_t> grid;
   DevBuf<int> ext;
   std::vector<WbShardMeta> meta;
+  int maxSegs=1;                       // most input files any rank holds
   wb_shard_stats st{};
 };
 
@@ -672,8 +673,14 @@ int haloExchange(wb_ctx *ctx,wb_comm *cm,WbShard &S,const std::vector<WbSegment>
   KCHECK();
   *msSelect+=clk.lap();
   // who sends what: every rank's [dest][segment] counts to everybody
-  std::vector<uint64_t> all((size_t)W*W*WB_SHARD_MAXSEG);
-  int rc=commAllGatherHost(cm,sendCnt.data(),all.data(),sendCnt.size()*sizeof(uint64_t));
+  // (only the columns any rank uses: the message stays a few hundred bytes for the usual one file per rank — a host
+  //  copy of tens of KB goes through the copy engine, behind whatever bulk upload another context has queued there)
+  const int MS=S.maxSegs;
+  std::vector<uint64_t> mineCnt((size_t)W*MS),allCnt((size_t)W*W*MS);
+  for (int k=0;k<W;k++)
+    for (int sg=0;sg<MS;sg++)
+      mineCnt[(size_t)k*MS+sg]=sendCnt[(size_t)k*WB_SHARD_MAXSEG+sg];
+  int rc=commAllGatherHost(cm,mineCnt.data(),allCnt.data(),mineCnt.size()*sizeof(uint64_t));
   if (rc)
     return rc;
   std::vector<uint64_t> rOff(W,0),rCnt(W,0);
@@ -682,9 +689,9 @@ int haloExchange(wb_ctx *ctx,wb_comm *cm,WbShard &S,const std::vector<WbSegment>
   for (int k=0;k<W;k++)
   {
     rOff[k]=total*sizeof(int4);
-    for (int s=0;s<WB_SHARD_MAXSEG;s++)
+    for (int s=0;s<MS;s++)
     {
-      const uint64_t c=all[((size_t)k*W+R)*WB_SHARD_MAXSEG+s];
+      const uint64_t c=allCnt[((size_t)k*W+R)*MS+s];
       cntFrom[(size_t)k*WB_SHARD_MAXSEG+s]=c;
       rCnt[k]+=c*sizeof(int4);
       total+=c;
@@ -809,9 +816,29 @@ extern "C" int wb_shard_run(wb_ctx *ctx,wb_comm *cm)
     }
     mine.seg[s].unit=ownSegs[s].unit;
   }
-  S.meta.resize(W);
-  if ((rc=commAllGatherHost(cm,&mine,S.meta.data(),sizeof(WbShardMeta))))
-    return rc;
+  S.meta.assign(W,WbShardMeta());
+  {
+    // the fixed part first, then the per-file headers padded to the largest file count of any rank
+    const size_t headBytes=offsetof(WbShardMeta,seg);
+    std::vector<uint8_t> heads(headBytes*W);
+    if ((rc=commAllGatherHost(cm,&mine,heads.data(),headBytes)))
+      return rc;
+    int maxSegs=1;
+    for (int k=0;k<W;k++)
+    {
+      memcpy(&S.meta[k],heads.data()+headBytes*k,headBytes);
+      if (S.meta[k].nSegs<0 || S.meta[k].nSegs>WB_SHARD_MAXSEG)
+        return fail(ctx,WB_ERR_ARG,"rank %d reports %d input files",k,S.meta[k].nSegs);
+      maxSegs=std::max(maxSegs,S.meta[k].nSegs);
+    }
+    S.maxSegs=maxSegs;
+    const size_t segBytes=sizeof(mine.seg[0])*(size_t)maxSegs;
+    std::vector<uint8_t> segs(segBytes*W);
+    if ((rc=commAllGatherHost(cm,mine.seg,segs.data(),segBytes)))
+      return rc;
+    for (int k=0;k<W;k++)
+      memcpy(S.meta[k].seg,segs.data()+segBytes*k,segBytes);
+  }
   std::vector<double> lo(W),hi(W),cuts(W+1);
   double zmax=-INFINITY;
   {

@@ -144,7 +144,7 @@ struct wb_ctx
   std::vector<uint32_t> hLevelOff,hLevelCnt;
   wb_stats stats{};
   bool tablesUploaded=false;
-  bool pacedCopies=true;              // wb_add_las keeps at most two chunk copies queued (WB_H2D_PACED=0: all at once)
+  bool pacedCopies=false;             // WB_H2D_PACED=1: wb_add_las keeps at most two chunk copies queued (no gain measured)
   bool storeHilbert=false;            // the store is a classify-only one (buildStore(ctx,true)): Hilbert order, no leaves
 };
 
@@ -353,7 +353,7 @@ extern "C" int wb_create(int device,wb_ctx **out)
     cudaStreamCreateWithPriority(&ctx->stLoad,cudaStreamNonBlocking,greatest);
     cudaEventCreateWithFlags(&ctx->evJoin,cudaEventDisableTiming);
     const char *paced=getenv("WB_H2D_PACED");
-    ctx->pacedCopies=!(paced && paced[0]=='0');
+    ctx->pacedCopies=paced && paced[0]=='1';
   }
   cudaEventCreate(&ctx->evA); cudaEventCreate(&ctx->evB); cudaEventCreate(&ctx->evC); cudaEventCreate(&ctx->evD);
   for (int i=0;i<2;i++)
@@ -591,10 +591,9 @@ extern "C" int wb_add_las(wb_ctx *ctx,const uint8_t *recs,uint64_t n,int fmt,int
   {
     uint64_t cnt=std::min(chunkRecs,n-done);
     uint8_t *dst=kept?kept+done*recLen:ctx->staging[b].p;
-    // At most two chunk copies are ever queued: the copy engine takes its work in order, and a context that is
-    // classifying on this device meanwhile (bench.py's pipelined e2e, any job that streams clouds) sends small
-    // host->device copies of its own between its kernels — behind sixty queued 60 MB chunks each of them would
-    // wait for the whole load.
+    // Optional pacing (at most two chunk copies queued).  The copy engine takes its work in order, so a context that
+    // classifies on this device meanwhile must keep its own host->device traffic to a few KB per call (inlined by the
+    // driver): see the segment-table upload in buildStore.  With that in place pacing changed nothing at 8 GPUs.
     if (used[b] && ctx->pacedCopies)
       CK(cudaEventSynchronize(ctx->evCopy[b]));
     if (used[b] && !kept)
@@ -894,7 +893,10 @@ static int buildStore(wb_ctx *ctx,bool hilbert)
     hs.n=(int)ctx->segs.size();
     for (int i=0;i<hs.n;i++)
       hs.s[i]=ctx->segs[i];
-    CK(cudaMemcpyAsync(ctx->dsegs.p,&hs,sizeof(hs),cudaMemcpyHostToDevice,st));
+    // only the entries in use: a host copy of more than a few KB is a copy-engine job and queues behind any bulk
+    // upload another context of this device has pending (measured: the whole 147 KB table cost the pipelined e2e
+    // its overlap, 499 -> 524 ms a step)
+    CK(cudaMemcpyAsync(ctx->dsegs.p,&hs,offsetof(WbSegments,s)+sizeof(WbSegment)*(size_t)hs.n,cudaMemcpyHostToDevice,st));
     CK(cudaStreamSynchronize(st));
   }
   wb_gather_kernel<<<gridFor(nv,256),256,0,st>>>(ctx->perm,nv,ctx->xi.p,ctx->yi.p,ctx->zi.p,ctx->dsegs.p,
@@ -1769,7 +1771,7 @@ extern "C" int wb_encode(wb_ctx *ctx,const wb_out_spec *spec,const uint64_t *des
     for (size_t i=0;i<ctx->recSegs.size();i++)
       hr.s[i]=ctx->recSegs[i];
     CK(ctx->drsegs.ensure(1));
-    CK(cudaMemcpyAsync(ctx->drsegs.p,&hr,sizeof(hr),cudaMemcpyHostToDevice,st));
+    CK(cudaMemcpyAsync(ctx->drsegs.p,&hr,sizeof(WbRecSeg)*std::max<size_t>(1,ctx->recSegs.size()),cudaMemcpyHostToDevice,st));
     CK(cudaStreamSynchronize(st));
   }
   // whose attributes a stored point carries: its own record, or the last record at the same XYZ
@@ -1844,7 +1846,7 @@ extern "C" int wb_census(wb_ctx *ctx,wb_census_result *out,uint64_t *missing,uin
     for (size_t i=0;i<ctx->recSegs.size();i++)
       hr.s[i]=ctx->recSegs[i];
     CK(ctx->drsegs.ensure(1));
-    CK(cudaMemcpyAsync(ctx->drsegs.p,&hr,sizeof(hr),cudaMemcpyHostToDevice,st));
+    CK(cudaMemcpyAsync(ctx->drsegs.p,&hr,sizeof(WbRecSeg)*std::max<size_t>(1,ctx->recSegs.size()),cudaMemcpyHostToDevice,st));
     CK(cudaStreamSynchronize(st));
   }
   const uint32_t *src=ctx->perm;
