@@ -256,9 +256,10 @@ extern "C" int simt_scan_classify(const double *sx,const double *sy,const double
   unsigned long long nList=0;
   if (m)
     launch(grid(m,256),256,[&]{ wb_segment_kernel(pairKey.data(),m,tStart.data(),tCount.data(),tileList.data(),&nList); });
+  const int bundle=wb_scan_bundle(nList,m);
   if (nList)
-    launch(grid(nList,WB_SCAN_WARPS*WB_SCAN_BUNDLE),WB_SCAN_WARPS*32,[&]{ wb_scan_kernel(tileList.data(),(uint32_t)nList,tStart.data(),tCount.data(),
-                                                          pairVal.data(),sx,sy,sz,snake,minHyp,tNPoints.data(),tTree.data(),
+    launch(grid(nList,WB_SCAN_WARPS*bundle),WB_SCAN_WARPS*32,[&]{ wb_scan_kernel(tileList.data(),(uint32_t)nList,tStart.data(),tCount.data(),
+                                                          pairVal.data(),sx,sy,sz,snake,minHyp,bundle,tNPoints.data(),tTree.data(),
                                                           tDensity.data(),tHyp.data(),tHeight.data()); });
   if (doPostscan)
   {

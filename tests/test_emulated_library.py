@@ -30,6 +30,17 @@ def test_gpu_parity_subset_passes_on_the_emulated_library():
     assert " passed" in out.stdout and "failed" not in out.stdout, tail
 
 
+def test_bundled_tile_scan_passes_on_the_emulated_library():
+    """The tile scan with 32 and with 5 tiles per warp (small scenes get 1 from wb_scan_bundle): same tile tables."""
+    subprocess.check_call(["make", "-s", "-C", SIMT, "libwolken_b200_emulated.so"])
+    for bundle in ("32", "5"):
+        env = dict(os.environ, WB_LIB=EMULATED, WB_SCAN_BUNDLE=bundle)
+        out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-m", "gpu",
+                              "-q", "-x", "-k", "pipeline_matches_oracle and 5000 or ragged_and_tiny or street_30k_tile3",
+                              "-p", "no:cacheprovider"], capture_output=True, text=True, env=env, cwd=ROOT, timeout=900)
+        assert out.returncode == 0, bundle + "\n" + out.stdout[-3000:] + out.stderr[-2000:]
+
+
 def test_sharded_path_passes_on_the_emulated_library():
     """wb_shard_run with ranks as host threads (LOCAL transport): header offsets that differ between ranks, records at
     the XYZ of another rank's point, records dropped by the return-number rule — labels equal the oracle's."""

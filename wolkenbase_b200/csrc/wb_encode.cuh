@@ -297,9 +297,8 @@ wb_census_mark_kernel(const uint32_t *__restrict__ src,unsigned long long nv,con
                       WbCensus *__restrict__ out)
 {
   unsigned long long j=(unsigned long long)blockIdx.x*blockDim.x+threadIdx.x;
-  if (j>=nv)
-    return;
-  const uint32_t i=src[j];
+  const bool have=j<nv;                             // whole warps stay: the first pass votes
+  const uint32_t i=have?src[j]:src[0];
   int lo=0,hi=segs->n-1;
   while (lo<hi)
   {
@@ -322,18 +321,24 @@ wb_census_mark_kernel(const uint32_t *__restrict__ src,unsigned long long nv,con
     t=__longlong_as_double((long long)u);
   }
   // n=lrint(t); n!=t || n<0 -> not test data (testpattern.cpp:68-70; n is an int there: numbers stay below 2^31)
-  if (!(t>=0) || t>=2147483648.0 || t!=rint(t))
-  {
-    if (!bits)
-      atomicAdd(&out->notInteger,1ull);
-    return;
-  }
-  const unsigned long long nn=(unsigned long long)t;
+  const bool bad=have && (!(t>=0) || t>=2147483648.0 || t!=rint(t));
+  const unsigned long long nn=(bad || !have)?0ull:(unsigned long long)t;
   if (!bits)
   {
-    atomicMax(&out->maxPlusOne,nn+1);
+    // first pass: one atomic per warp, not per thread (they all aim at the same two words)
+    const unsigned nBad=__popc(__ballot_sync(0xffffffffu,bad));
+    const unsigned top=__reduce_max_sync(0xffffffffu,(bad || !have)?0u:(unsigned)nn+1u);
+    if ((threadIdx.x&31)==0)
+    {
+      if (nBad)
+        atomicAdd(&out->notInteger,(unsigned long long)nBad);
+      if (top)
+        atomicMax(&out->maxPlusOne,(unsigned long long)top);
+    }
     return;
   }
+  if (bad || !have)
+    return;
   const unsigned long long m=1ull<<(nn&63);
   if (atomicOr(&bits[nn>>6],m)&m)
     atomicAdd(&out->duplicate,1ull);

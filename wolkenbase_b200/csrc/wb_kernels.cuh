@@ -11,6 +11,7 @@
 //   tiles    dense arrays indexed by flowsnake sequence number - lo
 #pragma once
 #include "wb_device.cuh"
+#include <cstdlib>
 #if defined(__CUDACC__) && !defined(WB_DEC_NO_BULK)
 #include <cuda/barrier>                 // cp.async.bulk (TMA, 1-D) for the decode kernel's staging
 #define WB_DEC_BULK 1
@@ -602,17 +603,41 @@ __device__ void wb_gausselim(WbMat3 &m)
 }
 
 #define WB_SCAN_WARPS 4
-#define WB_SCAN_BUNDLE 32             // tiles per warp
+#define WB_SCAN_BUNDLE 32             // most tiles per warp
+
+static inline int wb_scan_bundle(unsigned long long nTiles,unsigned long long nPairs)
+// Tiles per warp.  Bundling pays for the plane fit (one lane per tile instead of 32 lanes on one tile), which matters
+// when tiles are small (aerial: 10-60 points); a terrestrial scan has few, large tiles (C4: 69 k tiles of ~1 000
+// points), where a warp that walks 32 of them one after the other leaves the GPU a few thousand warps to run:
+// 162 ms against 24 ms with one tile per warp.  So: as many as keep about 64 points per bundled tile-batch and at
+// least ~10 k warps in flight, a power of two, at most 32.
+{
+  if (const char *e=getenv("WB_SCAN_BUNDLE"))          // tests: small scenes would always get 1
+  {
+    const int v=atoi(e);
+    if (v>=1 && v<=WB_SCAN_BUNDLE)
+      return v;
+  }
+  if (!nTiles)
+    return 1;
+  const unsigned long long avg=nPairs/nTiles+1;
+  unsigned long long b=2048/avg;
+  b=b<nTiles/9472?b:nTiles/9472;
+  int r=1;
+  while (r*2<=WB_SCAN_BUNDLE && (unsigned long long)r*2<=b)
+    r*=2;
+  return r;
+}
 
 __global__ void __launch_bounds__(WB_SCAN_WARPS*32)
 wb_scan_kernel(const uint32_t *__restrict__ tileList,uint32_t nList,
                const uint32_t *__restrict__ tStart,const uint32_t *__restrict__ tCount,
                const uint32_t *__restrict__ pairVal,
                const double *__restrict__ sx,const double *__restrict__ sy,const double *__restrict__ sz,
-               WbSnake snake,double minHyp,
+               WbSnake snake,double minHyp,int bundle,
                int *__restrict__ tNPoints,uint8_t *__restrict__ tTree,double *__restrict__ tDensity,
                double *__restrict__ tHyp,double *__restrict__ tHeight)
-// scanCylinder (scan.cpp:31-140): ONE WARP PER BUNDLE OF 32 NON-EMPTY TILES.
+// scanCylinder (scan.cpp:31-140): ONE WARP PER BUNDLE OF `bundle` (1..32, wb_scan_bundle) NON-EMPTY TILES.
 //   sums    tile after tile, the warp takes the tile's points (canonical order) 32 at a time, one per lane.  The eight
 //           normal-equation sums keep the reference's association (pairwisesum, manysum.cpp:120-154 = perfect binary
 //           trees over aligned power-of-two blocks, merged like a binary counter): inside a batch the tree is a
@@ -626,10 +651,10 @@ wb_scan_kernel(const uint32_t *__restrict__ tileList,uint32_t nList,
   __shared__ double lvAll[WB_SCAN_WARPS][8][28];
   __shared__ double totAll[WB_SCAN_WARPS][WB_SCAN_BUNDLE][8];
   const int lane=threadIdx.x&31,wi=threadIdx.x>>5;
-  const uint32_t first=(blockIdx.x*WB_SCAN_WARPS+wi)*WB_SCAN_BUNDLE;
+  const uint32_t first=(blockIdx.x*WB_SCAN_WARPS+wi)*(uint32_t)bundle;
   if (first>=nList)
     return;
-  const int nT=(int)min((uint32_t)WB_SCAN_BUNDLE,nList-first);
+  const int nT=(int)min((uint32_t)bundle,nList-first);
   double (*lv)[28]=lvAll[wi];
   // ---- lane = tile: where its points are, where its centre is
   uint32_t myT=0,myStart=0,myCnt=0;

@@ -1198,10 +1198,13 @@ extern "C" int wb_scan(wb_ctx *ctx)
   CK(cudaMemcpyAsync(&nList,ctx->counters.p+3,sizeof(nList),cudaMemcpyDeviceToHost,st));
   CK(cudaStreamSynchronize(st));
   if (nList)
-    wb_scan_kernel<<<gridFor(nList,WB_SCAN_WARPS*WB_SCAN_BUNDLE),WB_SCAN_WARPS*32,0,st>>>(ctx->tileList.p,(uint32_t)nList,ctx->tStart.p,ctx->tCount.p,
+  {
+    const int bundle=wb_scan_bundle(nList,ctx->nPairs);
+    wb_scan_kernel<<<gridFor(nList,(unsigned)(WB_SCAN_WARPS*bundle)),WB_SCAN_WARPS*32,0,st>>>(ctx->tileList.p,(uint32_t)nList,ctx->tStart.p,ctx->tCount.p,
                                               ctx->pairVals,ctx->sx.p,ctx->sy.p,ctx->sz.p,
-                                              ctx->snake,ctx->prm.minHyp,ctx->tNPoints.p,ctx->tTree.p,ctx->tDensity.p,
+                                              ctx->snake,ctx->prm.minHyp,bundle,ctx->tNPoints.p,ctx->tTree.p,ctx->tDensity.p,
                                               ctx->tHyp.p,ctx->tHeight.p);
+  }
   ctx->stats.kernel_launches+=2;
   KCHECK();
   CK(cudaEventRecord(ctx->evB,st));
