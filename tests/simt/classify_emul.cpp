@@ -218,10 +218,7 @@ extern "C" int simt_scan_classify(const double *sx,const double *sy,const double
     double t[512],co[512],si[512];
     wbhost::fillTanTables(t,co,si);
     memcpy(g_tanTable,t,sizeof(t)); memcpy(g_cosTable,co,sizeof(co)); memcpy(g_sinTable,si,sizeof(si));
-    memset(g_fwdTable,0,sizeof(g_fwdTable));
-    for (int i=0;i<6;i++)
-      for (int j=0;j<7;j++)
-        g_fwdTable[i*8+j]=wbhost::kFwdTable[i][j];
+    wbhost::fillFlowsnakeTables(g_fwdTable);
   }
   WbSnake snake;
   int lo,hi;
@@ -237,14 +234,14 @@ extern "C" int simt_scan_classify(const double *sx,const double *sy,const double
   for (uint64_t i=0;i<n;i++)
     off[i+1]=off[i]+cnt[i];
   const uint32_t m=off[n];
-  std::vector<unsigned long long> pairKey(m+1);
+  std::vector<uint32_t> pairKey(m+1);
   std::vector<uint32_t> pairVal(m+1);
   launch(grid(n,256),256,[&]{ wb_member_fill_kernel(cnt.data(),off.data(),tilesOf.data(),n,pairKey.data(),pairVal.data()); });
   {
     std::vector<uint32_t> idx(m);
     for (uint32_t i=0;i<m;i++) idx[i]=i;
     std::stable_sort(idx.begin(),idx.end(),[&](uint32_t a,uint32_t b){ return pairKey[a]<pairKey[b]; });
-    std::vector<unsigned long long> k2(m+1);
+    std::vector<uint32_t> k2(m+1);
     std::vector<uint32_t> v2(m+1);
     for (uint32_t i=0;i<m;i++) { k2[i]=pairKey[idx[i]]; v2[i]=pairVal[idx[i]]; }
     pairKey.swap(k2); pairVal.swap(v2);

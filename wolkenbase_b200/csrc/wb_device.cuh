@@ -33,7 +33,7 @@ struct WbParams
 __device__ double g_tanTable[512];
 __device__ double g_cosTable[512];
 __device__ double g_sinTable[512];
-__device__ unsigned char g_fwdTable[48];     // [6][8], flowsnake.cpp:46-54 padded to 8 columns
+__device__ unsigned char g_fwdTable[96];     // [6][8], flowsnake.cpp:46-54 padded to 8 columns, then its inverse (wb_host.h)
 
 // ---- exact helpers ---------------------------------------------------------------------
 
@@ -210,14 +210,9 @@ __device__ __forceinline__ bool wb_from_flowsnake(int ex,int ey,long long &n)
   #pragma unroll
   for (int i=10;i>=0;i--)
   {
-    int d;
-    for (d=0;d<7;d++)
-      if ((__ldg(&g_fwdTable[ori*8+d])&7)==dig[i])
-        break;
-    if (d==7)
-      return false;
-    ori=__ldg(&g_fwdTable[ori*8+d])>>4;
-    v=v*7+d;
+    const int t=__ldg(&g_fwdTable[48+ori*8+dig[i]]);   // the inverse table: which input digit gives dig[i] in this orientation
+    ori=t>>4;
+    v=v*7+(t&7);
   }
   n=v-1235829214LL;
   return true;

@@ -32,6 +32,20 @@ static const unsigned char kFwdTable[6][7]=
   {0x52,0x05,0x23,0x40,0x51,0x54,0x16}
 };
 
+inline void fillFlowsnakeTables(unsigned char out[96])
+// [ori*8+d] = kFwdTable (next orientation<<4 | output digit); [48+ori*8+digit] = its inverse per orientation
+// (next orientation<<4 | input digit d): every row's output digits are a permutation of 0..6
+{
+  for (int i=0;i<96;i++)
+    out[i]=0;
+  for (int i=0;i<6;i++)
+    for (int j=0;j<7;j++)
+    {
+      out[i*8+j]=kFwdTable[i][j];
+      out[48+i*8+(kFwdTable[i][j]&7)]=(unsigned char)((kFwdTable[i][j]&0xf0)|j);
+    }
+}
+
 inline void fillTanTables(double *tanT /*512*/,double *cosT /*512*/,double *sinT /*512*/)
 // angle.cpp:305-320 via sin/cos/tan(int) (angle.cpp:45-63): long double libm, rounded to double
 {

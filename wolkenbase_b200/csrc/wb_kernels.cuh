@@ -454,7 +454,7 @@ wb_member_count_kernel(const double *__restrict__ sx,const double *__restrict__ 
 __global__ void __launch_bounds__(256)
 wb_member_fill_kernel(const uint32_t *__restrict__ cnt,const uint32_t *__restrict__ off,
                       const uint4 *__restrict__ tilesOf,unsigned long long n,
-                      unsigned long long *__restrict__ pairKey,uint32_t *__restrict__ pairVal)
+                      uint32_t *__restrict__ pairKey,uint32_t *__restrict__ pairVal)
 {
   unsigned long long k=(unsigned long long)blockIdx.x*blockDim.x+threadIdx.x;
   if (k>=n)
@@ -470,7 +470,7 @@ wb_member_fill_kernel(const uint32_t *__restrict__ cnt,const uint32_t *__restric
 }
 
 __global__ void __launch_bounds__(256)
-wb_segment_kernel(const unsigned long long *__restrict__ pairKey,unsigned long long m,
+wb_segment_kernel(const uint32_t *__restrict__ pairKey,unsigned long long m,
                   uint32_t *__restrict__ tStart,uint32_t *__restrict__ tCount,
                   uint32_t *__restrict__ tileList,unsigned long long *__restrict__ nList)
 // start and count of every tile's run in the sorted (tile,point) pairs + the list of non-empty tiles
@@ -478,7 +478,7 @@ wb_segment_kernel(const unsigned long long *__restrict__ pairKey,unsigned long l
   unsigned long long i=(unsigned long long)blockIdx.x*blockDim.x+threadIdx.x;
   if (i>=m)
     return;
-  unsigned long long t=pairKey[i];
+  const uint32_t t=pairKey[i];
   if (i==0 || pairKey[i-1]!=t)
   {
     tStart[t]=(uint32_t)i;

@@ -132,8 +132,9 @@ wb_scan_apply_kernel(const uint32_t *__restrict__ in,uint32_t *__restrict__ out,
 
 // ---------------------------------------------------------------- radix sort
 
+template <typename K>                  // K = uint64_t (Morton / Hilbert keys) or uint32_t (tile numbers of the membership pairs)
 __global__ void __launch_bounds__(WB_SORT_THREADS)
-wb_sort_upsweep_kernel(const uint64_t *__restrict__ keys,uint64_t n,int shift,
+wb_sort_upsweep_kernel(const K *__restrict__ keys,uint64_t n,int shift,
                        uint32_t *__restrict__ table,uint32_t nBlocks)
 // table[digit*nBlocks+block] = number of keys of this block's tile with that digit
 {
@@ -152,9 +153,10 @@ wb_sort_upsweep_kernel(const uint64_t *__restrict__ keys,uint64_t n,int shift,
   table[(uint64_t)threadIdx.x*nBlocks+blockIdx.x]=hist[threadIdx.x];
 }
 
+template <typename K>
 __global__ void __launch_bounds__(WB_SORT_THREADS,WB_SORT_MINBLOCKS)
-wb_sort_downsweep_kernel(const uint64_t *__restrict__ keysIn,const uint32_t *__restrict__ valsIn,
-                         uint64_t *__restrict__ keysOut,uint32_t *__restrict__ valsOut,
+wb_sort_downsweep_kernel(const K *__restrict__ keysIn,const uint32_t *__restrict__ valsIn,
+                         K *__restrict__ keysOut,uint32_t *__restrict__ valsOut,
                          uint64_t n,int shift,const uint32_t *__restrict__ table,uint32_t nBlocks)
 {
   // warp w owns elements [w*32*ITEMS,(w+1)*32*ITEMS) of the tile, visited round by round
@@ -162,7 +164,7 @@ wb_sort_downsweep_kernel(const uint64_t *__restrict__ keysIn,const uint32_t *__r
   __shared__ uint32_t warpCnt[WB_SORT_WARPS][256];
   __shared__ uint32_t digitBase[256];     // start of each digit's run inside the tile (local order)
   __shared__ uint32_t globalBase[256];    // where that run goes in the output
-  __shared__ uint64_t skeys[WB_SORT_TILE];
+  __shared__ K skeys[WB_SORT_TILE];
   __shared__ uint32_t svals[WB_SORT_TILE];
   __shared__ uint32_t smscan[33];
   const int lane=threadIdx.x&31,w=threadIdx.x>>5;
@@ -171,13 +173,13 @@ wb_sort_downsweep_kernel(const uint64_t *__restrict__ keysIn,const uint32_t *__r
   for (int d=lane;d<256;d+=32)
     warpCnt[w][d]=0;
   __syncwarp();
-  uint64_t key[WB_SORT_ITEMS];
+  K key[WB_SORT_ITEMS];
   uint16_t off[WB_SORT_ITEMS];
   #pragma unroll
   for (int r=0;r<WB_SORT_ITEMS;r++)
   {
     uint64_t j=warpBase+(uint64_t)r*32+lane;
-    key[r]=j<n?keysIn[j]:~0ull;
+    key[r]=j<n?keysIn[j]:(K)~(K)0;
   }
   #pragma unroll
   for (int r=0;r<WB_SORT_ITEMS;r++)
@@ -234,7 +236,7 @@ wb_sort_downsweep_kernel(const uint64_t *__restrict__ keysIn,const uint32_t *__r
   uint32_t cnt=(uint32_t)(n-tileBase<WB_SORT_TILE?n-tileBase:WB_SORT_TILE);
   for (uint32_t p=threadIdx.x;p<cnt;p+=WB_SORT_THREADS)
   {
-    uint64_t k=skeys[p];
+    K k=skeys[p];
     uint32_t d=(uint32_t)((k>>shift)&255);
     uint64_t dst=(uint64_t)globalBase[d]+(p-digitBase[d]);
     keysOut[dst]=k;
@@ -274,7 +276,8 @@ static cudaError_t wb_exclusive_scan(const uint32_t *in,uint32_t *out,uint64_t n
 
 // Stable sort of (key,val) by key bits [beginBit,endBit).  Result ends in (keysA,valsA) if the
 // number of passes is even, else in (keysB,valsB); *inA tells which.
-static cudaError_t wb_radix_sort(uint64_t *keysA,uint32_t *valsA,uint64_t *keysB,uint32_t *valsB,
+template <typename K>
+static cudaError_t wb_radix_sort(K *keysA,uint32_t *valsA,K *keysB,uint32_t *valsB,
                                  uint64_t n,int beginBit,int endBit,uint32_t *table,uint64_t tableCap,
                                  uint32_t *blockSums,uint64_t blockSumsCap,cudaStream_t st,
                                  bool *inA,uint64_t *launches)
@@ -285,20 +288,20 @@ static cudaError_t wb_radix_sort(uint64_t *keysA,uint32_t *valsA,uint64_t *keysB
   uint64_t nb=wb_div_up(n,WB_SORT_TILE);
   if (nb*256>tableCap)
     return cudaErrorInvalidValue;
-  uint64_t *ki=keysA,*ko=keysB;
+  K *ki=keysA,*ko=keysB;
   uint32_t *vi=valsA,*vo=valsB;
   for (int shift=beginBit;shift<endBit;shift+=8)
   {
-    wb_sort_upsweep_kernel<<<(unsigned)nb,WB_SORT_THREADS,0,st>>>(ki,n,shift,table,(uint32_t)nb);
+    wb_sort_upsweep_kernel<K><<<(unsigned)nb,WB_SORT_THREADS,0,st>>>(ki,n,shift,table,(uint32_t)nb);
     if (launches)
       (*launches)++;
     cudaError_t e=wb_exclusive_scan(table,table,nb*256,blockSums,blockSumsCap,st,launches);
     if (e!=cudaSuccess)
       return e;
-    wb_sort_downsweep_kernel<<<(unsigned)nb,WB_SORT_THREADS,0,st>>>(ki,vi,ko,vo,n,shift,table,(uint32_t)nb);
+    wb_sort_downsweep_kernel<K><<<(unsigned)nb,WB_SORT_THREADS,0,st>>>(ki,vi,ko,vo,n,shift,table,(uint32_t)nb);
     if (launches)
       (*launches)++;
-    uint64_t *tk=ki; ki=ko; ko=tk;
+    K *tk=ki; ki=ko; ko=tk;
     uint32_t *tv=vi; vi=vo; vo=tv;
     *inA=!*inA;
   }

@@ -83,7 +83,8 @@ struct wb_ctx
   // device arrays (input order)
   DevBuf<int> xi,yi,zi;
   DevBuf<uint8_t> cls,ret,labelIn,labelSorted,leafDepth;
-  DevBuf<unsigned long long> keyA,keyB,pairKeyA,pairKeyB,counters;
+  DevBuf<unsigned long long> keyA,keyB,counters;
+  DevBuf<uint32_t> pairKeyA,pairKeyB;     // tile number of every (point, covering tile) pair: 32 bits, a third less sort traffic
   DevBuf<uint32_t> idxA,idxB,scr0,scr1,winner,pairValA,pairValB,table,blockSums;
   DevBuf<uint32_t> dupIn,dupRep;          // input indices of (lost duplicate, surviving point at the same XYZ)
   uint64_t nDup=0;
@@ -135,7 +136,7 @@ struct wb_ctx
   // results of build
   unsigned long long *keys=nullptr;   // sorted keys (keyA or keyB)
   uint32_t *perm=nullptr;             // sorted -> input
-  uint64_t *pairKeys=nullptr;
+  uint32_t *pairKeys=nullptr;
   uint32_t *pairVals=nullptr;
   uint64_t nPairs=0;
   uint32_t nLeaves=0,nChunks=0;
@@ -182,12 +183,9 @@ int uploadTables(wb_ctx *ctx)
   if (ctx->tablesUploaded)
     return WB_OK;
   double t[512],co[512],si[512];
-  unsigned char fw[48];
+  unsigned char fw[96];
   wbhost::fillTanTables(t,co,si);
-  memset(fw,0,sizeof(fw));
-  for (int i=0;i<6;i++)
-    for (int j=0;j<7;j++)
-      fw[i*8+j]=wbhost::kFwdTable[i][j];
+  wbhost::fillFlowsnakeTables(fw);
   CK(cudaMemcpyToSymbol(g_tanTable,t,sizeof(t)));
   CK(cudaMemcpyToSymbol(g_cosTable,co,sizeof(co)));
   CK(cudaMemcpyToSymbol(g_sinTable,si,sizeof(si)));
@@ -1183,15 +1181,15 @@ extern "C" int wb_scan(wb_ctx *ctx)
     bits++;
   bits=(bits+7)/8*8;
   bool inA=true;
-  CK(wb_radix_sort((uint64_t *)ctx->pairKeyA.p,ctx->pairValA.p,(uint64_t *)ctx->pairKeyB.p,ctx->pairValB.p,m,0,bits,
+  CK(wb_radix_sort(ctx->pairKeyA.p,ctx->pairValA.p,ctx->pairKeyB.p,ctx->pairValB.p,m,0,bits,
                    ctx->table.p,ctx->table.cap,ctx->blockSums.p,ctx->blockSums.cap,st,&inA,&ctx->stats.kernel_launches));
-  ctx->pairKeys=(uint64_t *)(inA?ctx->pairKeyA.p:ctx->pairKeyB.p);
+  ctx->pairKeys=inA?ctx->pairKeyA.p:ctx->pairKeyB.p;
   ctx->pairVals=inA?ctx->pairValA.p:ctx->pairValB.p;
   CK(cudaMemsetAsync(ctx->tNPoints.p,0,sizeof(int)*T,st));
   CK(cudaMemsetAsync(ctx->counters.p+3,0,sizeof(unsigned long long),st));
   CK(ctx->tileList.ensure(std::min<uint64_t>(T,(uint64_t)m)+1));
   if (m)
-    wb_segment_kernel<<<gridFor(m,256),256,0,st>>>((const unsigned long long *)ctx->pairKeys,m,ctx->tStart.p,ctx->tCount.p,
+    wb_segment_kernel<<<gridFor(m,256),256,0,st>>>(ctx->pairKeys,m,ctx->tStart.p,ctx->tCount.p,
                                                    ctx->tileList.p,ctx->counters.p+3);
   CK(cudaEventRecord(ctx->evC,st));
   unsigned long long nList=0;
