@@ -108,6 +108,7 @@ struct wb_ctx
   DevBuf<int> encMinMax;
   DevBuf<uint4> tilesOf;
   DevBuf<double> sx,sy,sz;
+  DevBuf<int4> packed;                    // (X, Y, Z, index of the file's header) per input point, for the gather
   DevBuf<uint8_t> staging[2];
   DevBuf<WbSegments> dsegs;
   DevBuf<WbNode> nodesA,nodesB;
@@ -388,7 +389,7 @@ extern "C" void wb_destroy(wb_ctx *ctx)
   ctx->tilesOf.release(); ctx->sx.release(); ctx->sy.release(); ctx->sz.release();
   ctx->staging[0].release(); ctx->staging[1].release(); ctx->dsegs.release();
   ctx->nodesA.release(); ctx->nodesB.release(); ctx->leaves.release(); ctx->bounds.release();
-  ctx->levelOff.release(); ctx->levelCnt.release();
+  ctx->levelOff.release(); ctx->levelCnt.release(); ctx->packed.release();
   ctx->hKeyA.release(); ctx->hKeyB.release(); ctx->hIdxA.release(); ctx->hIdxB.release(); ctx->hWinner.release(); ctx->hPerm.release();
   ctx->hx.release(); ctx->hy.release(); ctx->hz.release(); ctx->hLabel.release(); ctx->hBounds.release();
   ctx->tStart.release(); ctx->tCount.release(); ctx->tileList.release(); ctx->tNPoints.release(); ctx->tTree.release();
@@ -844,7 +845,7 @@ static int buildStore(wb_ctx *ctx,bool hilbert)
   const uint64_t n=ctx->n;
   cudaStream_t st=ctx->st;
   CK(ctx->keyA.ensure(n)); CK(ctx->keyB.ensure(n)); CK(ctx->idxA.ensure(n)); CK(ctx->idxB.ensure(n));
-  CK(ctx->sx.ensure(n)); CK(ctx->sy.ensure(n)); CK(ctx->sz.ensure(n));
+  CK(ctx->sx.ensure(n)); CK(ctx->sy.ensure(n)); CK(ctx->sz.ensure(n)); CK(ctx->packed.ensure(n));
   CK(ctx->scr0.ensure(n+1)); CK(ctx->scr1.ensure(n+1));
   CK(ctx->leafDepth.ensure(n));
   CK(ctx->labelIn.ensure(n)); CK(ctx->labelSorted.ensure(n));
@@ -857,9 +858,9 @@ static int buildStore(wb_ctx *ctx,bool hilbert)
     const WbSegment &sg=ctx->segs[s];
     if (!sg.count)
       continue;
-    wb_keygen_kernel<<<gridFor(sg.count,256),256,0,st>>>(ctx->xi.p,ctx->yi.p,ctx->zi.p,ctx->ret.p,sg.first,sg.count,sg,
+    wb_keygen_kernel<<<gridFor(sg.count,256),256,0,st>>>(ctx->xi.p,ctx->yi.p,ctx->zi.p,ctx->ret.p,sg.first,sg.count,sg,(int)s,
         ctx->geom.root_center[0],ctx->geom.root_center[1],ctx->geom.root_center[2],ctx->geom.root_side,hilbert?1:0,
-        ctx->keyA.p,ctx->idxA.p);
+        ctx->keyA.p,ctx->idxA.p,ctx->packed.p);
     ctx->stats.kernel_launches++;
   }
   KCHECK();
@@ -897,8 +898,7 @@ static int buildStore(wb_ctx *ctx,bool hilbert)
     CK(cudaMemcpyAsync(ctx->dsegs.p,&hs,offsetof(WbSegments,s)+sizeof(WbSegment)*(size_t)hs.n,cudaMemcpyHostToDevice,st));
     CK(cudaStreamSynchronize(st));
   }
-  wb_gather_kernel<<<gridFor(nv,256),256,0,st>>>(ctx->perm,nv,ctx->xi.p,ctx->yi.p,ctx->zi.p,ctx->dsegs.p,
-                                                ctx->sx.p,ctx->sy.p,ctx->sz.p);
+  wb_gather_kernel<<<gridFor(nv,256),256,0,st>>>(ctx->perm,nv,ctx->packed.p,ctx->dsegs.p,ctx->sx.p,ctx->sy.p,ctx->sz.p);
   ctx->stats.kernel_launches++;
   KCHECK();
   // ---- identical locations: one point per XYZ stays in the store (octree.cpp:620-662)
@@ -953,8 +953,8 @@ static int buildStore(wb_ctx *ctx,bool hilbert)
       ctx->nDup=nDup;
       ctx->nValid=nv-nDup;
       ctx->stats.n_points=ctx->nValid;
-      wb_gather_kernel<<<gridFor(ctx->nValid,256),256,0,st>>>(ctx->perm,ctx->nValid,ctx->xi.p,ctx->yi.p,ctx->zi.p,
-                                                             ctx->dsegs.p,ctx->sx.p,ctx->sy.p,ctx->sz.p);
+      wb_gather_kernel<<<gridFor(ctx->nValid,256),256,0,st>>>(ctx->perm,ctx->nValid,ctx->packed.p,ctx->dsegs.p,
+                                                             ctx->sx.p,ctx->sy.p,ctx->sz.p);
       ctx->stats.kernel_launches++;
       KCHECK();
     }
