@@ -180,9 +180,19 @@ float elapsed(cudaEvent_t a,cudaEvent_t b)
 }
 
 int uploadTables(wb_ctx *ctx)
+// The tables are __device__ globals: once per DEVICE, not per context (a second context of the same device must not
+// rewrite them under the kernels of the first).
 {
+  static std::mutex m;
+  static bool done[256]={};
   if (ctx->tablesUploaded)
     return WB_OK;
+  std::lock_guard<std::mutex> lk(m);
+  if (ctx->device>=0 && ctx->device<256 && done[ctx->device])
+  {
+    ctx->tablesUploaded=true;
+    return WB_OK;
+  }
   double t[512],co[512],si[512];
   unsigned char fw[96];
   wbhost::fillTanTables(t,co,si);
@@ -191,6 +201,8 @@ int uploadTables(wb_ctx *ctx)
   CK(cudaMemcpyToSymbol(g_cosTable,co,sizeof(co)));
   CK(cudaMemcpyToSymbol(g_sinTable,si,sizeof(si)));
   CK(cudaMemcpyToSymbol(g_fwdTable,fw,sizeof(fw)));
+  if (ctx->device>=0 && ctx->device<256)
+    done[ctx->device]=true;
   ctx->tablesUploaded=true;
   return WB_OK;
 }
