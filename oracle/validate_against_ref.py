@@ -36,6 +36,10 @@ CASES = [  # name, scene, n, seed, params
     ("urban_40k_slope2", 5, 40000, 9, {"max_slope": 2.0, "thickness": 0.1}),
     ("street_30k_tile3", 1, 30000, 4, {"tile_size": 3.0}),
     ("terrestrial_30k_slope05", 4, 30000, 6, {"max_slope": 0.5, "min_hyperboloid_size": 1.0}),
+    # round 2: a steep slope over small tiles, a thick layer under a large minimum hyperboloid, small tiles on format 6
+    ("aerial_25k_steep_tile05", 2, 25000, 13, {"max_slope": 3.0, "tile_size": 0.5}),
+    ("urban_20k_thick_bigmin", 5, 20000, 15, {"thickness": 0.3, "min_hyperboloid_size": 2.0}),
+    ("multitile_fmt6_30k_tile07", 3, 30000, 21, {"tile_size": 0.7, "max_slope": 1.5}),
 ]
 
 
