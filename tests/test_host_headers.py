@@ -45,3 +45,12 @@ def test_record_length_below_the_formats_minimum_is_not_a_las_file(tmp_path):
     out = subprocess.run([CLI, "--dump", str(tmp_path / "d"), _write(tmp_path, "short.las", short)],
                          capture_output=True, text=True, timeout=120)
     assert out.returncode == 1 and "not a LAS file" in out.stderr
+
+
+def test_cloud_surface_and_block_census_without_a_gpu():
+    """cloud.cpp's block view (getNumCloudBlocks / getCloudBlock) and testpattern.cpp's per-block census, in the
+    reference-shaped host library: wolkenbase_b200/host/hosttest.cpp (assertions, as the reference's wolkentest)."""
+    exe = os.path.join(ROOT, "wolkenbase_b200", "host", "hosttest")
+    subprocess.check_call(["make", "-s", "-C", os.path.dirname(exe)])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and "hosttest ok" in out.stdout, out.stdout + out.stderr
