@@ -60,7 +60,7 @@ def test_host_cli_passes_on_the_emulated_library():
     subprocess.check_call(["make", "-s", "-C", SIMT, "libwolken_b200_emulated.so"])
     env = dict(os.environ, LD_PRELOAD=EMULATED, WB_EMULATED="1")
     out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_host_cli.py"), "-m", "gpu",
-                          "-q", "-x", "-k", "reference_mode or embuffer or octstore_queries or cli_gpus_equals_oracle_and_one_gpu and 2-3",
+                          "-q", "-x", "-k", "reference_mode or embuffer or octstore_queries or census_after_writing or cli_gpus_equals_oracle_and_one_gpu and 2-3",
                           "-p", "no:cacheprovider"], capture_output=True, text=True, env=env, cwd=ROOT, timeout=900)
     tail = out.stdout[-3000:] + out.stderr[-2000:]
     assert out.returncode == 0, tail

@@ -333,3 +333,25 @@ def test_cli_gpus_equals_oracle_and_one_gpu(tmp_path, gpus, strips):
     assert ((recs[:, 15] & 31) == res.labels).all()
     assert open(tmp_path / ("o%d.las" % gpus), "rb").read() == open(tmp_path / "o1.las", "rb").read()
     assert open(tmp_path / ("d%d" % gpus), encoding="utf-8").read() == res.dump
+
+
+def test_cli_census_after_writing(tmp_path):
+    """censusPoints after every write (threads.cpp:613): the synthetic files carry the point number as GPS time; a
+    file with records cut out must be reported with exactly those numbers missing."""
+    cloud = synth.generate(2, 12000, seed=71)
+    gone = [5, 700, 701]
+    recs = np.delete(cloud.records, gone, axis=0)
+    cut = synth.Cloud(cloud.desc, cloud.header, np.ascontiguousarray(recs), cloud.bbox)
+    whole, holes = str(tmp_path / "whole.las"), str(tmp_path / "holes.las")
+    cloud.write(whole)
+    cut.write(holes)
+    a = subprocess.run([CLI, "-o", str(tmp_path / "a"), "--dump", str(tmp_path / "da"), whole], capture_output=True, text=True)
+    assert a.returncode == 0, a.stdout[-1500:] + a.stderr[-1500:]
+    assert "Max point %d" % cloud.n in a.stdout and "Missing points" not in a.stdout and "Duplicate point" not in a.stdout
+    b = subprocess.run([CLI, "-o", str(tmp_path / "b"), "--dump", str(tmp_path / "db"), holes], capture_output=True, text=True)
+    assert b.returncode == 0, b.stdout[-1500:] + b.stderr[-1500:]
+    assert "Max point %d" % cloud.n in b.stdout and "Missing points: 5,700,701" in b.stdout
+    # the host walk (records not on the device) says the same
+    c = subprocess.run([CLI, "-o", str(tmp_path / "c"), "--host-writer", "--census", "--dump", str(tmp_path / "dc"), holes],
+                       capture_output=True, text=True)
+    assert c.returncode == 0 and "Missing points: 5,700,701" in c.stdout, c.stdout[-1500:] + c.stderr[-1500:]
