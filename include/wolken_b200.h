@@ -117,6 +117,13 @@ int wb_add_las(wb_ctx *ctx,const uint8_t *recs,uint64_t n,int fmt,int rec_len,
  * (threads.cpp:485-500, 527-530) — the default here, decided per wb_add_las* call.  keep_all = 1 stores every
  * record, as a caller that feeds embufferPoint itself does (wolkencli.cpp:104-108). */
 int wb_set_return_zero_rule(wb_ctx *ctx,int keep_all);
+/* Of the records of every following wb_add_las* call keep those whose x = (offset+scale*X)*unit lies in [x_lo,x_hi),
+ * in their order; the others are as if they were not in the file (return-number rule still decided by the file's
+ * record 0).  For the ranks of a sharded run that are all handed the SAME whole files: rank r takes its x-interval
+ * (wolkencli --gpus N with fewer files than GPUs).  -INFINITY, +INFINITY switches it off; wb_clear does too.  Not
+ * together with wb_keep_records. */
+int wb_set_window(wb_ctx *ctx,double x_lo,double x_hi);
+int wb_num_loaded(wb_ctx *ctx,uint64_t *n);         /* records the context holds (all wb_add_las* calls so far) */
 /* Same, straight from the file (LasHeader::readPoint's seek+read per point, las.cpp:735-745,
  * becomes a pipeline): worker threads pread 1 Mi-record chunks starting at byte point_offset into a
  * ring of pinned buffers while earlier chunks are copied and decoded.  A short file is an error. */

@@ -355,3 +355,25 @@ def test_cli_census_after_writing(tmp_path):
     c = subprocess.run([CLI, "-o", str(tmp_path / "c"), "--host-writer", "--census", "--dump", str(tmp_path / "dc"), holes],
                        capture_output=True, text=True)
     assert c.returncode == 0 and "Missing points: 5,700,701" in c.stdout, c.stdout[-1500:] + c.stderr[-1500:]
+
+
+@pytest.mark.parametrize("gpus,files", [(3, 1), (4, 2)])
+def test_cli_gpus_on_fewer_files_than_gpus(tmp_path, gpus, files):
+    """One big file (or fewer files than GPUs): every worker reads every file and keeps its x-interval (wb_set_window);
+    the class bytes come back in input order.  Output identical to --gpus 1, labels equal to the oracle's."""
+    import torch
+    clouds, names = _strip_files(tmp_path, 2, 50000, files, seed=63)
+    env = dict(os.environ)
+    if os.environ.get("WB_EMULATED") or torch.cuda.device_count() < gpus:
+        env["WOLKEN_TRANSPORT"] = "local"
+    outs = {}
+    for g in (gpus, 1):
+        o = subprocess.run([CLI, "--gpus", str(g), "-o", str(tmp_path / ("o%d" % g)), "--lossless", "--separate-classes",
+                            "0", "--dump", str(tmp_path / ("d%d" % g))] + names, capture_output=True, text=True, env=env)
+        assert o.returncode == 0, o.stdout[-2000:] + o.stderr[-2000:]
+        outs[g] = o.stdout
+    assert "%d GPUs" % gpus in outs[gpus]
+    res = O.run([O.file_from_cloud(c) for c in clouds])
+    _, recs, _ = _read_las(str(tmp_path / ("o%d.las" % gpus)))
+    assert ((recs[:, 15] & 31) == res.labels).all()
+    assert open(tmp_path / ("o%d.las" % gpus), "rb").read() == open(tmp_path / "o1.las", "rb").read()

@@ -138,3 +138,44 @@ def test_many_files_per_rank():
     c = strips(2, 60000, 140)
     ref, sst, st = check([c[:70], c[70:]])
     assert all(s["n_halo_classify"] > 0 for s in sst)
+
+
+def _x_of(cloud):
+    ints = np.ascontiguousarray(cloud.records[:, :12]).view(np.int32).reshape(-1, 3)
+    return cloud.offset[0] + cloud.scale[0] * ints[:, 0].astype(np.float64)
+
+
+@pytest.mark.parametrize("world,scene,n", [(3, 2, 60000), (4, 3, 50000)])
+def test_whole_files_split_by_x_window(world, scene, n):
+    """Every rank is handed the SAME whole files and keeps its x-interval (wb_set_window: wolkencli --gpus N on one big
+    file).  Intervals cut at odd places, one file with zero-return records (the rule is decided by the FILE's record 0
+    on every rank) and identical locations across a cut."""
+    a = synth.generate(scene, n, seed=41)
+    recs = a.records.copy()
+    recs[4::11, 14] &= 0xf8 if a.fmt < 6 else 0xf0
+    assert recs[0, 14] & 7
+    x = _x_of(a)
+    qs = np.quantile(x, [k / world for k in range(1, world)])
+    cuts = [-np.inf] + [float(q) + 0.0137 for q in qs] + [np.inf]
+    # a record just right of the first cut takes the XYZ of one just left of it
+    left = np.where(x < cuts[1])[0][-1]
+    right = np.where(x >= cuts[1])[0][0]
+    recs[right, :12] = recs[left, :12]
+    f = plain(a, recs)
+    p = dict(PARAMS)
+    ref = O.run([O.file_from_cloud(f)], **p)
+    ofile = O.file_from_cloud(f)
+    O.run([ofile], classify=False, **p)
+    keep = ofile["_keep"]
+    labs, sst, st = multigpu.run_threads([[f]] * world, p, windows=[(cuts[r], cuts[r + 1]) for r in range(world)])
+    xf = _x_of(f)
+    rank = np.searchsorted(np.array(cuts[1:-1]), xf, side="right")
+    got = np.empty(f.n, dtype=np.uint8)
+    for r in range(world):
+        assert len(labs[r]) == int((rank == r).sum())
+        got[rank == r] = labs[r]
+    mism = int((got[keep] != ref.labels).sum())
+    assert mism <= sum(int(s["n_margin"]) for s in st) + int(ref.margin_count)
+    cls = (f.records[:, 15] & 31) if f.fmt < 6 else f.records[:, 16]
+    assert (got[~keep] == cls[~keep]).all()
+    assert all(s["por_max"] == float(ref.tiles["hyperboloidSize"].max()) * p["max_slope"] ** 2 for s in sst)

@@ -153,6 +153,8 @@ def lib():
             "wb_keep_records": [vp, C.c_int],
             "wb_census": [vp, C.POINTER(CensusResult), vp, C.c_uint64],
             "wb_device_count": [C.POINTER(C.c_int)],
+            "wb_set_window": [vp, C.c_double, C.c_double],
+            "wb_num_loaded": [vp, C.POINTER(C.c_uint64)],
             "wb_leaf_class_counts": [vp, vp, C.c_int, C.c_int, vp],
             "wb_encode": [vp, C.POINTER(OutSpec), vp, vp, C.c_uint32, vp, u64, vp],
             "wb_get_duplicates": [vp, vp, vp, u64],
@@ -195,7 +197,7 @@ EXPORTS = ["wb_create", "wb_destroy", "wb_last_error", "wb_reserve", "wb_clear",
            "wb_query_points", "wb_mark", "wb_mark_elapsed", "wb_set_return_zero_rule",
            "wb_comm_get_id", "wb_comm_init", "wb_local_group_create", "wb_local_group_destroy", "wb_comm_init_local",
            "wb_comm_init_custom", "wb_comm_destroy", "wb_shard_run", "wb_shard_get_labels", "wb_shard_get_stats",
-           "wb_set_labels", "wb_device_count", "wb_census"]
+           "wb_set_labels", "wb_device_count", "wb_census", "wb_set_window", "wb_num_loaded"]
 
 
 def _d(v):
@@ -483,6 +485,15 @@ class Context:
         lab = out if out is not None else np.empty(n, dtype=np.uint8)
         self._ck(self._L.wb_get_labels(self._h, lab.ctypes.data))
         return lab
+
+    def set_window(self, x_lo, x_hi):
+        """Keep only records with x in [x_lo, x_hi) from the following add_las* calls (wb_set_window)."""
+        self._ck(self._L.wb_set_window(self._h, float(x_lo), float(x_hi)))
+
+    def num_loaded(self):
+        n = C.c_uint64()
+        self._ck(self._L.wb_num_loaded(self._h, C.byref(n)))
+        return int(n.value)
 
     def census(self, cap=64):
         """censusPoints() (testpattern.cpp:84-123) over the store: dict with status, max_point, n_missing, n_duplicate

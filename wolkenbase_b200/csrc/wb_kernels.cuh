@@ -172,6 +172,60 @@ wb_decode_kernel(const uint8_t *__restrict__ recs,unsigned long long n,int fmt,i
   }
 }
 
+// ============================================================================ K1b: x-window of a rank
+// A rank of a sharded run may be handed WHOLE files and an x-interval (wb_set_window): of every file it keeps the
+// records whose x lies in [lo,hi), in file order — so that one big file can be classified by several GPUs without
+// being cut up first (each rank decodes all of it; decode is a millisecond per 100 M records).
+
+__global__ void __launch_bounds__(256)
+wb_window_flag_kernel(const int *__restrict__ xi,const uint8_t *__restrict__ ret,unsigned long long first,unsigned long long n,
+                      WbSegment seg,double lo,double hi,uint32_t *__restrict__ flag,unsigned long long *__restrict__ nDropped)
+// flag[t] = record first+t is inside; the dropped-record counter loses the dropped records that go away
+{
+  unsigned long long t=(unsigned long long)blockIdx.x*blockDim.x+threadIdx.x;
+  bool inside=false,gone=false;
+  if (t<n)
+  {
+    const double x=wb_coord(seg.offset[0],seg.scale[0],xi[first+t],seg.unit);
+    inside=x>=lo && x<hi;
+    gone=!inside && ret[first+t]==0;
+    flag[t]=inside?1u:0u;
+  }
+  const unsigned g=__ballot_sync(WB_FULL,gone);
+  if ((threadIdx.x&31)==0 && g)
+    atomicAdd(nDropped,(unsigned long long)(0ull-(unsigned long long)__popc(g)));
+}
+
+__global__ void __launch_bounds__(256)
+wb_window_scatter_kernel(const uint32_t *__restrict__ flag,const uint32_t *__restrict__ off,unsigned long long first,
+                         unsigned long long n,const int *__restrict__ xi,const int *__restrict__ yi,const int *__restrict__ zi,
+                         const uint8_t *__restrict__ cls,const uint8_t *__restrict__ ret,
+                         int *__restrict__ ox,int *__restrict__ oy,int *__restrict__ oz,uint8_t *__restrict__ oc,
+                         uint8_t *__restrict__ oret)
+{
+  unsigned long long t=(unsigned long long)blockIdx.x*blockDim.x+threadIdx.x;
+  if (t>=n || !flag[t])
+    return;
+  const uint32_t o=off[t];
+  ox[o]=xi[first+t]; oy[o]=yi[first+t]; oz[o]=zi[first+t];
+  oc[o]=cls[first+t];
+  oret[o]=ret[first+t];
+}
+
+__global__ void __launch_bounds__(256)
+wb_window_copy_back_kernel(const int *__restrict__ ix,const int *__restrict__ iy,const int *__restrict__ iz,
+                           const uint8_t *__restrict__ ic,const uint8_t *__restrict__ iret,unsigned long long m,
+                           unsigned long long first,int *__restrict__ xi,int *__restrict__ yi,int *__restrict__ zi,
+                           uint8_t *__restrict__ cls,uint8_t *__restrict__ ret)
+{
+  unsigned long long t=(unsigned long long)blockIdx.x*blockDim.x+threadIdx.x;
+  if (t>=m)
+    return;
+  xi[first+t]=ix[t]; yi[first+t]=iy[t]; zi[first+t]=iz[t];
+  cls[first+t]=ic[t];
+  ret[first+t]=iret[t];
+}
+
 // ============================================================================ K2: Morton keys
 
 __device__ __forceinline__ uint32_t wb_cell21(double v,double c,double side)

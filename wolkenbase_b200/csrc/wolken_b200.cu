@@ -147,6 +147,8 @@ struct wb_ctx
   wb_stats stats{};
   bool tablesUploaded=false;
   bool pacedCopies=false;             // WB_H2D_PACED=1: wb_add_las keeps at most two chunk copies queued (no gain measured)
+  bool windowOn=false;                // wb_set_window: keep only the records with x in [windowLo,windowHi)
+  double windowLo=0,windowHi=0;
   bool storeHilbert=false;            // the store is a classify-only one (buildStore(ctx,true)): Hilbert order, no leaves
 };
 
@@ -274,6 +276,55 @@ int decodeDevice(wb_ctx *ctx,const uint8_t *d,uint64_t first,uint64_t cnt,int fm
       ctx->cls.p+first,ctx->ret.p+first,ctx->counters.p+2);
   ctx->stats.kernel_launches++;
   KCHECK();
+  return WB_OK;
+}
+
+int applyWindow(wb_ctx *ctx,uint64_t n,const double scale[3],const double offset[3],double unit,uint64_t *kept)
+// The n records just decoded at [ctx->n,ctx->n+n): keep those inside the context's x-window, in their order.
+{
+  *kept=n;
+  if (!ctx->windowOn || !n)
+    return WB_OK;
+  if (ctx->keepRecords)
+    return fail(ctx,WB_ERR_STATE,"wb_set_window and wb_keep_records do not go together");
+  cudaStream_t st=ctx->st;
+  const uint64_t first=ctx->n;
+  WbSegment sg;
+  sg.first=first;
+  sg.count=n;
+  for (int k=0;k<3;k++)
+  {
+    sg.scale[k]=scale[k];
+    sg.offset[k]=offset[k];
+  }
+  sg.unit=unit;
+  TmpBuf<uint32_t> flag,off;
+  TmpBuf<int> tx,ty,tz;
+  TmpBuf<uint8_t> tc,tr;
+  CK(flag.ensure(n+1)); CK(off.ensure(n+1));
+  CK(ctx->blockSums.ensure(wb_div_up(n+1,WB_SCAN_TILE)+1024));
+  CK(cudaMemsetAsync(flag.p+n,0,sizeof(uint32_t),st));
+  wb_window_flag_kernel<<<gridFor(n,256),256,0,st>>>(ctx->xi.p,ctx->ret.p,first,n,sg,ctx->windowLo,ctx->windowHi,flag.p,
+                                                    ctx->counters.p+2);
+  ctx->stats.kernel_launches++;
+  KCHECK();
+  CK(wb_exclusive_scan(flag.p,off.p,n+1,ctx->blockSums.p,ctx->blockSums.cap,st,&ctx->stats.kernel_launches));
+  uint32_t m=0;
+  CK(cudaMemcpyAsync(&m,off.p+n,sizeof(uint32_t),cudaMemcpyDeviceToHost,st));
+  CK(cudaStreamSynchronize(st));
+  if (m<n)
+  {
+    CK(tx.ensure(m+1)); CK(ty.ensure(m+1)); CK(tz.ensure(m+1)); CK(tc.ensure(m+1)); CK(tr.ensure(m+1));
+    wb_window_scatter_kernel<<<gridFor(n,256),256,0,st>>>(flag.p,off.p,first,n,ctx->xi.p,ctx->yi.p,ctx->zi.p,ctx->cls.p,ctx->ret.p,
+                                                         tx.p,ty.p,tz.p,tc.p,tr.p);
+    if (m)
+      wb_window_copy_back_kernel<<<gridFor(m,256),256,0,st>>>(tx.p,ty.p,tz.p,tc.p,tr.p,m,first,ctx->xi.p,ctx->yi.p,ctx->zi.p,
+                                                             ctx->cls.p,ctx->ret.p);
+    ctx->stats.kernel_launches+=2;
+    KCHECK();
+    CK(cudaStreamSynchronize(st));
+  }
+  *kept=m;
   return WB_OK;
 }
 
@@ -467,6 +518,7 @@ extern "C" int wb_clear(wb_ctx *ctx)
   ctx->nLeaves=0;
   ctx->ownFirst=0;
   ctx->ownEnd=0xffffffffu;
+  ctx->windowOn=false;
   uint64_t launches=ctx->stats.kernel_launches;
   memset(&ctx->stats,0,sizeof(ctx->stats));
   ctx->stats.kernel_launches=launches;
@@ -561,7 +613,12 @@ extern "C" int wb_add_las_device(wb_ctx *ctx,const uint8_t *d,uint64_t n,int fmt
     CK(cudaMemcpyAsync(kept,d,(size_t)(n*recLen),cudaMemcpyDeviceToDevice,ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
   }
-  return addSegment(ctx,n,scale,offset,unit,kept,fmt,recLen);
+  {
+    uint64_t inside=n;
+    if ((rc=applyWindow(ctx,n,scale,offset,unit,&inside)))
+      return rc;
+    return addSegment(ctx,inside,scale,offset,unit,kept,fmt,recLen);
+  }
 }
 
 extern "C" int wb_add_las(wb_ctx *ctx,const uint8_t *recs,uint64_t n,int fmt,int recLen,
@@ -622,7 +679,12 @@ extern "C" int wb_add_las(wb_ctx *ctx,const uint8_t *recs,uint64_t n,int fmt,int
   CK(cudaEventRecord(ctx->evB,ld));
   CK(cudaStreamSynchronize(ld));
   ctx->stats.ms_h2d+=elapsed(ctx->evA,ctx->evB);       // copy and decode overlap: one figure for both
-  return addSegment(ctx,n,scale,offset,unit,kept,fmt,recLen);
+  {
+    uint64_t inside=n;
+    if ((rc=applyWindow(ctx,n,scale,offset,unit,&inside)))
+      return rc;
+    return addSegment(ctx,inside,scale,offset,unit,kept,fmt,recLen);
+  }
 }
 
 // ---- the reader pipeline: pread into a pinned ring on worker threads, H2D and decode behind it
@@ -797,7 +859,12 @@ extern "C" int wb_add_las_file(wb_ctx *ctx,const char *path,uint64_t pointOffset
   ctx->stats.ms_h2d+=elapsed(ctx->evA,ctx->evB);       // file read, copy and decode overlap: one figure
   if (kept)
     ctx->recBufs.push_back(kept);
-  return addSegment(ctx,n,scale,offset,unit,kept,fmt,recLen);
+  {
+    uint64_t inside=n;
+    if ((rc=applyWindow(ctx,n,scale,offset,unit,&inside)))
+      return rc;
+    return addSegment(ctx,inside,scale,offset,unit,kept,fmt,recLen);
+  }
 }
 
 extern "C" int wb_add_points_device(wb_ctx *ctx,const int32_t *dx,const int32_t *dy,const int32_t *dz,const uint8_t *dc,
@@ -1661,6 +1728,24 @@ extern "C" int wb_set_return_zero_rule(wb_ctx *ctx,int keep_all)
   if (!ctx)
     return WB_ERR_ARG;
   ctx->keepZeroReturns=keep_all!=0;
+  return WB_OK;
+}
+
+extern "C" int wb_set_window(wb_ctx *ctx,double x_lo,double x_hi)
+{
+  if (!ctx || !(x_lo<x_hi))
+    return WB_ERR_ARG;
+  ctx->windowOn=!(x_lo==-INFINITY && x_hi==INFINITY);
+  ctx->windowLo=x_lo;
+  ctx->windowHi=x_hi;
+  return WB_OK;
+}
+
+extern "C" int wb_num_loaded(wb_ctx *ctx,uint64_t *n)
+{
+  if (!ctx || !n)
+    return WB_ERR_ARG;
+  *n=ctx->n;
   return WB_OK;
 }
 

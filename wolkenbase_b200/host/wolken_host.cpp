@@ -1287,9 +1287,10 @@ struct RankBarrier
 };
 
 bool shardable()
-// every run is a whole file and there are at least two of them, in ascending x (wb_shard_run checks the order)
+// every run is a whole file.  With at least as many files as GPUs the files are dealt out as x-strips (ascending x:
+// wb_shard_run checks the order); with fewer — one big file — every worker reads every file and keeps its x-interval.
 {
-  if (g_nGpus<2 || g_files.size()<2)
+  if (g_nGpus<2 || g_files.empty())
     return false;
   for (auto &f:g_files)
     if (f.firstRec!=0 || f.count!=f.h->numberPoints())
@@ -1302,13 +1303,53 @@ bool classifySharded()
 // of its own records; they go into the (built) store of the first device with wb_set_labels, so that counting,
 // queries and the writers work as after a single-GPU classify.
 {
-  const int W=(int)min<size_t>(g_nGpus,g_files.size());
+  const bool windows=g_files.size()<(size_t)g_nGpus;
+  const int W=windows?g_nGpus:(int)min<size_t>(g_nGpus,g_files.size());
   const auto t0=chrono::steady_clock::now();
   size_t total=0;
   for (auto &f:g_files)
     total+=f.count;
+  // x-intervals for the window mode: equal-count quantiles of a sample of the records' x, moved onto boundaries of
+  // the octree's finest cells (side/2^21) — two points with the same Morton key then always fall into the same
+  // interval, so the order of equal keys (input order) is the single-GPU one on every rank
+  vector<double> cuts;
+  auto xOf=[](const LasHeader *h,size_t i)
+  {
+    int32_t X;
+    memcpy(&X,h->records()+i*(size_t)h->getPointLength(),4);
+    return (h->rawOffset(0)+h->rawScale(0)*(double)X)*h->getUnit();       // las.cpp:808, as wb_coord on the device
+  };
+  if (windows)
+  {
+    vector<double> sample;
+    const size_t step=max<size_t>(1,total/2000000);
+    for (auto &f:g_files)
+      for (size_t i=0;i<f.count;i+=step)
+        sample.push_back(xOf(f.h,i));
+    sort(sample.begin(),sample.end());
+    const double side=octRoot.getSide(),corner=octRoot.getCenter().getx()-0.5*side,cell=side/2097152.0;
+    cuts.assign(W+1,0);
+    cuts[0]=-INFINITY;
+    cuts[W]=INFINITY;
+    for (int r=1;r<W;r++)
+    {
+      double c=sample[sample.size()*(size_t)r/W];
+      if (cell>0)
+        c=corner+floor((c-corner)/cell+0.5)*cell;
+      cuts[r]=c;
+      if (!(cuts[r]>cuts[r-1]))
+      {
+        cerr<<"the points do not spread over "<<W<<" x-intervals\n";
+        return false;
+      }
+    }
+  }
   // contiguous groups of files, about total/W records each, none empty
   vector<size_t> firstFile(W+1,g_files.size());
+  if (windows)
+    for (int r=0;r<=W;r++)
+      firstFile[r]=r<W?0:g_files.size();             // every worker walks all files
+  else
   {
     size_t cum=0,i=0;
     for (int r=0;r<W;r++)
@@ -1340,6 +1381,7 @@ bool classifySharded()
     return false;
   }
   vector<uint8_t> labels(total);
+  vector<vector<uint8_t>> rankLabels(windows?W:0);   // window mode: each worker's records are a subsequence of the input
   vector<string> errors(W);
   shardReport=ShardReport();
   shardReport.ranks.assign(W,wb_shard_stats());
@@ -1357,25 +1399,52 @@ bool classifySharded()
     size_t firstRecord=0;
     for (size_t i=0;i<firstFile[r];i++)
       firstRecord+=g_files[i].count;
+    size_t nMine=0;
     if (ok)
     {
       wb_set_params(c,g_snakeTile,maxSlope,thickness,minHyperboloidSize);
-      for (size_t i=firstFile[r];ok && i<firstFile[r+1];i++)
+      vector<size_t> mine;                           // the files this worker reads
+      for (size_t i=windows?0:firstFile[r];ok && i<(windows?g_files.size():firstFile[r+1]);i++)
       {
         LasHeader *h=g_files[i].h;
         xyz a=h->minCorner(),b=h->maxCorner();
         double mn[3]={a.getx(),a.gety(),a.getz()},mx[3]={b.getx(),b.gety(),b.getz()};
+        if (windows)
+        {
+          // the part of the file's box inside the interval: all workers' boxes together span the files' own boxes,
+          // so the geometry (octree cube, tile lattice) is the single-GPU one
+          mn[0]=max(mn[0],cuts[r]);
+          mx[0]=min(mx[0],cuts[r+1]);
+          if (!(mn[0]<=mx[0]))
+            continue;                                // nothing of this file can lie in the interval
+        }
+        mine.push_back(i);
         ok=wb_add_extent(c,mn,mx)==WB_OK;
       }
-      for (size_t i=firstFile[r];ok && i<firstFile[r+1];i++)
+      if (ok && windows)
+        ok=wb_set_window(c,cuts[r],cuts[r+1])==WB_OK;
+      if (ok && mine.empty())
       {
+        ok=false;
+        errors[r]="no input file reaches this worker's x-interval";
+      }
+      for (size_t k=0;ok && k<mine.size();k++)
+      {
+        const size_t i=mine[k];
         LasHeader *h=g_files[i].h;
         double sc[3]={h->rawScale(0),h->rawScale(1),h->rawScale(2)},of[3]={h->rawOffset(0),h->rawOffset(1),h->rawOffset(2)};
         ok=wb_add_las_file(c,h->getFileName().c_str(),h->getPointOffset(),h->numberPoints(),h->getPointFormat(),
                            h->getPointLength(),sc,of,h->getUnit())==WB_OK;
       }
-      if (!ok)
+      if (!ok && errors[r].empty())
         errors[r]=wb_last_error(c);
+      if (ok && windows)
+      {
+        uint64_t kept=0;                             // records inside the interval = what the context holds now
+        ok=wb_num_loaded(c,&kept)==WB_OK;
+        nMine=kept;
+        rankLabels[r].resize(nMine+1);
+      }
     }
     if (gate.meet(ok))
     {
@@ -1384,14 +1453,14 @@ bool classifySharded()
       if (rc==WB_OK)
         rc=wb_shard_run(c,cm);
       if (rc==WB_OK)
-        rc=wb_shard_get_labels(c,labels.data()+firstRecord);
+        rc=wb_shard_get_labels(c,windows?rankLabels[r].data():labels.data()+firstRecord);
       if (rc!=WB_OK)
       {
         cerr<<"GPU "<<dev<<": "<<wb_last_error(c)<<endl;
         exit(4);
       }
       wb_shard_get_stats(c,&shardReport.ranks[r]);
-      shardReport.files[r]=firstFile[r+1]-firstFile[r];
+      shardReport.files[r]=windows?g_files.size():firstFile[r+1]-firstFile[r];
       shardReport.device[r]=dev;
     }
     if (cm)
@@ -1412,6 +1481,63 @@ bool classifySharded()
       cerr<<"GPU worker "<<r<<": "<<errors[r]<<endl;
       return false;
     }
+  if (windows)
+  {
+    // record i of the input belongs to the worker whose interval holds its x; each worker's class bytes come in the
+    // order of its records, which is the input's.  Two passes over chunks of the input, in parallel.
+    const int T=8;
+    vector<size_t> fileFirst(g_files.size()+1,0);
+    for (size_t i=0;i<g_files.size();i++)
+      fileFirst[i+1]=fileFirst[i]+g_files[i].count;
+    auto rankOf=[&](double x){ return (int)(upper_bound(cuts.begin()+1,cuts.end()-1,x)-(cuts.begin()+1)); };
+    vector<vector<size_t>> cnt(T,vector<size_t>(W,0));
+    auto span=[&](int t,size_t &a,size_t &b){ a=total*(size_t)t/T; b=total*(size_t)(t+1)/T; };
+    auto walk=[&](int t,bool fill,vector<size_t> pos)
+    {
+      size_t a,b;
+      span(t,a,b);
+      size_t f=upper_bound(fileFirst.begin(),fileFirst.end(),a)-fileFirst.begin()-1;
+      for (size_t i=a;i<b;i++)
+      {
+        while (i>=fileFirst[f+1])
+          f++;
+        const int r=rankOf(xOf(g_files[f].h,i-fileFirst[f]));
+        if (fill)
+          labels[i]=rankLabels[r][pos[r]++];
+        else
+          cnt[t][r]++;
+      }
+    };
+    {
+      vector<thread> th2;
+      for (int t=0;t<T;t++)
+        th2.emplace_back(walk,t,false,vector<size_t>());
+      for (auto &t:th2)
+        t.join();
+    }
+    vector<vector<size_t>> start(T,vector<size_t>(W,0));
+    for (int r=0;r<W;r++)
+    {
+      size_t acc=0;
+      for (int t=0;t<T;t++)
+      {
+        start[t][r]=acc;
+        acc+=cnt[t][r];
+      }
+      if (acc+1!=rankLabels[r].size())
+      {
+        cerr<<"internal: worker "<<r<<" kept "<<rankLabels[r].size()-1<<" records, the host counts "<<acc<<endl;
+        return false;
+      }
+    }
+    {
+      vector<thread> th2;
+      for (int t=0;t<T;t++)
+        th2.emplace_back(walk,t,true,start[t]);
+      for (auto &t:th2)
+        t.join();
+    }
+  }
   if (wb_set_labels(g_ctx,labels.data())!=WB_OK)
   {
     die("labels");

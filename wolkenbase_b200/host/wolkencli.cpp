@@ -7,8 +7,8 @@
 //     --points-per-file N        split outputs every N points (0 = no split)
 //     --separate-classes 0|1     one file per class (default 1, as the GUI)
 //     --gpus N, --threads N      spread scan, postscan and classify over N GPUs (startThreads(N), threads.cpp:91-113):
-//                                the input files are taken in ascending x and dealt out as N x-strips; needs at least
-//                                two files that do not interleave in x, else one GPU does the work
+//                                with at least N files they are taken in ascending x and dealt out as N x-strips; with
+//                                fewer (one big file) every GPU reads every file and keeps its x-interval
 //     --census                   after writing, count the stored points by their GPS time (test data carries the point
 //                                number there; censusPoints, threads.cpp:613): always done when the records are on
 //                                the GPU (the default writer), on request with --lossless / --host-writer

@@ -22,26 +22,34 @@ from . import api
 PARAMS = dict(tile_size=1.0, max_slope=1.0, thickness=0.0, min_hyperboloid_size=0.1)
 
 
-def load_rank(ctx, clouds, params=None, dev_records=None):
-    """The rank's own files into its context: header corners + records (host arrays, or device pointers)."""
+def load_rank(ctx, clouds, params=None, dev_records=None, window=None):
+    """The rank's own files into its context: header corners + records (host arrays, or device pointers).
+    window = (x_lo, x_hi): the rank is handed WHOLE files and keeps the records with x in that interval
+    (wb_set_window); its header boxes are clipped to it."""
     ctx.clear()
     ctx.set_params(**dict(PARAMS, **(params or {})))
+    if window is not None:
+        ctx.set_window(*window)
     for c in clouds:
-        ctx.add_extent(c.min_corner, c.max_corner)
+        mn, mx = list(c.min_corner), list(c.max_corner)
+        if window is not None:
+            mn[0], mx[0] = max(mn[0], window[0]), min(mx[0], window[1])
+        ctx.add_extent(mn, mx)
     for i, c in enumerate(clouds):
         if dev_records is not None:
             ctx.add_las_device(dev_records[i], c.n, c.fmt, c.rec_len, c.scale, c.offset)
         else:
             ctx.add_las(c.records, c.fmt, c.scale, c.offset)
-    return sum(c.n for c in clouds)
+    return ctx.num_loaded() if window is not None else sum(c.n for c in clouds)
 
 
 # ---------------------------------------------------------------------------- ranks as threads (LOCAL transport)
 
-def run_threads(clouds_per_rank, params=None, devices=None, transport="local"):
+def run_threads(clouds_per_rank, params=None, devices=None, transport="local", windows=None):
     """clouds_per_rank[r] = list of synth.Cloud-like files of rank r (ascending x).  Every rank runs in its own host
     thread on devices[r] (default: all on device 0).  transport "local": plain copies + a barrier; "nccl": one NCCL
     communicator per thread, which needs a distinct device per rank (what wolkencli --gpus N does).
+    windows[r] = (x_lo, x_hi): every rank is given the same whole files and keeps its x-interval.
     Returns (labels per rank, shard stats per rank, wb stats)."""
     W = len(clouds_per_rank)
     devices = devices or [0] * W
@@ -54,7 +62,7 @@ def run_threads(clouds_per_rank, params=None, devices=None, transport="local"):
         try:
             ctx = api.Context(devices[r])
             comm = api.Comm.local(ctx, group, r) if group is not None else api.Comm.nccl(ctx, uid, r, W)
-            n = load_rank(ctx, clouds_per_rank[r], params)
+            n = load_rank(ctx, clouds_per_rank[r], params, window=windows[r] if windows else None)
             ctx.shard_run(comm)
             out[r] = (ctx.shard_labels(n), ctx.shard_stats(), ctx.stats())
             comm.close()
